@@ -1,0 +1,133 @@
+/* unitex_b200 -- C ABI of the B200-native UniTEX hot path (libunitex_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  All data pointers are
+ * DEVICE pointers unless a comment says "host"; bf16 tensors are row-major with the stated leading dimension in
+ * elements; every call only enqueues work on `stream` (a cudaStream_t passed as void*).  Outputs are caller
+ * allocated and borrowed until the stream is synchronised.  Return value: 0 = ok, non-zero = error, message in
+ * utx_last_error() (thread-local).  No global state; one utx_flux handle per device.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the UniTEX repository root).
+ */
+#ifndef UNITEX_B200_H
+#define UNITEX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* utx_last_error(void);
+int utx_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * FLUX.1-dev MM-DiT transformer.  Replaces `self.transformer(...)` in PBRFluxPipeline.__call__
+ * (flux_piplines/texturing/pipeline.py:646-656; flux_piplines/delight/pipeline.py identical), i.e. diffusers'
+ * FluxTransformer2DModel.forward, and the Euler loop around it (:634-681).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct utx_flux utx_flux;
+
+typedef struct utx_flux_config {
+  int in_channels;            /* 64 */
+  int num_layers;             /* 19 double-stream blocks */
+  int num_single_layers;      /* 38 single-stream blocks */
+  int num_heads;              /* 24 */
+  int head_dim;               /* 128 (required) */
+  int joint_attention_dim;    /* 4096 */
+  int pooled_projection_dim;  /* 768 */
+  int guidance_embeds;        /* 1 */
+  int mlp_ratio;              /* 4 */
+} utx_flux_config;
+
+/* Weights are bf16 nn.Linear layout [out, in] (+ bias [out]); LoRA adapters already merged (utx_lora_merge). */
+typedef struct utx_double_block {
+  const void *w_qkv_img, *b_qkv_img;   /* [3D, D]  attn.to_q | to_k | to_v stacked on rows            */
+  const void *w_qkv_txt, *b_qkv_txt;   /* [3D, D]  attn.add_q_proj | add_k_proj | add_v_proj          */
+  const void *rms_q_img, *rms_k_img;   /* [128]    attn.norm_q / norm_k weights                        */
+  const void *rms_q_txt, *rms_k_txt;   /* [128]    attn.norm_added_q / norm_added_k                    */
+  const void *w_out_img, *b_out_img;   /* [D, D]   attn.to_out.0                                       */
+  const void *w_out_txt, *b_out_txt;   /* [D, D]   attn.to_add_out                                     */
+  const void *w_ff1_img, *b_ff1_img;   /* [4D, D]  ff.net.0.proj                                       */
+  const void *w_ff2_img, *b_ff2_img;   /* [D, 4D]  ff.net.2                                            */
+  const void *w_ff1_txt, *b_ff1_txt;   /* [4D, D]  ff_context.net.0.proj                               */
+  const void *w_ff2_txt, *b_ff2_txt;   /* [D, 4D]  ff_context.net.2                                    */
+} utx_double_block;
+
+typedef struct utx_single_block {
+  const void *w_qkvmlp, *b_qkvmlp;     /* [3D + 4D, D]  attn.to_q | to_k | to_v | proj_mlp             */
+  const void *rms_q, *rms_k;           /* [128]                                                        */
+  const void *w_out, *b_out;           /* [D, 5D]  proj_out over cat[attn, mlp]                        */
+} utx_single_block;
+
+typedef struct utx_flux_weights {
+  const void *w_x_embed, *b_x_embed;       /* [D, in_channels]       x_embedder                        */
+  const void *w_ctx_embed, *b_ctx_embed;   /* [D, joint_attention]   context_embedder                  */
+  const void *w_t1, *b_t1, *w_t2, *b_t2;   /* time_text_embed.timestep_embedder.linear_1/2             */
+  const void *w_g1, *b_g1, *w_g2, *b_g2;   /* time_text_embed.guidance_embedder.linear_1/2 (or NULL)   */
+  const void *w_p1, *b_p1, *w_p2, *b_p2;   /* time_text_embed.text_embedder.linear_1/2                 */
+  /* every adaLN linear stacked on rows, in execution order: per double block [norm1.linear (6D) |
+   * norm1_context.linear (6D)], per single block [norm.linear (3D)], then norm_out.linear (2D). */
+  const void *w_mod, *b_mod;               /* [(12 L + 3 Ls + 2) D, D]                                 */
+  const utx_double_block* double_blocks;   /* host array [num_layers]                                  */
+  const utx_single_block* single_blocks;   /* host array [num_single_layers]                           */
+  const void *w_proj_out, *b_proj_out;     /* [in_channels, D]       proj_out                          */
+} utx_flux_weights;
+
+int utx_flux_create(const utx_flux_config* cfg, utx_flux** out);
+void utx_flux_destroy(utx_flux* h);
+/* copies the pointer tables; the device memory stays owned by the caller */
+int utx_flux_set_weights(utx_flux* h, const utx_flux_weights* w);
+size_t utx_flux_workspace_bytes(const utx_flux* h, int s_txt, int s_img);
+/* Per-call constants: RoPE table from ids [s_txt + s_img, 3] fp32 (txt rows first -- torch.cat((txt_ids, img_ids)),
+ * pipeline.py:652-653), context embedding of enc [s_txt, joint_attention_dim] bf16 (the reference passes zeros,
+ * pipeline.py:538-543) and the pooled projection [pooled_projection_dim] fp32. */
+int utx_flux_prepare(utx_flux* h, void* workspace, size_t workspace_bytes, const float* ids, const void* enc,
+                     const float* pooled, int s_txt, int s_img, void* stream);
+/* One transformer forward: latents [s_img, in_channels] bf16 -> v_out [s_img, in_channels] bf16.
+ * `timestep` is t/1000 and `guidance` the raw scale, exactly as the reference passes them (:648-649); both are
+ * multiplied by 1000 in bf16 inside, like FluxTransformer2DModel.forward does on a bf16 model. */
+int utx_flux_forward(utx_flux* h, const void* latents, float timestep, float guidance, void* v_out, void* stream);
+/* The hot loop (:634-681): n_steps x { forward; latents[:s_noise] += (sigma[i+1]-sigma[i]) * v (fp32, stored bf16) }.
+ * Rows >= s_noise are the clean condition tokens and are never written, which is what the per-step re-imposition
+ * (:644-645) amounts to.  sigmas: HOST fp32 [n_steps + 1]. */
+int utx_flux_denoise(utx_flux* h, void* latents, int s_noise, const float* sigmas, int n_steps, float guidance,
+                     void* stream);
+
+/* Instrumentation for bench.py: kernel launches issued by the engine per category, and (after
+ * utx_flux_profile(h, 1)) the CUDA-event time of each category on the launching stream.  launches/ms: [4]
+ * indexed by UTX_PROF_*; reading synchronises on the recorded events. */
+enum { UTX_PROF_GEMM = 0, UTX_PROF_ATTN = 1, UTX_PROF_ELEM = 2, UTX_PROF_OTHER = 3, UTX_PROF_NCAT = 4 };
+int utx_flux_profile(utx_flux* h, int enable);
+int utx_flux_profile_read(utx_flux* h, long* launches, float* ms, int reset);
+
+/* W[out,in] (bf16, row stride ldw) += scale * B[out,rank] @ A[rank,in] (fp32).  Replaces peft's un-merged
+ * LoRA evaluation selected by pipeline.set_adapters (pipeline.py:108-118,245,263). */
+int utx_lora_merge(void* W, long ldw, const float* A, const float* B, int out_features, int in_features, int rank,
+                   float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Building blocks (exported for the parity tests; the engine above calls the same launchers).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* C[M,N] = epi(A[M,K] @ W[N,K]^T + bias).  epi: 0 bias, 1 bias+GELU(tanh), 2 res + gate*(.)  */
+int utx_gemm_bf16(const void* A, long lda, const void* W, long ldw, const void* bias, void* C, long ldc, int M, int N,
+                  int K, int epi, const float* gate, const void* res, long ldres, void* stream);
+/* two problems sharing N, K and the epilogue in one launch (txt + img streams) */
+int utx_gemm_bf16_grouped2(const void* A0, long lda0, const void* W0, const void* bias0, void* C0, long ldc0, int M0,
+                           const void* A1, long lda1, const void* W1, const void* bias1, void* C1, long ldc1, int M1,
+                           int N, int K, int epi, const float* gate0, const float* gate1, void* stream);
+/* softmax(q k^T / sqrt(128)) v over qkv [S, 3*H*128] (attention_processor.py:89-91) */
+int utx_attention_bf16(const void* qkv, long ld_qkv, void* out, long ld_out, int S, int H, void* stream);
+int utx_ln_modulate(const void* x, long ldx, void* y, long ldy, int rows, int D, int rows0, const float* shift0,
+                    const float* scale0, const float* shift1, const float* scale1, void* stream);
+int utx_rmsnorm_rope(void* qkv, long ld_qkv, int S, int H, int rows0, const void* wq0, const void* wk0,
+                     const void* wq1, const void* wk1, const float* cos_t, const float* sin_t, void* stream);
+int utx_gemv_bf16(const void* W, const void* b, const float* x, float* y, int N, int K, int silu_in, int accumulate,
+                  void* stream);
+int utx_rope_table(const float* ids, int S, float* cos_t, float* sin_t, void* stream);
+int utx_euler_update(void* latents, const void* v, int rows, int cols, float dsigma, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNITEX_B200_H */

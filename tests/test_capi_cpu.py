@@ -1,0 +1,66 @@
+"""CPU: the C-ABI library builds, loads without a driver, exports every symbol include/unitex_b200.h declares,
+and fails loudly (error code + message) instead of falling back."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared():
+    txt = (ROOT / "include" / "unitex_b200.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(utx_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/unitex_b200.h but not exported"
+    from unitex_b200 import _lib
+    assert set(_lib.exported_symbols()) == set(names)
+
+
+def test_error_reporting_no_fallback(lib):
+    assert lib.utx_version() >= 100
+    rc = lib.utx_gemm_bf16(None, 0, None, 0, None, None, 0, 0, 0, 0, 0, None, None, 0, None)
+    assert rc != 0 and b"null pointer" in lib.utx_last_error()
+    from unitex_b200 import _lib
+    with pytest.raises(_lib.UtxError):
+        _lib.check(rc, "utx_gemm_bf16")
+
+
+def test_ops_reject_cpu_tensors(lib):
+    from unitex_b200 import _lib, ops
+    with pytest.raises(_lib.UtxError):
+        ops.gemm(torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(128, 64, dtype=torch.bfloat16))
+
+
+def test_flux_handle_and_packing_on_cpu(lib):
+    """The host-side packing (state dict -> stacked qkv / modulation rows) is pure bookkeeping: check it on CPU."""
+    from oracle import flux_dit as fd
+    from unitex_b200.flux import FluxConfig, FluxTransformer
+    ocfg = fd.FluxConfig.tiny(2, 2)
+    P = fd.init_params(ocfg, 0, norm_weight_std=0.1)
+    cfg = FluxConfig(num_layers=2, num_single_layers=2, num_attention_heads=2, joint_attention_dim=256,
+                     pooled_projection_dim=64)
+    eng = FluxTransformer(cfg, device="cpu").load_state_dict(P)
+    D = cfg.inner_dim
+    bf = lambda t: t.to(torch.bfloat16)
+    assert torch.equal(eng.T["w_d1.qkv_img"][D:2 * D], bf(P["transformer_blocks.1.attn.to_k.weight"]))
+    assert torch.equal(eng.T["b_d0.qkv_txt"][2 * D:], bf(P["transformer_blocks.0.attn.add_v_proj.bias"]))
+    assert torch.equal(eng.T["w_s1.qkvmlp"][3 * D:], bf(P["single_transformer_blocks.1.proj_mlp.weight"]))
+    assert torch.equal(eng.T["w_s0.out"], bf(P["single_transformer_blocks.0.proj_out.weight"]))
+    assert torch.equal(eng.T["d1.rms_k_txt"], bf(P["transformer_blocks.1.attn.norm_added_k.weight"]))
+    mod = eng.T["w_mod"]
+    assert mod.shape == (cfg.n_mod_rows, D)
+    assert torch.equal(mod[6 * D:12 * D], bf(P["transformer_blocks.0.norm1_context.linear.weight"]))
+    assert torch.equal(mod[24 * D:27 * D], bf(P["single_transformer_blocks.0.norm.linear.weight"]))
+    assert torch.equal(mod[-2 * D:], bf(P["norm_out.linear.weight"]))
+    assert eng.lib.utx_flux_workspace_bytes(eng._handle, 128, 192) > (128 + 192) * D * 2 * 10
+    # calling the engine without prepare() is an error, not a silent no-op
+    assert eng.lib.utx_flux_forward(eng._handle, 1, 0.5, 3.5, 1, None) != 0

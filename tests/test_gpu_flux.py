@@ -1,0 +1,76 @@
+"""GPU parity of the whole DiT forward / Euler loop against the fp32 oracle (north_star: PSNR >= 40 dB on the latent)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PSNR_MIN_DB = 40.0     # BASELINE.json north_star tolerance
+
+
+def _setup(layers=(2, 2), heads=2, HL=16, WL=16, ctrl=(16, 16), dual=(16, 16), s_txt=128, seed=0, lora=False):
+    from oracle import flux_dit as fd
+    from oracle import flux_sampler as fs
+    from unitex_b200.flux import FluxConfig, FluxTransformer
+    ocfg = fd.FluxConfig.tiny(layers[0], layers[1], heads)
+    P = fd.init_params(ocfg, seed, norm_weight_std=0.1)
+    # the engine stores bf16: the oracle sees the same bf16-rounded weights, evaluated in fp32
+    P = {k: v.to(torch.bfloat16).float() for k, v in P.items()}
+    if lora:
+        L = fs.init_lora(P, ocfg, rank=8, seed=seed + 1, std=0.05)
+    cfg = FluxConfig(num_layers=layers[0], num_single_layers=layers[1], num_attention_heads=heads,
+                     joint_attention_dim=ocfg.joint_attention_dim, pooled_projection_dim=ocfg.pooled_projection_dim)
+    eng = FluxTransformer(cfg).load_state_dict(P)
+    if lora:
+        eng.merge_lora_(L, 0.8)
+        P = fs.merge_lora({k: v.to(torch.bfloat16) for k, v in P.items()}, L, 0.8)
+        P = {k: v.float() for k, v in P.items()}
+    img_ids = fs.build_ids(HL, WL, ctrl, dual)
+    g = torch.Generator().manual_seed(63)
+    s_noise = (HL // 2) * (WL // 2)
+    noise = torch.randn(1, s_noise, 64, generator=g).to(torch.bfloat16)
+    cond = torch.randn(1, img_ids.shape[0] - s_noise, 64, generator=g).to(torch.bfloat16)
+    return fd, fs, ocfg, P, eng, img_ids, noise, cond, s_txt, s_noise
+
+
+@pytest.mark.parametrize("lora", [False, True])
+def test_forward_matches_oracle(lib, lora):
+    fd, fs, ocfg, P, eng, img_ids, noise, cond, s_txt, s_noise = _setup(lora=lora)
+    ids = torch.cat([torch.zeros(s_txt, 3), img_ids])
+    g = torch.Generator().manual_seed(5)
+    enc = (torch.randn(s_txt, ocfg.joint_attention_dim, generator=g) * 0.5).to(torch.bfloat16)
+    pooled = torch.randn(ocfg.pooled_projection_dim, generator=g)
+    eng.prepare(ids, enc, pooled, s_txt=s_txt)
+    lat = torch.cat([noise, cond], 1)[0].cuda().contiguous()
+    t_in = float(torch.tensor(0.73).to(torch.bfloat16))
+    v = eng.forward(lat, t_in, 3.5)
+    torch.cuda.synchronize()
+    Pg = {k: w.cuda() for k, w in P.items()}
+    ref = fd.flux_forward(Pg, ocfg, lat[None].float(), torch.tensor([t_in]).cuda(), torch.tensor([3.5]).cuda(),
+                          pooled[None].cuda(), enc[None].float().cuda(), torch.zeros(s_txt, 3).cuda(), img_ids.cuda())[0]
+    db = fs.psnr(v.float(), ref)
+    assert torch.isfinite(v.float()).all()
+    assert db >= PSNR_MIN_DB, f"forward PSNR {db:.1f} dB"
+
+
+def test_denoise_matches_oracle_and_keeps_condition(lib):
+    fd, fs, ocfg, P, eng, img_ids, noise, cond, s_txt, s_noise = _setup(layers=(2, 3), HL=32, WL=16, ctrl=(32, 16), dual=None)
+    ids = torch.cat([torch.zeros(s_txt, 3), img_ids])
+    eng.prepare(ids, None, None, s_txt=s_txt)
+    lat = torch.cat([noise, cond], 1)[0].cuda().contiguous()
+    lat0 = lat.clone()
+    steps = 4
+    sig = fs.flow_match_sigmas(steps, s_noise)
+    eng.denoise_(lat, s_noise, sig, 3.5)
+    torch.cuda.synchronize()
+    assert torch.equal(lat[s_noise:], lat0[s_noise:])          # clean condition tokens never change (:644-645)
+    Pg = {k: w.cuda() for k, w in P.items()}
+    ref = fs.denoise(Pg, ocfg, noise.float().cuda(), cond.float().cuda(), img_ids.cuda(), num_steps=steps, S_txt=s_txt)[0]
+    db = fs.psnr(lat[:s_noise].float(), ref)
+    assert db >= PSNR_MIN_DB, f"denoise PSNR {db:.1f} dB"
+
+
+def test_product_path_does_not_import_oracle():
+    import subprocess, sys
+    code = ("import sys; import unitex_b200.flux, unitex_b200.ops; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'")
+    subprocess.run([sys.executable, "-c", code], check=True)

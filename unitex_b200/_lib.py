@@ -1,0 +1,97 @@
+"""ctypes binding of libunitex_b200.so (the C ABI declared in include/unitex_b200.h).
+
+There is no fallback: if the library is missing or a call fails this raises.  PyTorch is only used by the callers for
+device memory, streams and torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libunitex_b200.so"
+_lib = None
+
+vp, i32, f32, lng, fp = C.c_void_p, C.c_int, C.c_float, C.c_long, C.POINTER(C.c_float)
+
+
+class FluxConfigC(C.Structure):
+    _fields_ = [(n, i32) for n in ("in_channels", "num_layers", "num_single_layers", "num_heads", "head_dim",
+                                   "joint_attention_dim", "pooled_projection_dim", "guidance_embeds", "mlp_ratio")]
+
+
+_DBL = ("w_qkv_img", "b_qkv_img", "w_qkv_txt", "b_qkv_txt", "rms_q_img", "rms_k_img", "rms_q_txt", "rms_k_txt",
+        "w_out_img", "b_out_img", "w_out_txt", "b_out_txt", "w_ff1_img", "b_ff1_img", "w_ff2_img", "b_ff2_img",
+        "w_ff1_txt", "b_ff1_txt", "w_ff2_txt", "b_ff2_txt")
+_SGL = ("w_qkvmlp", "b_qkvmlp", "rms_q", "rms_k", "w_out", "b_out")
+
+
+class DoubleBlockC(C.Structure):
+    _fields_ = [(n, vp) for n in _DBL]
+
+
+class SingleBlockC(C.Structure):
+    _fields_ = [(n, vp) for n in _SGL]
+
+
+class FluxWeightsC(C.Structure):
+    _fields_ = ([(n, vp) for n in ("w_x_embed", "b_x_embed", "w_ctx_embed", "b_ctx_embed", "w_t1", "b_t1", "w_t2", "b_t2",
+                                   "w_g1", "b_g1", "w_g2", "b_g2", "w_p1", "b_p1", "w_p2", "b_p2", "w_mod", "b_mod")]
+                + [("double_blocks", C.POINTER(DoubleBlockC)), ("single_blocks", C.POINTER(SingleBlockC)),
+                   ("w_proj_out", vp), ("b_proj_out", vp)])
+
+
+_SIGS = {
+    "utx_last_error": (C.c_char_p, []),
+    "utx_version": (i32, []),
+    "utx_flux_create": (i32, [C.POINTER(FluxConfigC), C.POINTER(vp)]),
+    "utx_flux_destroy": (None, [vp]),
+    "utx_flux_set_weights": (i32, [vp, C.POINTER(FluxWeightsC)]),
+    "utx_flux_workspace_bytes": (C.c_size_t, [vp, i32, i32]),
+    "utx_flux_prepare": (i32, [vp, vp, C.c_size_t, vp, vp, vp, i32, i32, vp]),
+    "utx_flux_forward": (i32, [vp, vp, f32, f32, vp, vp]),
+    "utx_flux_denoise": (i32, [vp, vp, i32, fp, i32, f32, vp]),
+    "utx_flux_profile": (i32, [vp, i32]),
+    "utx_flux_profile_read": (i32, [vp, C.POINTER(C.c_long), fp, i32]),
+    "utx_lora_merge": (i32, [vp, lng, vp, vp, i32, i32, i32, f32, vp]),
+    "utx_gemm_bf16": (i32, [vp, lng, vp, lng, vp, vp, lng, i32, i32, i32, i32, vp, vp, lng, vp]),
+    "utx_gemm_bf16_grouped2": (i32, [vp, lng, vp, vp, vp, lng, i32, vp, lng, vp, vp, vp, lng, i32, i32, i32, i32, vp, vp, vp]),
+    "utx_attention_bf16": (i32, [vp, lng, vp, lng, i32, i32, vp]),
+    "utx_ln_modulate": (i32, [vp, lng, vp, lng, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "utx_rmsnorm_rope": (i32, [vp, lng, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "utx_gemv_bf16": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "utx_rope_table": (i32, [vp, i32, vp, vp, vp]),
+    "utx_euler_update": (i32, [vp, vp, i32, i32, f32, vp]),
+}
+
+
+class UtxError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def load():
+    """Load the shared library (built by unitex_b200.build); raises if absent -- no CPU/torch fallback exists."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise UtxError(f"{_LIB_PATH} not found: run `python -m unitex_b200.build` (nvcc, sm_100a). "
+                           "unitex_b200 has no fallback path.")
+        lib = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise UtxError(f"{what} failed (rc={rc}): {load().utx_last_error().decode()}")

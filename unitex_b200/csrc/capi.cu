@@ -1,0 +1,85 @@
+// extern "C" surface for the building-block launchers (include/unitex_b200.h).  No torch types cross this boundary.
+#include "../../include/unitex_b200.h"
+#include "common.h"
+#include "kernels.h"
+
+using namespace utx;
+
+extern "C" {
+
+const char* utx_last_error(void) { return get_error(); }
+int utx_version(void) { return 100; }
+
+int utx_gemm_bf16(const void* A, long lda, const void* W, long ldw, const void* bias, void* C, long ldc, int M, int N,
+                  int K, int epi, const float* gate, const void* res, long ldres, void* stream) {
+  UTX_CHECK(A && W && C, "utx_gemm_bf16: null pointer");
+  GemmArgs a{};
+  a.N = N; a.K = K; a.epi = epi; a.gelu_col_start = 0; a.nprob = 1;
+  a.prob[0] = GemmProblem{static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, M, static_cast<bf16*>(C),
+                          ldc, static_cast<const bf16*>(bias), gate, static_cast<const bf16*>(res), ldres, 0, nullptr, 0};
+  return gemm_bf16_tn(a, static_cast<cudaStream_t>(stream));
+}
+
+int utx_gemm_bf16_grouped2(const void* A0, long lda0, const void* W0, const void* bias0, void* C0, long ldc0, int M0,
+                           const void* A1, long lda1, const void* W1, const void* bias1, void* C1, long ldc1, int M1,
+                           int N, int K, int epi, const float* gate0, const float* gate1, void* stream) {
+  UTX_CHECK(A0 && W0 && C0 && A1 && W1 && C1, "utx_gemm_bf16_grouped2: null pointer");
+  GemmArgs a{};
+  a.N = N; a.K = K; a.epi = epi; a.gelu_col_start = 0; a.nprob = 2;
+  // EPI_GATE_RES in grouped form is residual-in-place (res == C), as the engine uses it
+  a.prob[0] = GemmProblem{static_cast<const bf16*>(A0), lda0, static_cast<const bf16*>(W0), K, M0,
+                          static_cast<bf16*>(C0), ldc0, static_cast<const bf16*>(bias0), gate0,
+                          epi == EPI_GATE_RES ? static_cast<const bf16*>(C0) : nullptr, ldc0, 0, nullptr, 0};
+  a.prob[1] = GemmProblem{static_cast<const bf16*>(A1), lda1, static_cast<const bf16*>(W1), K, M1,
+                          static_cast<bf16*>(C1), ldc1, static_cast<const bf16*>(bias1), gate1,
+                          epi == EPI_GATE_RES ? static_cast<const bf16*>(C1) : nullptr, ldc1, 0, nullptr, 0};
+  return gemm_bf16_tn(a, static_cast<cudaStream_t>(stream));
+}
+
+int utx_attention_bf16(const void* qkv, long ld_qkv, void* out, long ld_out, int S, int H, void* stream) {
+  UTX_CHECK(qkv && out, "utx_attention_bf16: null pointer");
+  return attention_bf16(static_cast<const bf16*>(qkv), ld_qkv, static_cast<bf16*>(out), ld_out, S, H,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int utx_ln_modulate(const void* x, long ldx, void* y, long ldy, int rows, int D, int rows0, const float* shift0,
+                    const float* scale0, const float* shift1, const float* scale1, void* stream) {
+  UTX_CHECK(x && y && shift1 && scale1, "utx_ln_modulate: null pointer");
+  return ln_modulate(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, rows, D, rows0, shift0, scale0,
+                     shift1, scale1, static_cast<cudaStream_t>(stream));
+}
+
+int utx_rmsnorm_rope(void* qkv, long ld_qkv, int S, int H, int rows0, const void* wq0, const void* wk0,
+                     const void* wq1, const void* wk1, const float* cos_t, const float* sin_t, void* stream) {
+  UTX_CHECK(qkv && wq1 && wk1 && cos_t && sin_t, "utx_rmsnorm_rope: null pointer");
+  return rmsnorm_rope(static_cast<bf16*>(qkv), ld_qkv, S, H, rows0, static_cast<const bf16*>(wq0),
+                      static_cast<const bf16*>(wk0), static_cast<const bf16*>(wq1), static_cast<const bf16*>(wk1),
+                      cos_t, sin_t, static_cast<cudaStream_t>(stream));
+}
+
+int utx_gemv_bf16(const void* W, const void* b, const float* x, float* y, int N, int K, int silu_in, int accumulate,
+                  void* stream) {
+  UTX_CHECK(W && x && y, "utx_gemv_bf16: null pointer");
+  return gemv_bf16(static_cast<const bf16*>(W), static_cast<const bf16*>(b), x, y, N, K, silu_in, accumulate,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int utx_rope_table(const float* ids, int S, float* cos_t, float* sin_t, void* stream) {
+  UTX_CHECK(ids && cos_t && sin_t, "utx_rope_table: null pointer");
+  return rope_table(ids, S, cos_t, sin_t, static_cast<cudaStream_t>(stream));
+}
+
+int utx_euler_update(void* latents, const void* v, int rows, int cols, float dsigma, void* stream) {
+  UTX_CHECK(latents && v, "utx_euler_update: null pointer");
+  return euler_update(static_cast<bf16*>(latents), static_cast<const bf16*>(v), rows, cols, dsigma,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int utx_lora_merge(void* W, long ldw, const float* A, const float* B, int out_features, int in_features, int rank,
+                   float scale, void* stream) {
+  UTX_CHECK(W && A && B, "utx_lora_merge: null pointer");
+  return lora_merge(static_cast<bf16*>(W), ldw, A, B, out_features, in_features, rank, scale,
+                    static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

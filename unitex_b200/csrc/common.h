@@ -1,0 +1,48 @@
+// Host-side shared helpers: error reporting for the C ABI and TMA descriptor creation.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace utx {
+
+// Last-error slot behind utx_last_error() (thread-local: the ABI has no global state).
+void set_error(const std::string& msg);
+const char* get_error();
+
+#define UTX_CHECK(cond, msg)                                                           \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      ::utx::set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + (msg)); \
+      return 1;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+#define UTX_CUDA(expr)                                                                 \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      ::utx::set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + \
+                       cudaGetErrorString(_e));                                        \
+      return 2;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+#define UTX_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != 0) return _r;      \
+  } while (0)
+
+// 2-D bf16 tensor map: global [rows, cols] with row stride ld (elements), box [box_rows, box_cols],
+// 128B swizzle when box_cols*2 == 128, no swizzle otherwise.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols);
+
+int num_sms();
+
+}  // namespace utx

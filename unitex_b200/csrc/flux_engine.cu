@@ -1,0 +1,320 @@
+// FLUX.1-dev MM-DiT forward + flow-match Euler loop, orchestrated on the host in C++ over the sm_100a kernels.
+// Replaces diffusers' FluxTransformer2DModel.forward as called at flux_piplines/texturing/pipeline.py:646-656 and the
+// loop :634-681.  Token layout in the residual buffer: [txt rows | img rows] from the start, so the double-stream
+// blocks address the two streams as row ranges of one buffer (grouped GEMM launches) and the torch.cat before the
+// single-stream blocks costs nothing.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/unitex_b200.h"
+#include "common.h"
+#include "kernels.h"
+
+using namespace utx;
+
+struct utx_flux {
+  utx_flux_config cfg;
+  utx_flux_weights w;
+  std::vector<utx_double_block> dbl;
+  std::vector<utx_single_block> sgl;
+  bool has_weights = false;
+  // per-call state (set by prepare)
+  int s_txt = 0, s_img = 0;
+  bf16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *cat = nullptr, *ctx0 = nullptr, *v_tmp = nullptr;
+  float *cos_t = nullptr, *sin_t = nullptr, *mod = nullptr, *temb = nullptr, *sincos = nullptr, *hvec = nullptr,
+        *pooled = nullptr;
+  bool prepared = false;
+  // instrumentation: launches per category and (when profiling) CUDA-event time per category
+  bool profile = false;
+  long launches[UTX_PROF_NCAT] = {0, 0, 0, 0};
+  float prof_ms[UTX_PROF_NCAT] = {0, 0, 0, 0};
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, int>> ev_used;   // (category, index of start event); stop = start + 1
+  size_t ev_next = 0;
+};
+
+namespace {
+
+// Runs one launcher under a category: counts the launch and, when profiling, brackets it with events on `st`.
+template <class F>
+int run_cat(utx_flux* h, int cat, cudaStream_t st, F&& f) {
+  h->launches[cat]++;
+  if (!h->profile) return f();
+  if (h->ev_next + 2 > h->ev_pool.size()) {
+    for (int i = 0; i < 256; ++i) {
+      cudaEvent_t e;
+      UTX_CUDA(cudaEventCreate(&e));
+      h->ev_pool.push_back(e);
+    }
+  }
+  const size_t i0 = h->ev_next;
+  h->ev_next += 2;
+  UTX_CUDA(cudaEventRecord(h->ev_pool[i0], st));
+  int r = f();
+  UTX_CUDA(cudaEventRecord(h->ev_pool[i0 + 1], st));
+  h->ev_used.emplace_back(cat, static_cast<int>(i0));
+  return r;
+}
+#define CAT_GEMM(expr) UTX_TRY(run_cat(h, UTX_PROF_GEMM, st, [&] { return (expr); }))
+#define CAT_ATTN(expr) UTX_TRY(run_cat(h, UTX_PROF_ATTN, st, [&] { return (expr); }))
+#define CAT_ELEM(expr) UTX_TRY(run_cat(h, UTX_PROF_ELEM, st, [&] { return (expr); }))
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+inline int D_of(const utx_flux_config& c) { return c.num_heads * c.head_dim; }
+inline long n_mod_rows(const utx_flux_config& c) {
+  return static_cast<long>(12 * c.num_layers + 3 * c.num_single_layers + 2) * D_of(c);
+}
+// round-to-nearest-even fp32 -> bf16 -> fp32, on the host (mirrors torch's .to(torch.bfloat16))
+inline float bf16_round(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return f;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  u &= 0xffff0000u;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+struct WsLayout {
+  size_t x, xn, qkv, cat, ctx0, v_tmp, cos_t, sin_t, mod, temb, sincos, hvec, pooled, total;
+};
+WsLayout ws_layout(const utx_flux_config& c, int s_txt, int s_img) {
+  const size_t S = static_cast<size_t>(s_txt) + s_img, D = D_of(c);
+  WsLayout L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    return o;
+  };
+  L.x = take(S * D * 2);
+  L.xn = take(S * D * 2);
+  L.qkv = take(S * 3 * D * 2);
+  L.cat = take(S * (1 + c.mlp_ratio) * D * 2);
+  L.ctx0 = take(static_cast<size_t>(s_txt) * D * 2);
+  L.v_tmp = take(static_cast<size_t>(s_img) * c.in_channels * 2);
+  L.cos_t = take(S * 128 * 4);
+  L.sin_t = take(S * 128 * 4);
+  L.mod = take(n_mod_rows(c) * 4);
+  L.temb = take(D * 4);
+  L.sincos = take(512 * 4);
+  L.hvec = take(D * 4);
+  L.pooled = take(static_cast<size_t>(c.pooled_projection_dim) * 4);
+  L.total = off;
+  return L;
+}
+
+int gemm1(const bf16* A, long lda, const bf16* W, long ldw, const bf16* bias, bf16* C, long ldc, int M, int N, int K,
+          int epi, const float* gate, const bf16* res, long ldres, cudaStream_t st, int gelu_start = 0,
+          int split_col = 0, bf16* C2 = nullptr, long ldc2 = 0) {
+  GemmArgs a{};
+  a.N = N; a.K = K; a.epi = epi; a.gelu_col_start = gelu_start; a.nprob = 1;
+  a.prob[0] = GemmProblem{A, lda, W, ldw, M, C, ldc, bias, gate, res, ldres, split_col, C2, ldc2};
+  return gemm_bf16_tn(a, st);
+}
+
+// txt rows [0, s_txt) with the *_txt weights and img rows [s_txt, S) with the *_img weights, one launch
+int gemm_streams(const utx_flux* h, const bf16* A, long lda, const void* W_txt, const void* b_txt, const void* W_img,
+                 const void* b_img, long ldw, bf16* C, long ldc, int N, int K, int epi, const float* gate_txt,
+                 const float* gate_img, const bf16* res, long ldres, cudaStream_t st) {
+  GemmArgs a{};
+  a.N = N; a.K = K; a.epi = epi; a.gelu_col_start = 0; a.nprob = 2;
+  const long st_rows = h->s_txt;
+  a.prob[0] = GemmProblem{A, lda, static_cast<const bf16*>(W_txt), ldw, h->s_txt, C, ldc,
+                          static_cast<const bf16*>(b_txt), gate_txt, res, ldres, 0, nullptr, 0};
+  a.prob[1] = GemmProblem{A + st_rows * lda, lda, static_cast<const bf16*>(W_img), ldw, h->s_img, C + st_rows * ldc, ldc,
+                          static_cast<const bf16*>(b_img), gate_img, res ? res + st_rows * ldres : nullptr, ldres, 0,
+                          nullptr, 0};
+  return gemm_bf16_tn(a, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int utx_flux_create(const utx_flux_config* cfg, utx_flux** out) {
+  UTX_CHECK(cfg && out, "utx_flux_create: null argument");
+  UTX_CHECK(cfg->head_dim == 128, "utx_flux_create: head_dim must be 128");
+  UTX_CHECK(cfg->num_heads > 0 && (cfg->num_heads * 128) % 256 == 0, "utx_flux_create: num_heads must be even");
+  UTX_CHECK(cfg->in_channels % 64 == 0 && cfg->joint_attention_dim % 64 == 0 && cfg->pooled_projection_dim % 8 == 0,
+            "utx_flux_create: in_channels/joint_attention_dim must be multiples of 64");
+  UTX_CHECK(cfg->mlp_ratio == 4, "utx_flux_create: mlp_ratio must be 4");
+  utx_flux* h = new utx_flux();
+  h->cfg = *cfg;
+  *out = h;
+  return 0;
+}
+
+void utx_flux_destroy(utx_flux* h) {
+  if (!h) return;
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  delete h;
+}
+
+int utx_flux_set_weights(utx_flux* h, const utx_flux_weights* w) {
+  UTX_CHECK(h && w && w->double_blocks && w->single_blocks, "utx_flux_set_weights: null argument");
+  h->w = *w;
+  h->dbl.assign(w->double_blocks, w->double_blocks + h->cfg.num_layers);
+  h->sgl.assign(w->single_blocks, w->single_blocks + h->cfg.num_single_layers);
+  h->w.double_blocks = h->dbl.data();
+  h->w.single_blocks = h->sgl.data();
+  h->has_weights = true;
+  return 0;
+}
+
+size_t utx_flux_workspace_bytes(const utx_flux* h, int s_txt, int s_img) {
+  if (!h) return 0;
+  return ws_layout(h->cfg, s_txt, s_img).total;
+}
+
+int utx_flux_prepare(utx_flux* h, void* workspace, size_t workspace_bytes, const float* ids, const void* enc,
+                     const float* pooled, int s_txt, int s_img, void* stream) {
+  UTX_CHECK(h && h->has_weights, "utx_flux_prepare: weights not set");
+  UTX_CHECK(workspace && ids && enc && pooled, "utx_flux_prepare: null argument");
+  UTX_CHECK(s_txt >= 0 && s_img > 0, "utx_flux_prepare: bad sequence lengths");
+  UTX_CHECK((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "utx_flux_prepare: workspace must be 256B aligned");
+  const WsLayout L = ws_layout(h->cfg, s_txt, s_img);
+  UTX_CHECK(workspace_bytes >= L.total, "utx_flux_prepare: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* b = static_cast<uint8_t*>(workspace);
+  h->s_txt = s_txt; h->s_img = s_img;
+  h->x = reinterpret_cast<bf16*>(b + L.x); h->xn = reinterpret_cast<bf16*>(b + L.xn);
+  h->qkv = reinterpret_cast<bf16*>(b + L.qkv); h->cat = reinterpret_cast<bf16*>(b + L.cat);
+  h->ctx0 = reinterpret_cast<bf16*>(b + L.ctx0); h->v_tmp = reinterpret_cast<bf16*>(b + L.v_tmp);
+  h->cos_t = reinterpret_cast<float*>(b + L.cos_t); h->sin_t = reinterpret_cast<float*>(b + L.sin_t);
+  h->mod = reinterpret_cast<float*>(b + L.mod); h->temb = reinterpret_cast<float*>(b + L.temb);
+  h->sincos = reinterpret_cast<float*>(b + L.sincos); h->hvec = reinterpret_cast<float*>(b + L.hvec);
+  h->pooled = reinterpret_cast<float*>(b + L.pooled);
+  const int D = D_of(h->cfg);
+  UTX_TRY(rope_table(ids, s_txt + s_img, h->cos_t, h->sin_t, st));
+  if (s_txt > 0)
+    UTX_TRY(gemm1(static_cast<const bf16*>(enc), h->cfg.joint_attention_dim, static_cast<const bf16*>(h->w.w_ctx_embed),
+                  h->cfg.joint_attention_dim, static_cast<const bf16*>(h->w.b_ctx_embed), h->ctx0, D, s_txt, D,
+                  h->cfg.joint_attention_dim, EPI_BIAS, nullptr, nullptr, 0, st));
+  UTX_CUDA(cudaMemcpyAsync(h->pooled, pooled, sizeof(float) * h->cfg.pooled_projection_dim, cudaMemcpyDeviceToDevice,
+                           st));
+  h->prepared = true;
+  return 0;
+}
+
+int utx_flux_forward(utx_flux* h, const void* latents, float timestep, float guidance, void* v_out, void* stream) {
+  UTX_CHECK(h && h->prepared, "utx_flux_forward: call utx_flux_prepare first");
+  UTX_CHECK(latents && v_out, "utx_flux_forward: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const utx_flux_config& c = h->cfg;
+  const utx_flux_weights& w = h->w;
+  const int D = D_of(c), M4 = 4 * D, H = c.num_heads;
+  const int s_txt = h->s_txt, s_img = h->s_img, S = s_txt + s_img;
+  const long ldc5 = 5L * D;
+
+  // timestep.to(bf16) * 1000 and guidance.to(bf16) * 1000, each product rounded to bf16 [ext transformer forward]
+  const float t_eff = bf16_round(bf16_round(timestep) * 1000.0f);
+  const float g_eff = bf16_round(bf16_round(guidance) * 1000.0f);
+  CAT_ELEM(time_sinusoid(t_eff, g_eff, h->sincos, st));
+  auto B = [](const void* p) { return static_cast<const bf16*>(p); };
+  // temb = MLP_t(sin) + MLP_g(sin) + MLP_p(pooled)
+  CAT_ELEM(gemv_bf16(B(w.w_t1), B(w.b_t1), h->sincos, h->hvec, D, 256, 0, 0, st));
+  CAT_ELEM(gemv_bf16(B(w.w_t2), B(w.b_t2), h->hvec, h->temb, D, D, 1, 0, st));
+  if (c.guidance_embeds) {
+    CAT_ELEM(gemv_bf16(B(w.w_g1), B(w.b_g1), h->sincos + 256, h->hvec, D, 256, 0, 0, st));
+    CAT_ELEM(gemv_bf16(B(w.w_g2), B(w.b_g2), h->hvec, h->temb, D, D, 1, 1, st));
+  }
+  CAT_ELEM(gemv_bf16(B(w.w_p1), B(w.b_p1), h->pooled, h->hvec, D, c.pooled_projection_dim, 0, 0, st));
+  CAT_ELEM(gemv_bf16(B(w.w_p2), B(w.b_p2), h->hvec, h->temb, D, D, 1, 1, st));
+  // every adaLN modulation vector of the step in one HBM-bound pass
+  CAT_ELEM(gemv_bf16(B(w.w_mod), B(w.b_mod), h->temb, h->mod, static_cast<int>(n_mod_rows(c)), D, 1, 0, st));
+
+  // embedders: x = [ctx0 | x_embedder(latents)]
+  if (s_txt > 0)
+    UTX_CUDA(cudaMemcpyAsync(h->x, h->ctx0, static_cast<size_t>(s_txt) * D * 2, cudaMemcpyDeviceToDevice, st));
+  CAT_GEMM(gemm1(B(latents), c.in_channels, B(w.w_x_embed), c.in_channels, B(w.b_x_embed), h->x + static_cast<long>(s_txt) * D,
+                D, s_img, D, c.in_channels, EPI_BIAS, nullptr, nullptr, 0, st));
+
+  const float* mod = h->mod;
+  for (int i = 0; i < c.num_layers; ++i) {
+    const utx_double_block& b = h->dbl[i];
+    const float* mi = mod + static_cast<long>(i) * 12 * D;   // img: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+    const float* mt = mi + 6L * D;                           // txt: same order
+    CAT_ELEM(ln_modulate(h->x, D, h->xn, D, S, D, s_txt, mt, mt + D, mi, mi + D, st));
+    CAT_GEMM(gemm_streams(h, h->xn, D, b.w_qkv_txt, b.b_qkv_txt, b.w_qkv_img, b.b_qkv_img, D, h->qkv, 3L * D, 3 * D, D,
+                         EPI_BIAS, nullptr, nullptr, nullptr, 0, st));
+    CAT_ELEM(rmsnorm_rope(h->qkv, 3L * D, S, H, s_txt, B(b.rms_q_txt), B(b.rms_k_txt), B(b.rms_q_img), B(b.rms_k_img),
+                         h->cos_t, h->sin_t, st));
+    CAT_ATTN(attention_bf16(h->qkv, 3L * D, h->cat, ldc5, S, H, st));
+    CAT_GEMM(gemm_streams(h, h->cat, ldc5, b.w_out_txt, b.b_out_txt, b.w_out_img, b.b_out_img, D, h->x, D, D, D,
+                         EPI_GATE_RES, mt + 2L * D, mi + 2L * D, h->x, D, st));
+    CAT_ELEM(ln_modulate(h->x, D, h->xn, D, S, D, s_txt, mt + 3L * D, mt + 4L * D, mi + 3L * D, mi + 4L * D, st));
+    CAT_GEMM(gemm_streams(h, h->xn, D, b.w_ff1_txt, b.b_ff1_txt, b.w_ff1_img, b.b_ff1_img, D, h->cat + D, ldc5, M4, D,
+                         EPI_BIAS_GELU, nullptr, nullptr, nullptr, 0, st));
+    CAT_GEMM(gemm_streams(h, h->cat + D, ldc5, b.w_ff2_txt, b.b_ff2_txt, b.w_ff2_img, b.b_ff2_img, M4, h->x, D, D, M4,
+                         EPI_GATE_RES, mt + 5L * D, mi + 5L * D, h->x, D, st));
+  }
+  const float* mod_s = mod + static_cast<long>(c.num_layers) * 12 * D;
+  for (int i = 0; i < c.num_single_layers; ++i) {
+    const utx_single_block& b = h->sgl[i];
+    const float* ms = mod_s + static_cast<long>(i) * 3 * D;   // shift, scale, gate
+    CAT_ELEM(ln_modulate(h->x, D, h->xn, D, S, D, 0, ms, ms + D, ms, ms + D, st));
+    // one GEMM for to_q|to_k|to_v|proj_mlp: q,k,v -> qkv buffer, GELU(mlp) -> cat[:, D:]
+    CAT_GEMM(gemm1(h->xn, D, B(b.w_qkvmlp), D, B(b.b_qkvmlp), h->qkv, 3L * D, S, 7 * D, D, EPI_BIAS_GELU, nullptr,
+                  nullptr, 0, st, 3 * D, 3 * D, h->cat + D, ldc5));
+    CAT_ELEM(rmsnorm_rope(h->qkv, 3L * D, S, H, 0, B(b.rms_q), B(b.rms_k), B(b.rms_q), B(b.rms_k), h->cos_t, h->sin_t,
+                         st));
+    CAT_ATTN(attention_bf16(h->qkv, 3L * D, h->cat, ldc5, S, H, st));
+    CAT_GEMM(gemm1(h->cat, ldc5, B(b.w_out), ldc5, B(b.b_out), h->x, D, S, D, 5 * D, EPI_GATE_RES, ms + 2L * D, h->x, D,
+                  st));
+  }
+  // AdaLayerNormContinuous (chunk order: scale, shift) + proj_out on the img rows
+  const float* mf = mod_s + static_cast<long>(c.num_single_layers) * 3 * D;
+  bf16* ximg = h->x + static_cast<long>(s_txt) * D;
+  bf16* xnimg = h->xn + static_cast<long>(s_txt) * D;
+  CAT_ELEM(ln_modulate(ximg, D, xnimg, D, s_img, D, 0, mf + D, mf, mf + D, mf, st));
+  CAT_GEMM(gemm1(xnimg, D, B(w.w_proj_out), D, B(w.b_proj_out), static_cast<bf16*>(v_out), c.in_channels, s_img,
+                c.in_channels, D, EPI_BIAS, nullptr, nullptr, 0, st));
+  return 0;
+}
+
+int utx_flux_denoise(utx_flux* h, void* latents, int s_noise, const float* sigmas, int n_steps, float guidance,
+                     void* stream) {
+  UTX_CHECK(h && h->prepared, "utx_flux_denoise: call utx_flux_prepare first");
+  UTX_CHECK(latents && sigmas && n_steps >= 0, "utx_flux_denoise: bad argument");
+  UTX_CHECK(s_noise > 0 && s_noise <= h->s_img, "utx_flux_denoise: s_noise out of range");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < n_steps; ++i) {
+    // t = 1000 sigma (fp32) -> .to(bf16) (:643) -> / 1000 in bf16 (:648)
+    const float t_in = bf16_round(bf16_round(sigmas[i] * 1000.0f) / 1000.0f);
+    UTX_TRY(utx_flux_forward(h, latents, t_in, guidance, h->v_tmp, stream));
+    CAT_ELEM(euler_update(static_cast<bf16*>(latents), h->v_tmp, s_noise, h->cfg.in_channels, sigmas[i + 1] - sigmas[i],
+                          st));
+  }
+  return 0;
+}
+
+int utx_flux_profile(utx_flux* h, int enable) {
+  UTX_CHECK(h, "utx_flux_profile: null handle");
+  h->profile = enable != 0;
+  return 0;
+}
+
+int utx_flux_profile_read(utx_flux* h, long* launches, float* ms, int reset) {
+  UTX_CHECK(h && launches && ms, "utx_flux_profile_read: null argument");
+  for (auto& u : h->ev_used) {
+    float t = 0.f;
+    UTX_CUDA(cudaEventSynchronize(h->ev_pool[u.second + 1]));
+    UTX_CUDA(cudaEventElapsedTime(&t, h->ev_pool[u.second], h->ev_pool[u.second + 1]));
+    h->prof_ms[u.first] += t;
+  }
+  h->ev_used.clear();
+  h->ev_next = 0;
+  for (int i = 0; i < UTX_PROF_NCAT; ++i) {
+    launches[i] = h->launches[i];
+    ms[i] = h->prof_ms[i];
+    if (reset) {
+      h->launches[i] = 0;
+      h->prof_ms[i] = 0.f;
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

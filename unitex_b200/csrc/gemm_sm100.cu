@@ -1,0 +1,316 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C = epilogue(A[M,K] @ W[N,K]^T + bias).
+//
+//   warp 0      TMA producer  (cp.async.bulk.tensor, 128B-swizzled K-major tiles, STAGES-deep mbarrier ring)
+//   warp 1      MMA issuer    (one thread, tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16 per instruction)
+//   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
+//   warps 4..7  epilogue      (tcgen05.ld 32x32b -> bias / GELU-tanh / gate*x+residual -> bf16 -> global)
+//
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.  Up to two
+// problems that share (N, K, epilogue) are scheduled in one launch (the txt and img streams of an MM-DiT double block),
+// so the 512-token txt stream does not cost a mostly idle wave of its own.  Tiles are walked in bands of GROUP_M
+// row-blocks (row-block fastest) so that concurrently resident CTAs share one weight column-block out of L2 and the
+// activation band stays L2 resident.
+//
+// Every Linear of the FLUX DiT (reference call site flux_piplines/texturing/pipeline.py:646) runs
+// through this kernel; LoRA adapters are merged into W beforehand (a5).
+#include "common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace utx {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GROUP_M = 16;
+constexpr int kThreads = 256;
+
+struct DevProblem {
+  int M;
+  int tiles_m;
+  bf16* C;
+  long ldc;
+  const bf16* bias;
+  const float* gate;
+  const bf16* res;
+  long ldres;
+  int split_col;
+  bf16* C2;
+  long ldc2;
+};
+struct DevParams {
+  int N, K;
+  int tiles_n;
+  int nprob;
+  int epi;
+  int gelu_col_start;
+  int total_tiles;
+  DevProblem prob[2];
+};
+
+struct TileCoord {
+  int pi, m_blk, n_blk;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const DevParams& p, int t) {
+  TileCoord tc;
+  tc.pi = 0;
+  const int t0 = p.prob[0].tiles_m * p.tiles_n;
+  if (p.nprob > 1 && t >= t0) {
+    tc.pi = 1;
+    t -= t0;
+  }
+  const int tiles_m = p.prob[tc.pi].tiles_m;
+  const int band_sz = GROUP_M * p.tiles_n;
+  const int band = t / band_sz;
+  const int r = t - band * band_sz;
+  const int rows = min(GROUP_M, tiles_m - band * GROUP_M);
+  tc.m_blk = band * GROUP_M + r % rows;
+  tc.n_blk = r / rows;
+  return tc;
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;   // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                    const DevParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nk = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmB0);
+    if (p.nprob > 1) {
+      prefetch_tmap(&tmA1);
+      prefetch_tmap(&tmB1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      const CUtensorMap* ta = tc.pi ? &tmA1 : &tmA0;
+      const CUtensorMap* tb = tc.pi ? &tmB1 : &tmB0;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], L::STAGE_BYTES);
+        uint8_t* st = smem + s * L::STAGE_BYTES;
+        tma_load_2d(st, ta, &full[s], kb * BK, tc.m_blk * BM);
+        tma_load_2d(st + L::A_BYTES, tb, &full[s], kb * BK, tc.n_blk * BN);
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    int s = 0, as = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      mbar_wait(&tempty[as], aph ^ 1);   // epilogue drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = make_sdesc(a_addr + k * 32, 16, 1024);
+          const uint64_t db = make_sdesc(b_addr + k * 32, 16, 1024);
+          umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty[s]);                    // smem stage reusable once these MMAs retire
+        if (kb == nk - 1) umma_commit(&tfull[as]); // accumulator complete
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (warp w owns TMEM lanes 32*(w%4)..)
+    const int ew = warp - 4;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      const DevProblem& pr = p.prob[tc.pi];
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const int row = tc.m_blk * BM + ew * 32 + lane;
+      const bool row_ok = row < pr.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+      bf16* crow;
+      int col_shift = 0;
+      if (pr.split_col > 0 && tc.n_blk * BN >= pr.split_col) {
+        crow = pr.C2 + static_cast<long>(row) * pr.ldc2;
+        col_shift = pr.split_col;
+      } else {
+        crow = pr.C + static_cast<long>(row) * pr.ldc;
+      }
+      const bf16* rrow = pr.res ? pr.res + static_cast<long>(row) * pr.ldres : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = tc.n_blk * BN + c * 32;
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < p.N) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+              if (pr.bias) {
+                const uint4 b = *reinterpret_cast<const uint4*>(pr.bias + col);
+                f[0] += bf16lo(b.x); f[1] += bf16hi(b.x); f[2] += bf16lo(b.y); f[3] += bf16hi(b.y);
+                f[4] += bf16lo(b.z); f[5] += bf16hi(b.z); f[6] += bf16lo(b.w); f[7] += bf16hi(b.w);
+              }
+              if (p.epi == EPI_BIAS_GELU) {
+                if (col >= p.gelu_col_start) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
+                }
+              } else if (p.epi == EPI_GATE_RES) {
+                const float4 g0 = *reinterpret_cast<const float4*>(pr.gate + col);
+                const float4 g1 = *reinterpret_cast<const float4*>(pr.gate + col + 4);
+                const uint4 r = *reinterpret_cast<const uint4*>(rrow + col);
+                f[0] = fmaf(g0.x, f[0], bf16lo(r.x)); f[1] = fmaf(g0.y, f[1], bf16hi(r.x));
+                f[2] = fmaf(g0.z, f[2], bf16lo(r.y)); f[3] = fmaf(g0.w, f[3], bf16hi(r.y));
+                f[4] = fmaf(g1.x, f[4], bf16lo(r.z)); f[5] = fmaf(g1.y, f[5], bf16hi(r.z));
+                f[6] = fmaf(g1.z, f[6], bf16lo(r.w)); f[7] = fmaf(g1.w, f[7], bf16hi(r.w));
+              }
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]);
+              o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]);
+              o.w = pack_bf16x2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(crow + (col - col_shift)) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+template <int BN, int STAGES>
+int launch(const GemmArgs& a, cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES>;
+  DevParams p{};
+  p.N = a.N;
+  p.K = a.K;
+  p.tiles_n = (a.N + BN - 1) / BN;
+  p.nprob = a.nprob;
+  p.epi = a.epi;
+  p.gelu_col_start = a.gelu_col_start;
+  CUtensorMap tm[4];
+  int total = 0;
+  for (int i = 0; i < a.nprob; ++i) {
+    const GemmProblem& g = a.prob[i];
+    DevProblem& d = p.prob[i];
+    d.M = g.M;
+    d.tiles_m = (g.M + BM - 1) / BM;
+    d.C = g.C; d.ldc = g.ldc; d.bias = g.bias; d.gate = g.gate; d.res = g.res; d.ldres = g.ldres;
+    d.split_col = g.split_col; d.C2 = g.C2; d.ldc2 = g.ldc2;
+    total += d.tiles_m * p.tiles_n;
+    UTX_TRY(make_tmap_2d_bf16(&tm[2 * i], g.A, g.M, a.K, g.lda, BM, BK));
+    UTX_TRY(make_tmap_2d_bf16(&tm[2 * i + 1], g.W, a.N, a.K, g.ldw, BN, BK));
+  }
+  if (a.nprob == 1) {
+    tm[2] = tm[0];
+    tm[3] = tm[1];
+  }
+  p.total_tiles = total;
+  if (total == 0) return 0;
+  auto kern = gemm_bf16_tn_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, kThreads, L::TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
+  UTX_CHECK(a.nprob == 1 || a.nprob == 2, "gemm: nprob must be 1 or 2");
+  UTX_CHECK(a.K % BK == 0 && a.K > 0, "gemm: K must be a positive multiple of 64");
+  UTX_CHECK(a.N % 8 == 0 && a.N > 0, "gemm: N must be a positive multiple of 8");
+  for (int i = 0; i < a.nprob; ++i) {
+    const GemmProblem& g = a.prob[i];
+    UTX_CHECK(g.M >= 0, "gemm: negative M");
+    UTX_CHECK(g.ldc % 8 == 0 && (g.res == nullptr || g.ldres % 8 == 0), "gemm: ldc/ldres must be multiples of 8");
+    UTX_CHECK(a.epi != EPI_GATE_RES || (g.gate && g.res), "gemm: EPI_GATE_RES needs gate and res");
+    UTX_CHECK(g.split_col == 0 || (g.split_col % 256 == 0 && g.C2 && g.ldc2 % 8 == 0), "gemm: bad column split");
+  }
+  if (a.N % 256 == 0) return launch<256, 4>(a, stream);
+  if (a.N % 128 == 0) return launch<128, 6>(a, stream);
+  return launch<64, 8>(a, stream);
+}
+
+}  // namespace utx
