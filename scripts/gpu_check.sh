@@ -1,14 +1,20 @@
 #!/bin/bash
-# One gpurun trip: GPU parity tests file by file (each under its own timeout so a hung kernel cannot eat the box),
-# smoke, then a short bench.  Everything lands in gpurun_out/.
+# One gpurun trip: GPU parity tests group by group (each group in its own process under its own timeout, so a trapped
+# or hung kernel cannot poison the others), smoke, then a short bench.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
+rm -f gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-for f in tests/test_gpu_kernels.py tests/test_gpu_flux.py ${EXTRA_TESTS}; do
-  n=$(basename $f .py)
-  timeout -k 10 ${TEST_TIMEOUT:-300} python -m pytest $f -q -m gpu -x --timeout 120 ${PYTEST_ARGS} > gpurun_out/$n.log 2>&1
-  echo "$n exit $?" | tee -a gpurun_out/summary.txt
-  tail -5 gpurun_out/$n.log
-done
+run() {  # name, file, -k expression
+  timeout -k 10 ${TEST_TIMEOUT:-300} python -m pytest "$2" -q -m gpu --timeout 200 -k "$3" > gpurun_out/$1.log 2>&1
+  echo "$1 exit $?" | tee -a gpurun_out/summary.txt
+  grep -E "passed|failed|error" gpurun_out/$1.log | tail -2
+  grep -E "^(FAILED|ERROR)" gpurun_out/$1.log | head -12
+}
+run elem tests/test_gpu_kernels.py "ln_modulate or rope or gemv"
+run gemm tests/test_gpu_kernels.py "gemm"
+run attn tests/test_gpu_kernels.py "attention"
+run flux tests/test_gpu_flux.py "flux or oracle or denoise or forward"
+for f in ${EXTRA_TESTS}; do run $(basename $f .py) $f ""; done
 timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" | tee -a gpurun_out/summary.txt
 tail -3 gpurun_out/smoke.log
