@@ -127,6 +127,42 @@ int utx_gemv_bf16(const void* W, const void* b, const float* x, float* y, int N,
 int utx_rope_table(const float* ids, int S, float* cos_t, float* sin_t, void* stream);
 int utx_euler_update(void* latents, const void* v, int rows, int cols, float dsigma, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Bake: rasterise -> back-project -> UV bake.  Replaces nvdiffrast, the Slang LBVH ray tracer and the torch tail of
+ * NVDiffRendererInverse (TextureTools/texturetools/render/nvdiffrast/renderer_inverse.py).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* dr.rasterize (renderer_inverse.py:183,273; renderer_base.py:142): pos [B or 1, V, 4] clip space fp32, tri [F,3] int32
+ * -> rast [B,H,W,4] = (u, v, z/w, triangle_id + 1), 0 = background.  workspace: utx_rasterize_workspace_bytes. */
+size_t utx_rasterize_workspace_bytes(int B, int H, int W);
+int utx_rasterize(const float* pos, int pos_batched, int V, const int32_t* tri, int F, int B, int H, int W,
+                  float* rast_out, void* workspace, void* stream);
+/* dr.interpolate (renderer_inverse.py:188,277,288): out[b,y,x,:] = u a0 + v a1 + (1-u-v) a2 */
+int utx_interpolate(const float* attr, int attr_batched, int V, int C, const float* rast, const int32_t* tri, int B, int H,
+                    int W, float* out, void* stream);
+/* vertices_homo @ (P @ W2C)^T (renderer_inverse.py:178,263): out [n, V, 4] */
+int utx_transform_points(const float* vert, int V, const float* mats, int n, float* out, void* stream);
+/* RayTracing(vertices, faces) / update_raw (raytracing/__init__.py:12-80; rt_aprmis/bvhhelpers.py:20-83): builds the
+ * same LBVH the reference builds into `nodes` (utx_bvh_nodes_bytes(F) bytes, 48 B per node). */
+size_t utx_bvh_nodes_bytes(int F);
+size_t utx_bvh_workspace_bytes(int F);
+int utx_bvh_build(const float* vert, int V, const int32_t* tri, int F, void* nodes, void* workspace, size_t workspace_bytes,
+                  void* stream);
+/* reference node layout for inspection: info [2F-1, 3] (left, right, prim), aabb [2F-1, 6] */
+int utx_bvh_export(const void* nodes, int F, int32_t* info, float* aabb, void* stream);
+/* intersects_closest (rt_aprmis/__init__.py:36-86): hit u8 [N], tri_idx i32 [N] (-1 = miss), loc [N,3], uv [N,2] */
+int utx_bvh_intersect(const void* nodes, const float* vert, const int32_t* tri, const float* rays_o, const float* rays_d,
+                      long long N, unsigned char* hit, int32_t* tri_idx, float* loc, float* uv, void* stream);
+/* uv_to_pcd + bake_mv_to_uv_reproject_blur (renderer_inverse.py:243-365,574-633) fused.  rast2d: UV raster [H2,W2,4];
+ * view_mats/view_dirs/priority/grid_lo: HOST arrays ([n,16] P@W2C row-major, [n,3] = -c2w[:3,2], [n], [3]);
+ * images_rgba: device [n,H,W,4] = view colour + visible alpha; blur_k2d: device [49].  Outputs: mask2d u8 [H2*W2],
+ * mask_vis u8 [n, H2*W2], color [H2*W2, 3] fp32, nn_index i32 [H2*W2] or NULL. */
+size_t utx_uv_bake_workspace_bytes(int H2, int W2);
+int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
+                int n_views, const float* view_mats, const float* view_dirs, const int32_t* priority,
+                const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
+                const float* grid_lo, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color,
+                int32_t* nn_index, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,281 @@
+"""Oracle for the bake path (TEST INFRASTRUCTURE, see oracle/__init__.py).
+
+Geometric kernels (rasterise / interpolate / LBVH / intersect) are the C restatement in oracle/bake_ref.c.  Everything
+after them restates the reference's torch code with the same torch calls, on the CPU:
+  uv_to_pcd                        TextureTools/texturetools/render/nvdiffrast/renderer_inverse.py:243-365
+  get_boundary_mask                :435-444
+  bake_mv_to_uv_reproject_blur     :574-633   (k=1 nearest neighbour restated as exact brute force, lowest index on ties;
+                                               torch_kdtree@86961f7d [ext] leaves ties unspecified)
+  lens_blur_torch                  texturetools/image/lens_blur.py:82-93,109-121,172-195,260-280
+  pull_push                        texturetools/texture/stitching/mip.py:9-96
+PARITY UNPINNED (no golden vectors in the reference); pinned here by analytic tests in tests/test_oracle_bake.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import build_c
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(str(build_c.build()))
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def rasterize(pos: np.ndarray, tri: np.ndarray, H: int, W: int) -> np.ndarray:
+    pos = np.ascontiguousarray(pos, np.float32)
+    tri = np.ascontiguousarray(tri, np.int32)
+    B, V = pos.shape[0], pos.shape[1]
+    out = np.zeros((B, H, W, 4), np.float32)
+    lib().ora_rasterize(_ptr(pos), 1, V, _ptr(tri), tri.shape[0], B, H, W, _ptr(out))
+    return out
+
+
+def interpolate(attr: np.ndarray, rast: np.ndarray, tri: np.ndarray) -> np.ndarray:
+    attr = np.ascontiguousarray(attr, np.float32)
+    rast = np.ascontiguousarray(rast, np.float32)
+    tri = np.ascontiguousarray(tri, np.int32)
+    batched = attr.ndim == 3
+    V, Cn = attr.shape[-2], attr.shape[-1]
+    B, H, W, _ = rast.shape
+    out = np.zeros((B, H, W, Cn), np.float32)
+    lib().ora_interpolate(_ptr(attr), int(batched), V, Cn, _ptr(rast), _ptr(tri), B, H, W, _ptr(out))
+    return out
+
+
+def lbvh_build(vert: np.ndarray, tri: np.ndarray):
+    vert = np.ascontiguousarray(vert, np.float32)
+    tri = np.ascontiguousarray(tri, np.int32)
+    Fn = tri.shape[0]
+    info = np.zeros((2 * Fn - 1, 3), np.int32)
+    aabb = np.zeros((2 * Fn - 1, 6), np.float32)
+    srt = np.zeros((Fn, 2), np.int32)
+    lib().ora_lbvh_build(_ptr(vert), vert.shape[0], _ptr(tri), Fn, _ptr(info), _ptr(aabb), _ptr(srt))
+    return info, aabb, srt
+
+
+def intersect(vert, tri, info, aabb, rays_o, rays_d):
+    vert = np.ascontiguousarray(vert, np.float32)
+    tri = np.ascontiguousarray(tri, np.int32)
+    o = np.ascontiguousarray(rays_o, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(np.broadcast_to(rays_d, rays_o.shape), np.float32).reshape(-1, 3)
+    N = o.shape[0]
+    hit = np.zeros(N, np.uint8)
+    tid = np.zeros(N, np.int32)
+    pos = np.zeros((N, 3), np.float32)
+    uv = np.zeros((N, 2), np.float32)
+    lib().ora_intersect(_ptr(vert), _ptr(tri), _ptr(info), _ptr(aabb), _ptr(o), _ptr(d), C.c_int64(N), _ptr(hit), _ptr(tid),
+                        _ptr(pos), _ptr(uv))
+    return hit.astype(bool), tid, pos, uv
+
+
+# ------------------------------------------------------------------------------------------------ cameras
+def intr_to_proj_ortho(intr: torch.Tensor, near=0.01, far=1000.0) -> torch.Tensor:
+    """camera/conversion.py:19-27, perspective=False branch + the y-row negation."""
+    p = torch.zeros(4, 4)
+    p[0, 0], p[1, 1] = intr[0, 0], intr[1, 1]
+    p[2, 2] = -2.0 / (far - near)
+    p[3, 3] = 1.0
+    p[0, 3] = -(2 * intr[0, 2] - 1)
+    p[1, 3] = -(2 * intr[1, 2] - 1)
+    p[2, 3] = -(far + near) / (far - near)
+    p[1, :] = -p[1, :]
+    return p
+
+
+def c2w_to_w2c(c2w: torch.Tensor) -> torch.Tensor:
+    w2c = torch.zeros_like(c2w)
+    w2c[..., :3, :3] = c2w[..., :3, :3].transpose(-1, -2)
+    w2c[..., :3, 3:] = -c2w[..., :3, :3].transpose(-1, -2) @ c2w[..., :3, 3:]
+    w2c[..., 3, 3] = 1.0
+    return w2c
+
+
+# ------------------------------------------------------------------------------------------------ torch tail
+def lens_blur_torch(img: torch.Tensor, radius: float = 3.0, exposure_gamma: float = 5.0) -> torch.Tensor:
+    """image/lens_blur.py:260-280 with components=5 (parameter row 4, scale 1.2)."""
+    params = [[4.892608, 1.685979, -22.356787, 85.91246], [4.71187, 4.998496, 35.918936, -28.875618],
+              [4.052795, 8.244168, -13.212253, -1.578428], [2.929212, 11.900859, 0.507991, 1.816328],
+              [1.512961, 16.116382, 0.138051, -0.01]]
+    scale = 1.2
+    size = int(math.ceil(radius)) * 2 + 1
+    ax = torch.linspace(-radius, radius, size, dtype=torch.float32) * scale * (1 / radius)
+    comps = []
+    for a, b, _, _ in params:
+        k = torch.zeros(size, dtype=torch.complex64)
+        k.real = torch.exp(-a * ax ** 2) * torch.cos(b * ax ** 2)
+        k.imag = torch.exp(-a * ax ** 2) * torch.sin(b * ax ** 2)
+        comps.append(k.reshape(1, size))
+    total = 0.0
+    for k, (_, _, A, B) in zip(comps, params):
+        kr, ki = k[0].real, k[0].imag
+        total = total + (A * (kr[:, None] * kr[None] - ki[:, None] * ki[None]) + B * (kr[:, None] * ki[None] + ki[:, None] * kr[None])).sum()
+    comps = [k / total.sqrt() for k in comps]
+    img = torch.pow(img, exposure_gamma)
+    Cn = img.shape[1]
+    acc = 0.0
+    for k, (_, _, A, B) in zip(comps, params):
+        kr = k.real[None, None].repeat(Cn, 1, 1, 1)
+        ki = k.imag[None, None].repeat(Cn, 1, 1, 1)
+        pad = [0, size // 2]
+        ir = F.conv2d(img, kr, padding=pad, groups=Cn)
+        ii = F.conv2d(img, ki, padding=pad, groups=Cn)
+        krt, kit, padt = kr.transpose(-1, -2), ki.transpose(-1, -2), pad[::-1]
+        f1 = F.conv2d(ir, krt, padding=padt, groups=Cn)
+        f2 = F.conv2d(ir, kit, padding=padt, groups=Cn)
+        f3 = F.conv2d(ii, krt, padding=padt, groups=Cn)
+        f4 = F.conv2d(ii, kit, padding=padt, groups=Cn)
+        acc = acc + ((f1 - f4) * A + (f2 + f3) * B)
+    out = torch.clamp(acc, 0, None)
+    out = torch.pow(out, 1.0 / exposure_gamma)
+    return torch.clamp(out, 0, 1)
+
+
+def pull_push(map_Kd: torch.Tensor, map_mask: torch.Tensor):
+    """texture/stitching/mip.py:51-96 ([N,C,H,W], [N,1,H,W] bool)."""
+    B, Cn, H, W = map_Kd.shape
+    n_level = max(min(int(math.log2(H)), int(math.log2(W))) - 2, 0)
+    if n_level == 0:
+        return map_Kd, map_mask
+    map_Kd = torch.where(map_mask, map_Kd, torch.zeros((), dtype=map_Kd.dtype))
+
+    def mip(Kd, mask):
+        alpha = F.avg_pool2d(mask.float(), 2, 2, 0)
+        Kdm = F.avg_pool2d(Kd, 2, 2, 0)
+        bnd = (alpha > 0) & (alpha < 1)
+        Kdm = torch.where(bnd, Kdm / torch.where(bnd, alpha, torch.ones_like(alpha)), Kdm)
+        return Kdm, alpha > 0
+
+    def fill(Kd, mask, Kdm):
+        k = torch.tensor([[[0.5625, 0.1875], [0.1875, 0.0625]], [[0.1875, 0.5625], [0.0625, 0.1875]],
+                          [[0.1875, 0.0625], [0.5625, 0.1875]], [[0.0625, 0.1875], [0.1875, 0.5625]]], dtype=Kd.dtype)[:, None]
+        Hm, Wm = Kdm.shape[-2:]
+        pad = F.pad(Kdm, [1, 1, 1, 1], mode="replicate")
+        conv = F.conv2d(pad, k.repeat(Cn, 1, 1, 1), None, 1, 0, 1, Cn)
+        conv = conv.reshape(B, Cn, 2, 2, Hm + 1, Wm + 1).permute(0, 1, 4, 2, 5, 3).reshape(B, Cn, (Hm + 1) * 2, (Wm + 1) * 2)
+        return torch.where(mask, Kd, conv[:, :, 1:-1, 1:-1])
+
+    Ks, Ms = [], []
+    K, M = map_Kd, map_mask
+    for _ in range(n_level):
+        K, M = mip(K, M)
+        Ks.append(K)
+        Ms.append(M)
+    K = Ks[-1]
+    for lvl in range(n_level - 1, 0, -1):
+        K = fill(Ks[lvl - 1], Ms[lvl - 1], K)
+    return fill(map_Kd, map_mask, K), map_mask
+
+
+def boundary_mask(mask: torch.Tensor, k: int = 3) -> torch.Tensor:
+    """:435-444 on [N,H,W,1] bool."""
+    a = mask.float().permute(0, 3, 1, 2)
+    inner = (a - (1.0 - F.max_pool2d(1.0 - a, 2 * (k // 2) + 1, 1, k // 2))) > 0
+    outer = (F.max_pool2d(a, 2 * (k // 2) + 1, 1, k // 2) - a) > 0
+    return (inner | outer).permute(0, 2, 3, 1)
+
+
+def nearest_index(src: torch.Tensor, dst: torch.Tensor, chunk: int = 2048) -> torch.Tensor:
+    """Exact 1-NN of each dst point among src ([N,3], [M,3] fp32): fp32 squared distance ((dx^2+dy^2)+dz^2), lowest index
+    on ties."""
+    out = torch.empty(dst.shape[0], dtype=torch.int64)
+    for i in range(0, dst.shape[0], chunk):
+        d = src[None, :, :] - dst[i:i + chunk, None, :]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        out[i:i + chunk] = torch.argmin(d2, dim=1)      # first minimum = lowest index
+    return out
+
+
+@torch.no_grad()
+def infer_reproject(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, image_attrs: torch.Tensor,
+                    H: int, W: int, H2: int, W2: int, angle_deg: float = 100.0, index=(0, 3, 4, 1, 2, 5)) -> Dict[str, torch.Tensor]:
+    """NVDiffRendererInverse.infer(method='reproject', perspective=False, filt_gradient_points=False) (:635-726)."""
+    vert = np.ascontiguousarray(vert, np.float32)
+    tri = np.ascontiguousarray(tri, np.int32)
+    tri_uv = np.ascontiguousarray(tri_uv, np.int32)
+    n = c2ws.shape[0]
+    V = torch.from_numpy(vert)
+    mats = torch.matmul(intr_to_proj_ortho(intrinsics), c2w_to_w2c(c2ws))                   # [n,4,4]
+    vh = torch.cat([V, torch.ones_like(V[:, :1])], -1)
+    clip = torch.matmul(vh, mats.permute(0, 2, 1))                                           # :263  [n,V,4]
+    # mv_to_pcd :183-214
+    rast_mv = torch.from_numpy(rasterize(clip.numpy(), tri, H, W))
+    alpha_vis = (rast_mv[..., 3:4] > 0).float()
+    # uv_to_pcd
+    uvc = np.concatenate([uv, np.zeros_like(uv[:, :1]), np.ones_like(uv[:, :1])], -1)[None].astype(np.float32)
+    rast2 = rasterize(uvc, tri_uv, H2, W2)
+    mask_2d = torch.from_numpy(rast2[..., 3:4] > 0)
+    tid_2d = torch.from_numpy(rast2[..., 3]).long() - 1                                      # [1,H2,W2]
+    pos_2d = torch.from_numpy(interpolate(vert, rast2, tri))                                 # [1,H2,W2,3]
+    Ft = torch.from_numpy(tri.astype(np.int64))
+    areas = torch.linalg.cross(V[Ft[:, 1]] - V[Ft[:, 0]], V[Ft[:, 2]] - V[Ft[:, 0]], dim=-1)
+    normals = F.normalize(areas, dim=-1)
+    fn_2d = normals[torch.where(mask_2d[..., 0], tid_2d, torch.zeros_like(tid_2d))]          # [1,H2,W2,3]
+    rays_d = (-c2ws[:, :3, 2])[:, None, None, :]
+    rays_o = pos_2d - (2.0 * math.sqrt(3.0)) * rays_d
+    rays_d = F.normalize(rays_d, dim=-1)
+    rays_o, rays_d = torch.broadcast_tensors(rays_o, rays_d)
+    ndc_v = clip[..., :2] / clip[..., 3:4]
+    ndc_2d = torch.from_numpy(interpolate(ndc_v.numpy(), np.repeat(rast2, n, 0), tri))       # :288
+    img = torch.cat([image_attrs, alpha_vis], -1)
+    samp = F.grid_sample(img.permute(0, 3, 1, 2), ndc_2d, mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    col_2d, alpha_2d = samp[..., :3], samp[..., 3:4]
+    m = mask_2d[0, ..., 0]
+    info, aabb, _ = lbvh_build(vert, tri)
+    ro, rd = rays_o[:, m], rays_d[:, m]                                                      # [n,Nv,3]
+    _, rt, _, _ = intersect(vert, tri, info, aabb, ro.numpy(), rd.numpy())
+    rt = torch.from_numpy(rt.astype(np.int64)).reshape(n, -1)
+    tv = tid_2d[0][m]
+    ok = (rt == tv[None]) & (rt != -1)
+    cosv = F.cosine_similarity(rd, fn_2d[0][m][None].expand(n, -1, -1), dim=-1)
+    ok = ok & (cosv < math.cos(math.radians(angle_deg)))
+    vis = torch.zeros(n, H2, W2, 1, dtype=torch.bool)
+    vis[:, m, 0] = ok
+    raw_vis = vis.clone()
+    for k in (3, 5):                                                                          # :329-339 with kernel_mode=7
+        ker = F.pad(torch.full((1, 1, k - 2, k - 2), -1.0), (1, 1, 1, 1), value=float(k * k))
+        conv = F.conv2d(vis.float().permute(0, 3, 1, 2), ker, stride=1, padding=k // 2).permute(0, 2, 3, 1)
+        vis = vis | (conv >= ((k - 1) ** 2 - 1) * ((k - 2) ** 2))
+    vis = vis & mask_2d & (alpha_2d > 0.999)
+    # bake_mv_to_uv_reproject_blur
+    color = torch.zeros(1, H2, W2, 3)
+    cur = torch.zeros(1, H2, W2, 1, dtype=torch.bool)
+    bnd = torch.zeros(1, H2, W2, 1, dtype=torch.bool)
+    owner = torch.full((H2, W2), -1, dtype=torch.int64)
+    for i in index:
+        extra = (~cur) & vis[i:i + 1]
+        color = torch.where(extra, col_2d[i:i + 1], color)
+        owner[extra[0, ..., 0]] = i
+        cur = cur | extra
+        bnd = bnd | boundary_mask(extra, 3)
+    bnd = F.max_pool2d(bnd.float().permute(0, 3, 1, 2), 3, 1, 1).permute(0, 2, 3, 1) > 0
+    bnd = ((1.0 - F.max_pool2d(1.0 - mask_2d.float().permute(0, 3, 1, 2), 7, 1, 3).permute(0, 2, 3, 1)) > 0) & bnd
+    vis_m = cur[0, ..., 0] & m
+    inv_m = (~cur[0, ..., 0]) & m
+    nn_index = torch.full((H2 * W2,), -1, dtype=torch.int64)
+    if inv_m.any() and vis_m.any():
+        src_idx = torch.nonzero(vis_m.reshape(-1))[:, 0]
+        idx = nearest_index(pos_2d[0][vis_m], pos_2d[0][inv_m])
+        color[0][inv_m] = color[0][vis_m][idx]
+        nn_index[inv_m.reshape(-1)] = src_idx[idx]
+    pre_blur = color.clone()
+    blur = lens_blur_torch(color.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    color = torch.where(bnd, blur, color)
+    color_2d = pull_push(color.permute(0, 3, 1, 2), mask_2d.permute(0, 3, 1, 2))[0].permute(0, 2, 3, 1)
+    return {"mask_2d": mask_2d, "mask_2d_visiable": vis, "raw_visible": raw_vis, "color_2d": color_2d, "tid_2d": tid_2d,
+            "owner": owner, "seam": bnd, "nn_index": nn_index, "pre_blur": pre_blur, "rast_2d": torch.from_numpy(rast2),
+            "alpha_mv": alpha_vis, "rays_tid": rt}

@@ -1,0 +1,102 @@
+"""GPU parity of the bake path against the C/torch oracle: bit-exact for triangle ids, barycentrics, tree topology,
+visibility masks and nearest-neighbour indices; fp32 tolerance for colours (north_star: "bit-exact UV indices")."""
+import numpy as np
+import pytest
+import torch
+
+from tests.bake_meshes import analytic_color, two_spheres, uv_sphere
+
+pytestmark = pytest.mark.gpu
+
+COLOR_ATOL = 2e-4     # fp32 colours: different summation order in the 7x7 blur / bilinear fetch
+
+
+def _views():
+    from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics
+    return generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]], generate_intrinsics(1.0, 1.0, fov=False)
+
+
+@pytest.mark.parametrize("res", [(64, 64), (200, 136)])
+def test_rasterize_interpolate_bit_exact(lib, res):
+    from oracle import bake as ob
+    from unitex_b200 import bake as ub
+    v, f, uv, fuv = two_spheres(14, 28)
+    c2ws, intr = _views()
+    mats = torch.matmul(ub.intr_to_proj(intr, perspective=False), ub.c2w_to_w2c(c2ws))
+    clip = ub.transform_points(torch.from_numpy(v).cuda(), mats.cuda())
+    H, W = res
+    rast = ub.rasterize(clip, torch.from_numpy(f).cuda(), (H, W))
+    attr = ub.interpolate(torch.from_numpy(v).cuda(), rast, torch.from_numpy(f).cuda())
+    torch.cuda.synchronize()
+    ref = ob.rasterize(clip.cpu().numpy(), f, H, W)
+    assert (ref[..., 3] > 0).sum() > 0.1 * ref[..., 3].size
+    assert np.array_equal(rast.cpu().numpy(), ref)                       # ids, u, v, z/w: bit for bit
+    assert np.array_equal(attr.cpu().numpy(), ob.interpolate(v, ref, f))
+    # UV-space pass (shared geometry, all z = 0)
+    uvc = torch.from_numpy(np.concatenate([uv, np.zeros_like(uv[:, :1]), np.ones_like(uv[:, :1])], -1)[None]).cuda()
+    r2 = ub.rasterize(uvc, torch.from_numpy(fuv).cuda(), (128, 128))
+    assert np.array_equal(r2.cpu().numpy(), ob.rasterize(uvc.cpu().numpy(), fuv, 128, 128))
+
+
+def test_lbvh_and_intersect_bit_exact(lib):
+    from oracle import bake as ob
+    from unitex_b200.bake import RayTracing
+    v, f, _, _ = two_spheres(18, 36)
+    rt = RayTracing(torch.from_numpy(v), torch.from_numpy(f.astype(np.int64)))
+    info, aabb = rt.export()
+    rinfo, raabb, _ = ob.lbvh_build(v, f)
+    assert np.array_equal(info.cpu().numpy(), rinfo) and np.array_equal(aabb.cpu().numpy(), raabb)
+    g = np.random.default_rng(0)
+    N = 20000
+    o = g.normal(size=(N, 3)).astype(np.float32) * 1.5
+    d = (g.normal(size=(N, 3)) * 0.3 - o).astype(np.float32)            # roughly towards the scene; some miss
+    d[:500] = np.array([0, 0, -1], np.float32)                          # axis-aligned rays hit the 1e-6 zero-direction path
+    hit, _, tid, loc, uv = rt.intersects_closest(torch.from_numpy(o), torch.from_numpy(d))
+    torch.cuda.synchronize()
+    rh, rtid, rpos, ruv = ob.intersect(v, f, rinfo, raabb, o, d)
+    assert 0.2 < rh.mean() < 0.99
+    assert np.array_equal(hit.cpu().numpy(), rh) and np.array_equal(tid.cpu().numpy(), rtid.astype(np.int64))
+    assert np.array_equal(loc.cpu().numpy(), rpos) and np.array_equal(uv.cpu().numpy(), ruv)
+    assert tid.dtype == torch.int64 and (tid[~hit] == -1).all()
+
+
+def test_uv_bake_matches_oracle(lib):
+    from oracle import bake as ob
+    from unitex_b200 import bake as ub
+    v, f, uv, fuv = two_spheres(16, 32)
+    c2ws, intr = _views()
+    H = W = 96
+    H2 = W2 = 128
+    mats = torch.matmul(ob.intr_to_proj_ortho(intr), ob.c2w_to_w2c(c2ws))
+    vh = torch.cat([torch.from_numpy(v), torch.ones(len(v), 1)], -1)
+    rast = ob.rasterize(torch.matmul(vh, mats.permute(0, 2, 1)).numpy(), f, H, W)
+    img = torch.from_numpy(analytic_color(ob.interpolate(v, rast, f)) * (rast[..., 3:4] > 0)).float()
+    ref = ob.infer_reproject(v, f, uv, fuv, c2ws, intr, img, H, W, H2, W2)
+    r = ub.NVDiffRendererInverse(pbr_mesh=ub.BakeMesh(v, f, uv, fuv))
+    _, vis, m2, col = r.infer(r.pbr_mesh, c2ws, intr, img, H=H, W=W, H2D=H2, W2D=W2, perspective=False,
+                              ray_normal_angle_threhold=100.0, method="reproject", filt_gradient_points=False)
+    torch.cuda.synchronize()
+    assert vis.shape == (6, H2, W2, 1) and m2.shape == (1, H2, W2, 1) and col.shape == (1, H2, W2, 3)
+    assert torch.equal(m2.cpu(), ref["mask_2d"])
+    assert torch.equal(r.last_rast2d.cpu(), ref["rast_2d"])                                  # bit-exact UV triangle ids + barycentrics
+    assert torch.equal(vis.cpu(), ref["mask_2d_visiable"])                                   # bit-exact visibility masks
+    nn = r.last_nn_index.cpu().long()
+    assert (ref["nn_index"] >= 0).sum() > 100
+    assert torch.equal(nn, ref["nn_index"])                                                  # exact 1-NN, same tie rule
+    err = (col.cpu() - ref["color_2d"]).abs()
+    assert err.max().item() < COLOR_ATOL, err.max().item()
+
+
+def test_raytracing_plugin_surface(lib):
+    """Same call surface as texturetools.raytracing.RayTracing (raytracing/__init__.py:12-80)."""
+    from unitex_b200.bake import RayTracing
+    v, f, _ = uv_sphere(10, 20)
+    rt = RayTracing(torch.from_numpy(v), torch.from_numpy(f.astype(np.int64)), backend="aprmis")
+    o = torch.tensor([[[0.0, 0.0, 3.0], [0.0, 2.0, 3.0]]])                # batch shape [1,2]
+    d = torch.tensor([0.0, 0.0, -1.0])
+    hit, front, tri_idx, loc, uvv = rt.intersects_closest(o, d)
+    assert front is None and hit.shape == (1, 2) and loc.shape == (1, 2, 3) and uvv.shape == (1, 2, 2)
+    assert hit.tolist() == [[True, False]] and tri_idx[0, 1] == -1
+    rt.update_raw(torch.from_numpy(v * 2), torch.from_numpy(f.astype(np.int64)))
+    hit2, _, _, loc2, _ = rt.intersects_closest(o, d)
+    assert hit2.tolist() == [[True, False]] and abs(abs(loc2[0, 0, 2].item()) - 1.2) < 0.05

@@ -61,6 +61,18 @@ _SIGS = {
     "utx_gemv_bf16": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "utx_rope_table": (i32, [vp, i32, vp, vp, vp]),
     "utx_euler_update": (i32, [vp, vp, i32, i32, f32, vp]),
+    "utx_rasterize_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
+    "utx_rasterize": (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]),
+    "utx_interpolate": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp]),
+    "utx_transform_points": (i32, [vp, i32, vp, i32, vp, vp]),
+    "utx_bvh_nodes_bytes": (C.c_size_t, [i32]),
+    "utx_bvh_workspace_bytes": (C.c_size_t, [i32]),
+    "utx_bvh_build": (i32, [vp, i32, vp, i32, vp, vp, C.c_size_t, vp]),
+    "utx_bvh_export": (i32, [vp, i32, vp, vp, vp]),
+    "utx_bvh_intersect": (i32, [vp, vp, vp, vp, vp, C.c_longlong, vp, vp, vp, vp, vp]),
+    "utx_uv_bake_workspace_bytes": (C.c_size_t, [i32, i32]),
+    "utx_uv_bake": (i32, [vp, i32, vp, i32, vp, vp, i32, i32, i32, fp, fp, C.POINTER(C.c_int32), vp, i32, i32, f32, vp, f32,
+                          fp, f32, vp, vp, vp, vp, vp, C.c_size_t, vp]),
 }
 
 

@@ -1,0 +1,307 @@
+"""Host side of the B200 bake path: cameras, the ray-tracer plug-in, rasterise/interpolate wrappers and
+`NVDiffRendererInverse` -- same names and call surface as the reference's TextureTools modules
+(texturetools/camera/conversion.py, camera/generator.py, raytracing/__init__.py,
+render/nvdiffrast/renderer_inverse.py) with every kernel in libunitex_b200.so.  No nvdiffrast / slangtorch /
+torch_kdtree / trimesh.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import _p, _stream
+
+
+# ------------------------------------------------------------------------------------------------ cameras (b2)
+def intr_to_proj(intr_mtx: torch.Tensor, near=0.01, far=1000.0, perspective=True) -> torch.Tensor:
+    """camera/conversion.py:8-28 (GL projection, y row negated for the rasteriser's row-0-at-y=-1 convention)."""
+    proj = torch.zeros((*intr_mtx.shape[:-2], 4, 4), dtype=intr_mtx.dtype, device=intr_mtx.device)
+    if perspective:
+        proj[..., 0, 0] = 2 * intr_mtx[..., 0, 0]
+        proj[..., 1, 1] = 2 * intr_mtx[..., 1, 1]
+        proj[..., 2, 2] = -(far + near) / (far - near)
+        proj[..., 0, 2] = 2 * intr_mtx[..., 0, 2] - 1
+        proj[..., 1, 2] = 2 * intr_mtx[..., 1, 2] - 1
+        proj[..., 3, 2] = -1.0
+        proj[..., 2, 3] = -2.0 * far * near / (far - near)
+    else:
+        proj[..., 0, 0] = intr_mtx[..., 0, 0]
+        proj[..., 1, 1] = intr_mtx[..., 1, 1]
+        proj[..., 2, 2] = -2.0 / (far - near)
+        proj[..., 3, 3] = 1.0
+        proj[..., 0, 3] = -(2 * intr_mtx[..., 0, 2] - 1)
+        proj[..., 1, 3] = -(2 * intr_mtx[..., 1, 2] - 1)
+        proj[..., 2, 3] = -(far + near) / (far - near)
+    proj[..., 1, :] = -proj[..., 1, :]
+    return proj
+
+
+def c2w_to_w2c(c2w: torch.Tensor) -> torch.Tensor:
+    """camera/conversion.py:50-57."""
+    w2c = torch.zeros((*c2w.shape[:-2], 4, 4), dtype=c2w.dtype, device=c2w.device)
+    w2c[..., :3, :3] = c2w[..., :3, :3].transpose(-1, -2)
+    w2c[..., :3, 3:] = -c2w[..., :3, :3].transpose(-1, -2) @ c2w[..., :3, 3:]
+    w2c[..., 3, 3] = 1.0
+    return w2c
+
+
+def generate_intrinsics(f_x: float, f_y: float, fov=True, degree=False) -> torch.Tensor:
+    """camera/generator.py:93-114."""
+    if fov:
+        if degree:
+            f_x, f_y = math.radians(f_x), math.radians(f_y)
+        f_x, f_y = 1 / (2 * math.tan(f_x / 2)), 1 / (2 * math.tan(f_y / 2))
+    return torch.as_tensor([[f_x, 0.0, 0.5], [0.0, f_y, 0.5], [0.0, 0.0, 1.0]], dtype=torch.float32)
+
+
+def generate_box_views_c2ws(radius=2.8) -> torch.Tensor:
+    """camera/generator.py:153-185: front(+z), right(+x), back(-z), left(-x), top(+y), down(-y)."""
+    r = radius
+    return torch.tensor([
+        [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, r], [0, 0, 0, 1]],
+        [[0, 0, 1, r], [0, 1, 0, 0], [-1, 0, 0, 0], [0, 0, 0, 1]],
+        [[-1, 0, 0, 0], [0, 1, 0, 0], [0, 0, -1, -r], [0, 0, 0, 1]],
+        [[0, 0, -1, -r], [0, 1, 0, 0], [1, 0, 0, 0], [0, 0, 0, 1]],
+        [[1, 0, 0, 0], [0, 0, 1, r], [0, -1, 0, 0], [0, 0, 0, 1]],
+        [[-1, 0, 0, 0], [0, 0, -1, -r], [0, -1, 0, 0], [0, 0, 0, 1]],
+    ], dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------ raster wrappers
+def _f32(t, device):
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def rasterize(pos: torch.Tensor, tri: torch.Tensor, resolution: Tuple[int, int]) -> torch.Tensor:
+    """dr.rasterize: pos [B,V,4] (or [1,V,4] shared), tri [F,3] int32 -> [B,H,W,4] (u, v, z/w, id+1)."""
+    L = _lib.load()
+    H, W = resolution
+    pos = pos.contiguous()
+    B, V = pos.shape[0], pos.shape[1]
+    tri = tri.to(torch.int32).contiguous()
+    out = torch.empty(B, H, W, 4, device=pos.device, dtype=torch.float32)
+    ws = torch.empty(L.utx_rasterize_workspace_bytes(B, H, W), device=pos.device, dtype=torch.uint8)
+    _lib.check(L.utx_rasterize(_p(pos), 1, V, _p(tri), tri.shape[0], B, H, W, _p(out), _p(ws), _stream()), "utx_rasterize")
+    return out
+
+
+def interpolate(attr: torch.Tensor, rast: torch.Tensor, tri: torch.Tensor) -> torch.Tensor:
+    """dr.interpolate: attr [V,C] or [B,V,C]; rast [B,H,W,4] -> [B,H,W,C]."""
+    L = _lib.load()
+    batched = attr.dim() == 3
+    attr = attr.contiguous()
+    V, Cn = attr.shape[-2], attr.shape[-1]
+    B, H, W, _ = rast.shape
+    tri = tri.to(torch.int32).contiguous()
+    out = torch.empty(B, H, W, Cn, device=rast.device, dtype=torch.float32)
+    _lib.check(L.utx_interpolate(_p(attr), int(batched), V, Cn, _p(rast.contiguous()), _p(tri), B, H, W, _p(out), _stream()),
+               "utx_interpolate")
+    return out
+
+
+def transform_points(vertices: torch.Tensor, mats: torch.Tensor) -> torch.Tensor:
+    """[V,3] x [n,4,4] -> clip [n,V,4]  (vertices_homo @ M^T, renderer_inverse.py:177-178)."""
+    L = _lib.load()
+    vertices, mats = vertices.contiguous(), mats.contiguous()
+    n, V = mats.shape[0], vertices.shape[0]
+    out = torch.empty(n, V, 4, device=vertices.device, dtype=torch.float32)
+    _lib.check(L.utx_transform_points(_p(vertices), V, _p(mats), n, _p(out), _stream()), "utx_transform_points")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ ray tracer plug-in (b4)
+class RayTracing:
+    """Drop-in for texturetools.raytracing.RayTracing (raytracing/__init__.py:12-80); one backend: the B200 LBVH."""
+
+    def __init__(self, vertices: torch.Tensor, faces: torch.Tensor, backend: Optional[str] = None, device="cuda"):
+        self.device = torch.device(device)
+        self.update_raw(vertices, faces)
+
+    def update_raw(self, vertices: torch.Tensor, faces: torch.Tensor):
+        L = _lib.load()
+        self.vertices = _f32(vertices, self.device)
+        self.faces = faces.to(device=self.device, dtype=torch.int32).contiguous()
+        F = self.faces.shape[0]
+        self.nodes = torch.empty(L.utx_bvh_nodes_bytes(F), device=self.device, dtype=torch.uint8)
+        ws = torch.empty(L.utx_bvh_workspace_bytes(F), device=self.device, dtype=torch.uint8)
+        _lib.check(L.utx_bvh_build(_p(self.vertices), self.vertices.shape[0], _p(self.faces), F, _p(self.nodes), _p(ws),
+                                   ws.numel(), _stream()), "utx_bvh_build")
+
+    def export(self):
+        """(info [2F-1,3] int32, aabb [2F-1,6] fp32) in the reference's LBVHNode layout."""
+        L = _lib.load()
+        n = 2 * self.faces.shape[0] - 1
+        info = torch.empty(n, 3, device=self.device, dtype=torch.int32)
+        aabb = torch.empty(n, 6, device=self.device, dtype=torch.float32)
+        _lib.check(L.utx_bvh_export(_p(self.nodes), self.faces.shape[0], _p(info), _p(aabb), _stream()), "utx_bvh_export")
+        return info, aabb
+
+    def intersects_closest(self, rays_o: torch.Tensor, rays_d: torch.Tensor):
+        """-> (hit bool[...], front None, tri_idx int64[...] (-1 = miss), loc [...,3], uv [...,2])"""
+        L = _lib.load()
+        rays_o, rays_d = torch.broadcast_tensors(rays_o, rays_d)
+        shape = rays_o.shape[:-1]
+        o = _f32(rays_o, self.device).reshape(-1, 3)
+        d = _f32(rays_d, self.device).reshape(-1, 3)
+        N = o.shape[0]
+        hit = torch.empty(N, device=self.device, dtype=torch.uint8)
+        tid = torch.empty(N, device=self.device, dtype=torch.int32)
+        loc = torch.empty(N, 3, device=self.device, dtype=torch.float32)
+        uv = torch.empty(N, 2, device=self.device, dtype=torch.float32)
+        _lib.check(L.utx_bvh_intersect(_p(self.nodes), _p(self.vertices), _p(self.faces), _p(o), _p(d), N, _p(hit), _p(tid),
+                                       _p(loc), _p(uv), _stream()), "utx_bvh_intersect")
+        return hit.bool().reshape(shape), None, tid.to(torch.int64).reshape(shape), loc.reshape(*shape, 3), uv.reshape(*shape, 2)
+
+
+# ------------------------------------------------------------------------------------------------ lens-blur kernel (b9)
+_LENS5 = [[4.892608, 1.685979, -22.356787, 85.91246], [4.71187, 4.998496, 35.918936, -28.875618],
+          [4.052795, 8.244168, -13.212253, -1.578428], [2.929212, 11.900859, 0.507991, 1.816328],
+          [1.512961, 16.116382, 0.138051, -0.01]]   # yehar.com 5-component parameters (image/lens_blur.py:45-50)
+
+
+def lens_blur_kernel_2d(radius: float = 3.0, scale: float = 1.2) -> np.ndarray:
+    """Effective real 2-D kernel of lens_blur_torch(radius=3, components=5) (image/lens_blur.py:82-93,109-121,172-195,
+    260-280): K[i,j] = sum_c A_c Re(k_c[i] k_c[j]) + B_c Im(k_c[i] k_c[j]), all components normalised together."""
+    size = int(math.ceil(radius)) * 2 + 1
+    ax = np.linspace(-radius, radius, size, dtype=np.float32).astype(np.float64) * scale * (1 / radius)
+    ks = [np.exp(-a * ax ** 2) * (np.cos(b * ax ** 2) + 1j * np.sin(b * ax ** 2)) for a, b, _, _ in _LENS5]
+    total = 0.0
+    for k, (_, _, A, B) in zip(ks, _LENS5):
+        kk = np.outer(k, k)
+        total += (A * kk.real + B * kk.imag).sum()
+    ks = [k / math.sqrt(total) for k in ks]
+    K = np.zeros((size, size))
+    for k, (_, _, A, B) in zip(ks, _LENS5):
+        kk = np.outer(k, k)          # [vertical tap, horizontal tap]
+        K += A * kk.real + B * kk.imag
+    return K.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ mesh container (b3)
+class BakeMesh:
+    """The fields of PBRMesh the bake reads (mesh/structure_v2.py:25-77): vertices [V,3], faces [F,3], uvs_2d [V2,2] in
+    [-1,1] (uv*2-1, :287), faces_2d [F,3]; lazy LBVH like PBRMesh.optix."""
+
+    def __init__(self, vertices, faces, uvs_2d, faces_2d, device="cuda"):
+        self.device = torch.device(device)
+        self.vertices = _f32(torch.as_tensor(vertices), self.device)
+        self.faces = torch.as_tensor(faces).to(device=self.device, dtype=torch.int32).contiguous()
+        self.uvs_2d = _f32(torch.as_tensor(uvs_2d), self.device)
+        self.faces_2d = torch.as_tensor(faces_2d).to(device=self.device, dtype=torch.int32).contiguous()
+        assert self.faces.shape == self.faces_2d.shape
+        self._optix = None
+
+    @property
+    def optix(self) -> RayTracing:
+        if self._optix is None:
+            self._optix = RayTracing(self.vertices, self.faces, device=self.device)
+        return self._optix
+
+
+def load_obj(path: str):
+    """Minimal OBJ reader (v / vt / f with v/vt[/vn] corners, polygons fan-triangulated) -> (V[,3], F[,3], UV[,2], F_uv[,3])."""
+    v, vt, f, ft = [], [], [], []
+    with open(path) as fh:
+        for line in fh:
+            if line.startswith("v "):
+                v.append([float(x) for x in line.split()[1:4]])
+            elif line.startswith("vt "):
+                vt.append([float(x) for x in line.split()[1:3]])
+            elif line.startswith("f "):
+                c = [p.split("/") for p in line.split()[1:]]
+                vi = [int(p[0]) for p in c]
+                ti = [int(p[1]) if len(p) > 1 and p[1] else 0 for p in c]
+                for k in range(1, len(vi) - 1):
+                    f.append([vi[0], vi[k], vi[k + 1]])
+                    ft.append([ti[0], ti[k], ti[k + 1]])
+    V, UV = np.asarray(v, np.float32), np.asarray(vt, np.float32)
+    Fv, Ft = np.asarray(f, np.int64), np.asarray(ft, np.int64)
+    Fv = np.where(Fv < 0, Fv + len(V) + 1, Fv) - 1
+    Ft = np.where(Ft < 0, Ft + len(UV) + 1, Ft) - 1
+    return V, Fv.astype(np.int32), UV, Ft.astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------ NVDiffRendererInverse (b5-b7)
+class NVDiffRendererInverse:
+    """Drop-in for render/nvdiffrast/renderer_inverse.py::NVDiffRendererInverse, method='reproject' path."""
+
+    def __init__(self, device="cuda", pbr_mesh: Optional[BakeMesh] = None):
+        self.device = torch.device(device)
+        self.pbr_mesh = pbr_mesh
+        self.index = [0, 3, 4, 1, 2, 5]      # frtbld ==> fblrtd   (renderer_inverse.py:44)
+        self.query_field_function = None
+        self._k2d = torch.from_numpy(lens_blur_kernel_2d()).to(self.device).contiguous()
+        self.last_nn_index = None
+
+    def clear(self):
+        self.pbr_mesh = None
+        self.query_field_function = None
+
+    def update_from_file(self, path: str):
+        V, F, UV, Ft = load_obj(path)
+        self.pbr_mesh = BakeMesh(V, F, UV * 2.0 - 1.0, Ft, device=self.device)
+        return self
+
+    def register_query_field(self, fn):
+        self.query_field_function = fn
+
+    def _view_mats(self, c2ws, intrinsics, perspective):
+        return torch.matmul(intr_to_proj(intrinsics.float().cpu(), perspective=perspective), c2w_to_w2c(c2ws.float().cpu()))
+
+    def mv_to_pcd(self, c2ws, intrinsics, render_size, image_attrs=None, perspective=True, **_):
+        """:159-241 with filt_gradient_points=False (what pipeline.py:343-347 passes): the visible alpha is the raster mask."""
+        H, W = (render_size, render_size) if isinstance(render_size, int) else render_size
+        mats = self._view_mats(c2ws, intrinsics, perspective).to(self.device)
+        clip = transform_points(self.pbr_mesh.vertices, mats)
+        rast = rasterize(clip, self.pbr_mesh.faces, (H, W))
+        mask = rast[..., 3:4] > 0
+        return {"mask": mask, "alpha": mask.float(), "mask_visiable": mask, "alpha_visiable": mask.float(), "rast": rast}
+
+    def infer(self, blank_mesh, c2ws: torch.Tensor, intrinsics: torch.Tensor, image_attrs: torch.Tensor, H=512, W=512,
+              H2D=2048, W2D=2048, perspective=True, grad_norm_threhold=0.20, ray_normal_angle_threhold=115.0,
+              grid_interpolate_mode="torch", method="reproject", reproject_method="lens", reproject_inpainting=False,
+              return_mv_reproject_uv=False, filt_gradient_points=True, **kw):
+        """:635-726.  Returns (textured_mesh, mask_2d_visiable [n,H2D,W2D,1] bool, mask_2d [1,H2D,W2D,1] bool,
+        color_2d [1,H2D,W2D,3] fp32).  textured_mesh is left to the caller's exporter (io layer)."""
+        if method != "reproject" or reproject_method != "lens" or reproject_inpainting or perspective or filt_gradient_points:
+            raise NotImplementedError("B200 bake implements the path CustomRGBTextureFullPipeline uses: orthographic, "
+                                      "method='reproject', lens blur, no inpainting, filt_gradient_points=False "
+                                      "(pipeline.py:335-348)")
+        if isinstance(blank_mesh, str):
+            self.update_from_file(blank_mesh)
+        elif isinstance(blank_mesh, BakeMesh):
+            self.pbr_mesh = blank_mesh
+        m = self.pbr_mesh
+        L = _lib.load()
+        n = c2ws.shape[0]
+        assert n == len(self.index), "the reference bake is hard-wired to 6 views (renderer_inverse.py:171,256,589)"
+        mv = self.mv_to_pcd(c2ws, intrinsics, (H, W), perspective=perspective)
+        rgba = torch.cat([_f32(image_attrs, self.device), mv["alpha_visiable"]], dim=-1).contiguous()
+        uv_clip = torch.cat([m.uvs_2d, torch.zeros_like(m.uvs_2d[:, :1]), torch.ones_like(m.uvs_2d[:, :1])], dim=-1)[None]
+        rast2d = rasterize(uv_clip, m.faces_2d, (H2D, W2D))
+        mats = self._view_mats(c2ws, intrinsics, perspective).contiguous()
+        dirs = (-c2ws[:, :3, 2]).float().cpu().contiguous()
+        prio = (C.c_int32 * n)(*self.index)
+        lo = m.vertices.min(dim=0).values.cpu()
+        ext = float((m.vertices.max(dim=0).values.cpu() - lo).max()) * 1.0001 + 1e-6
+        lo_arr = (C.c_float * 3)(*[float(x) for x in lo])
+        T = H2D * W2D
+        mask2d = torch.empty(T, device=self.device, dtype=torch.uint8)
+        mask_vis = torch.empty(n, T, device=self.device, dtype=torch.uint8)
+        color = torch.empty(T, 3, device=self.device, dtype=torch.float32)
+        nn_index = torch.empty(T, device=self.device, dtype=torch.int32)
+        ws = torch.empty(L.utx_uv_bake_workspace_bytes(H2D, W2D), device=self.device, dtype=torch.uint8)
+        cos_t = float(np.float32(math.cos(math.radians(ray_normal_angle_threhold))))
+        _lib.check(L.utx_uv_bake(_p(m.vertices), m.vertices.shape[0], _p(m.faces), m.faces.shape[0], _p(m.optix.nodes),
+                                 _p(rast2d), H2D, W2D, n, mats.numpy().ctypes.data_as(_lib.fp), dirs.numpy().ctypes.data_as(_lib.fp),
+                                 prio, _p(rgba), H, W, cos_t, _p(self._k2d), 5.0, lo_arr, ext, _p(mask2d), _p(mask_vis), _p(color),
+                                 _p(nn_index), _p(ws), ws.numel(), _stream()), "utx_uv_bake")
+        self.last_nn_index = nn_index
+        self.last_rast2d = rast2d
+        return (None, mask_vis.bool().reshape(n, H2D, W2D, 1), mask2d.bool().reshape(1, H2D, W2D, 1),
+                color.reshape(1, H2D, W2D, 3))

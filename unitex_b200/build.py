@@ -41,7 +41,9 @@ def _compile(src: Path) -> Path:
     dig = _digest(src)
     if obj.exists() and stamp.exists() and stamp.read_text() == dig:
         return obj
-    cmd = [NVCC, *FLAGS, "-c", str(src), "-o", str(obj)]
+    # bake_* kernels decide triangle ids: no FMA contraction, so the C oracle (-ffp-contract=off) matches bit for bit
+    extra = ["-fmad=false"] if src.name.startswith("bake_") else []
+    cmd = [NVCC, *FLAGS, *extra, "-c", str(src), "-o", str(obj)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     (OBJ / (src.stem + ".log")).write_text(r.stdout + r.stderr)
     if r.returncode != 0:

@@ -1,0 +1,282 @@
+// LBVH build + closest-hit query: the reference's ray-tracer plug-in (RayTracing.intersects_closest / update_raw,
+// TextureTools/texturetools/raytracing/__init__.py:12-80, default backend rt_aprmis/__init__.py:10-86, kernels
+// rt_aprmis/bvhworkers/*.slang) rebuilt for B200.
+//
+// Same tree as the reference, built differently:
+//   * per-triangle AABB + scene bounds in one pass (atomics on order-preserving ints instead of 6 torch reductions)
+//   * 30-bit Morton codes (identical arithmetic), sorted with a multi-block device radix sort (the reference runs a
+//     single-workgroup sort on ONE SM -- its slowest stage); stable, so ties keep element order exactly like its LSD sort
+//   * Karras-2012 hierarchy, identical delta / range / split rules incl. the duplicate-code tie-break on sorted index
+//   * ONE bottom-up refit pass with per-node arrival counters instead of one launch per tree level + host sync
+//   * nodes packed in 48 B (aabb[6], left, right, prim) = three 16 B loads, instead of two strided arrays
+// The traversal keeps the reference's order and quirks (intersect_test2.slang:63-146), because they decide which
+// triangle id a ray reports and `rays_tid == tid_2d` is the bake's visibility test (renderer_inverse.py:321-323).
+// Built with -fmad=false (see bake_raster.cu).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "bake_trace.cuh"
+#include "common.h"
+#include "kernels.h"
+
+namespace utx {
+namespace {
+
+struct __align__(16) Node {
+  float bb[6];
+  int left, right, prim;
+  int pad[3];
+};
+static_assert(sizeof(Node) == 48, "node must be 48 bytes");
+
+__device__ __forceinline__ int f2ord(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void bounds_init_kernel(int* bounds) {
+  if (threadIdx.x < 3) bounds[threadIdx.x] = 0x7fffffff;
+  else if (threadIdx.x < 6) bounds[threadIdx.x] = static_cast<int>(0x80000000u);
+}
+
+// get_elements.slang:1-40
+__global__ void __launch_bounds__(256) elements_kernel(const float* __restrict__ vert, const int* __restrict__ tri, int F,
+                                                       float* __restrict__ eab, int* __restrict__ bounds) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  float mn[3] = {1e9f, 1e9f, 1e9f}, mx[3] = {-1e9f, -1e9f, -1e9f};
+  if (f < F) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float* v = vert + static_cast<size_t>(tri[f * 3 + k]) * 3;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = fminf(mn[a], v[a]);
+        mx[a] = fmaxf(mx[a], v[a]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float lo = fminf(mn[a], mx[a]), hi = fmaxf(mn[a], mx[a]);
+      eab[static_cast<size_t>(f) * 6 + a] = lo;
+      eab[static_cast<size_t>(f) * 6 + 3 + a] = hi;
+      mn[a] = lo;
+      mx[a] = hi;
+    }
+  }
+  // scene AABB: warp reduce, one atomic per warp per component
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float lo = f < F ? mn[a] : INFINITY, hi = f < F ? mx[a] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(bounds + a, f2ord(lo));
+      atomicMax(bounds + 3 + a, f2ord(hi));
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned expand_bits(unsigned v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+// lbvh_morton_codes.slang:24-79
+__global__ void __launch_bounds__(256) morton_kernel(const float* __restrict__ eab, const int* __restrict__ bounds, int F,
+                                                     unsigned* __restrict__ codes, unsigned* __restrict__ elem) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  float m[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float lo = eab[static_cast<size_t>(f) * 6 + a], hi = eab[static_cast<size_t>(f) * 6 + 3 + a];
+    const float center = lo + 0.5f * (hi - lo);
+    const float gmin = ord2f(bounds[a]), gmax = ord2f(bounds[3 + a]);
+    float x = (center - gmin) / (gmax - gmin);
+    x = fminf(fmaxf(x * 1024.0f, 0.0f), 1023.0f);
+    m[a] = x;
+  }
+  codes[f] = expand_bits(static_cast<unsigned>(m[0])) * 4 + expand_bits(static_cast<unsigned>(m[1])) * 2 +
+             expand_bits(static_cast<unsigned>(m[2]));
+  elem[f] = static_cast<unsigned>(f);
+}
+
+__device__ __forceinline__ int find_msb(unsigned v) { return v == 0 ? -1 : 31 - __clz(v); }
+__device__ __forceinline__ int delta(int i, unsigned code_i, int j, int n, const unsigned* __restrict__ codes) {
+  if (j < 0 || j > n - 1) return -1;
+  const unsigned code_j = codes[j];
+  if (code_i == code_j) return 32 + 31 - find_msb(static_cast<unsigned>(i) ^ static_cast<unsigned>(j));
+  return 31 - find_msb(code_i ^ code_j);
+}
+
+// lbvh_hierarchy.slang:109-244
+__global__ void __launch_bounds__(256) hierarchy_kernel(int F, const unsigned* __restrict__ codes,
+                                                        const unsigned* __restrict__ elem, const float* __restrict__ eab,
+                                                        Node* __restrict__ nodes, int* __restrict__ parent,
+                                                        int* __restrict__ arrivals) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= F) return;
+  const int LEAF = F - 1;
+  {
+    const int e = static_cast<int>(elem[g]);
+    Node n;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) n.bb[a] = eab[static_cast<size_t>(e) * 6 + a];
+    n.left = 0; n.right = 0; n.prim = e;
+    n.pad[0] = n.pad[1] = n.pad[2] = 0;
+    nodes[LEAF + g] = n;
+  }
+  if (g == 0) parent[0] = 0;
+  if (g >= F - 1) return;
+  arrivals[g] = 0;
+  const unsigned code = codes[g];
+  const int dL = delta(g, code, g - 1, F, codes), dR = delta(g, code, g + 1, F, codes);
+  const int d = (dR >= dL) ? 1 : -1;
+  const int dmin = min(dL, dR);
+  int lmax = 2;
+  while (delta(g, code, g + lmax * d, F, codes) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t > 0; t >>= 1)
+    if (delta(g, code, g + (l + t) * d, F, codes) > dmin) l += t;
+  const int j = g + l * d;
+  const int first = min(g, j), last = max(g, j);
+  const unsigned fcode = codes[first];
+  const int common = delta(first, fcode, last, F, codes);
+  int split = first, stride = last - first;
+  do {
+    stride = (stride + 1) >> 1;
+    const int ns = split + stride;
+    if (ns < last && delta(first, fcode, ns, F, codes) > common) split = ns;
+  } while (stride > 1);
+  const int ca = (split == first) ? LEAF + split : split;
+  const int cb = (split + 1 == last) ? LEAF + split + 1 : split + 1;
+  Node n;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { n.bb[a] = 1e9f; n.bb[3 + a] = -1e9f; }
+  n.left = ca; n.right = cb; n.prim = 0;
+  n.pad[0] = n.pad[1] = n.pad[2] = 0;
+  nodes[g] = n;
+  parent[ca] = g;
+  parent[cb] = g;
+}
+
+// lbvh_bounding_boxes.slang:149-389 collapsed into one pass: the second thread to arrive at a node unions its children.
+__global__ void __launch_bounds__(256) refit_kernel(int F, Node* __restrict__ nodes, const int* __restrict__ parent,
+                                                    int* __restrict__ arrivals) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= F || F < 2) return;
+  int n = parent[F - 1 + g];
+  for (;;) {
+    __threadfence();
+    if (atomicAdd(arrivals + n, 1) == 0) return;
+    __threadfence();
+    const int ca = nodes[n].left, cb = nodes[n].right;
+    volatile const float* A = nodes[ca].bb;
+    volatile const float* B = nodes[cb].bb;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      nodes[n].bb[a] = fminf(A[a], B[a]);
+      nodes[n].bb[3 + a] = fmaxf(A[3 + a], B[3 + a]);
+    }
+    if (n == 0) return;
+    n = parent[n];
+  }
+}
+
+__global__ void __launch_bounds__(256) export_kernel(const Node* __restrict__ nodes, int n, int* __restrict__ info,
+                                                     float* __restrict__ aabb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Node nd = nodes[i];
+  info[i * 3] = nd.left; info[i * 3 + 1] = nd.right; info[i * 3 + 2] = nd.prim;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) aabb[static_cast<size_t>(i) * 6 + a] = nd.bb[a];
+}
+
+}  // namespace
+
+namespace {
+__global__ void __launch_bounds__(128) intersect_kernel(const void* __restrict__ nodes, const float* __restrict__ vert,
+                                                        const int* __restrict__ tri, const float* __restrict__ rays_o,
+                                                        const float* __restrict__ rays_d, long long N,
+                                                        unsigned char* __restrict__ hit, int* __restrict__ tid,
+                                                        float* __restrict__ pos, float* __restrict__ uv) {
+  const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const float o[3] = {rays_o[r * 3], rays_o[r * 3 + 1], rays_o[r * 3 + 2]};
+  float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
+  const float len = sqrtf(dot3f(d[0], d[1], d[2], d[0], d[1], d[2]));
+  d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
+  const RayHit h = bvh_trace(nodes, vert, tri, o, d);
+  hit[r] = static_cast<unsigned char>(h.any);
+  tid[r] = h.any ? h.tid : -1;
+  pos[r * 3] = h.any ? o[0] + h.t * d[0] : 0.f;
+  pos[r * 3 + 1] = h.any ? o[1] + h.t * d[1] : 0.f;
+  pos[r * 3 + 2] = h.any ? o[2] + h.t * d[2] : 0.f;
+  uv[r * 2] = h.u;
+  uv[r * 2 + 1] = h.v;
+}
+}  // namespace
+
+static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t bvh_nodes_bytes(int F) { return static_cast<size_t>(2 * F - 1) * sizeof(Node); }
+
+size_t bvh_workspace_bytes(int F) {
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, static_cast<unsigned*>(nullptr), static_cast<unsigned*>(nullptr),
+                                  static_cast<unsigned*>(nullptr), static_cast<unsigned*>(nullptr), F);
+  return al256(static_cast<size_t>(F) * 24) + 4 * al256(static_cast<size_t>(F) * 4) + al256(static_cast<size_t>(2 * F) * 4) +
+         al256(static_cast<size_t>(F) * 4) + 256 + al256(cub_bytes);
+}
+
+int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, void* workspace, size_t ws_bytes,
+              cudaStream_t stream) {
+  (void)V;
+  UTX_CHECK(F >= 2, "bvh_build: need at least 2 triangles");
+  UTX_CHECK(ws_bytes >= bvh_workspace_bytes(F), "bvh_build: workspace too small");
+  UTX_CHECK((reinterpret_cast<uintptr_t>(nodes_out) & 15) == 0, "bvh_build: nodes must be 16B aligned");
+  uint8_t* p = static_cast<uint8_t*>(workspace);
+  float* eab = reinterpret_cast<float*>(p); p += al256(static_cast<size_t>(F) * 24);
+  unsigned* codes = reinterpret_cast<unsigned*>(p); p += al256(static_cast<size_t>(F) * 4);
+  unsigned* codes2 = reinterpret_cast<unsigned*>(p); p += al256(static_cast<size_t>(F) * 4);
+  unsigned* elem = reinterpret_cast<unsigned*>(p); p += al256(static_cast<size_t>(F) * 4);
+  unsigned* elem2 = reinterpret_cast<unsigned*>(p); p += al256(static_cast<size_t>(F) * 4);
+  int* parent = reinterpret_cast<int*>(p); p += al256(static_cast<size_t>(2 * F) * 4);
+  int* arrivals = reinterpret_cast<int*>(p); p += al256(static_cast<size_t>(F) * 4);
+  int* bounds = reinterpret_cast<int*>(p); p += 256;
+  size_t cub_bytes = ws_bytes - static_cast<size_t>(p - static_cast<uint8_t*>(workspace));
+  const unsigned grid = (F + 255) / 256;
+  bounds_init_kernel<<<1, 32, 0, stream>>>(bounds);
+  elements_kernel<<<grid, 256, 0, stream>>>(vert, tri, F, eab, bounds);
+  morton_kernel<<<grid, 256, 0, stream>>>(eab, bounds, F, codes, elem);
+  UTX_CUDA(cub::DeviceRadixSort::SortPairs(p, cub_bytes, codes, codes2, elem, elem2, F, 0, 32, stream));
+  Node* nodes = static_cast<Node*>(nodes_out);
+  hierarchy_kernel<<<grid, 256, 0, stream>>>(F, codes2, elem2, eab, nodes, parent, arrivals);
+  refit_kernel<<<grid, 256, 0, stream>>>(F, nodes, parent, arrivals);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bvh_export(const void* nodes, int F, int* info, float* aabb, cudaStream_t stream) {
+  const int n = 2 * F - 1;
+  export_kernel<<<(n + 255) / 256, 256, 0, stream>>>(static_cast<const Node*>(nodes), n, info, aabb);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int bvh_intersect(const void* nodes, const float* vert, const int* tri, const float* rays_o, const float* rays_d,
+                  long long N, unsigned char* hit, int* tid, float* pos, float* uv, cudaStream_t stream) {
+  if (N == 0) return 0;
+  intersect_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, stream>>>(nodes, vert, tri, rays_o, rays_d, N, hit, tid,
+                                                                               pos, uv);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace utx

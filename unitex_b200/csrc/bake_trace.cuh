@@ -1,0 +1,79 @@
+// Closest-hit traversal of the packed LBVH (48 B nodes: aabb[6], left, right, prim), shared by the standalone
+// intersect kernel and the fused UV-bake texel kernel.  Order and quirks follow the reference's bvh_hit
+// (TextureTools/texturetools/raytracing/rt_aprmis/bvhworkers/intersect_test2.slang:63-146): push left, push right, pop
+// right first; slab test against the running closest t; Moller-Trumbore without a t-range test; the reported triangle is
+// the LAST accepted leaf.  Translation units including this are built with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace utx {
+
+struct RayHit {
+  int any, tid;
+  float t, u, v;
+};
+__device__ __forceinline__ float dot3f(float ax, float ay, float az, float bx, float by, float bz) {
+  return (ax * bx + ay * by) + az * bz;
+}
+__device__ __forceinline__ bool aabb_hit_dev(const float* o, const float* d, float tmin, float tmax, const float* bb) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float di = d[i];
+    if (di == 0.0f) di = 0.000001f;
+    const float inv = 1.0f / di;
+    float t0 = (bb[i] - o[i]) * inv, t1 = (bb[3 + i] - o[i]) * inv;
+    if (inv < 0.0f) { const float t = t1; t1 = t0; t0 = t; }
+    tmin = t0 > tmin ? t0 : tmin;
+    tmax = t1 < tmax ? t1 : tmax;
+    if (tmax < tmin) return false;
+  }
+  return true;
+}
+// `d` must already be normalised exactly like the reference does (d / |d|).
+__device__ __forceinline__ RayHit bvh_trace(const void* __restrict__ nodes_v, const float* __restrict__ vert, const int* __restrict__ tri,
+                            const float* o, const float* d) {
+  const float4* nodes = static_cast<const float4*>(nodes_v);
+  int stack[64];
+  int count = 0;
+  stack[count++] = 0;
+  float closest = 1e9f;
+  RayHit h;
+  h.any = 0; h.tid = -1; h.t = 0.f; h.u = 0.f; h.v = 0.f;
+  while (count > 0) {
+    const int n = stack[--count];
+    const float4 q0 = __ldg(nodes + static_cast<size_t>(n) * 3), q1 = __ldg(nodes + static_cast<size_t>(n) * 3 + 1);
+    const float bb[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
+    if (!aabb_hit_dev(o, d, 0.0f, closest, bb)) continue;
+    const int l = __float_as_int(q1.z), r = __float_as_int(q1.w);
+    if (l != 0 && r != 0) {
+      if (count + 2 <= 64) {
+        stack[count++] = l;
+        stack[count++] = r;
+      }
+    } else if (l == 0 && r == 0) {
+      const int p = __float_as_int(__ldg(nodes + static_cast<size_t>(n) * 3 + 2).x);
+      const float *a = vert + static_cast<size_t>(tri[p * 3]) * 3, *b = vert + static_cast<size_t>(tri[p * 3 + 1]) * 3,
+                  *c = vert + static_cast<size_t>(tri[p * 3 + 2]) * 3;
+      const float e1x = b[0] - a[0], e1y = b[1] - a[1], e1z = b[2] - a[2];
+      const float e2x = c[0] - a[0], e2y = c[1] - a[1], e2z = c[2] - a[2];
+      const float px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;
+      const float det = dot3f(e1x, e1y, e1z, px, py, pz);
+      const float eps = 1e-9f;
+      if (det > -eps && det < eps) continue;
+      const float inv = 1.0f / det;
+      const float tx = o[0] - a[0], ty = o[1] - a[1], tz = o[2] - a[2];
+      const float u = dot3f(tx, ty, tz, px, py, pz) * inv;
+      if (u < 0 || u > 1) continue;
+      const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+      const float v = dot3f(d[0], d[1], d[2], qx, qy, qz) * inv;
+      if (v < 0 || u + v > 1) continue;
+      const float t = dot3f(e2x, e2y, e2z, qx, qy, qz) * inv;   // no t-range test (reference quirk)
+      closest = t < closest ? t : closest;
+      h.any = 1; h.tid = p; h.t = closest; h.u = u; h.v = v;   // last accepted leaf wins (reference quirk)
+    }
+  }
+  return h;
+}
+
+
+}  // namespace utx

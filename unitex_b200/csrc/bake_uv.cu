@@ -1,0 +1,517 @@
+// Fused UV bake: NVDiffRendererInverse.uv_to_pcd + bake_mv_to_uv_reproject_blur
+// (TextureTools/texturetools/render/nvdiffrast/renderer_inverse.py:243-365, 574-633) without the per-view
+// [n, H2D, W2D, *] rays / ndc / colour tensors and the ~40 masked_select / masked_scatter compactions of the reference.
+//
+//   texel pass      per covered texel: position + face normal from the UV raster, then per view: orthographic ray,
+//                   ray/normal angle test, projected bilinear fetch of (rgb, alpha), LBVH closest-hit, `tid == raster tid`
+//                   -> one visibility bit and one alpha bit per view                                   (:277-325, :343)
+//   repair          the "misjudgment repair" convolutions as exact integer stencils on the 6-bit planes: k=3 ORs in a
+//                   texel when any 8-neighbour is visible, k=5 when >= 6 of the 16 ring texels are      (:329-339)
+//   compose         and-with-coverage/alpha, first-visible-view-wins in priority order, winning colour re-fetched (:591-603)
+//   seam mask       3x3 boundary of every view's claim = "a 3x3 neighbour has a different owner", dilated 3x3, kept where
+//                   the 7x7 erosion of the chart mask holds                                              (:435-444, :603-605)
+//   nn fill         invisible covered texels take the colour of the 3-D nearest visible texel (exact 1-NN, uniform grid,
+//                   lowest index on ties)                                                                (:606-615)
+//   lens blur       7x7 effective kernel of the 5-component complex separable blur, evaluated ONLY on seam texels
+//                   (image/lens_blur.py:260-280; the reference blurs the whole atlas, then keeps seam texels) (:621-624)
+//   pull-push       alpha-weighted 2x2 pyramid + bilinear up-fill of texels outside the charts (texture/stitching/mip.py:51-96)
+// HBM-bound by contract: one thread per texel, row-major so a warp reads/writes 32 consecutive texels.
+// Built with -fmad=false.
+#include <cub/device/device_scan.cuh>
+
+#include <vector>
+
+#include "bake_trace.cuh"
+#include "common.h"
+#include "kernels.h"
+
+namespace utx {
+namespace {
+
+constexpr int MAXV = 8;
+
+struct Views {
+  int n;
+  float mat[MAXV][16];   // P @ W2C, row-major
+  float dir[MAXV][3];    // -c2w[:3, 2]
+  int priority[MAXV];
+};
+
+__device__ __forceinline__ float norm3(float x, float y, float z) { return sqrtf((x * x + y * y) + z * z); }
+
+// grid_sample(mode=bilinear, padding_mode=zeros, align_corners=False) of a [H, W, C<=4] image
+template <int C>
+__device__ __forceinline__ void bilinear(const float* __restrict__ img, int H, int W, float gx, float gy, float* out) {
+  const float ix = ((gx + 1.0f) * W - 1.0f) / 2.0f, iy = ((gy + 1.0f) * H - 1.0f) / 2.0f;
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+  const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix, wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
+  const float w[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};   // nw, ne, sw, se
+  const int xs[4] = {x0, x0 + 1, x0, x0 + 1}, ys[4] = {y0, y0, y0 + 1, y0 + 1};
+#pragma unroll
+  for (int c = 0; c < C; ++c) out[c] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (xs[k] >= 0 && xs[k] < W && ys[k] >= 0 && ys[k] < H) {
+      const float* p = img + (static_cast<size_t>(ys[k]) * W + xs[k]) * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) out[c] = out[c] + p[c] * w[k];
+    }
+  }
+}
+
+// ndc (x, y) of a texel in view `v`: barycentric interpolation of the per-vertex ndc like dr.interpolate(vertices_ndc) (:288)
+__device__ __forceinline__ void texel_ndc(const float* m, const float* p0, const float* p1, const float* p2, float u, float v,
+                                          float* gx, float* gy) {
+  float nx[3], ny[3];
+  const float* ps[3] = {p0, p1, p2};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float* p = ps[k];
+    const float cx = ((m[0] * p[0] + m[1] * p[1]) + m[2] * p[2]) + m[3];
+    const float cy = ((m[4] * p[0] + m[5] * p[1]) + m[6] * p[2]) + m[7];
+    const float cw = ((m[12] * p[0] + m[13] * p[1]) + m[14] * p[2]) + m[15];
+    nx[k] = cx / cw;
+    ny[k] = cy / cw;
+  }
+  const float w = (1.0f - u) - v;
+  *gx = (u * nx[0] + v * nx[1]) + w * nx[2];
+  *gy = (u * ny[0] + v * ny[1]) + w * ny[2];
+}
+
+__global__ void __launch_bounds__(128) texel_kernel(const float4* __restrict__ rast, int T, const float* __restrict__ vert,
+                                                    const int* __restrict__ tri, const void* __restrict__ nodes,
+                                                    const Views vw, const float* __restrict__ images /*[n,H,W,4] rgba*/,
+                                                    int H, int W, float cos_thresh, unsigned char* __restrict__ raw_vis,
+                                                    unsigned char* __restrict__ alpha_ok, float* __restrict__ pos_out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float4 r = rast[t];
+  const int f = static_cast<int>(r.w) - 1;
+  if (f < 0) {
+    raw_vis[t] = 0;
+    alpha_ok[t] = 0;
+    pos_out[t * 3] = pos_out[t * 3 + 1] = pos_out[t * 3 + 2] = 0.f;
+    return;
+  }
+  const float *p0 = vert + static_cast<size_t>(tri[f * 3]) * 3, *p1 = vert + static_cast<size_t>(tri[f * 3 + 1]) * 3,
+              *p2 = vert + static_cast<size_t>(tri[f * 3 + 2]) * 3;
+  const float u = r.x, v = r.y, w = (1.0f - u) - v;
+  float pos[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) pos[a] = (u * p0[a] + v * p1[a]) + w * p2[a];
+  pos_out[t * 3] = pos[0]; pos_out[t * 3 + 1] = pos[1]; pos_out[t * 3 + 2] = pos[2];
+  // face normal = normalize(cross(v1 - v0, v2 - v0))   (structure_v2.py:49-50; F.normalize eps 1e-12)
+  const float e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+  float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+  const float nl = fmaxf(norm3(n[0], n[1], n[2]), 1e-12f);
+  n[0] = n[0] / nl; n[1] = n[1] / nl; n[2] = n[2] / nl;
+  const float nn = fmaxf(norm3(n[0], n[1], n[2]), 1e-8f);
+  unsigned vis = 0, aok = 0;
+  const float k2s3 = 3.4641016151377544f;   // float32(2 * sqrt(3)), renderer_inverse.py:284
+  for (int i = 0; i < vw.n; ++i) {
+    const float* dr = vw.dir[i];
+    const float o[3] = {pos[0] - k2s3 * dr[0], pos[1] - k2s3 * dr[1], pos[2] - k2s3 * dr[2]};
+    const float dl = fmaxf(norm3(dr[0], dr[1], dr[2]), 1e-12f);
+    float d[3] = {dr[0] / dl, dr[1] / dl, dr[2] / dl};                  // F.normalize (:285)
+    // cosine_similarity(d, n) with torch's normalise-first formulation, eps 1e-8
+    const float dn = fmaxf(norm3(d[0], d[1], d[2]), 1e-8f);
+    const float cosv = ((d[0] / dn) * (n[0] / nn) + (d[1] / dn) * (n[1] / nn)) + (d[2] / dn) * (n[2] / nn);
+    float gx, gy;
+    texel_ndc(vw.mat[i], p0, p1, p2, u, v, &gx, &gy);
+    float rgba[4];
+    bilinear<4>(images + static_cast<size_t>(i) * H * W * 4, H, W, gx, gy, rgba);
+    if (rgba[3] > 0.999f) aok |= 1u << i;
+    if (cosv < cos_thresh) {
+      const float len = norm3(d[0], d[1], d[2]);                        // the tracer normalises again (intersect_test2.slang:283)
+      d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
+      const RayHit h = bvh_trace(nodes, vert, tri, o, d);
+      if (h.any && h.tid == f) vis |= 1u << i;
+    }
+  }
+  raw_vis[t] = static_cast<unsigned char>(vis);
+  alpha_ok[t] = static_cast<unsigned char>(aok);
+}
+
+// k = 3: conv >= 3  <=>  at least one of the 8 ring texels set (9 r - c >= 3, c <= 1)
+__global__ void __launch_bounds__(256) repair3_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out,
+                                                      int H, int W) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * W) return;
+  const int y = t / W, x = t % W;
+  unsigned acc = in[t];
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      if (dy == 0 && dx == 0) continue;
+      const int yy = y + dy, xx = x + dx;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) acc |= in[yy * W + xx];
+    }
+  out[t] = static_cast<unsigned char>(acc);
+}
+// k = 5: 25 r - c >= 135 with c <= 9  <=>  r >= 6 of the 16 ring texels
+__global__ void __launch_bounds__(256) repair5_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out,
+                                                      int H, int W, int n_views) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * W) return;
+  const int y = t / W, x = t % W;
+  int cnt[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) cnt[i] = 0;
+  for (int dy = -2; dy <= 2; ++dy)
+    for (int dx = -2; dx <= 2; ++dx) {
+      if (abs(dy) != 2 && abs(dx) != 2) continue;
+      const int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const unsigned b = in[yy * W + xx];
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) cnt[i] += (b >> i) & 1u;
+    }
+  unsigned acc = in[t];
+  for (int i = 0; i < n_views; ++i)
+    if (cnt[i] >= 6) acc |= 1u << i;
+  out[t] = static_cast<unsigned char>(acc);
+}
+
+__global__ void __launch_bounds__(128) compose_kernel(const float4* __restrict__ rast, int T, const float* __restrict__ vert,
+                                                      const int* __restrict__ tri, const Views vw,
+                                                      const float* __restrict__ images, int H, int W,
+                                                      const unsigned char* __restrict__ vis_rep,
+                                                      const unsigned char* __restrict__ alpha_ok,
+                                                      unsigned char* __restrict__ mask2d, unsigned char* __restrict__ mask_vis,
+                                                      signed char* __restrict__ owner, float* __restrict__ color) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float4 r = rast[t];
+  const int f = static_cast<int>(r.w) - 1;
+  const unsigned bits = f >= 0 ? (vis_rep[t] & alpha_ok[t]) : 0u;
+  mask2d[t] = f >= 0;
+  for (int i = 0; i < vw.n; ++i) mask_vis[static_cast<size_t>(i) * T + t] = (bits >> i) & 1u;
+  int own = -1;
+  for (int k = 0; k < vw.n; ++k) {
+    const int i = vw.priority[k];
+    if ((bits >> i) & 1u) { own = i; break; }
+  }
+  owner[t] = static_cast<signed char>(own);
+  float c[3] = {0.f, 0.f, 0.f};
+  if (own >= 0) {
+    const float *p0 = vert + static_cast<size_t>(tri[f * 3]) * 3, *p1 = vert + static_cast<size_t>(tri[f * 3 + 1]) * 3,
+                *p2 = vert + static_cast<size_t>(tri[f * 3 + 2]) * 3;
+    float gx, gy, rgba[4];
+    texel_ndc(vw.mat[own], p0, p1, p2, r.x, r.y, &gx, &gy);
+    bilinear<4>(images + static_cast<size_t>(own) * H * W * 4, H, W, gx, gy, rgba);
+    c[0] = rgba[0]; c[1] = rgba[1]; c[2] = rgba[2];
+  }
+  color[t * 3] = c[0]; color[t * 3 + 1] = c[1]; color[t * 3 + 2] = c[2];
+}
+
+__global__ void __launch_bounds__(256) seam0_kernel(const signed char* __restrict__ owner, unsigned char* __restrict__ b0,
+                                                    int H, int W) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * W) return;
+  const int y = t / W, x = t % W;
+  const int o = owner[t];
+  int diff = 0;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int yy = y + dy, xx = x + dx;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) diff |= owner[yy * W + xx] != o;
+    }
+  b0[t] = static_cast<unsigned char>(diff);
+}
+__global__ void __launch_bounds__(256) seam1_kernel(const unsigned char* __restrict__ b0,
+                                                    const unsigned char* __restrict__ mask2d,
+                                                    unsigned char* __restrict__ seam, int H, int W) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * W) return;
+  const int y = t / W, x = t % W;
+  int any = 0, all = 1;
+  for (int dy = -3; dy <= 3; ++dy)
+    for (int dx = -3; dx <= 3; ++dx) {
+      const int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      if (abs(dy) <= 1 && abs(dx) <= 1) any |= b0[yy * W + xx];
+      all &= mask2d[yy * W + xx];
+    }
+  seam[t] = static_cast<unsigned char>(any && all);
+}
+
+// ------------------------------------------------------------------------------------------------ exact 1-NN fill
+struct GridParams {
+  float lo[3];
+  float inv_h, h;
+  int G;
+};
+__device__ __forceinline__ int cell_of(const GridParams& g, const float* p, int* c) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    int v = static_cast<int>(floorf((p[a] - g.lo[a]) * g.inv_h));
+    c[a] = min(max(v, 0), g.G - 1);
+  }
+  return (c[2] * g.G + c[1]) * g.G + c[0];
+}
+__global__ void __launch_bounds__(256) nn_count_kernel(const signed char* __restrict__ owner, const float* __restrict__ pos,
+                                                       int T, GridParams g, int* __restrict__ counts) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T || owner[t] < 0) return;
+  int c[3];
+  atomicAdd(counts + cell_of(g, pos + static_cast<size_t>(t) * 3, c), 1);
+}
+__global__ void __launch_bounds__(256) nn_fill_kernel(const signed char* __restrict__ owner, const float* __restrict__ pos,
+                                                      int T, GridParams g, const int* __restrict__ starts,
+                                                      int* __restrict__ cursor, int* __restrict__ items) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T || owner[t] < 0) return;
+  int c[3];
+  const int cell = cell_of(g, pos + static_cast<size_t>(t) * 3, c);
+  items[starts[cell] + atomicAdd(cursor + cell, 1)] = t;
+}
+__global__ void __launch_bounds__(128) nn_query_kernel(const unsigned char* __restrict__ mask2d,
+                                                       const signed char* __restrict__ owner, const float* __restrict__ pos,
+                                                       int T, GridParams g, const int* __restrict__ starts,
+                                                       const int* __restrict__ counts, const int* __restrict__ items,
+                                                       const float* color_in, float* color_out, int* __restrict__ nn_index) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  if (nn_index) nn_index[t] = -1;
+  if (!mask2d[t] || owner[t] >= 0) return;
+  const float* q = pos + static_cast<size_t>(t) * 3;
+  int c[3];
+  cell_of(g, q, c);
+  float best = INFINITY;
+  int best_i = -1;
+  for (int r = 0; r < g.G; ++r) {
+    for (int dz = -r; dz <= r; ++dz) {
+      const int z = c[2] + dz;
+      if (z < 0 || z >= g.G) continue;
+      for (int dy = -r; dy <= r; ++dy) {
+        const int y = c[1] + dy;
+        if (y < 0 || y >= g.G) continue;
+        const bool shell_zy = (abs(dz) == r) || (abs(dy) == r);
+        for (int dx = -r; dx <= r; dx += (shell_zy || r == 0) ? 1 : 2 * r) {
+          const int x = c[0] + dx;
+          if (x < 0 || x >= g.G) continue;
+          const int cell = (z * g.G + y) * g.G + x;
+          const int s = starts[cell], n = counts[cell];
+          for (int k = 0; k < n; ++k) {
+            const int j = items[s + k];
+            const float ddx = pos[static_cast<size_t>(j) * 3] - q[0], ddy = pos[static_cast<size_t>(j) * 3 + 1] - q[1],
+                        ddz = pos[static_cast<size_t>(j) * 3 + 2] - q[2];
+            const float d2 = (ddx * ddx + ddy * ddy) + ddz * ddz;
+            if (d2 < best || (d2 == best && j < best_i)) { best = d2; best_i = j; }
+          }
+        }
+      }
+    }
+    // every unvisited cell is at least r*h away (minus the query's clamp into the grid, which only happens outside it)
+    const float reach = r * g.h;
+    if (best_i >= 0 && best <= reach * reach) break;
+  }
+  if (nn_index) nn_index[t] = best_i;
+  if (best_i >= 0) {
+    color_out[t * 3] = color_in[static_cast<size_t>(best_i) * 3];
+    color_out[t * 3 + 1] = color_in[static_cast<size_t>(best_i) * 3 + 1];
+    color_out[t * 3 + 2] = color_in[static_cast<size_t>(best_i) * 3 + 2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ lens blur on seams
+__global__ void __launch_bounds__(256) lens_blur_kernel(const float* __restrict__ color_in, const unsigned char* __restrict__ seam,
+                                                        const float* __restrict__ k2d /*[49]*/, float gamma, int H, int W,
+                                                        float* __restrict__ color_out) {
+  __shared__ float ks[49];
+  if (threadIdx.x < 49) ks[threadIdx.x] = k2d[threadIdx.x];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * W) return;
+  float c[3] = {color_in[t * 3], color_in[t * 3 + 1], color_in[t * 3 + 2]};
+  if (seam[t]) {
+    const int y = t / W, x = t % W;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int dy = -3; dy <= 3; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = -3; dx <= 3; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        const float kw = ks[(dy + 3) * 7 + (dx + 3)];
+        const float* p = color_in + (static_cast<size_t>(yy) * W + xx) * 3;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) acc[a] = acc[a] + kw * powf(p[a], gamma);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) c[a] = fminf(fmaxf(powf(fmaxf(acc[a], 0.f), 1.0f / gamma), 0.f), 1.f);
+  }
+  color_out[t * 3] = c[0]; color_out[t * 3 + 1] = c[1]; color_out[t * 3 + 2] = c[2];
+}
+
+// ------------------------------------------------------------------------------------------------ pull-push
+__global__ void __launch_bounds__(256) pp_init_kernel(const float* __restrict__ color, const unsigned char* __restrict__ mask,
+                                                      int T, float* __restrict__ c0, unsigned char* __restrict__ m0) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const bool m = mask[t] != 0;
+  m0[t] = m;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) c0[t * 3 + a] = m ? color[t * 3 + a] : 0.f;
+}
+__global__ void __launch_bounds__(256) pp_down_kernel(const float* __restrict__ c, const unsigned char* __restrict__ m, int H,
+                                                      int W, float* __restrict__ cd, unsigned char* __restrict__ md) {
+  const int Hd = H / 2, Wd = W / 2;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Hd * Wd) return;
+  const int y = t / Wd, x = t % Wd;
+  const int i00 = (2 * y) * W + 2 * x, i01 = i00 + 1, i10 = i00 + W, i11 = i10 + 1;
+  const float a = (((m[i00] ? 1.f : 0.f) + (m[i01] ? 1.f : 0.f)) + (m[i10] ? 1.f : 0.f) + (m[i11] ? 1.f : 0.f)) * 0.25f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float v = (((c[i00 * 3 + k] + c[i01 * 3 + k]) + c[i10 * 3 + k]) + c[i11 * 3 + k]) * 0.25f;
+    if (a > 0.f && a < 1.f) v = v / a;
+    cd[t * 3 + k] = v;
+  }
+  md[t] = a > 0.f;
+}
+__global__ void __launch_bounds__(256) pp_up_kernel(float* __restrict__ c, const unsigned char* __restrict__ m, int H, int W,
+                                                    const float* __restrict__ cd) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * W || m[t]) return;
+  const int Hd = H / 2, Wd = W / 2;
+  const int y = t / W, x = t % W;
+  const int yn = y >> 1, xn = x >> 1;
+  const int yf = min(max(yn + ((y & 1) ? 1 : -1), 0), Hd - 1), xf = min(max(xn + ((x & 1) ? 1 : -1), 0), Wd - 1);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float v = ((0.5625f * cd[(yn * Wd + xn) * 3 + k] + 0.1875f * cd[(yn * Wd + xf) * 3 + k]) +
+                     0.1875f * cd[(yf * Wd + xn) * 3 + k]) + 0.0625f * cd[(yf * Wd + xf) * 3 + k];
+    c[t * 3 + k] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) transform_points_kernel(const float* __restrict__ vert, int V,
+                                                               const float* __restrict__ mats, int n,
+                                                               float4* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(n) * V) return;
+  const int b = static_cast<int>(i / V), v = static_cast<int>(i % V);
+  const float* m = mats + b * 16;
+  const float* p = vert + static_cast<size_t>(v) * 3;
+  float o[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) o[r] = ((m[r * 4] * p[0] + m[r * 4 + 1] * p[1]) + m[r * 4 + 2] * p[2]) + m[r * 4 + 3];
+  out[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
+constexpr int NN_G = 128;
+
+}  // namespace
+
+int transform_points(const float* vert, int V, const float* mats, int n, float* out, cudaStream_t stream) {
+  const long long tot = static_cast<long long>(n) * V;
+  if (tot == 0) return 0;
+  transform_points_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, stream>>>(vert, V, mats, n,
+                                                                                        reinterpret_cast<float4*>(out));
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t uv_bake_workspace_bytes(int H2, int W2) {
+  const size_t T = static_cast<size_t>(H2) * W2;
+  size_t pyr_c = 0, pyr_m = 0;
+  for (int h = H2, w = W2, l = 0; l < 16 && h >= 1 && w >= 1; ++l, h /= 2, w /= 2) {
+    pyr_c += al(static_cast<size_t>(h) * w * 12);
+    pyr_m += al(static_cast<size_t>(h) * w);
+  }
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, static_cast<int*>(nullptr), static_cast<int*>(nullptr),
+                                NN_G * NN_G * NN_G);
+  return 6 * al(T) + al(T * 12) * 3 + al(T * 4) * 2 + 3 * al(static_cast<size_t>(NN_G) * NN_G * NN_G * 4) + al(scan_bytes) +
+         pyr_c + pyr_m + 4096;
+}
+
+int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
+            int n_views, const float* view_mats_host, const float* view_dirs_host, const int* priority_host,
+            const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
+            const float* grid_lo_host, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color_out,
+            int* nn_index_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  (void)V; (void)F;
+  UTX_CHECK(n_views >= 1 && n_views <= MAXV, "uv_bake: 1..8 views");
+  UTX_CHECK(H2 >= 8 && W2 >= 8 && (H2 & (H2 - 1)) == 0 && (W2 & (W2 - 1)) == 0, "uv_bake: atlas must be a power of two >= 8");
+  UTX_CHECK(ws_bytes >= uv_bake_workspace_bytes(H2, W2), "uv_bake: workspace too small");
+  const int T = H2 * W2;
+  Views vw;
+  vw.n = n_views;
+  for (int i = 0; i < n_views; ++i) {
+    for (int k = 0; k < 16; ++k) vw.mat[i][k] = view_mats_host[i * 16 + k];
+    for (int k = 0; k < 3; ++k) vw.dir[i][k] = view_dirs_host[i * 3 + k];
+    vw.priority[i] = priority_host[i];
+  }
+  uint8_t* p = static_cast<uint8_t*>(workspace);
+  auto take = [&](size_t b) { uint8_t* q = p; p += al(b); return q; };
+  unsigned char* raw = take(T); unsigned char* aok = take(T); unsigned char* rep3 = take(T); unsigned char* rep5 = take(T);
+  unsigned char* b0 = take(T); unsigned char* seam = take(T);
+  float* pos = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
+  float* col_a = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
+  float* col_b = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
+  signed char* owner = reinterpret_cast<signed char*>(take(static_cast<size_t>(T) * 4));
+  int* items = reinterpret_cast<int*>(take(static_cast<size_t>(T) * 4));
+  const size_t ncell = static_cast<size_t>(NN_G) * NN_G * NN_G;
+  int* counts = reinterpret_cast<int*>(take(ncell * 4));
+  int* starts = reinterpret_cast<int*>(take(ncell * 4));
+  int* cursor = reinterpret_cast<int*>(take(ncell * 4));
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, starts, static_cast<int>(ncell));
+  void* scan_tmp = take(scan_bytes);
+
+  const unsigned g128 = (T + 127) / 128, g256 = (T + 255) / 256;
+  const float4* rast = reinterpret_cast<const float4*>(rast2d);
+  texel_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, nodes, vw, images_rgba, H, W, cos_thresh, raw, aok, pos);
+  repair3_kernel<<<g256, 256, 0, stream>>>(raw, rep3, H2, W2);
+  repair5_kernel<<<g256, 256, 0, stream>>>(rep3, rep5, H2, W2, n_views);
+  compose_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, vw, images_rgba, H, W, rep5, aok, mask2d, mask_vis, owner, col_a);
+  seam0_kernel<<<g256, 256, 0, stream>>>(owner, b0, H2, W2);
+  seam1_kernel<<<g256, 256, 0, stream>>>(b0, mask2d, seam, H2, W2);
+  // exact 1-NN fill of covered-but-invisible texels
+  GridParams gp;
+  for (int a = 0; a < 3; ++a) gp.lo[a] = grid_lo_host[a];
+  gp.G = NN_G;
+  gp.h = grid_extent / NN_G;
+  gp.inv_h = NN_G / grid_extent;
+  UTX_CUDA(cudaMemsetAsync(counts, 0, ncell * 4, stream));
+  UTX_CUDA(cudaMemsetAsync(cursor, 0, ncell * 4, stream));
+  nn_count_kernel<<<g256, 256, 0, stream>>>(owner, pos, T, gp, counts);
+  UTX_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, counts, starts, static_cast<int>(ncell), stream));
+  nn_fill_kernel<<<g256, 256, 0, stream>>>(owner, pos, T, gp, starts, cursor, items);
+  nn_query_kernel<<<g128, 128, 0, stream>>>(mask2d, owner, pos, T, gp, starts, counts, items, col_a, col_a, nn_index_out);
+  // seam blur (reads col_a, writes col_b)
+  lens_blur_kernel<<<g256, 256, 0, stream>>>(col_a, seam, blur_k2d, blur_gamma, H2, W2, col_b);
+  // pull-push
+  int levels = 0;
+  for (int s = (H2 < W2 ? H2 : W2); s > 1; s >>= 1) ++levels;
+  levels = levels - 2 > 0 ? levels - 2 : 0;
+  if (levels == 0) {
+    UTX_CUDA(cudaMemcpyAsync(color_out, col_b, static_cast<size_t>(T) * 12, cudaMemcpyDeviceToDevice, stream));
+  } else {
+    std::vector<float*> pc(levels + 1);
+    std::vector<unsigned char*> pm(levels + 1);
+    pc[0] = color_out;
+    pm[0] = take(T);
+    pp_init_kernel<<<g256, 256, 0, stream>>>(col_b, mask2d, T, pc[0], pm[0]);
+    int h = H2, w = W2;
+    for (int l = 1; l <= levels; ++l) {
+      pc[l] = reinterpret_cast<float*>(take(static_cast<size_t>(h / 2) * (w / 2) * 12));
+      pm[l] = take(static_cast<size_t>(h / 2) * (w / 2));
+      pp_down_kernel<<<((h / 2) * (w / 2) + 255) / 256, 256, 0, stream>>>(pc[l - 1], pm[l - 1], h, w, pc[l], pm[l]);
+      h /= 2; w /= 2;
+    }
+    for (int l = levels; l >= 1; --l) {
+      const int hh = H2 >> (l - 1), ww = W2 >> (l - 1);
+      pp_up_kernel<<<(hh * ww + 255) / 256, 256, 0, stream>>>(pc[l - 1], pm[l - 1], hh, ww, pc[l]);
+    }
+  }
+  UTX_CHECK(static_cast<size_t>(p - static_cast<uint8_t*>(workspace)) <= ws_bytes, "uv_bake: workspace overrun");
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace utx

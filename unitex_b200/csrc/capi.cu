@@ -82,4 +82,49 @@ int utx_lora_merge(void* W, long ldw, const float* A, const float* B, int out_fe
                     static_cast<cudaStream_t>(stream));
 }
 
+size_t utx_rasterize_workspace_bytes(int B, int H, int W) { return rasterize_workspace_bytes(B, H, W); }
+int utx_rasterize(const float* pos, int pos_batched, int V, const int32_t* tri, int F, int B, int H, int W,
+                  float* rast_out, void* workspace, void* stream) {
+  UTX_CHECK(pos && tri && rast_out && workspace, "utx_rasterize: null pointer");
+  return rasterize(pos, pos_batched, V, tri, F, B, H, W, rast_out, workspace, static_cast<cudaStream_t>(stream));
+}
+int utx_interpolate(const float* attr, int attr_batched, int V, int C, const float* rast, const int32_t* tri, int B, int H,
+                    int W, float* out, void* stream) {
+  UTX_CHECK(attr && rast && tri && out, "utx_interpolate: null pointer");
+  return interpolate(attr, attr_batched, V, C, rast, tri, B, H, W, out, static_cast<cudaStream_t>(stream));
+}
+int utx_transform_points(const float* vert, int V, const float* mats, int n, float* out, void* stream) {
+  UTX_CHECK(vert && mats && out, "utx_transform_points: null pointer");
+  return transform_points(vert, V, mats, n, out, static_cast<cudaStream_t>(stream));
+}
+size_t utx_bvh_nodes_bytes(int F) { return bvh_nodes_bytes(F); }
+size_t utx_bvh_workspace_bytes(int F) { return bvh_workspace_bytes(F); }
+int utx_bvh_build(const float* vert, int V, const int32_t* tri, int F, void* nodes, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  UTX_CHECK(vert && tri && nodes && workspace, "utx_bvh_build: null pointer");
+  return bvh_build(vert, V, tri, F, nodes, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+int utx_bvh_export(const void* nodes, int F, int32_t* info, float* aabb, void* stream) {
+  UTX_CHECK(nodes && info && aabb, "utx_bvh_export: null pointer");
+  return bvh_export(nodes, F, info, aabb, static_cast<cudaStream_t>(stream));
+}
+int utx_bvh_intersect(const void* nodes, const float* vert, const int32_t* tri, const float* rays_o, const float* rays_d,
+                      long long N, unsigned char* hit, int32_t* tri_idx, float* loc, float* uv, void* stream) {
+  UTX_CHECK(nodes && vert && tri && rays_o && rays_d && hit && tri_idx && loc && uv, "utx_bvh_intersect: null pointer");
+  return bvh_intersect(nodes, vert, tri, rays_o, rays_d, N, hit, tri_idx, loc, uv, static_cast<cudaStream_t>(stream));
+}
+size_t utx_uv_bake_workspace_bytes(int H2, int W2) { return uv_bake_workspace_bytes(H2, W2); }
+int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
+                int n_views, const float* view_mats, const float* view_dirs, const int32_t* priority,
+                const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
+                const float* grid_lo, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color,
+                int32_t* nn_index, void* workspace, size_t workspace_bytes, void* stream) {
+  UTX_CHECK(vert && tri && nodes && rast2d && view_mats && view_dirs && priority && images_rgba && blur_k2d && grid_lo &&
+                mask2d && mask_vis && color && workspace,
+            "utx_uv_bake: null pointer");
+  return uv_bake(vert, V, tri, F, nodes, rast2d, H2, W2, n_views, view_mats, view_dirs, priority, images_rgba, H, W,
+                 cos_thresh, blur_k2d, blur_gamma, grid_lo, grid_extent, mask2d, mask_vis, color, nn_index, workspace,
+                 workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -69,4 +69,28 @@ int euler_update(bf16* latents, const bf16* v, int rows, int cols, float dsigma,
 int lora_merge(bf16* W, long ldw, const float* A, const float* B, int out_f, int in_f, int rank, float scale,
                cudaStream_t stream);
 
+
+// ------------------------------------------------------------------ bake: rasterise / interpolate / LBVH / fused UV bake
+size_t rasterize_workspace_bytes(int B, int H, int W);
+// pos [B or 1, V, 4] clip space, tri [F,3] -> rast [B,H,W,4] = (u, v, z/w, id+1)
+int rasterize(const float* pos, int pos_batched, int V, const int* tri, int F, int B, int H, int W, float* rast_out,
+              void* workspace, cudaStream_t stream);
+int interpolate(const float* attr, int attr_batched, int V, int C, const float* rast, const int* tri, int B, int H, int W,
+                float* out, cudaStream_t stream);
+// out[b, v, :] = mats[b] (row-major 4x4) @ [vert[v], 1]
+int transform_points(const float* vert, int V, const float* mats, int n, float* out, cudaStream_t stream);
+size_t bvh_nodes_bytes(int F);
+size_t bvh_workspace_bytes(int F);
+int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, void* workspace, size_t ws_bytes,
+              cudaStream_t stream);
+int bvh_export(const void* nodes, int F, int* info, float* aabb, cudaStream_t stream);
+int bvh_intersect(const void* nodes, const float* vert, const int* tri, const float* rays_o, const float* rays_d,
+                  long long N, unsigned char* hit, int* tid, float* pos, float* uv, cudaStream_t stream);
+size_t uv_bake_workspace_bytes(int H2, int W2);
+int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
+            int n_views, const float* view_mats_host, const float* view_dirs_host, const int* priority_host,
+            const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
+            const float* grid_lo_host, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color_out,
+            int* nn_index_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
 }  // namespace utx
