@@ -163,6 +163,22 @@ int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void*
                 const float* grid_lo, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color,
                 int32_t* nn_index, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * FLUX VAE building blocks (AutoencoderKL; flux_piplines/texturing/pipeline.py:226-238 encode, :688-692 decode).
+ * Activations NHWC bf16; a 3x3 conv = utx_im2col3x3 + utx_gemm_bf16 with W arranged [Cout, ky, kx, Cin].
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* out [N*Ho*Wo, Kpad] (zero padded beyond 9*C); up = 1|2 nearest upsample folded in; pad = top/left padding */
+int utx_im2col3x3(const void* x, int N, int Hin, int Win, int C, int up, int stride, int pad, int Ho, int Wo, int Kpad,
+                  void* out, void* stream);
+/* GroupNorm(G, eps 1e-6, affine fp32) [+ SiLU]; stats_ws: N*G*2 doubles */
+int utx_groupnorm_nhwc(const void* x, void* y, int N, int HW, int C, int G, const float* gamma, const float* beta, int silu,
+                       void* stats_ws, void* stream);
+/* C fp32 [M,N] = scale * (A @ W^T + bias) */
+int utx_gemm_bf16_f32out(const void* A, long lda, const void* W, long ldw, const void* bias, float* C, long ldc, int M, int N,
+                         int K, float scale, void* stream);
+int utx_softmax_rows(const float* S, long lds, void* P, long ldp, int M, int N, void* stream);
+int utx_transpose_bf16(const void* x, long ldx, void* y, long ldy, int R, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ run gemm tests/test_gpu_kernels.py "gemm"
 run attn tests/test_gpu_kernels.py "attention"
 run flux tests/test_gpu_flux.py "flux or oracle or denoise or forward"
 run pipe tests/test_gpu_pipeline.py "pipeline"
+run vae tests/test_gpu_vae.py "vae or decode or encode or pipeline"
 run bake tests/test_gpu_bake.py "bake or raster or lbvh or raytracing"
 for f in ${EXTRA_TESTS}; do run $(basename $f .py) $f ""; done
 timeout -k 10 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1

@@ -70,6 +70,11 @@ _SIGS = {
     "utx_bvh_build": (i32, [vp, i32, vp, i32, vp, vp, C.c_size_t, vp]),
     "utx_bvh_export": (i32, [vp, i32, vp, vp, vp]),
     "utx_bvh_intersect": (i32, [vp, vp, vp, vp, vp, C.c_longlong, vp, vp, vp, vp, vp]),
+    "utx_im2col3x3": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "utx_groupnorm_nhwc": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
+    "utx_gemm_bf16_f32out": (i32, [vp, lng, vp, lng, vp, vp, lng, i32, i32, i32, f32, vp]),
+    "utx_softmax_rows": (i32, [vp, lng, vp, lng, i32, i32, vp]),
+    "utx_transpose_bf16": (i32, [vp, lng, vp, lng, i32, i32, vp]),
     "utx_uv_bake_workspace_bytes": (C.c_size_t, [i32, i32]),
     "utx_uv_bake": (i32, [vp, i32, vp, i32, vp, vp, i32, i32, i32, fp, fp, C.POINTER(C.c_int32), vp, i32, i32, f32, vp, f32,
                           fp, f32, vp, vp, vp, vp, vp, C.c_size_t, vp]),

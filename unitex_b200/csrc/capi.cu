@@ -127,4 +127,34 @@ int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void*
                  workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int utx_im2col3x3(const void* x, int N, int Hin, int Win, int C, int up, int stride, int pad, int Ho, int Wo, int Kpad,
+                  void* out, void* stream) {
+  UTX_CHECK(x && out, "utx_im2col3x3: null pointer");
+  return im2col3x3(static_cast<const bf16*>(x), N, Hin, Win, C, up, stride, pad, Ho, Wo, Kpad, static_cast<bf16*>(out),
+                   static_cast<cudaStream_t>(stream));
+}
+int utx_groupnorm_nhwc(const void* x, void* y, int N, int HW, int C, int G, const float* gamma, const float* beta, int silu,
+                       void* stats_ws, void* stream) {
+  UTX_CHECK(x && y && gamma && beta && stats_ws, "utx_groupnorm_nhwc: null pointer");
+  return groupnorm_nhwc(static_cast<const bf16*>(x), static_cast<bf16*>(y), N, HW, C, G, gamma, beta, silu,
+                        static_cast<double*>(stats_ws), static_cast<cudaStream_t>(stream));
+}
+int utx_gemm_bf16_f32out(const void* A, long lda, const void* W, long ldw, const void* bias, float* C, long ldc, int M, int N,
+                         int K, float scale, void* stream) {
+  UTX_CHECK(A && W && C, "utx_gemm_bf16_f32out: null pointer");
+  GemmArgs a{};
+  a.N = N; a.K = K; a.epi = EPI_BIAS_F32; a.gelu_col_start = 0; a.out_scale = scale; a.nprob = 1;
+  a.prob[0] = GemmProblem{static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, M, reinterpret_cast<bf16*>(C),
+                          ldc, static_cast<const bf16*>(bias), nullptr, nullptr, 0, 0, nullptr, 0};
+  return gemm_bf16_tn(a, static_cast<cudaStream_t>(stream));
+}
+int utx_softmax_rows(const float* S, long lds, void* P, long ldp, int M, int N, void* stream) {
+  UTX_CHECK(S && P, "utx_softmax_rows: null pointer");
+  return softmax_rows(S, lds, static_cast<bf16*>(P), ldp, M, N, static_cast<cudaStream_t>(stream));
+}
+int utx_transpose_bf16(const void* x, long ldx, void* y, long ldy, int R, int C, void* stream) {
+  UTX_CHECK(x && y, "utx_transpose_bf16: null pointer");
+  return transpose_bf16(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, R, C, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -45,6 +45,7 @@ struct DevParams {
   int nprob;
   int epi;
   int gelu_col_start;
+  float out_scale;
   int total_tiles;
   DevProblem prob[2];
 };
@@ -228,6 +229,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 f[4] = fmaf(g1.x, f[4], bf16lo(r.z)); f[5] = fmaf(g1.y, f[5], bf16hi(r.z));
                 f[6] = fmaf(g1.z, f[6], bf16lo(r.w)); f[7] = fmaf(g1.w, f[7], bf16hi(r.w));
               }
+              if (p.epi == EPI_BIAS_F32) {   // fp32 output (attention scores of the VAE mid block): C is float*, ldc in floats
+                float* crow32 = reinterpret_cast<float*>(pr.C) + static_cast<long>(row) * pr.ldc + (col - col_shift);
+                *reinterpret_cast<float4*>(crow32) = make_float4(f[0] * p.out_scale, f[1] * p.out_scale, f[2] * p.out_scale, f[3] * p.out_scale);
+                *reinterpret_cast<float4*>(crow32 + 4) = make_float4(f[4] * p.out_scale, f[5] * p.out_scale, f[6] * p.out_scale, f[7] * p.out_scale);
+                continue;
+              }
               uint4 o;
               o.x = pack_bf16x2(f[0], f[1]);
               o.y = pack_bf16x2(f[2], f[3]);
@@ -264,6 +271,7 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
   p.nprob = a.nprob;
   p.epi = a.epi;
   p.gelu_col_start = a.gelu_col_start;
+  p.out_scale = a.out_scale;
   CUtensorMap tm[4];
   int total = 0;
   for (int i = 0; i < a.nprob; ++i) {
@@ -305,6 +313,7 @@ int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
     const GemmProblem& g = a.prob[i];
     UTX_CHECK(g.M >= 0, "gemm: negative M");
     UTX_CHECK(g.ldc % 8 == 0 && (g.res == nullptr || g.ldres % 8 == 0), "gemm: ldc/ldres must be multiples of 8");
+    UTX_CHECK(a.epi != EPI_BIAS_F32 || g.split_col == 0, "gemm: fp32 output cannot be combined with a column split");
     UTX_CHECK(a.epi != EPI_GATE_RES || (g.gate && g.res), "gemm: EPI_GATE_RES needs gate and res");
     UTX_CHECK(g.split_col == 0 || (g.split_col % 256 == 0 && g.C2 && g.ldc2 % 8 == 0), "gemm: bad column split");
   }

@@ -16,6 +16,7 @@ enum GemmEpilogue : int {
   EPI_BIAS = 0,        // C = acc + bias
   EPI_BIAS_GELU = 1,   // C = gelu_tanh(acc + bias) for columns >= gelu_col_start, acc + bias below
   EPI_GATE_RES = 2,    // C = res + gate[n] * (acc + bias)        (res may alias C)
+  EPI_BIAS_F32 = 3,    // C (float*, ldc in floats) = out_scale * (acc + bias)
 };
 struct GemmProblem {
   const bf16* A;   // [M, K] row-major, row stride lda
@@ -38,6 +39,7 @@ struct GemmArgs {
   int N, K;
   int epi;
   int gelu_col_start;
+  float out_scale;       // EPI_BIAS_F32 only
   int nprob;             // 1 or 2 problems sharing N, K and the epilogue (txt + img streams)
   GemmProblem prob[2];
 };
@@ -92,5 +94,14 @@ int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, 
             const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
             const float* grid_lo_host, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color_out,
             int* nn_index_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+
+// ------------------------------------------------------------------ VAE (NHWC bf16; convs = im2col + gemm_bf16_tn)
+int im2col3x3(const bf16* x, int N, int Hin, int Win, int C, int up, int stride, int pad, int Ho, int Wo, int Kpad, bf16* out,
+              cudaStream_t stream);
+int groupnorm_nhwc(const bf16* x, bf16* y, int N, int HW, int C, int G, const float* gamma, const float* beta, int silu,
+                   double* stats_ws, cudaStream_t stream);
+int softmax_rows(const float* S, long lds, bf16* P, long ldp, int M, int N, cudaStream_t stream);
+int transpose_bf16(const bf16* x, long ldx, bf16* y, long ldy, int R, int Cc, cudaStream_t stream);
 
 }  // namespace utx
