@@ -83,9 +83,16 @@ def test_gemm_grouped_two_streams(lib):
     _check_bf16(C[M0:], X[M0:].float() @ W1.float().T + b1.float(), name="grouped img")
 
 
+@pytest.fixture(params=["1", "2"])
+def attn_impl(request, monkeypatch):
+    """Both attention kernels stay under test: 1 = one query tile per CTA, P via smem; 2 = two-tile ping-pong, P in TMEM."""
+    monkeypatch.setenv("UTX_ATTN_IMPL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("S,H,qscale", [(128, 2, 1.0), (256, 2, 1.0), (1280, 2, 1.0), (1000, 3, 1.0), (640, 2, 6.0),
-                                        (2432, 4, 1.0)])
-def test_attention(lib, S, H, qscale):
+                                        (2432, 4, 1.0), (300, 1, 1.0)])
+def test_attention(lib, attn_impl, S, H, qscale):
     from unitex_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(S + H)
     qkv = torch.randn(S, 3 * H * 128, device="cuda", generator=g)
@@ -101,7 +108,7 @@ def test_attention(lib, S, H, qscale):
     assert (out.float() - ref).abs().max().item() < 0.05 * ref.abs().max().item() + 2e-2
 
 
-def test_attention_matches_explicit_bf16_p(lib):
+def test_attention_matches_explicit_bf16_p(lib, attn_impl):
     """Tighter: emulate the kernel's one deliberate rounding (P -> bf16 before PV) in fp32 torch."""
     from unitex_b200 import ops
     S, H = 384, 2

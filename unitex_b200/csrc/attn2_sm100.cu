@@ -1,0 +1,260 @@
+// Joint attention v2: two 128-row query tiles per CTA ping-ponging on the tensor pipe, P kept in TMEM.
+//   out = softmax(q k^T / sqrt(128)) v   (flux_piplines/texturing/attention_processor.py:89-91)
+//
+// Why (profiles/r01_summary.md): v1 runs one softmax warp per SM sub-partition, so MUFU sits at 33 % and the tensor pipe
+// at 31 %.  Here a CTA owns 256 query rows of one head:
+//   warp 0        TMA producer: Q_A, Q_B once; K_j / V_j tiles through two 2-deep mbarrier rings
+//   warp 1        MMA issuer (one thread).  Per kv tile j:  O_A += P_A V_j ; S_A = Q_A K_{j+1}^T ; O_B += P_B V_j ;
+//                 S_B = Q_B K_{j+1}^T  -- so while warpgroup A does softmax(S_A) the pipe runs tile B's MMAs and vice versa
+//   warp 2        TMEM allocator (all 512 columns: S_A | S_B | O_A | O_B, 128 fp32 columns each)
+//   warps 4-7     softmax warpgroup A (thread == query row), warps 8-11 warpgroup B
+// P = exp2(S*scale - m) is rounded to bf16 and written back over the first 64 columns of its own S tile
+// (tcgen05.st, two bf16 per 32-bit column), and the PV product reads it from there as the A operand (TS-mode MMA): no smem
+// round trip for P, half the smem operand traffic of the PV MMAs.  S is read from TMEM twice (row max, then exponentials
+// in 32-column chunks) to keep the softmax threads at ~120 registers.  O / l are rescaled lazily (running max grows by > 8).
+// `tcgen05.commit` of S_X(j+1) retires every earlier MMA of the issuing thread, so "S_X(j+1) ready" also means
+// "PV_X(j) done": no separate barrier guards the O rescale or the P overwrite.
+#include "common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace utx {
+namespace {
+
+constexpr int HD = 128;
+constexpr int BQ = 128;       // rows per softmax warpgroup
+constexpr int BKV = 128;
+constexpr int kThreads = 384;
+constexpr int TILE_BYTES = 128 * HD * 2;
+constexpr int HALF_BYTES = TILE_BYTES / 2;
+constexpr int OFF_Q = 0;                   // 2 tiles
+constexpr int OFF_K = 2 * TILE_BYTES;      // 2 stages
+constexpr int OFF_V = 4 * TILE_BYTES;      // 2 stages
+constexpr int OFF_BAR = 6 * TILE_BYTES;
+constexpr int SMEM_TOTAL = OFF_BAR + 32 * 8 + 1024;
+constexpr float kRescaleThreshold = 8.0f;
+
+enum Bar { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, P_FULL = 11, O_FULL = 13, NUM_BARS = 14 };
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, long ld_out, int S, int H,
+                  float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * BQ);
+  const int head = blockIdx.y;
+  const int D = H * HD;
+  const int n_kv = (S + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) prefetch_tmap(&tm_qkv);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NUM_BARS; ++i) mbar_init(&bar[i], (i == P_FULL || i == P_FULL + 1) ? 4 : 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    mbar_arrive_expect_tx(&bar[Q_FULL], 2 * TILE_BYTES);
+    for (int x = 0; x < 2; ++x) {
+      tma_load_2d(smem + OFF_Q + x * TILE_BYTES, &tm_qkv, &bar[Q_FULL], head * HD, q0 + x * BQ);
+      tma_load_2d(smem + OFF_Q + x * TILE_BYTES + HALF_BYTES, &tm_qkv, &bar[Q_FULL], head * HD + 64, q0 + x * BQ);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&bar[K_EMPTY + s], ph ^ 1);
+      mbar_arrive_expect_tx(&bar[K_FULL + s], TILE_BYTES);
+      uint8_t* kd = smem + OFF_K + s * TILE_BYTES;
+      tma_load_2d(kd, &tm_qkv, &bar[K_FULL + s], D + head * HD, j * BKV);
+      tma_load_2d(kd + HALF_BYTES, &tm_qkv, &bar[K_FULL + s], D + head * HD + 64, j * BKV);
+      mbar_wait(&bar[V_EMPTY + s], ph ^ 1);
+      mbar_arrive_expect_tx(&bar[V_FULL + s], TILE_BYTES);
+      uint8_t* vd = smem + OFF_V + s * TILE_BYTES;
+      tma_load_2d(vd, &tm_qkv, &bar[V_FULL + s], 2 * D + head * HD, j * BKV);
+      tma_load_2d(vd + HALF_BYTES, &tm_qkv, &bar[V_FULL + s], 2 * D + head * HD + 64, j * BKV);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);   // Q (smem, K-major) x K (smem, K-major)
+    constexpr uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);    // P (TMEM)          x V (smem, MN-major)
+    auto issue_S = [&](int x, int j) {   // S_x = Q_x K_j^T
+      const uint32_t q_addr = smem_u32(smem + OFF_Q + x * TILE_BYTES);
+      const uint32_t k_addr = smem_u32(smem + OFF_K + (j & 1) * TILE_BYTES);
+#pragma unroll
+      for (int kk = 0; kk < HD / 16; ++kk) {
+        const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
+        umma_ss(tmem_base + x * 128, make_sdesc(q_addr + off, 16, 1024), make_sdesc(k_addr + off, 16, 1024), idesc_s, kk != 0);
+      }
+      umma_commit(&bar[S_FULL + x]);
+    };
+    auto issue_PV = [&](int x, int j) {  // O_x += P_x V_j, P_x bf16 in the first 64 columns of S_x
+      const uint32_t v_addr = smem_u32(smem + OFF_V + (j & 1) * TILE_BYTES);
+#pragma unroll
+      for (int kk = 0; kk < BKV / 16; ++kk)
+        umma_ts(tmem_base + 256 + x * 128, tmem_base + x * 128 + kk * 8, make_sdesc(v_addr + kk * 16 * 128, HALF_BYTES, 1024),
+                idesc_o, (j | kk) != 0);
+    };
+    mbar_wait(&bar[Q_FULL], 0);
+    mbar_wait(&bar[K_FULL], 0);
+    tc_fence_after();
+    issue_S(0, 0);
+    issue_S(1, 0);
+    umma_commit(&bar[K_EMPTY]);
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j & 1, sn = (j + 1) & 1;
+      const bool more = j + 1 < n_kv;
+      mbar_wait(&bar[V_FULL + s], (j >> 1) & 1);
+      mbar_wait(&bar[P_FULL], j & 1);
+      tc_fence_after();
+      issue_PV(0, j);
+      if (more) {
+        mbar_wait(&bar[K_FULL + sn], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        issue_S(0, j + 1);
+      }
+      mbar_wait(&bar[P_FULL + 1], j & 1);
+      tc_fence_after();
+      issue_PV(1, j);
+      umma_commit(&bar[V_EMPTY + s]);
+      if (more) {
+        issue_S(1, j + 1);
+        umma_commit(&bar[K_EMPTY + sn]);
+      }
+    }
+    umma_commit(&bar[O_FULL]);
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax warpgroups: thread == query row
+    const int x = (warp - 4) >> 2;                 // 0 = tile A, 1 = tile B
+    const int ew = (warp - 4) & 3;                 // == warp % 4: the TMEM lane quarter this warp may touch
+    const int r = ew * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + x * 128;
+    const uint32_t tO = tmem_base + lane_off + 256 + x * 128;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&bar[S_FULL + x], j & 1);
+      tc_fence_after();
+      const int kv_valid = S - j * BKV;
+      const bool ragged = kv_valid < BKV;
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        tmem_ld32(tS + c * 32, sv);
+        tmem_ld_wait();
+        if (!ragged) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        }
+      }
+      const float m_new = mx * scale_log2;
+      const bool upd = m_new > m_used + kRescaleThreshold;
+      const float m_next = upd ? m_new : m_used;
+      const float alpha = upd ? ex2_approx(m_used - m_next) : 1.0f;
+      m_used = m_next;
+      if (j > 0 && __any_sync(0xffffffffu, upd)) {     // PV_x(j-1) has retired (see header): O_x is consistent
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t ov[32];
+          tmem_ld32(tO + c * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st32(tO + c * 32, ov);
+        }
+      }
+      // pass 2: exponentials, 32 columns at a time, P written back over S (16 packed columns per chunk)
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        tmem_ld32(tS + c * 32, sv);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), scale_log2, -m_next));
+          float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), scale_log2, -m_next));
+          if (ragged) {
+            if (c * 32 + i >= kv_valid) p0 = 0.f;
+            if (c * 32 + i + 1 >= kv_valid) p1 = 0.f;
+          }
+          lsum += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st16(tS + c * 16, pk);
+      }
+      l = l * alpha + lsum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[P_FULL + x]);
+    }
+    // ---------------------------------------------------------------- epilogue
+    mbar_wait(&bar[O_FULL], 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    const int row = q0 + x * BQ + r;
+    bf16* orow = out + static_cast<long>(row) * ld_out + head * HD;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t ov[32];
+      tmem_ld32(tO + c * 32, ov);
+      tmem_ld_wait();
+      if (row < S) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream) {
+  UTX_CHECK(S > 0 && H > 0, "attention: empty problem");
+  UTX_CHECK(ld_qkv >= 3L * H * HD && ld_out % 8 == 0, "attention: bad leading dimensions");
+  CUtensorMap tm;
+  UTX_TRY(make_tmap_2d_bf16(&tm, qkv, S, 3L * H * HD, ld_qkv, 128, 64));
+  static bool attr_set = false;
+  if (!attr_set) {
+    UTX_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    attr_set = true;
+  }
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  dim3 grid((S + 2 * BQ - 1) / (2 * BQ), H);
+  attention2_kernel<<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace utx

@@ -12,6 +12,8 @@
 //               TMEM round trip of O is rare), P rounded to bf16 into 128B-swizzled smem for the PV MMA.
 // S_{j+1} is issued before softmax_j finishes, so QK^T of the next tile and PV of the previous one overlap the
 // exponentials of the current one.
+#include <cstdlib>
+
 #include "common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -242,7 +244,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ 
 
 }  // namespace
 
+int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream);
+
 int attention_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream) {
+  // UTX_ATTN_IMPL=1: one query tile per CTA, P through smem (this file).  =2 (default): two-tile ping-pong, P in TMEM
+  // (attn2_sm100.cu).  Both stay built so the parity tests can run either.
+  const char* impl = getenv("UTX_ATTN_IMPL");
+  if (impl == nullptr || impl[0] != '1') return attention2_bf16(qkv, ld_qkv, out, ld_out, S, H, stream);
   UTX_CHECK(S > 0 && H > 0, "attention: empty problem");
   UTX_CHECK(ld_qkv >= 3L * H * HD && ld_out % 8 == 0, "attention: bad leading dimensions");
   CUtensorMap tm;
