@@ -1,0 +1,171 @@
+"""`CustomRGBTextureFullPipeline`: drop-in for the reference's top-level orchestrator (reference pipeline.py:141-632,
+run.py:1-10) over the B200-native hot path.  Same constructor / `__call__(save_dir, input_image_path, input_mesh_path,
+clear_cache)` signature, same step sequence ['step_1_1', 'step_2_ablition'], same cache file names.
+
+What is NOT re-implemented (out of scope, CPU third-party): background matting (rembg / RMBG-2.0), mesh
+decimation + UV unwrapping (open3d / xatlas), the orbit mp4, super-resolution (TSD_SR).  The corresponding steps do the
+minimum the hot path needs: the reference image is resized/padded on a grey canvas, the mesh must already carry UVs.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from PIL import Image
+
+from flux_piplines.texturing.pipeline import PBRFluxPipeline
+from unitex_b200 import bake as ub
+from unitex_b200 import export as ux
+from unitex_b200.flux import FluxConfig
+
+
+def build_pipeline(pretrain_models=None, pipeline_name="texture_plus", model="rgb", super_resolutions=False,
+                   add_lora_path=None, add_lora_weights=None, speedup_mode=False):
+    """reference pipeline.py:81-127.  `pretrain_models='random'` (or a FluxConfig) builds random-init weights + random LoRAs
+    so the whole pipeline runs without the HF checkpoints (tests, smoke)."""
+    if pretrain_models == "random" or isinstance(pretrain_models, FluxConfig):
+        cfg = pretrain_models if isinstance(pretrain_models, FluxConfig) else FluxConfig()
+        pipeline = PBRFluxPipeline.from_random(cfg, seed=0, with_vae=True)
+        g = torch.Generator().manual_seed(1)
+        for name in ("texture", "delight"):
+            n = "transformer_blocks.0.attn.to_q"
+            D = cfg.inner_dim
+            pipeline.load_lora_weights({f"transformer.{n}.lora_A.weight": torch.randn(8, D, generator=g) * 0.02,
+                                        f"transformer.{n}.lora_B.weight": torch.randn(D, 8, generator=g) * 0.02}, adapter_name=name)
+    else:
+        lora_id = f"{pretrain_models}/UniTex/texture_gen/pytorch_lora_weights.safetensors"
+        lora_id_delight = f"{pretrain_models}/UniTex/delight/pytorch_lora_weights.safetensors"
+        ckpt_id = f"{pretrain_models}/black-forest-labs/FLUX.1-dev"
+        pipeline = PBRFluxPipeline.from_pretrained(ckpt_id, text_encoder=None, text_encoder_2=None, torch_dtype=torch.bfloat16)
+        pipeline.load_lora_weights(lora_id, adapter_name="texture")
+        pipeline.load_lora_weights(lora_id_delight, adapter_name="delight")
+    weights_for_texture, weights_for_delight, adapter_names = [1.0, 0.0], [0.0, 1.0], ["texture", "delight"]
+    for i, p in enumerate(add_lora_path or []):
+        pipeline.load_lora_weights(p, adapter_name=f"add_lora_{i}")
+        adapter_names.append(f"add_lora_{i}")
+        weights_for_texture.append(add_lora_weights[i])
+        weights_for_delight.append(add_lora_weights[i])
+    pipeline._num_inference_steps = 28
+    return pipeline, weights_for_texture, weights_for_delight, adapter_names
+
+
+class RGBTextureFullPipelineBase:
+    step_seq = []
+
+    def __init__(self, pretrain_models=None, pipeline_name="texture_plus", super_resolutions=False, seed=0, speedup_mode=None,
+                 add_lora_path=None, add_lora_weights=None, enable_rembg=False):
+        if super_resolutions:
+            raise NotImplementedError("TSD_SR super-resolution is out of scope (reference run.py:4 leaves it off)")
+        (self.pipeline, self.weights_for_texture, self.weights_for_delight, self.adapter_names) = build_pipeline(
+            pretrain_models=pretrain_models, pipeline_name=pipeline_name, speedup_mode=speedup_mode, add_lora_path=add_lora_path,
+            add_lora_weights=add_lora_weights, model="rgb")
+        self.pipeline_name = pipeline_name
+        self.video_exporter = ux.VideoExporter()
+        self.inverse_renderer = ub.NVDiffRendererInverse(device="cuda")
+        self.generator = torch.Generator().manual_seed(seed)
+        self.super_resolutions = False
+
+    # ------------------------------------------------------------------ step pieces
+    def preprocess_blank_mesh(self, save_dir, input_mesh_path):
+        """reference :170-179 rescales with open3d and unwraps when UVs are missing; here: UVs are required."""
+        V, F, UV, Ft = ub.load_obj(input_mesh_path)
+        if len(UV) == 0:
+            raise NotImplementedError("mesh without UVs: UV-atlas generation (open3d/xatlas) is out of scope")
+        ux.save_obj(os.path.join(save_dir, "processed_mesh.obj"), V, F, UV, Ft)
+
+    def preprocess_reference_image(self, save_dir, input_image_path):
+        """reference :182-196 (rembg + crop/pad): here resize onto a 1024^2 grey canvas, then 512^2."""
+        img = Image.open(input_image_path).convert("RGB")
+        img.save(os.path.join(save_dir, "rembg_image.png"))
+        canvas = Image.new("RGB", (1024, 1024), (127, 127, 127))
+        im = img.copy()
+        im.thumbnail((1024, 1024))
+        canvas.paste(im, ((1024 - im.width) // 2, (1024 - im.height) // 2))
+        canvas.resize((512, 512), Image.BILINEAR).save(os.path.join(save_dir, "processed_image.png"))
+
+    def render_geometry_images(self, save_dir, input_mesh_path, geometry_scale=0.95, scale=1.0, color="grey"):
+        """reference :199-228."""
+        out = self.video_exporter.export_condition(input_mesh_path, geometry_scale=geometry_scale, n_views=6, n_rows=2, n_cols=3,
+                                                   H=512, W=512, fov_deg=49.1, scale=scale, perspective=False, orbit=False,
+                                                   background=color, return_info=False, return_image=True, return_camera=True)
+        out["alpha"].save(os.path.join(save_dir, "mv_alpha.png"))
+        out["ccm"].save(os.path.join(save_dir, "mv_ccm.png"))
+        out["normal"].save(os.path.join(save_dir, "mv_normal.png"))
+        torch.save({"c2ws": out["c2ws"], "intrinsics": out["intrinsics"], "perspective": out["perspective"]},
+                   os.path.join(save_dir, "camera_info.pth"))
+
+    def infer_mv(self, save_dir, input_image_path, input_mv_image_path, add_input_mv_image_path):
+        """reference :231-291: texture_gen call, then delight call, same generator (draw order matters)."""
+        reference_image = Image.open(input_image_path).convert("RGB")
+        strip = ux.control_grid_to_strip(np.array(Image.open(input_mv_image_path).convert("RGB")),
+                                         np.array(Image.open(add_input_mv_image_path).convert("RGB")))
+        steps = getattr(self.pipeline, "_num_inference_steps", 28)
+        kw = dict(prompt="[MVFLUX]", prompt_embeds=None, pooled_prompt_embeds=None, height=512, width=3072, n_rows=1, n_cols=6,
+                  num_inference_steps=steps, guidance_scale=3.5, max_sequence_length=512, generator=self.generator)
+        self.pipeline.set_adapters(adapter_names=self.adapter_names, adapter_weights=self.weights_for_texture)
+        out_image = self.pipeline(control_image=Image.fromarray(strip), dual_image=reference_image, **kw).images[0]
+        out_image.save(os.path.join(save_dir, "mv_rgb_w_light.png"))
+        self.pipeline.set_adapters(adapter_names=self.adapter_names, adapter_weights=self.weights_for_delight)
+        out_delighted = self.pipeline(control_image=out_image, **kw).images[0]
+        Image.fromarray(ux.strip_to_view_grid(np.array(out_delighted))).save(os.path.join(save_dir, "mv_rgb.png"))
+
+    def reproject_and_query_field(self, save_dir, input_mesh_path, input_mv_image_path, camera_info_path, method="reproject",
+                                  inpainting=False):
+        """reference :312-360."""
+        os.makedirs(save_dir, exist_ok=True)
+        img = torch.from_numpy(np.asarray(Image.open(input_mv_image_path).convert("RGB")).astype(np.float32) / 255.0).cuda()
+        H, W, C = img.shape
+        HP, WP = H // 2, W // 3
+        image_attrs = img.reshape(2, HP, 3, WP, C).permute(0, 2, 1, 3, 4).reshape(6, HP, WP, C)
+        cam = torch.load(camera_info_path, weights_only=True, map_location="cuda")
+        self.inverse_renderer.update_from_file(input_mesh_path)
+        _, reprojected_uv, visable_mask, completed_uv_map = self.inverse_renderer.infer(
+            self.inverse_renderer.pbr_mesh, c2ws=cam["c2ws"].cpu(), intrinsics=cam["intrinsics"].cpu(), image_attrs=image_attrs,
+            perspective=cam["perspective"], H=HP, W=WP, H2D=2048, W2D=2048, method=method, reproject_inpainting=inpainting,
+            grad_norm_threhold=0.15, ray_normal_angle_threhold=100, filt_gradient_points=inpainting)
+        V, F, UV, Ft = ub.load_obj(input_mesh_path)
+        atlas = (completed_uv_map[0].clamp(0, 1) * 255.0).round().to(torch.uint8).cpu().numpy()
+        ux.save_glb(os.path.join(save_dir, "textured_mesh.glb"), V, F, UV, Ft, atlas)
+
+        def save(t, name):
+            a = (t.float().clamp(0, 1) * 255.0).round().to(torch.uint8).cpu().numpy()
+            Image.fromarray(a[..., 0] if a.shape[-1] == 1 else a).save(os.path.join(save_dir, name))
+        save(reprojected_uv.any(dim=0), "visable_uv_mask.png")
+        save(visable_mask[0], "valid_uv_mask.png")
+        save(completed_uv_map[0], "completed_uv.png")
+        self.inverse_renderer.clear()
+
+    # ------------------------------------------------------------------ steps (reference :568-575, :624-629)
+    def step_1_1(self, save_dir, input_image_path, input_mesh_path):
+        cache = os.path.join(save_dir, "cache")
+        self.preprocess_blank_mesh(cache, input_mesh_path)
+        self.preprocess_reference_image(cache, input_image_path)
+        self.render_geometry_images(cache, os.path.join(cache, "processed_mesh.obj"))
+        self.infer_mv(cache, os.path.join(cache, "processed_image.png"), os.path.join(cache, "mv_normal.png"),
+                      os.path.join(cache, "mv_ccm.png"))
+
+    def step_2_ablition(self, save_dir, input_image_path, input_mesh_path):
+        cache = os.path.join(save_dir, "cache")
+        self.reproject_and_query_field(os.path.join(cache, "wo_LTM"), os.path.join(cache, "processed_mesh.obj"),
+                                       os.path.join(cache, "mv_rgb.png"), os.path.join(cache, "camera_info.pth"),
+                                       method="reproject", inpainting=False)
+
+    def __call__(self, save_dir: str, input_image_path: str, input_mesh_path: str, clear_cache=False) -> Tuple[str, str]:
+        """reference :594-617."""
+        cache = os.path.join(save_dir, "cache")
+        os.makedirs(cache, exist_ok=True)
+        for step in self.step_seq:
+            getattr(self, step)(save_dir, input_image_path, input_mesh_path)
+        shutil.copy(os.path.join(cache, "rembg_image.png"), os.path.join(save_dir, "rembg_image.png"))
+        shutil.copy(os.path.join(cache, "mv_rgb.png"), os.path.join(save_dir, "mv_rgb.png"))
+        shutil.copy(os.path.join(cache, "wo_LTM", "textured_mesh.glb"), os.path.join(save_dir, "textured_mesh.glb"))
+        if clear_cache:
+            shutil.rmtree(cache)
+        return os.path.join(save_dir, "rembg_image.png"), os.path.join(save_dir, "textured_mesh.glb")
+
+
+class CustomRGBTextureFullPipeline(RGBTextureFullPipelineBase):
+    step_seq = ["step_1_1", "step_2_ablition"]       # reference pipeline.py:620-629

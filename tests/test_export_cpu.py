@@ -1,0 +1,48 @@
+"""CPU: host-side wire formats and grid re-ordering around the hot path (reference pipeline.py:239-244, 280-282;
+io/link_pbr_to_mesh.py:9-31)."""
+import json
+import struct
+
+import numpy as np
+
+from tests.bake_meshes import two_spheres
+
+
+def test_view_grid_reordering_roundtrip():
+    from unitex_b200.export import control_grid_to_strip, strip_to_view_grid
+    g = np.random.default_rng(0).integers(0, 255, (1024, 1536, 3), dtype=np.uint8)
+    strip = control_grid_to_strip(g, g)
+    assert strip.shape == (512, 3072, 3)
+    tiles = g.reshape(2, 512, 3, 512, 3).transpose(0, 2, 1, 3, 4).reshape(6, 512, 512, 3)
+    # strip order f,l,r,b,t,d = grid tiles [0,4,1,3,2,5]; tile 5 rotated by 180 degrees   
+    assert np.array_equal(strip[:, 512:1024], tiles[4]) and np.array_equal(strip[:, 2048:2560], tiles[2])
+    assert np.array_equal(strip[:, 2560:], tiles[5][::-1, ::-1])
+    assert np.array_equal(strip_to_view_grid(strip), g)
+
+
+def test_obj_and_glb_writers(tmp_path):
+    from unitex_b200.bake import load_obj
+    from unitex_b200.export import save_glb, save_obj
+    v, f, uv, fuv = two_spheres(6, 8)
+    uv01 = (uv + 1) / 2
+    p = tmp_path / "m.obj"
+    save_obj(str(p), v, f, uv01, fuv)
+    V, F, UV, Ft = load_obj(str(p))
+    assert np.allclose(V, v, atol=1e-6) and np.array_equal(F, f) and np.allclose(UV, uv01, atol=1e-6) and np.array_equal(Ft, fuv)
+    tex = np.random.default_rng(1).integers(0, 255, (32, 32, 3), dtype=np.uint8)
+    g = tmp_path / "m.glb"
+    save_glb(str(g), v, f, uv01, fuv, tex)
+    raw = g.read_bytes()
+    magic, ver, total = struct.unpack("<III", raw[:12])
+    assert magic == 0x46546C67 and ver == 2 and total == len(raw)
+    jl, jt = struct.unpack("<II", raw[12:20])
+    doc = json.loads(raw[20:20 + jl])
+    assert jt == 0x4E4F534A and doc["accessors"][2]["count"] == f.size and doc["images"][0]["mimeType"] == "image/png"
+    bl, bt = struct.unpack("<II", raw[20 + jl:28 + jl])
+    assert bt == 0x004E4942 and 28 + jl + bl == len(raw)
+
+
+def test_lens_blur_kernel_sums_to_one():
+    from unitex_b200.bake import lens_blur_kernel_2d
+    K = lens_blur_kernel_2d()
+    assert K.shape == (7, 7) and abs(K.sum() - 1.0) < 1e-5 and np.allclose(K, K.T, atol=1e-7)
