@@ -79,6 +79,34 @@ __global__ void __launch_bounds__(256) elements_kernel(const float* __restrict__
   }
 }
 
+// points as degenerate boxes (nearest-neighbour tree over the visible texels, bake_uv.cu)
+__global__ void __launch_bounds__(256) point_elements_kernel(const float* __restrict__ pts, int n, float* __restrict__ eab,
+                                                             int* __restrict__ bounds) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  float p[3] = {0.f, 0.f, 0.f};
+  if (f < n) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      p[a] = pts[static_cast<size_t>(f) * 3 + a];
+      eab[static_cast<size_t>(f) * 6 + a] = p[a];
+      eab[static_cast<size_t>(f) * 6 + 3 + a] = p[a];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float lo = f < n ? p[a] : INFINITY, hi = f < n ? p[a] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(bounds + a, f2ord(lo));
+      atomicMax(bounds + 3 + a, f2ord(hi));
+    }
+  }
+}
+
 __device__ __forceinline__ unsigned expand_bits(unsigned v) {
   v = (v * 0x00010001u) & 0xFF0000FFu;
   v = (v * 0x00000101u) & 0x0F00F00Fu;
@@ -235,10 +263,9 @@ size_t bvh_workspace_bytes(int F) {
          al256(static_cast<size_t>(F) * 4) + 256 + al256(cub_bytes);
 }
 
-int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, void* workspace, size_t ws_bytes,
-              cudaStream_t stream) {
-  (void)V;
-  UTX_CHECK(F >= 2, "bvh_build: need at least 2 triangles");
+static int build_tree(const float* vert, const int* tri, const float* pts, int F, void* nodes_out, void* workspace,
+                      size_t ws_bytes, cudaStream_t stream) {
+  UTX_CHECK(F >= 2, "bvh_build: need at least 2 elements");
   UTX_CHECK(ws_bytes >= bvh_workspace_bytes(F), "bvh_build: workspace too small");
   UTX_CHECK((reinterpret_cast<uintptr_t>(nodes_out) & 15) == 0, "bvh_build: nodes must be 16B aligned");
   uint8_t* p = static_cast<uint8_t*>(workspace);
@@ -253,7 +280,8 @@ int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, 
   size_t cub_bytes = ws_bytes - static_cast<size_t>(p - static_cast<uint8_t*>(workspace));
   const unsigned grid = (F + 255) / 256;
   bounds_init_kernel<<<1, 32, 0, stream>>>(bounds);
-  elements_kernel<<<grid, 256, 0, stream>>>(vert, tri, F, eab, bounds);
+  if (pts) point_elements_kernel<<<grid, 256, 0, stream>>>(pts, F, eab, bounds);
+  else elements_kernel<<<grid, 256, 0, stream>>>(vert, tri, F, eab, bounds);
   morton_kernel<<<grid, 256, 0, stream>>>(eab, bounds, F, codes, elem);
   UTX_CUDA(cub::DeviceRadixSort::SortPairs(p, cub_bytes, codes, codes2, elem, elem2, F, 0, 32, stream));
   Node* nodes = static_cast<Node*>(nodes_out);
@@ -261,6 +289,17 @@ int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, 
   refit_kernel<<<grid, 256, 0, stream>>>(F, nodes, parent, arrivals);
   UTX_CUDA(cudaGetLastError());
   return 0;
+}
+
+int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, void* workspace, size_t ws_bytes,
+              cudaStream_t stream) {
+  (void)V;
+  return build_tree(vert, tri, nullptr, F, nodes_out, workspace, ws_bytes, stream);
+}
+
+// LBVH over n points (leaf prim = point index): the search structure of the bake's exact 1-NN fill
+int point_bvh_build(const float* pts, int n, void* nodes_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  return build_tree(nullptr, nullptr, pts, n, nodes_out, workspace, ws_bytes, stream);
 }
 
 int bvh_export(const void* nodes, int F, int* info, float* aabb, cudaStream_t stream) {

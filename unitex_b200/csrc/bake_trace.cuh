@@ -76,4 +76,47 @@ __device__ __forceinline__ RayHit bvh_trace(const void* __restrict__ nodes_v, co
 }
 
 
+// Exact nearest neighbour of q among the points of a point-LBVH: fp32 squared distance ((dx^2+dy^2)+dz^2), lowest point id on
+// ties (`ids` maps the tree's point index to the caller's id).  Boxes are pruned only when their (slightly deflated)
+// distance bound exceeds the best distance, so rounding can never drop the true nearest point.
+__device__ __forceinline__ int nn_trace(const void* __restrict__ nodes_v, const float* __restrict__ pts,
+                                        const int* __restrict__ ids, const float* q, float* best_d2_out) {
+  const float4* nodes = static_cast<const float4*>(nodes_v);
+  int stack[64];
+  int count = 0;
+  stack[count++] = 0;
+  float best = INFINITY;
+  int best_id = -1;
+  while (count > 0) {
+    const int n = stack[--count];
+    const float4 q0 = __ldg(nodes + static_cast<size_t>(n) * 3), q1 = __ldg(nodes + static_cast<size_t>(n) * 3 + 1);
+    const float bx = fmaxf(fmaxf(q0.x - q[0], q[0] - q0.w), 0.f), by = fmaxf(fmaxf(q0.y - q[1], q[1] - q1.x), 0.f),
+                bz = fmaxf(fmaxf(q0.z - q[2], q[2] - q1.y), 0.f);
+    const float bd = ((bx * bx + by * by) + bz * bz) * 0.999999f;
+    if (bd > best) continue;
+    const int l = __float_as_int(q1.z), r = __float_as_int(q1.w);
+    if (l == 0 && r == 0) {
+      const int pidx = __float_as_int(__ldg(nodes + static_cast<size_t>(n) * 3 + 2).x);
+      const float dx = pts[static_cast<size_t>(pidx) * 3] - q[0], dy = pts[static_cast<size_t>(pidx) * 3 + 1] - q[1],
+                  dz = pts[static_cast<size_t>(pidx) * 3 + 2] - q[2];
+      const float d2 = (dx * dx + dy * dy) + dz * dz;
+      const int id = ids[pidx];
+      if (d2 < best || (d2 == best && id < best_id)) { best = d2; best_id = id; }
+    } else if (count + 2 <= 64) {
+      // visit the nearer child first: push the farther one below it
+      const float4 a0 = __ldg(nodes + static_cast<size_t>(l) * 3), a1 = __ldg(nodes + static_cast<size_t>(l) * 3 + 1);
+      const float ax = fmaxf(fmaxf(a0.x - q[0], q[0] - a0.w), 0.f), ay = fmaxf(fmaxf(a0.y - q[1], q[1] - a1.x), 0.f),
+                  az = fmaxf(fmaxf(a0.z - q[2], q[2] - a1.y), 0.f);
+      const float4 c0 = __ldg(nodes + static_cast<size_t>(r) * 3), c1 = __ldg(nodes + static_cast<size_t>(r) * 3 + 1);
+      const float cx = fmaxf(fmaxf(c0.x - q[0], q[0] - c0.w), 0.f), cy = fmaxf(fmaxf(c0.y - q[1], q[1] - c1.x), 0.f),
+                  cz = fmaxf(fmaxf(c0.z - q[2], q[2] - c1.y), 0.f);
+      const float dl = (ax * ax + ay * ay) + az * az, dr = (cx * cx + cy * cy) + cz * cz;
+      if (dl <= dr) { stack[count++] = r; stack[count++] = l; }
+      else { stack[count++] = l; stack[count++] = r; }
+    }
+  }
+  if (best_d2_out) *best_d2_out = best;
+  return best_id;
+}
+
 }  // namespace utx

@@ -236,81 +236,41 @@ __global__ void __launch_bounds__(256) seam1_kernel(const unsigned char* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ exact 1-NN fill
-struct GridParams {
-  float lo[3];
-  float inv_h, h;
-  int G;
-};
-__device__ __forceinline__ int cell_of(const GridParams& g, const float* p, int* c) {
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    int v = static_cast<int>(floorf((p[a] - g.lo[a]) * g.inv_h));
-    c[a] = min(max(v, 0), g.G - 1);
-  }
-  return (c[2] * g.G + c[1]) * g.G + c[0];
+// Visible texels are compacted in index order (flags -> exclusive scan -> scatter), an LBVH is built over their 3-D
+// positions (same builder as the triangle tree, bake_bvh.cu) and every covered-but-invisible texel walks it for its exact
+// nearest neighbour.  Cost is logarithmic in the number of visible texels and independent of how far the hidden region is
+// from the nearest visible one (the first version used a uniform grid whose ring search was 88 % of the bake).
+__global__ void __launch_bounds__(256) nn_flag_kernel(const signed char* __restrict__ owner, int T, int* __restrict__ flags) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) flags[t] = owner[t] >= 0;
 }
-__global__ void __launch_bounds__(256) nn_count_kernel(const signed char* __restrict__ owner, const float* __restrict__ pos,
-                                                       int T, GridParams g, int* __restrict__ counts) {
+__global__ void __launch_bounds__(256) nn_compact_kernel(const signed char* __restrict__ owner, const int* __restrict__ offs,
+                                                         const float* __restrict__ pos, int T, int* __restrict__ ids,
+                                                         float* __restrict__ pts) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T || owner[t] < 0) return;
-  int c[3];
-  atomicAdd(counts + cell_of(g, pos + static_cast<size_t>(t) * 3, c), 1);
-}
-__global__ void __launch_bounds__(256) nn_fill_kernel(const signed char* __restrict__ owner, const float* __restrict__ pos,
-                                                      int T, GridParams g, const int* __restrict__ starts,
-                                                      int* __restrict__ cursor, int* __restrict__ items) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T || owner[t] < 0) return;
-  int c[3];
-  const int cell = cell_of(g, pos + static_cast<size_t>(t) * 3, c);
-  items[starts[cell] + atomicAdd(cursor + cell, 1)] = t;
+  const int k = offs[t];
+  ids[k] = t;
+  pts[static_cast<size_t>(k) * 3] = pos[static_cast<size_t>(t) * 3];
+  pts[static_cast<size_t>(k) * 3 + 1] = pos[static_cast<size_t>(t) * 3 + 1];
+  pts[static_cast<size_t>(k) * 3 + 2] = pos[static_cast<size_t>(t) * 3 + 2];
 }
 __global__ void __launch_bounds__(128) nn_query_kernel(const unsigned char* __restrict__ mask2d,
                                                        const signed char* __restrict__ owner, const float* __restrict__ pos,
-                                                       int T, GridParams g, const int* __restrict__ starts,
-                                                       const int* __restrict__ counts, const int* __restrict__ items,
-                                                       const float* color_in, float* color_out, int* __restrict__ nn_index) {
+                                                       int T, const void* __restrict__ nodes, const float* __restrict__ pts,
+                                                       const int* __restrict__ ids, int n_pts, const float* color_in,
+                                                       float* color_out, int* __restrict__ nn_index) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   if (nn_index) nn_index[t] = -1;
-  if (!mask2d[t] || owner[t] >= 0) return;
-  const float* q = pos + static_cast<size_t>(t) * 3;
-  int c[3];
-  cell_of(g, q, c);
-  float best = INFINITY;
-  int best_i = -1;
-  for (int r = 0; r < g.G; ++r) {
-    for (int dz = -r; dz <= r; ++dz) {
-      const int z = c[2] + dz;
-      if (z < 0 || z >= g.G) continue;
-      for (int dy = -r; dy <= r; ++dy) {
-        const int y = c[1] + dy;
-        if (y < 0 || y >= g.G) continue;
-        const bool shell_zy = (abs(dz) == r) || (abs(dy) == r);
-        for (int dx = -r; dx <= r; dx += (shell_zy || r == 0) ? 1 : 2 * r) {
-          const int x = c[0] + dx;
-          if (x < 0 || x >= g.G) continue;
-          const int cell = (z * g.G + y) * g.G + x;
-          const int s = starts[cell], n = counts[cell];
-          for (int k = 0; k < n; ++k) {
-            const int j = items[s + k];
-            const float ddx = pos[static_cast<size_t>(j) * 3] - q[0], ddy = pos[static_cast<size_t>(j) * 3 + 1] - q[1],
-                        ddz = pos[static_cast<size_t>(j) * 3 + 2] - q[2];
-            const float d2 = (ddx * ddx + ddy * ddy) + ddz * ddz;
-            if (d2 < best || (d2 == best && j < best_i)) { best = d2; best_i = j; }
-          }
-        }
-      }
-    }
-    // every unvisited cell is at least r*h away (minus the query's clamp into the grid, which only happens outside it)
-    const float reach = r * g.h;
-    if (best_i >= 0 && best <= reach * reach) break;
-  }
-  if (nn_index) nn_index[t] = best_i;
-  if (best_i >= 0) {
-    color_out[t * 3] = color_in[static_cast<size_t>(best_i) * 3];
-    color_out[t * 3 + 1] = color_in[static_cast<size_t>(best_i) * 3 + 1];
-    color_out[t * 3 + 2] = color_in[static_cast<size_t>(best_i) * 3 + 2];
+  if (!mask2d[t] || owner[t] >= 0 || n_pts == 0) return;
+  const float q[3] = {pos[static_cast<size_t>(t) * 3], pos[static_cast<size_t>(t) * 3 + 1], pos[static_cast<size_t>(t) * 3 + 2]};
+  const int best = n_pts == 1 ? ids[0] : nn_trace(nodes, pts, ids, q, nullptr);
+  if (nn_index) nn_index[t] = best;
+  if (best >= 0) {
+    color_out[t * 3] = color_in[static_cast<size_t>(best) * 3];
+    color_out[t * 3 + 1] = color_in[static_cast<size_t>(best) * 3 + 1];
+    color_out[t * 3 + 2] = color_in[static_cast<size_t>(best) * 3 + 2];
   }
 }
 
@@ -402,7 +362,6 @@ __global__ void __launch_bounds__(256) transform_points_kernel(const float* __re
 }
 
 inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
-constexpr int NN_G = 128;
 
 }  // namespace
 
@@ -423,10 +382,9 @@ size_t uv_bake_workspace_bytes(int H2, int W2) {
     pyr_m += al(static_cast<size_t>(h) * w);
   }
   size_t scan_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, static_cast<int*>(nullptr), static_cast<int*>(nullptr),
-                                NN_G * NN_G * NN_G);
-  return 6 * al(T) + al(T * 12) * 3 + al(T * 4) * 2 + 3 * al(static_cast<size_t>(NN_G) * NN_G * NN_G * 4) + al(scan_bytes) +
-         pyr_c + pyr_m + 4096;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, static_cast<int*>(nullptr), static_cast<int*>(nullptr), static_cast<int>(T));
+  return 6 * al(T) + al(T * 12) * 4 + al(T * 4) * 4 + al(scan_bytes) + al(bvh_nodes_bytes(static_cast<int>(T))) +
+         al(bvh_workspace_bytes(static_cast<int>(T))) + pyr_c + pyr_m + 8192;
 }
 
 int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
@@ -454,13 +412,12 @@ int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, 
   float* col_a = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
   float* col_b = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
   signed char* owner = reinterpret_cast<signed char*>(take(static_cast<size_t>(T) * 4));
-  int* items = reinterpret_cast<int*>(take(static_cast<size_t>(T) * 4));
-  const size_t ncell = static_cast<size_t>(NN_G) * NN_G * NN_G;
-  int* counts = reinterpret_cast<int*>(take(ncell * 4));
-  int* starts = reinterpret_cast<int*>(take(ncell * 4));
-  int* cursor = reinterpret_cast<int*>(take(ncell * 4));
+  int* ids = reinterpret_cast<int*>(take(static_cast<size_t>(T) * 4));
+  int* flags = reinterpret_cast<int*>(take(static_cast<size_t>(T) * 4));
+  int* offs = reinterpret_cast<int*>(take(static_cast<size_t>(T) * 4 + 4));
+  float* pts = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
   size_t scan_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, starts, static_cast<int>(ncell));
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flags, offs, T);
   void* scan_tmp = take(scan_bytes);
 
   const unsigned g128 = (T + 127) / 128, g256 = (T + 255) / 256;
@@ -472,17 +429,23 @@ int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, 
   seam0_kernel<<<g256, 256, 0, stream>>>(owner, b0, H2, W2);
   seam1_kernel<<<g256, 256, 0, stream>>>(b0, mask2d, seam, H2, W2);
   // exact 1-NN fill of covered-but-invisible texels
-  GridParams gp;
-  for (int a = 0; a < 3; ++a) gp.lo[a] = grid_lo_host[a];
-  gp.G = NN_G;
-  gp.h = grid_extent / NN_G;
-  gp.inv_h = NN_G / grid_extent;
-  UTX_CUDA(cudaMemsetAsync(counts, 0, ncell * 4, stream));
-  UTX_CUDA(cudaMemsetAsync(cursor, 0, ncell * 4, stream));
-  nn_count_kernel<<<g256, 256, 0, stream>>>(owner, pos, T, gp, counts);
-  UTX_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, counts, starts, static_cast<int>(ncell), stream));
-  nn_fill_kernel<<<g256, 256, 0, stream>>>(owner, pos, T, gp, starts, cursor, items);
-  nn_query_kernel<<<g128, 128, 0, stream>>>(mask2d, owner, pos, T, gp, starts, counts, items, col_a, col_a, nn_index_out);
+  (void)grid_lo_host; (void)grid_extent;
+  nn_flag_kernel<<<g256, 256, 0, stream>>>(owner, T, flags);
+  UTX_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, flags, offs, T, stream));
+  nn_compact_kernel<<<g256, 256, 0, stream>>>(owner, offs, pos, T, ids, pts);
+  int last_off = 0, last_flag = 0;   // number of visible texels: the tree builder needs it on the host (one sync per bake)
+  UTX_CUDA(cudaMemcpyAsync(&last_off, offs + (T - 1), 4, cudaMemcpyDeviceToHost, stream));
+  UTX_CUDA(cudaMemcpyAsync(&last_flag, flags + (T - 1), 4, cudaMemcpyDeviceToHost, stream));
+  UTX_CUDA(cudaStreamSynchronize(stream));
+  const int n_pts = last_off + last_flag;
+  void* nn_nodes = nullptr;
+  if (n_pts >= 2) {
+    nn_nodes = take(bvh_nodes_bytes(n_pts));
+    const size_t wsb = bvh_workspace_bytes(n_pts);
+    void* nn_ws = take(wsb);
+    UTX_TRY(point_bvh_build(pts, n_pts, nn_nodes, nn_ws, wsb, stream));
+  }
+  nn_query_kernel<<<g128, 128, 0, stream>>>(mask2d, owner, pos, T, nn_nodes, pts, ids, n_pts, col_a, col_a, nn_index_out);
   // seam blur (reads col_a, writes col_b)
   lens_blur_kernel<<<g256, 256, 0, stream>>>(col_a, seam, blur_k2d, blur_gamma, H2, W2, col_b);
   // pull-push

@@ -85,6 +85,7 @@ size_t bvh_nodes_bytes(int F);
 size_t bvh_workspace_bytes(int F);
 int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, void* workspace, size_t ws_bytes,
               cudaStream_t stream);
+int point_bvh_build(const float* pts, int n, void* nodes_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int bvh_export(const void* nodes, int F, int* info, float* aabb, cudaStream_t stream);
 int bvh_intersect(const void* nodes, const float* vert, const int* tri, const float* rays_o, const float* rays_d,
                   long long N, unsigned char* hit, int* tid, float* pos, float* uv, cudaStream_t stream);
