@@ -178,8 +178,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
           tmem_st32(tO + c * 32, ov);
         }
       }
-      // pass 2: exponentials, 32 columns at a time, P written back over S (16 packed columns per chunk)
-      float lsum = 0.f;
+      // pass 2: exponentials, 32 columns at a time, P written back over S (16 packed columns per chunk).  Packed fp32x2
+      // scale/sum; every 4th pair takes the FMA-pipe polynomial instead of MUFU.EX2.
+      uint64_t lsum2 = pack2(0.f, 0.f);
+      const uint64_t sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_next, -m_next);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t sv[32];
@@ -187,18 +189,33 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), scale_log2, -m_next));
-          float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), scale_log2, -m_next));
-          if (ragged) {
-            if (c * 32 + i >= kv_valid) p0 = 0.f;
-            if (c * 32 + i + 1 >= kv_valid) p1 = 0.f;
+        for (int i = 0; i < 16; ++i) {
+          const uint64_t x2 = fma2(pack2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sc2, nm2);
+          uint64_t p2;
+          if ((i & 3) == 3) {
+            p2 = exp2_poly2(x2);
+          } else {
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            p2 = pack2(ex2_approx(x0), ex2_approx(x1));
           }
-          lsum += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+          if (ragged) {
+            float p0, p1;
+            unpack2(p2, p0, p1);
+            if (c * 32 + 2 * i >= kv_valid) p0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= kv_valid) p1 = 0.f;
+            p2 = pack2(p0, p1);
+          }
+          lsum2 = add2(lsum2, p2);
+          float p0, p1;
+          unpack2(p2, p0, p1);
+          pk[i] = pack_bf16x2(p0, p1);
         }
         tmem_st16(tS + c * 16, pk);
       }
+      float ls0, ls1;
+      unpack2(lsum2, ls0, ls1);
+      const float lsum = ls0 + ls1;
       l = l * alpha + lsum;
       tmem_st_wait();
       tc_fence_before();

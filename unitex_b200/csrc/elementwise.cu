@@ -80,35 +80,51 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
 
 // ----------------------------------------------------------------------------- per-head RMSNorm + RoPE (in place)
 // attention_processor.py:56-59,73-76 (norm_q/norm_k/norm_added_*) and :85-87 (apply_rotary_emb).
-// One warp per (token, head, q|k): 128 elements = 4 per lane = two rotation pairs.
+// One warp per (token, q|k, pair of heads): 256 contiguous elements, one 16-byte load/store per lane; each half-warp
+// owns one head (RMS reduction over 16 lanes), each lane four rotation pairs.
 __global__ void __launch_bounds__(256) rmsnorm_rope_kernel(bf16* __restrict__ qkv, long ld, int S, int H, int rows0,
                                                            const bf16* __restrict__ wq0, const bf16* __restrict__ wk0,
                                                            const bf16* __restrict__ wq1, const bf16* __restrict__ wk1,
                                                            const float* __restrict__ cos_t,
                                                            const float* __restrict__ sin_t) {
   const long gw = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long total = static_cast<long>(S) * H * 2;
+  const int HP = H >> 1;
+  const long total = static_cast<long>(S) * HP * 2;
   if (gw >= total) return;
   const int lane = threadIdx.x & 31;
   const int which = static_cast<int>(gw % 2);          // 0 = q, 1 = k
-  const int head = static_cast<int>((gw / 2) % H);
-  const int tok = static_cast<int>(gw / (2L * H));
-  bf16* p = qkv + static_cast<long>(tok) * ld + static_cast<long>(which) * H * 128 + head * 128 + lane * 4;
-  const uint2 raw = *reinterpret_cast<const uint2*>(p);
-  float f[4] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y)};
-  const float ss = warp_sum(f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3]);
+  const int hp = static_cast<int>((gw / 2) % HP);
+  const int tok = static_cast<int>(gw / (2L * HP));
+  const int e0 = (lane & 15) * 8;                      // element offset inside the head
+  bf16* p = qkv + static_cast<long>(tok) * ld + static_cast<long>(which) * H * 128 + hp * 256 + lane * 8;
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  float f[8];
+  unpack8(raw, f);
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float rs = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
   const bf16* w = tok < rows0 ? (which ? wk0 : wq0) : (which ? wk1 : wq1);
-  const uint2 wr = *reinterpret_cast<const uint2*>(w + lane * 4);
-  const float wv[4] = {bf16lo(wr.x), bf16hi(wr.x), bf16lo(wr.y), bf16hi(wr.y)};
+  float wv[8];
+  unpack8(*reinterpret_cast<const uint4*>(w + e0), wv);
+  const float* ct = cos_t + static_cast<long>(tok) * 128 + e0;
+  const float* st = sin_t + static_cast<long>(tok) * 128 + e0;
+  const float4 c0 = *reinterpret_cast<const float4*>(ct), c1 = *reinterpret_cast<const float4*>(ct + 4);
+  const float4 s0 = *reinterpret_cast<const float4*>(st), s1 = *reinterpret_cast<const float4*>(st + 4);
+  const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+  const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) f[j] = f[j] * rs * wv[j];
-  const float4 c = *reinterpret_cast<const float4*>(cos_t + static_cast<long>(tok) * 128 + lane * 4);
-  const float4 s = *reinterpret_cast<const float4*>(sin_t + static_cast<long>(tok) * 128 + lane * 4);
+  for (int j = 0; j < 8; ++j) f[j] = f[j] * rs * wv[j];
+  float o[8];
   // out[2i] = x[2i] cos - x[2i+1] sin ; out[2i+1] = x[2i+1] cos + x[2i] sin
-  const float o0 = f[0] * c.x - f[1] * s.x, o1 = f[1] * c.y + f[0] * s.y;
-  const float o2 = f[2] * c.z - f[3] * s.z, o3 = f[3] * c.w + f[2] * s.w;
-  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    o[j] = f[j] * cv[j] - f[j + 1] * sv[j];
+    o[j + 1] = f[j + 1] * cv[j + 1] + f[j] * sv[j + 1];
+  }
+  *reinterpret_cast<uint4*>(p) = pack8(o);
 }
 
 // ----------------------------------------------------------------------------- GEMV  y = W f(x) + b
@@ -249,8 +265,8 @@ int ln_modulate(const bf16* x, long ldx, bf16* y, long ldy, int rows, int D, int
 int rmsnorm_rope(bf16* qkv, long ld_qkv, int S, int H, int rows0, const bf16* wq0, const bf16* wk0, const bf16* wq1,
                  const bf16* wk1, const float* cos_t, const float* sin_t, cudaStream_t stream) {
   if (S == 0) return 0;
-  UTX_CHECK(ld_qkv % 4 == 0, "rmsnorm_rope: ld must be a multiple of 4");
-  const long warps = static_cast<long>(S) * H * 2;
+  UTX_CHECK(ld_qkv % 8 == 0 && H % 2 == 0, "rmsnorm_rope: ld must be a multiple of 8 and H even");
+  const long warps = static_cast<long>(S) * H;
   const int wpb = 8;
   rmsnorm_rope_kernel<<<static_cast<unsigned>((warps + wpb - 1) / wpb), 32 * wpb, 0, stream>>>(
       qkv, ld_qkv, S, H, rows0, wq0, wk0, wq1, wk1, cos_t, sin_t);

@@ -209,6 +209,48 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32x2 arithmetic (sm_100): two lanes per 64-bit register pair, one issue slot
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for a pair on the FMA pipe (x <= 0 expected; clamped at -126): Cody-Waite split with the 1.5*2^23 rounding trick and
+// a cubic for 2^f on [-0.5, 0.5] (max rel. error ~1e-4, far below the bf16 rounding of P).  Takes MUFU pressure off the
+// softmax (the exponentials, not the MMAs, bound flash attention at head_dim 128 on this part).
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const uint64_t xc = pack2(x0, x1);
+  const uint64_t magic = pack2(12582912.0f, 12582912.0f), nmagic = pack2(-12582912.0f, -12582912.0f);
+  const uint64_t xr = add2(xc, magic);                         // low mantissa bits = round(x)
+  const uint64_t n = add2(xr, nmagic);
+  const uint64_t f = fma2(n, pack2(-1.0f, -1.0f), xc);         // x - round(x)
+  uint64_t p = fma2(f, pack2(0.077119f, 0.077119f), pack2(0.227564f, 0.227564f));
+  p = fma2(p, f, pack2(0.695146f, 0.695146f));
+  p = fma2(p, f, pack2(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  unpack2(p, p0, p1);
+  unpack2(xr, r0, r1);
+  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+  return pack2(p0, p1);
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
