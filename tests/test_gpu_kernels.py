@@ -26,13 +26,20 @@ def _check_bf16(out, ref, tol_ulp=1.0, frac=0.999, name=""):
     assert err.max().item() <= 4.0 * tol_ulp + 4.0, f"{name}: max err {err.max().item()} ulp"
 
 
+@pytest.fixture(params=["1", "2"])
+def gemm_impl(request, monkeypatch):
+    """1 = one CTA per 128x256 tile; 2 = cta_group::2 pairs on 256x256 tiles (used when N % 256 == 0)."""
+    monkeypatch.setenv("UTX_GEMM_IMPL", request.param)
+    return request.param
+
+
 GEMM_SHAPES = [(128, 256, 64), (256, 512, 256), (1000, 768, 1280), (512, 64, 256), (130, 200, 128),
                (384, 128, 3072), (2304, 3072, 3072), (640, 1792, 256)]
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 @pytest.mark.parametrize("epi", [0, 1, 2])
-def test_gemm(lib, M, N, K, epi):
+def test_gemm(lib, gemm_impl, M, N, K, epi):
     from unitex_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + epi)
     A = _bf(torch.randn(M, K, device="cuda", generator=g))
@@ -55,7 +62,7 @@ def test_gemm(lib, M, N, K, epi):
     _check_bf16(out, ref, tol_ulp=1.0 if epi != 1 else 1.5, name=f"gemm {M}x{N}x{K} epi{epi}")
 
 
-def test_gemm_strided_views_and_no_bias(lib):
+def test_gemm_strided_views_and_no_bias(lib, gemm_impl):
     from unitex_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(5)
     big = _bf(torch.randn(300, 1280, device="cuda", generator=g))
@@ -69,7 +76,7 @@ def test_gemm_strided_views_and_no_bias(lib):
     assert outbig[:, :256].abs().max() == 0 and outbig[:, 512:].abs().max() == 0
 
 
-def test_gemm_grouped_two_streams(lib):
+def test_gemm_grouped_two_streams(lib, gemm_impl):
     from unitex_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(11)
     K, N, M0, M1 = 256, 768, 128, 1152

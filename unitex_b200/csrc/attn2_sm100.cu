@@ -10,8 +10,9 @@
 //   warps 4-7     softmax warpgroup A (thread == query row), warps 8-11 warpgroup B
 // P = exp2(S*scale - m) is rounded to bf16 and written back over the first 64 columns of its own S tile
 // (tcgen05.st, two bf16 per 32-bit column), and the PV product reads it from there as the A operand (TS-mode MMA): no smem
-// round trip for P, half the smem operand traffic of the PV MMAs.  S is read from TMEM twice (row max, then exponentials
-// in 32-column chunks) to keep the softmax threads at ~120 registers.  O / l are rescaled lazily (running max grows by > 8).
+// round trip for P, half the smem operand traffic of the PV MMAs.  S is read from TMEM twice (row max with four loads in
+// flight, then exponentials with the next 32-column chunk prefetched) so the softmax threads stay under 168 registers.
+// O / l are rescaled lazily (running max grows by > 8).
 // `tcgen05.commit` of S_X(j+1) retires every earlier MMA of the issuing thread, so "S_X(j+1) ready" also means
 // "PV_X(j) done": no separate barrier guards the O rescale or the P overwrite.
 #include "common.h"
@@ -61,7 +62,6 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
   if (warp == 0 && lane == 0) {
     // ---------------------------------------------------------------- TMA producer
     mbar_arrive_expect_tx(&bar[Q_FULL], 2 * TILE_BYTES);
@@ -146,22 +146,26 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
       tc_fence_after();
       const int kv_valid = S - j * BKV;
       const bool ragged = kv_valid < BKV;
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld32(tS + c * 32, sv);
-        tmem_ld_wait();
-        if (!ragged) {
+      // row max: four tcgen05.ld in flight, one wait (the first version paid the TMEM round trip eight times per tile and
+      // was latency bound: tensor pipe 44 %, r01_attention2_kernel profile)
+      uint32_t sv[4][32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
-        } else {
+      for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, sv[c]);
+      tmem_ld_wait();
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (!ragged) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[c][i]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(sv[i]));
-        }
+            if (c * 32 + i < kv_valid) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[c][i]));
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = mx * scale_log2;
       const bool upd = m_new > m_used + kRescaleThreshold;
       const float m_next = upd ? m_new : m_used;
@@ -178,19 +182,21 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
           tmem_st32(tO + c * 32, ov);
         }
       }
-      // pass 2: exponentials, 32 columns at a time, P written back over S (16 packed columns per chunk).  Packed fp32x2
-      // scale/sum; every 4th pair takes the FMA-pipe polynomial instead of MUFU.EX2.
+      // exponentials: S re-read in 32-column chunks with the next chunk's load in flight behind the current chunk's math;
+      // packed fp32x2 scale/sum, every 4th pair on the FMA pipe; P written back over S (16 packed columns per chunk)
       uint64_t lsum2 = pack2(0.f, 0.f);
       const uint64_t sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_next, -m_next);
-#pragma unroll 1
+      uint32_t buf[2][32];
+      tmem_ld32(tS, buf[0]);
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld32(tS + c * 32, sv);
         tmem_ld_wait();
+        if (c + 1 < 4) tmem_ld32(tS + (c + 1) * 32, buf[(c + 1) & 1]);
+        const uint32_t* cur = buf[c & 1];
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const uint64_t x2 = fma2(pack2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sc2, nm2);
+          const uint64_t x2 = fma2(pack2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), sc2, nm2);
           uint64_t p2;
           if ((i & 3) == 3) {
             p2 = exp2_poly2(x2);

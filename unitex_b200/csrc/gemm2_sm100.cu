@@ -1,0 +1,259 @@
+// 2-CTA (cta_group::2) variant of the bf16 GEMM:  C = epilogue(A[M,K] @ W[N,K]^T + bias), 256 x 256 tiles per CTA PAIR.
+//
+// Why (profiles/r01_summary.md): the 1-CTA kernel streams 48 KB of operands per 512 MMA-cycles into smem AND reads them
+// back out for the MMA (96 + 96 B/clk against a 128 B/clk shared-memory port), which pins the tensor pipe at ~70 % active.
+// A pair of CTAs on one TPC shares the weight tile: each CTA stages its 128 A rows and HALF of the 256 W rows (32 KB per
+// stage), the leader issues tcgen05.mma.cta_group::2 (M = 256 across the two SMs) and each SM reads 64 B/clk.
+//   every CTA : warp 0 TMA producer (its A rows, its half of W; complete_tx on the LEADER's full barrier),
+//               warp 2 TMEM allocator (cta_group::2), warps 4-7 epilogue for its own 128 accumulator rows
+//   leader    : warp 1 MMA issuer; its commits are multicast to both CTAs' empty / tmem-full barriers;
+//               both CTAs' epilogue warps arrive remotely on the leader's tmem-empty barrier.
+// Epilogues, grouping of two problems and the band-swizzled tile walk are those of gemm_sm100.cu.
+#include <cstdlib>
+
+#include "common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace utx {
+namespace {
+
+constexpr int BM = 128;        // rows per CTA (256 per pair)
+constexpr int BN = 256;        // tile columns; each CTA stages BN/2 rows of W
+constexpr int BK = 64;
+constexpr int STAGES = 6;
+constexpr int GROUP_M = 8;     // bands of 8 pair-row-blocks (2048 rows)
+constexpr int kThreads = 256;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = (BN / 2) * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+constexpr int SMEM_TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+
+struct DevProblem {
+  int M, tiles_m;
+  bf16* C; long ldc;
+  const bf16* bias; const float* gate; const bf16* res; long ldres;
+  int split_col; bf16* C2; long ldc2;
+};
+struct DevParams {
+  int N, K, tiles_n, nprob, epi, gelu_col_start;
+  float out_scale;
+  int total_tiles;
+  DevProblem prob[2];
+};
+struct TileCoord { int pi, m_blk, n_blk; };
+
+__device__ __forceinline__ TileCoord decode_tile(const DevParams& p, int t) {
+  TileCoord tc;
+  tc.pi = 0;
+  const int t0 = p.prob[0].tiles_m * p.tiles_n;
+  if (p.nprob > 1 && t >= t0) { tc.pi = 1; t -= t0; }
+  const int tiles_m = p.prob[tc.pi].tiles_m;
+  const int band_sz = GROUP_M * p.tiles_n;
+  const int band = t / band_sz;
+  const int r = t - band * band_sz;
+  const int rows = min(GROUP_M, tiles_m - band * GROUP_M);
+  tc.m_blk = band * GROUP_M + r % rows;
+  tc.n_blk = r / rows;
+  return tc;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                     const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const DevParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nk = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0); prefetch_tmap(&tmB0);
+    if (p.nprob > 1) { prefetch_tmap(&tmA1); prefetch_tmap(&tmB1); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }   // 4 epilogue warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, 2 * BN);
+  tc_fence_before();
+  cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = pair; t < p.total_tiles; t += npairs) {
+      const TileCoord tc = decode_tile(p, t);
+      const CUtensorMap* ta = tc.pi ? &tmA1 : &tmA0;
+      const CUtensorMap* tb = tc.pi ? &tmB1 : &tmB0;
+      const int row_a = tc.m_blk * (2 * BM) + static_cast<int>(rank) * BM;
+      const int row_b = tc.n_blk * BN + static_cast<int>(rank) * (BN / 2);
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * STAGE_BYTES);   // bytes of BOTH CTAs land on the leader's barrier
+        uint8_t* st = smem + s * STAGE_BYTES;
+        tma_load_2d_2sm(st, ta, &full[s], kb * BK, row_a);
+        tma_load_2d_2sm(st + A_BYTES, tb, &full[s], kb * BK, row_b);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
+    constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+    int s = 0, as = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int t = pair; t < p.total_tiles; t += npairs) {
+      mbar_wait(&tempty[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_ss_2sm(d_tmem, make_sdesc(a_addr + k * 32, 16, 1024), make_sdesc(b_addr + k * 32, 16, 1024), idesc, (kb | k) != 0);
+        umma_commit_2sm(&empty[s]);
+        if (kb == nk - 1) umma_commit_2sm(&tfull[as]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (both CTAs, own 128 accumulator rows)
+    const int ew = warp - 4;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = pair; t < p.total_tiles; t += npairs) {
+      const TileCoord tc = decode_tile(p, t);
+      const DevProblem& pr = p.prob[tc.pi];
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const int row = tc.m_blk * (2 * BM) + static_cast<int>(rank) * BM + ew * 32 + lane;
+      const bool row_ok = row < pr.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+      bf16* crow;
+      int col_shift = 0;
+      if (pr.split_col > 0 && tc.n_blk * BN >= pr.split_col) {
+        crow = pr.C2 + static_cast<long>(row) * pr.ldc2;
+        col_shift = pr.split_col;
+      } else {
+        crow = pr.C + static_cast<long>(row) * pr.ldc;
+      }
+      const bf16* rrow = pr.res ? pr.res + static_cast<long>(row) * pr.ldres : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = tc.n_blk * BN + c * 32;
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < p.N) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+              if (pr.bias) {
+                const uint4 b = *reinterpret_cast<const uint4*>(pr.bias + col);
+                f[0] += bf16lo(b.x); f[1] += bf16hi(b.x); f[2] += bf16lo(b.y); f[3] += bf16hi(b.y);
+                f[4] += bf16lo(b.z); f[5] += bf16hi(b.z); f[6] += bf16lo(b.w); f[7] += bf16hi(b.w);
+              }
+              if (p.epi == EPI_BIAS_GELU) {
+                if (col >= p.gelu_col_start) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
+                }
+              } else if (p.epi == EPI_GATE_RES) {
+                const float4 g0 = *reinterpret_cast<const float4*>(pr.gate + col);
+                const float4 g1 = *reinterpret_cast<const float4*>(pr.gate + col + 4);
+                const uint4 r = *reinterpret_cast<const uint4*>(rrow + col);
+                f[0] = fmaf(g0.x, f[0], bf16lo(r.x)); f[1] = fmaf(g0.y, f[1], bf16hi(r.x));
+                f[2] = fmaf(g0.z, f[2], bf16lo(r.y)); f[3] = fmaf(g0.w, f[3], bf16hi(r.y));
+                f[4] = fmaf(g1.x, f[4], bf16lo(r.z)); f[5] = fmaf(g1.y, f[5], bf16hi(r.z));
+                f[6] = fmaf(g1.z, f[6], bf16lo(r.w)); f[7] = fmaf(g1.w, f[7], bf16hi(r.w));
+              }
+              if (p.epi == EPI_BIAS_F32) {
+                float* crow32 = reinterpret_cast<float*>(pr.C) + static_cast<long>(row) * pr.ldc + col;
+                *reinterpret_cast<float4*>(crow32) = make_float4(f[0] * p.out_scale, f[1] * p.out_scale, f[2] * p.out_scale, f[3] * p.out_scale);
+                *reinterpret_cast<float4*>(crow32 + 4) = make_float4(f[4] * p.out_scale, f[5] * p.out_scale, f[6] * p.out_scale, f[7] * p.out_scale);
+                continue;
+              }
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]);
+              o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]);
+              o.w = pack_bf16x2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(crow + (col - col_shift)) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty[as], 0);   // the leader's MMA thread waits for both CTAs' epilogues
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // neither CTA may exit (or free TMEM) while its peer can still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BN);
+  }
+}
+
+}  // namespace
+
+// returns -1 when the shape does not fit this kernel (caller falls back to the 1-CTA kernel)
+int gemm2_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
+  if (a.N % BN != 0) return -1;
+  DevParams p{};
+  p.N = a.N; p.K = a.K; p.tiles_n = a.N / BN; p.nprob = a.nprob; p.epi = a.epi; p.gelu_col_start = a.gelu_col_start;
+  p.out_scale = a.out_scale;
+  CUtensorMap tm[4];
+  int total = 0;
+  for (int i = 0; i < a.nprob; ++i) {
+    const GemmProblem& g = a.prob[i];
+    DevProblem& d = p.prob[i];
+    d.M = g.M; d.tiles_m = (g.M + 2 * BM - 1) / (2 * BM);
+    d.C = g.C; d.ldc = g.ldc; d.bias = g.bias; d.gate = g.gate; d.res = g.res; d.ldres = g.ldres;
+    d.split_col = g.split_col; d.C2 = g.C2; d.ldc2 = g.ldc2;
+    total += d.tiles_m * p.tiles_n;
+    UTX_TRY(make_tmap_2d_bf16(&tm[2 * i], g.A, g.M, a.K, g.lda, BM, BK));
+    UTX_TRY(make_tmap_2d_bf16(&tm[2 * i + 1], g.W, a.N, a.K, g.ldw, BN / 2, BK));
+  }
+  if (a.nprob == 1) { tm[2] = tm[0]; tm[3] = tm[1]; }
+  p.total_tiles = total;
+  if (total == 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UTX_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    attr_set = true;
+  }
+  const int max_pairs = num_sms() / 2;
+  const int pairs = total < max_pairs ? total : max_pairs;
+  gemm2_bf16_tn_kernel<<<2 * pairs, kThreads, SMEM_TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace utx

@@ -13,6 +13,8 @@
 //
 // Every Linear of the FLUX DiT (reference call site flux_piplines/texturing/pipeline.py:646) runs
 // through this kernel; LoRA adapters are merged into W beforehand (a5).
+#include <cstdlib>
+
 #include "common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -305,6 +307,8 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
+int gemm2_bf16_tn(const GemmArgs& a, cudaStream_t stream);   // 2-CTA pairs, gemm2_sm100.cu; -1 = shape not supported
+
 int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
   UTX_CHECK(a.nprob == 1 || a.nprob == 2, "gemm: nprob must be 1 or 2");
   UTX_CHECK(a.K % BK == 0 && a.K > 0, "gemm: K must be a positive multiple of 64");
@@ -316,6 +320,12 @@ int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
     UTX_CHECK(a.epi != EPI_BIAS_F32 || g.split_col == 0, "gemm: fp32 output cannot be combined with a column split");
     UTX_CHECK(a.epi != EPI_GATE_RES || (g.gate && g.res), "gemm: EPI_GATE_RES needs gate and res");
     UTX_CHECK(g.split_col == 0 || (g.split_col % 256 == 0 && g.C2 && g.ldc2 % 8 == 0), "gemm: bad column split");
+  }
+  // UTX_GEMM_IMPL=2: cta_group::2 kernel (256x256 tiles per CTA pair) for N % 256 == 0; anything else: this file.
+  const char* impl = getenv("UTX_GEMM_IMPL");
+  if (impl != nullptr && impl[0] == '2' && a.N % 256 == 0) {
+    const int r = gemm2_bf16_tn(a, stream);
+    if (r >= 0) return r;
   }
   if (a.N % 256 == 0) return launch<256, 4>(a, stream);
   if (a.N % 128 == 0) return launch<128, 6>(a, stream);
