@@ -100,3 +100,23 @@ def test_raytracing_plugin_surface(lib):
     rt.update_raw(torch.from_numpy(v * 2), torch.from_numpy(f.astype(np.int64)))
     hit2, _, _, loc2, _ = rt.intersects_closest(o, d)
     assert hit2.tolist() == [[True, False]] and abs(abs(loc2[0, 0, 2].item()) - 1.2) < 0.05
+
+
+def test_uv_bake_matches_committed_golden(lib):
+    """CUDA path vs tests/golden/bake_two_spheres.npz: triangle ids, visibility, ownership, 1-NN indices exact."""
+    import os
+    from unitex_b200 import bake as ub
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "bake_two_spheres.npz"))
+    v, f, uv, fuv = two_spheres(10, 20)
+    c2ws, intr = _views()
+    r = ub.NVDiffRendererInverse(pbr_mesh=ub.BakeMesh(v, f, uv, fuv))
+    _, vis, m2, col = r.infer(r.pbr_mesh, c2ws, intr, torch.from_numpy(z["image"]), H=48, W=48, H2D=64, W2D=64, perspective=False,
+                              ray_normal_angle_threhold=100.0, method="reproject", filt_gradient_points=False)
+    torch.cuda.synchronize()
+    tid = r.last_rast2d[0, ..., 3].cpu().numpy().astype(np.int32) - 1
+    assert np.array_equal(tid[None], z["tid_2d"])
+    assert np.array_equal(np.packbits(vis.cpu().numpy()), z["mask_vis"])
+    assert np.array_equal(r.last_nn_index.cpu().numpy().reshape(-1), z["nn_index"])
+    assert np.abs(col.cpu().numpy() - z["color_2d"].astype(np.float32)).max() < 2e-3
+    info, _ = r.pbr_mesh.optix.export()
+    assert np.array_equal(info.cpu().numpy(), z["lbvh_info"])

@@ -74,3 +74,23 @@ def test_product_path_does_not_import_oracle():
     code = ("import sys; import unitex_b200.flux, unitex_b200.ops; "
             "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'")
     subprocess.run([sys.executable, "-c", code], check=True)
+
+
+def test_denoise_matches_committed_golden(lib):
+    """CUDA path vs tests/golden/dit_tiny_denoise.npz (oracle-generated fixture, make_golden.py)."""
+    import os
+    import numpy as np
+    from oracle import flux_dit as fd
+    from oracle import flux_sampler as fs
+    from unitex_b200.flux import FluxConfig, FluxTransformer
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "dit_tiny_denoise.npz"))
+    ocfg = fd.FluxConfig.tiny(1, 1)
+    P = {k: v.to(torch.bfloat16).float() for k, v in fd.init_params(ocfg, 0, norm_weight_std=0.1).items()}
+    eng = FluxTransformer(FluxConfig(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=256,
+                                     pooled_projection_dim=64)).load_state_dict(P)
+    eng.prepare(torch.cat([torch.zeros(128, 3), torch.from_numpy(z["ids"])]), None, None, s_txt=128)
+    lat = torch.cat([torch.from_numpy(z["noise"]), torch.from_numpy(z["cond"])], 1)[0].to(torch.bfloat16).cuda().contiguous()
+    eng.denoise_(lat, 64, z["sigmas"], 3.5)
+    torch.cuda.synchronize()
+    db = fs.psnr(lat[:64].float().cpu(), torch.from_numpy(z["out"])[0])
+    assert db >= PSNR_MIN_DB, db
