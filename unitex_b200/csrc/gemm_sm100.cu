@@ -321,9 +321,10 @@ int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
     UTX_CHECK(a.epi != EPI_GATE_RES || (g.gate && g.res), "gemm: EPI_GATE_RES needs gate and res");
     UTX_CHECK(g.split_col == 0 || (g.split_col % 256 == 0 && g.C2 && g.ldc2 % 8 == 0), "gemm: bad column split");
   }
-  // UTX_GEMM_IMPL=2: cta_group::2 kernel (256x256 tiles per CTA pair) for N % 256 == 0; anything else: this file.
+  // Default: cta_group::2 kernel (256x256 tiles per CTA pair, gemm2_sm100.cu) whenever N % 256 == 0 -- 2-3 % faster at the
+  // DiT shapes (profiles/r01_microbench_gemm.json).  UTX_GEMM_IMPL=1 forces the 1-CTA kernel of this file.
   const char* impl = getenv("UTX_GEMM_IMPL");
-  if (impl != nullptr && impl[0] == '2' && a.N % 256 == 0) {
+  if ((impl == nullptr || impl[0] != '1') && a.N % 256 == 0) {
     const int r = gemm2_bf16_tn(a, stream);
     if (r >= 0) return r;
   }
