@@ -267,6 +267,7 @@ def run_ours(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_bake:
         out["uv_bake"] = bench_uv_bake(dev)
+        out["vae_decode"] = bench_vae_decode(dev)
     if world == 1 and not args.no_cpu_baseline:
         dt, cores = cpu_block_seconds(1)
         out["cpu_baseline"] = {"value": 1.0 / (57.0 * dt), "unit": UNIT, "cores": cores, "kind": "port",
@@ -274,6 +275,29 @@ def run_ours(args, rank, world, local_rank):
                                          "rows for LN/MLP/proj_out, quarter of the heads for attention over all keys), "
                                          "eager oracle port of the diffusers CPU path, bf16 weights; step = 57 x 4 x sample"}
     print(json.dumps(out), flush=True)
+
+
+def bench_vae_decode(dev):
+    """BASELINE config 3 side measurement: FLUX VAE decode of the 1024^2 canvas ([1,16,128,128] -> [1,3,1024,1024]),
+    random-init weights, CUDA events.  Algorithmic FLOPs 10.47 T."""
+    import torch
+    from unitex_b200.vae import AutoencoderKLB200
+    vae = AutoencoderKLB200.from_random(seed=1, device=dev)
+    z = torch.randn(1, 16, 128, 128, device=dev, generator=torch.Generator(device=dev).manual_seed(3)).to(torch.bfloat16)
+    for _ in range(2):
+        img = vae.decode(z)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        img = vae.decode(z)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    del vae
+    torch.cuda.empty_cache()
+    return {"metric": "VAE decode ms @1024^2", "ms": ms, "tflops": 10.47e12 / (ms * 1e-3) / 1e12, "finite": bool(torch.isfinite(img.float()).all()),
+            "note": "im2col + tcgen05 GEMM convolutions, NHWC bf16; implicit-GEMM fusion is the next step (DESIGN 6)"}
 
 
 def bench_uv_bake(dev):
