@@ -253,10 +253,12 @@ def run_ours(args, rank, world, local_rank):
                    "tokens": S_TOT, "per_gpu_batch": 1, "parallelism": f"dp{world} (one independent grid per rank)",
                    "l2": "inputs larger than L2: 23.8 GB of weights stream through every step",
                    "timing": "CUDA events on the launching stream, max over ranks"},
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05)", "achieved": gemm_tf, "peak": peak_sus,
-                     "unit": "TFLOP/s", "frac": gemm_tf / peak_sus, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "tensor", "kernel": "gemm2_bf16_tn_kernel (tcgen05 cta_group::2; 1-CTA gemm_bf16_tn_kernel for narrow N)",
+                     "achieved": gemm_tf, "peak": peak_sus, "unit": "TFLOP/s", "frac": gemm_tf / peak_sus,
+                     "traffic": 1.024e9, "traffic_note": "dram read+write of ONE qkv-shaped launch (M 9728, N 9216, K 3072) from profiles/r01_gemm_bf16_tn.ncu-rep; algorithmic 296 MB",
+                     "peak_source": peak_src,
                      "launches_per_step": n_gemm, "flops_per_step": f_gemm, "ms_per_step": cat_ms["gemm"] / args.steps,
-                     "attention": {"kernel": "attention_kernel (tcgen05)", "achieved": attn_tf, "frac": attn_tf / peak_sus,
+                     "attention": {"kernel": "attention2_kernel (tcgen05, P in TMEM)", "achieved": attn_tf, "frac": attn_tf / peak_sus,
                                    "flops_per_step": f_attn, "ms_per_step": cat_ms["attn"] / args.steps},
                      "elementwise_ms_per_step": cat_ms["elem"] / args.steps,
                      "whole_step": {"achieved": total / (step_ms * 1e-3) / 1e12, "frac": total / (step_ms * 1e-3) / 1e12 / peak_sus}},
