@@ -112,6 +112,10 @@ int utx_lora_merge(void* W, long ldw, const float* A, const float* B, int out_fe
 /* C[M,N] = epi(A[M,K] @ W[N,K]^T + bias).  epi: 0 bias, 1 bias+GELU(tanh), 2 res + gate*(.)  */
 int utx_gemm_bf16(const void* A, long lda, const void* W, long ldw, const void* bias, void* C, long ldc, int M, int N,
                   int K, int epi, const float* gate, const void* res, long ldres, void* stream);
+/* QKV projection with the joint attention's per-head RMSNorm(eps 1e-6, weight) + RoPE fused into the epilogue for the
+ * q and k thirds (attention_processor.py:43-59,85-87): C[M, 3*Hd*128]; wq/wk [128] bf16; cos/sin [>= row_offset+M, 128] fp32 */
+int utx_gemm_bf16_qkv(const void* A, long lda, const void* W, const void* bias, void* C, long ldc, int M, int heads, int K,
+                      const void* wq, const void* wk, const float* cos_t, const float* sin_t, int row_offset, void* stream);
 /* two problems sharing N, K and the epilogue in one launch (txt + img streams) */
 int utx_gemm_bf16_grouped2(const void* A0, long lda0, const void* W0, const void* bias0, void* C0, long ldc0, int M0,
                            const void* A1, long lda1, const void* W1, const void* bias1, void* C1, long ldc1, int M1,
@@ -152,6 +156,11 @@ int utx_bvh_export(const void* nodes, int F, int32_t* info, float* aabb, void* s
 /* intersects_closest (rt_aprmis/__init__.py:36-86): hit u8 [N], tri_idx i32 [N] (-1 = miss), loc [N,3], uv [N,2] */
 int utx_bvh_intersect(const void* nodes, const float* vert, const int32_t* tri, const float* rays_o, const float* rays_d,
                       long long N, unsigned char* hit, int32_t* tri_idx, float* loc, float* uv, void* stream);
+/* knn(src, dst, k=1) (pcd/knn/__init__.py:104-114, default backend torch_kdtree): exact nearest source point of every
+ * dst point, lowest index on ties.  index int64 [M], score fp32 [M] = Euclidean distance.  nodes: utx_bvh_nodes_bytes(n_src),
+ * workspace: utx_bvh_workspace_bytes(n_src). */
+int utx_knn1(const float* src, int n_src, const float* dst, long long M, long long* index, float* score, void* nodes,
+             void* workspace, size_t workspace_bytes, void* stream);
 /* uv_to_pcd + bake_mv_to_uv_reproject_blur (renderer_inverse.py:243-365,574-633) fused.  rast2d: UV raster [H2,W2,4];
  * view_mats/view_dirs/priority/grid_lo: HOST arrays ([n,16] P@W2C row-major, [n,3] = -c2w[:3,2], [n], [3]);
  * images_rgba: device [n,H,W,4] = view colour + visible alpha; blur_k2d: device [49].  Outputs: mask2d u8 [H2*W2],

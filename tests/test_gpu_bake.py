@@ -120,3 +120,19 @@ def test_uv_bake_matches_committed_golden(lib):
     assert np.abs(col.cpu().numpy() - z["color_2d"].astype(np.float32)).max() < 2e-3
     info, _ = r.pbr_mesh.optix.export()
     assert np.array_equal(info.cpu().numpy(), z["lbvh_info"])
+
+
+def test_knn_plugin_exact(lib):
+    """knn(src, dst, k=1) drop-in (pcd/knn/__init__.py:104-114) vs exact brute force with the same tie rule."""
+    from oracle import bake as ob
+    from unitex_b200.bake import knn
+    g = torch.Generator().manual_seed(0)
+    src = torch.rand(20000, 3, generator=g)
+    src[100] = src[7]                                    # an exact duplicate: lowest index must win
+    dst = torch.cat([torch.rand(3000, 3, generator=g), src[100:101]])
+    score, index = knn(src, dst, k=1)
+    torch.cuda.synchronize()
+    ref = ob.nearest_index(src, dst)
+    assert index.shape == (3001, 1) and index.dtype == torch.int64
+    assert torch.equal(index[:, 0].cpu(), ref) and index[-1, 0] == 7
+    assert torch.allclose(score[:, 0].cpu(), (src[ref] - dst).norm(dim=-1), atol=1e-6)

@@ -173,6 +173,33 @@ def test_rope_table_and_rmsnorm_rope(lib):
     assert torch.equal(got.view(S, 3, H, 128)[:, 2], qkv.view(S, 3, H, 128)[:, 2])       # v untouched
 
 
+def test_gemm_qkv_fused_norm_rope(lib, gemm_impl):
+    """QKV GEMM with RMSNorm + RoPE in the epilogue == fp32 reference of Linear -> RMSNorm -> RoPE (v untouched)."""
+    from oracle import flux_dit as fd
+    from oracle import flux_sampler as fs
+    from unitex_b200 import ops
+    H, K, off = 4, 512, 64
+    cfg = fd.FluxConfig.tiny(heads=H)
+    ids = torch.cat([torch.zeros(off, 3), fs.build_ids(32, 48, (32, 48), None)]).cuda()
+    M = ids.shape[0] - off
+    cos, sin = ops.rope_table(ids)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    A = _bf(torch.randn(M, K, device="cuda", generator=g))
+    W = _bf(torch.randn(3 * H * 128, K, device="cuda", generator=g) / math.sqrt(K))
+    b = _bf(torch.randn(3 * H * 128, device="cuda", generator=g) * 0.1)
+    wq, wk = (_bf(1 + 0.2 * torch.randn(128, device="cuda", generator=g)) for _ in range(2))
+    out = ops.gemm_qkv(A, W, b, H, wq, wk, cos, sin, row_offset=off)
+    torch.cuda.synchronize()
+    lin = (A.float() @ W.float().T + b.float()).view(M, 3, H, 128)
+    rc, rs = cos[off:], sin[off:]
+    ref_q = fd.apply_rope(fd.rms_norm(lin[:, 0].transpose(0, 1)[None], wq.float()), rc, rs)[0].transpose(0, 1)
+    ref_k = fd.apply_rope(fd.rms_norm(lin[:, 1].transpose(0, 1)[None], wk.float()), rc, rs)[0].transpose(0, 1)
+    o = out.view(M, 3, H, 128)
+    _check_bf16(o[:, 0], ref_q, name="q")
+    _check_bf16(o[:, 1], ref_k, name="k")
+    _check_bf16(o[:, 2], lin[:, 2], name="v")
+
+
 def test_gemv_euler_lora(lib):
     from unitex_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(9)

@@ -54,6 +54,7 @@ _SIGS = {
     "utx_flux_profile_read": (i32, [vp, C.POINTER(C.c_long), fp, i32]),
     "utx_lora_merge": (i32, [vp, lng, vp, vp, i32, i32, i32, f32, vp]),
     "utx_gemm_bf16": (i32, [vp, lng, vp, lng, vp, vp, lng, i32, i32, i32, i32, vp, vp, lng, vp]),
+    "utx_gemm_bf16_qkv": (i32, [vp, lng, vp, vp, vp, lng, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     "utx_gemm_bf16_grouped2": (i32, [vp, lng, vp, vp, vp, lng, i32, vp, lng, vp, vp, vp, lng, i32, i32, i32, i32, vp, vp, vp]),
     "utx_attention_bf16": (i32, [vp, lng, vp, lng, i32, i32, vp]),
     "utx_ln_modulate": (i32, [vp, lng, vp, lng, i32, i32, i32, vp, vp, vp, vp, vp]),
@@ -75,6 +76,7 @@ _SIGS = {
     "utx_gemm_bf16_f32out": (i32, [vp, lng, vp, lng, vp, vp, lng, i32, i32, i32, f32, vp]),
     "utx_softmax_rows": (i32, [vp, lng, vp, lng, i32, i32, vp]),
     "utx_transpose_bf16": (i32, [vp, lng, vp, lng, i32, i32, vp]),
+    "utx_knn1": (i32, [vp, i32, vp, C.c_longlong, vp, vp, vp, vp, C.c_size_t, vp]),
     "utx_uv_bake_workspace_bytes": (C.c_size_t, [i32, i32]),
     "utx_uv_bake": (i32, [vp, i32, vp, i32, vp, vp, i32, i32, i32, fp, fp, C.POINTER(C.c_int32), vp, i32, i32, f32, vp, f32,
                           fp, f32, vp, vp, vp, vp, vp, C.c_size_t, vp]),

@@ -158,6 +158,24 @@ class RayTracing:
         return hit.bool().reshape(shape), None, tid.to(torch.int64).reshape(shape), loc.reshape(*shape, 3), uv.reshape(*shape, 2)
 
 
+def knn(src: torch.Tensor, dst: torch.Tensor, k: int = 1, backend: Optional[str] = None, batch_size: Optional[int] = None,
+        device="cuda"):
+    """Drop-in for texturetools.pcd.knn (pcd/knn/__init__.py:104-114) for the k=1 case the bake uses
+    (renderer_inverse.py:611): -> (score [M,1] fp32 distance, index [M,1] int64), exact, lowest index on ties."""
+    if k != 1:
+        raise NotImplementedError("only k=1 is on the UniTEX hot path")
+    L = _lib.load()
+    dev = torch.device(device)
+    s, d = _f32(src, dev), _f32(dst, dev)
+    n, M = s.shape[0], d.shape[0]
+    index = torch.empty(M, device=dev, dtype=torch.int64)
+    score = torch.empty(M, device=dev, dtype=torch.float32)
+    nodes = torch.empty(max(L.utx_bvh_nodes_bytes(max(n, 2)), 64), device=dev, dtype=torch.uint8)
+    ws = torch.empty(L.utx_bvh_workspace_bytes(max(n, 2)), device=dev, dtype=torch.uint8)
+    _lib.check(L.utx_knn1(_p(s), n, _p(d), M, _p(index), _p(score), _p(nodes), _p(ws), ws.numel(), _stream()), "utx_knn1")
+    return score[:, None], index[:, None]
+
+
 # ------------------------------------------------------------------------------------------------ lens-blur kernel (b9)
 _LENS5 = [[4.892608, 1.685979, -22.356787, 85.91246], [4.71187, 4.998496, 35.918936, -28.875618],
           [4.052795, 8.244168, -13.212253, -1.578428], [2.929212, 11.900859, 0.507991, 1.816328],

@@ -245,8 +245,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
     tc_fence_after();
     const int row = q0 + x * BQ + r;
     if (is_split) {
-      // un-normalised O (fp32), running max and row sum of this key range -> workspace [tail unit][split][256 rows][130]
-      float* prow = partial + ((static_cast<long>(unit - n_full) * n_splits + split) * (2 * BQ) + x * BQ + r) * 130;
+      // un-normalised O (fp32), running max and row sum of this key range -> workspace [tail unit][split][256 rows][132]
+      float* prow = partial + ((static_cast<long>(unit - n_full) * n_splits + split) * (2 * BQ) + x * BQ + r) * 132;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t ov[32];
@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(128) attn2_merge_kernel(const float* __restric
   const int unit = n_full + tail_unit;
   const int row = (unit % n_qblocks) * (2 * BQ) + rr, head = unit / n_qblocks;
   if (row >= S) return;
-  const float* base = partial + (static_cast<long>(tail_unit) * n_splits * (2 * BQ) + rr) * 130;
-  const long sstride = static_cast<long>(2 * BQ) * 130;
+  const float* base = partial + (static_cast<long>(tail_unit) * n_splits * (2 * BQ) + rr) * 132;
+  const long sstride = static_cast<long>(2 * BQ) * 132;
   float mstar = -INFINITY;
   for (int s = 0; s < n_splits; ++s) mstar = fmaxf(mstar, base[s * sstride + 128]);
   float num = 0.f, den = 0.f;
@@ -318,7 +318,7 @@ size_t attention2_workspace_bytes(int S, int H) {
   const int rem = units % sms;
   const int n_splits = rem > 0 ? sms / rem : 1;
   if (rem == 0 || n_splits < 2) return 0;
-  return static_cast<size_t>(rem) * n_splits * (2 * BQ) * 130 * sizeof(float);
+  return static_cast<size_t>(rem) * n_splits * (2 * BQ) * 132 * sizeof(float);
 }
 
 int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream) {
@@ -344,7 +344,7 @@ int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S,
   if (rem == 0 || n_splits < 2) {
     n_full = units; rem = 0; n_splits = 1;
   } else {
-    const size_t need = static_cast<size_t>(rem) * n_splits * (2 * BQ) * 130 * sizeof(float);
+    const size_t need = static_cast<size_t>(rem) * n_splits * (2 * BQ) * 132 * sizeof(float);
     if (need > partial_bytes) {
       if (partial) UTX_CUDA(cudaFree(partial));
       UTX_CUDA(cudaMalloc(&partial, need));

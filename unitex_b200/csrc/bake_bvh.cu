@@ -302,6 +302,37 @@ int point_bvh_build(const float* pts, int n, void* nodes_out, void* workspace, s
   return build_tree(nullptr, nullptr, pts, n, nodes_out, workspace, ws_bytes, stream);
 }
 
+namespace {
+__global__ void __launch_bounds__(128) knn1_kernel(const void* __restrict__ nodes, const float* __restrict__ src, int n_src,
+                                                   const float* __restrict__ dst, long long M, long long* __restrict__ index,
+                                                   float* __restrict__ score) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float q[3] = {dst[i * 3], dst[i * 3 + 1], dst[i * 3 + 2]};
+  float d2 = 0.f;
+  int best = 0;
+  if (n_src == 1) {
+    const float dx = src[0] - q[0], dy = src[1] - q[1], dz = src[2] - q[2];
+    d2 = (dx * dx + dy * dy) + dz * dz;
+  } else {
+    best = nn_trace(nodes, src, nullptr, q, &d2);
+  }
+  index[i] = best;
+  score[i] = sqrtf(d2);
+}
+}  // namespace
+
+// knn(src, dst, k=1) of pcd/knn/__init__.py:104-114 (exact, lowest index on ties): index int64 [M], score = distance [M]
+int knn1(const float* src, int n_src, const float* dst, long long M, long long* index, float* score, void* nodes, void* workspace,
+         size_t ws_bytes, cudaStream_t stream) {
+  UTX_CHECK(n_src >= 1, "knn1: empty source set");
+  if (n_src >= 2) UTX_TRY(point_bvh_build(src, n_src, nodes, workspace, ws_bytes, stream));
+  if (M == 0) return 0;
+  knn1_kernel<<<static_cast<unsigned>((M + 127) / 128), 128, 0, stream>>>(nodes, src, n_src, dst, M, index, score);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int bvh_export(const void* nodes, int F, int* info, float* aabb, cudaStream_t stream) {
   const int n = 2 * F - 1;
   export_kernel<<<(n + 255) / 256, 256, 0, stream>>>(static_cast<const Node*>(nodes), n, info, aabb);

@@ -100,7 +100,7 @@ __device__ __forceinline__ int nn_trace(const void* __restrict__ nodes_v, const 
       const float dx = pts[static_cast<size_t>(pidx) * 3] - q[0], dy = pts[static_cast<size_t>(pidx) * 3 + 1] - q[1],
                   dz = pts[static_cast<size_t>(pidx) * 3 + 2] - q[2];
       const float d2 = (dx * dx + dy * dy) + dz * dz;
-      const int id = ids[pidx];
+      const int id = ids ? ids[pidx] : pidx;
       if (d2 < best || (d2 == best && id < best_id)) { best = d2; best_id = id; }
     } else if (count + 2 <= 64) {
       // visit the nearer child first: push the farther one below it

@@ -20,6 +20,18 @@ int utx_gemm_bf16(const void* A, long lda, const void* W, long ldw, const void* 
   return gemm_bf16_tn(a, static_cast<cudaStream_t>(stream));
 }
 
+int utx_gemm_bf16_qkv(const void* A, long lda, const void* W, const void* bias, void* C, long ldc, int M, int heads, int K,
+                      const void* wq, const void* wk, const float* cos_t, const float* sin_t, int row_offset, void* stream) {
+  UTX_CHECK(A && W && C && wq && wk && cos_t && sin_t, "utx_gemm_bf16_qkv: null pointer");
+  GemmArgs a{};
+  a.N = 3 * heads * 128; a.K = K; a.epi = EPI_BIAS; a.nprob = 1;
+  a.qk_cols = 2 * heads * 128; a.cos_t = cos_t; a.sin_t = sin_t;
+  a.prob[0] = GemmProblem{static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), K, M, static_cast<bf16*>(C), ldc,
+                          static_cast<const bf16*>(bias), nullptr, nullptr, 0, 0, nullptr, 0, static_cast<const bf16*>(wq),
+                          static_cast<const bf16*>(wk), row_offset};
+  return gemm_bf16_tn(a, static_cast<cudaStream_t>(stream));
+}
+
 int utx_gemm_bf16_grouped2(const void* A0, long lda0, const void* W0, const void* bias0, void* C0, long ldc0, int M0,
                            const void* A1, long lda1, const void* W1, const void* bias1, void* C1, long ldc1, int M1,
                            int N, int K, int epi, const float* gate0, const float* gate1, void* stream) {
@@ -112,6 +124,11 @@ int utx_bvh_intersect(const void* nodes, const float* vert, const int32_t* tri, 
                       long long N, unsigned char* hit, int32_t* tri_idx, float* loc, float* uv, void* stream) {
   UTX_CHECK(nodes && vert && tri && rays_o && rays_d && hit && tri_idx && loc && uv, "utx_bvh_intersect: null pointer");
   return bvh_intersect(nodes, vert, tri, rays_o, rays_d, N, hit, tri_idx, loc, uv, static_cast<cudaStream_t>(stream));
+}
+int utx_knn1(const float* src, int n_src, const float* dst, long long M, long long* index, float* score, void* nodes,
+             void* workspace, size_t workspace_bytes, void* stream) {
+  UTX_CHECK(src && dst && index && score && nodes && workspace, "utx_knn1: null pointer");
+  return knn1(src, n_src, dst, M, index, score, nodes, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 size_t utx_uv_bake_workspace_bytes(int H2, int W2) { return uv_bake_workspace_bytes(H2, W2); }
 int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,

@@ -107,25 +107,31 @@ WsLayout ws_layout(const utx_flux_config& c, int s_txt, int s_img) {
 
 int gemm1(const bf16* A, long lda, const bf16* W, long ldw, const bf16* bias, bf16* C, long ldc, int M, int N, int K,
           int epi, const float* gate, const bf16* res, long ldres, cudaStream_t st, int gelu_start = 0,
-          int split_col = 0, bf16* C2 = nullptr, long ldc2 = 0) {
+          int split_col = 0, bf16* C2 = nullptr, long ldc2 = 0, int qk_cols = 0, const bf16* wq = nullptr,
+          const bf16* wk = nullptr, const float* cos_t = nullptr, const float* sin_t = nullptr) {
   GemmArgs a{};
   a.N = N; a.K = K; a.epi = epi; a.gelu_col_start = gelu_start; a.nprob = 1;
-  a.prob[0] = GemmProblem{A, lda, W, ldw, M, C, ldc, bias, gate, res, ldres, split_col, C2, ldc2};
+  a.qk_cols = qk_cols; a.cos_t = cos_t; a.sin_t = sin_t;
+  a.prob[0] = GemmProblem{A, lda, W, ldw, M, C, ldc, bias, gate, res, ldres, split_col, C2, ldc2, wq, wk, 0};
   return gemm_bf16_tn(a, st);
 }
 
 // txt rows [0, s_txt) with the *_txt weights and img rows [s_txt, S) with the *_img weights, one launch
 int gemm_streams(const utx_flux* h, const bf16* A, long lda, const void* W_txt, const void* b_txt, const void* W_img,
                  const void* b_img, long ldw, bf16* C, long ldc, int N, int K, int epi, const float* gate_txt,
-                 const float* gate_img, const bf16* res, long ldres, cudaStream_t st) {
+                 const float* gate_img, const bf16* res, long ldres, cudaStream_t st, int qk_cols = 0,
+                 const void* wq_txt = nullptr, const void* wk_txt = nullptr, const void* wq_img = nullptr,
+                 const void* wk_img = nullptr) {
   GemmArgs a{};
   a.N = N; a.K = K; a.epi = epi; a.gelu_col_start = 0; a.nprob = 2;
+  a.qk_cols = qk_cols; a.cos_t = h->cos_t; a.sin_t = h->sin_t;
   const long st_rows = h->s_txt;
   a.prob[0] = GemmProblem{A, lda, static_cast<const bf16*>(W_txt), ldw, h->s_txt, C, ldc,
-                          static_cast<const bf16*>(b_txt), gate_txt, res, ldres, 0, nullptr, 0};
+                          static_cast<const bf16*>(b_txt), gate_txt, res, ldres, 0, nullptr, 0,
+                          static_cast<const bf16*>(wq_txt), static_cast<const bf16*>(wk_txt), 0};
   a.prob[1] = GemmProblem{A + st_rows * lda, lda, static_cast<const bf16*>(W_img), ldw, h->s_img, C + st_rows * ldc, ldc,
                           static_cast<const bf16*>(b_img), gate_img, res ? res + st_rows * ldres : nullptr, ldres, 0,
-                          nullptr, 0};
+                          nullptr, 0, static_cast<const bf16*>(wq_img), static_cast<const bf16*>(wk_img), h->s_txt};
   return gemm_bf16_tn(a, st);
 }
 
@@ -237,10 +243,10 @@ int utx_flux_forward(utx_flux* h, const void* latents, float timestep, float gui
     const float* mi = mod + static_cast<long>(i) * 12 * D;   // img: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
     const float* mt = mi + 6L * D;                           // txt: same order
     CAT_ELEM(ln_modulate(h->x, D, h->xn, D, S, D, s_txt, mt, mt + D, mi, mi + D, st));
+    // q|k|v projection of both streams; per-head RMSNorm + RoPE of q and k fused into the epilogue
     CAT_GEMM(gemm_streams(h, h->xn, D, b.w_qkv_txt, b.b_qkv_txt, b.w_qkv_img, b.b_qkv_img, D, h->qkv, 3L * D, 3 * D, D,
-                         EPI_BIAS, nullptr, nullptr, nullptr, 0, st));
-    CAT_ELEM(rmsnorm_rope(h->qkv, 3L * D, S, H, s_txt, B(b.rms_q_txt), B(b.rms_k_txt), B(b.rms_q_img), B(b.rms_k_img),
-                         h->cos_t, h->sin_t, st));
+                         EPI_BIAS, nullptr, nullptr, nullptr, 0, st, 2 * D, b.rms_q_txt, b.rms_k_txt, b.rms_q_img,
+                         b.rms_k_img));
     CAT_ATTN(attention_bf16(h->qkv, 3L * D, h->cat, ldc5, S, H, st));
     CAT_GEMM(gemm_streams(h, h->cat, ldc5, b.w_out_txt, b.b_out_txt, b.w_out_img, b.b_out_img, D, h->x, D, D, D,
                          EPI_GATE_RES, mt + 2L * D, mi + 2L * D, h->x, D, st));
@@ -256,10 +262,9 @@ int utx_flux_forward(utx_flux* h, const void* latents, float timestep, float gui
     const float* ms = mod_s + static_cast<long>(i) * 3 * D;   // shift, scale, gate
     CAT_ELEM(ln_modulate(h->x, D, h->xn, D, S, D, 0, ms, ms + D, ms, ms + D, st));
     // one GEMM for to_q|to_k|to_v|proj_mlp: q,k,v -> qkv buffer, GELU(mlp) -> cat[:, D:]
+    // (RMSNorm + RoPE of q and k fused into the same epilogue)
     CAT_GEMM(gemm1(h->xn, D, B(b.w_qkvmlp), D, B(b.b_qkvmlp), h->qkv, 3L * D, S, 7 * D, D, EPI_BIAS_GELU, nullptr,
-                  nullptr, 0, st, 3 * D, 3 * D, h->cat + D, ldc5));
-    CAT_ELEM(rmsnorm_rope(h->qkv, 3L * D, S, H, 0, B(b.rms_q), B(b.rms_k), B(b.rms_q), B(b.rms_k), h->cos_t, h->sin_t,
-                         st));
+                  nullptr, 0, st, 3 * D, 3 * D, h->cat + D, ldc5, 2 * D, B(b.rms_q), B(b.rms_k), h->cos_t, h->sin_t));
     CAT_ATTN(attention_bf16(h->qkv, 3L * D, h->cat, ldc5, S, H, st));
     CAT_GEMM(gemm1(h->cat, ldc5, B(b.w_out), ldc5, B(b.b_out), h->x, D, S, D, 5 * D, EPI_GATE_RES, ms + 2L * D, h->x, D,
                   st));

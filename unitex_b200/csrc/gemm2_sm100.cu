@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "common.h"
+#include "gemm_epilogue.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -30,18 +31,12 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int BAR_OFF = STAGES * STAGE_BYTES;
 constexpr int SMEM_TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
 
-struct DevProblem {
-  int M, tiles_m;
-  bf16* C; long ldc;
-  const bf16* bias; const float* gate; const bf16* res; long ldres;
-  int split_col; bf16* C2; long ldc2;
-};
 struct DevParams {
-  int N, K, tiles_n, nprob, epi, gelu_col_start;
-  float out_scale;
-  int total_tiles;
-  DevProblem prob[2];
+  int K, tiles_n, nprob, total_tiles;
+  EpiParams e;
+  EpiProblem prob[2];
 };
+
 struct TileCoord { int pi, m_blk, n_blk; };
 
 __device__ __forceinline__ TileCoord decode_tile(const DevParams& p, int t) {
@@ -141,70 +136,12 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
     uint32_t aph = 0;
     for (int t = pair; t < p.total_tiles; t += npairs) {
       const TileCoord tc = decode_tile(p, t);
-      const DevProblem& pr = p.prob[tc.pi];
+      const EpiProblem& pr = p.prob[tc.pi];
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const int row = tc.m_blk * (2 * BM) + static_cast<int>(rank) * BM + ew * 32 + lane;
-      const bool row_ok = row < pr.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-      bf16* crow;
-      int col_shift = 0;
-      if (pr.split_col > 0 && tc.n_blk * BN >= pr.split_col) {
-        crow = pr.C2 + static_cast<long>(row) * pr.ldc2;
-        col_shift = pr.split_col;
-      } else {
-        crow = pr.C + static_cast<long>(row) * pr.ldc;
-      }
-      const bf16* rrow = pr.res ? pr.res + static_cast<long>(row) * pr.ldres : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = tc.n_blk * BN + c * 32;
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < p.N) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-              if (pr.bias) {
-                const uint4 b = *reinterpret_cast<const uint4*>(pr.bias + col);
-                f[0] += bf16lo(b.x); f[1] += bf16hi(b.x); f[2] += bf16lo(b.y); f[3] += bf16hi(b.y);
-                f[4] += bf16lo(b.z); f[5] += bf16hi(b.z); f[6] += bf16lo(b.w); f[7] += bf16hi(b.w);
-              }
-              if (p.epi == EPI_BIAS_GELU) {
-                if (col >= p.gelu_col_start) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
-                }
-              } else if (p.epi == EPI_GATE_RES) {
-                const float4 g0 = *reinterpret_cast<const float4*>(pr.gate + col);
-                const float4 g1 = *reinterpret_cast<const float4*>(pr.gate + col + 4);
-                const uint4 r = *reinterpret_cast<const uint4*>(rrow + col);
-                f[0] = fmaf(g0.x, f[0], bf16lo(r.x)); f[1] = fmaf(g0.y, f[1], bf16hi(r.x));
-                f[2] = fmaf(g0.z, f[2], bf16lo(r.y)); f[3] = fmaf(g0.w, f[3], bf16hi(r.y));
-                f[4] = fmaf(g1.x, f[4], bf16lo(r.z)); f[5] = fmaf(g1.y, f[5], bf16hi(r.z));
-                f[6] = fmaf(g1.z, f[6], bf16lo(r.w)); f[7] = fmaf(g1.w, f[7], bf16hi(r.w));
-              }
-              if (p.epi == EPI_BIAS_F32) {
-                float* crow32 = reinterpret_cast<float*>(pr.C) + static_cast<long>(row) * pr.ldc + col;
-                *reinterpret_cast<float4*>(crow32) = make_float4(f[0] * p.out_scale, f[1] * p.out_scale, f[2] * p.out_scale, f[3] * p.out_scale);
-                *reinterpret_cast<float4*>(crow32 + 4) = make_float4(f[4] * p.out_scale, f[5] * p.out_scale, f[6] * p.out_scale, f[7] * p.out_scale);
-                continue;
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(crow + (col - col_shift)) = o;
-            }
-          }
-        }
-      }
+      epilogue_tile<BN>(p.e, pr, taddr, row, tc.n_blk * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty[as], 0);   // the leader's MMA thread waits for both CTAs' epilogues
@@ -227,16 +164,17 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
 int gemm2_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
   if (a.N % BN != 0) return -1;
   DevParams p{};
-  p.N = a.N; p.K = a.K; p.tiles_n = a.N / BN; p.nprob = a.nprob; p.epi = a.epi; p.gelu_col_start = a.gelu_col_start;
-  p.out_scale = a.out_scale;
+  p.K = a.K;
+  p.tiles_n = a.N / BN;
+  p.nprob = a.nprob;
+  p.e = EpiParams{a.N, a.epi, a.gelu_col_start, a.out_scale, a.qk_cols, a.cos_t, a.sin_t};
   CUtensorMap tm[4];
   int total = 0;
   for (int i = 0; i < a.nprob; ++i) {
     const GemmProblem& g = a.prob[i];
-    DevProblem& d = p.prob[i];
-    d.M = g.M; d.tiles_m = (g.M + 2 * BM - 1) / (2 * BM);
-    d.C = g.C; d.ldc = g.ldc; d.bias = g.bias; d.gate = g.gate; d.res = g.res; d.ldres = g.ldres;
-    d.split_col = g.split_col; d.C2 = g.C2; d.ldc2 = g.ldc2;
+    EpiProblem& d = p.prob[i];
+    d = EpiProblem{g.M, (g.M + 2 * BM - 1) / (2 * BM), g.C, g.ldc, g.bias, g.gate, g.res, g.ldres, g.split_col, g.C2, g.ldc2,
+                   g.wq, g.wk, g.row_offset};
     total += d.tiles_m * p.tiles_n;
     UTX_TRY(make_tmap_2d_bf16(&tm[2 * i], g.A, g.M, a.K, g.lda, BM, BK));
     UTX_TRY(make_tmap_2d_bf16(&tm[2 * i + 1], g.W, a.N, a.K, g.ldw, BN / 2, BK));

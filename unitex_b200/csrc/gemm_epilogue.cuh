@@ -1,0 +1,161 @@
+// Shared epilogue of the two tcgen05 GEMM kernels (gemm_sm100.cu: 1 CTA per 128 x BN tile; gemm2_sm100.cu: CTA pairs).
+// One thread owns one accumulator row of the tile (tcgen05.ld 32x32b: lane == row), so row-wise reductions are thread-local:
+// besides bias / GELU-tanh / gate*x+residual / fp32 output, columns below `qk_cols` (the q and k thirds of a QKV
+// projection) get the per-head RMSNorm(eps 1e-6, weight) + RoPE of the joint attention
+// (flux_piplines/texturing/attention_processor.py:56-59,73-76,85-87) fused in, which removes a 240 MB read-modify-write
+// pass over the qkv buffer per block.
+#pragma once
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace utx {
+
+struct EpiProblem {
+  int M;
+  int tiles_m;
+  bf16* C;
+  long ldc;
+  const bf16* bias;
+  const float* gate;
+  const bf16* res;
+  long ldres;
+  int split_col;
+  bf16* C2;
+  long ldc2;
+  const bf16* wq;      // [128] RMSNorm weights of this problem's q / k heads (qk_cols > 0)
+  const bf16* wk;
+  int row_offset;      // token index of row 0 (img stream of a grouped launch starts at s_txt)
+};
+struct EpiParams {
+  int N, epi, gelu_col_start;
+  float out_scale;
+  int qk_cols;         // 0 = off; else 2*D: columns [0, D) are q heads, [D, 2D) k heads, 128 columns per head
+  const float* cos_t;  // [S, 128] fp32
+  const float* sin_t;
+};
+
+__device__ __forceinline__ void epi_store8(const EpiParams& p, const EpiProblem& pr, float (&f)[8], int row, int col,
+                                           bf16* crow, int col_shift, const bf16* rrow) {
+  if (p.epi == EPI_BIAS_GELU) {
+    if (col >= p.gelu_col_start) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
+    }
+  } else if (p.epi == EPI_GATE_RES) {
+    const float4 g0 = *reinterpret_cast<const float4*>(pr.gate + col);
+    const float4 g1 = *reinterpret_cast<const float4*>(pr.gate + col + 4);
+    const uint4 r = *reinterpret_cast<const uint4*>(rrow + col);
+    f[0] = fmaf(g0.x, f[0], bf16lo(r.x)); f[1] = fmaf(g0.y, f[1], bf16hi(r.x));
+    f[2] = fmaf(g0.z, f[2], bf16lo(r.y)); f[3] = fmaf(g0.w, f[3], bf16hi(r.y));
+    f[4] = fmaf(g1.x, f[4], bf16lo(r.z)); f[5] = fmaf(g1.y, f[5], bf16hi(r.z));
+    f[6] = fmaf(g1.z, f[6], bf16lo(r.w)); f[7] = fmaf(g1.w, f[7], bf16hi(r.w));
+  } else if (p.epi == EPI_BIAS_F32) {   // C is float*, ldc in floats (attention scores of the VAE mid block)
+    float* c32 = reinterpret_cast<float*>(pr.C) + static_cast<long>(row) * pr.ldc + col;
+    *reinterpret_cast<float4*>(c32) = make_float4(f[0] * p.out_scale, f[1] * p.out_scale, f[2] * p.out_scale, f[3] * p.out_scale);
+    *reinterpret_cast<float4*>(c32 + 4) = make_float4(f[4] * p.out_scale, f[5] * p.out_scale, f[6] * p.out_scale, f[7] * p.out_scale);
+    return;
+  }
+  *reinterpret_cast<uint4*>(crow + (col - col_shift)) =
+      make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+__device__ __forceinline__ void epi_add_bias8(const bf16* bias, int col, float (&f)[8]) {
+  if (bias) {
+    const uint4 b = *reinterpret_cast<const uint4*>(bias + col);
+    f[0] += bf16lo(b.x); f[1] += bf16hi(b.x); f[2] += bf16lo(b.y); f[3] += bf16hi(b.y);
+    f[4] += bf16lo(b.z); f[5] += bf16hi(b.z); f[6] += bf16lo(b.w); f[7] += bf16hi(b.w);
+  }
+}
+
+// taddr: TMEM address of this warp's lane quarter at the tile's first accumulator column.  All 32 lanes must call this.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, const EpiProblem& pr, uint32_t taddr, int row, int n0) {
+  const bool row_ok = row < pr.M;
+  bf16* crow;
+  int col_shift = 0;
+  if (pr.split_col > 0 && n0 >= pr.split_col) {
+    crow = pr.C2 + static_cast<long>(row) * pr.ldc2;
+    col_shift = pr.split_col;
+  } else {
+    crow = pr.C + static_cast<long>(row) * pr.ldc;
+  }
+  const bf16* rrow = pr.res ? pr.res + static_cast<long>(row) * pr.ldres : nullptr;
+  if (BN >= 128 && p.qk_cols > 0 && n0 < p.qk_cols) {
+    // ---- q / k heads: RMSNorm over the head's 128 columns, weight, RoPE; one head = 4 chunks of 32 accumulator columns
+    const int D = p.qk_cols >> 1;
+#pragma unroll 1
+    for (int hc = 0; hc < BN / 128; ++hc) {
+      const int col0 = n0 + hc * 128;
+      uint32_t v[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(taddr + hc * 128 + c * 32, v[c]);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[c][g * 8 + j]);
+          epi_add_bias8(pr.bias, col0 + c * 32 + g * 8, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ss = fmaf(f[j], f[j], ss);
+            v[c][g * 8 + j] = __float_as_uint(f[j]);
+          }
+        }
+      const float rs = rsqrtf(ss * (1.0f / 128.0f) + 1e-6f);
+      const bf16* w = col0 >= D ? pr.wk : pr.wq;
+      const long tok = static_cast<long>(row) + pr.row_offset;
+      const float* ct = p.cos_t + tok * 128;
+      const float* st = p.sin_t + tok * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int e = c * 32 + g * 8;   // element offset inside the head
+          const uint4 wr = *reinterpret_cast<const uint4*>(w + e);
+          const float wv[8] = {bf16lo(wr.x), bf16hi(wr.x), bf16lo(wr.y), bf16hi(wr.y), bf16lo(wr.z), bf16hi(wr.z), bf16lo(wr.w), bf16hi(wr.w)};
+          const float4 c0 = *reinterpret_cast<const float4*>(ct + e), c1 = *reinterpret_cast<const float4*>(ct + e + 4);
+          const float4 s0 = *reinterpret_cast<const float4*>(st + e), s1 = *reinterpret_cast<const float4*>(st + e + 4);
+          const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          float x[8], o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[c][g * 8 + j]) * rs * wv[j];
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            o[j] = x[j] * cv[j] - x[j + 1] * sv[j];
+            o[j + 1] = x[j + 1] * cv[j + 1] + x[j] * sv[j + 1];
+          }
+          *reinterpret_cast<uint4*>(crow + (col0 + e - col_shift)) =
+              make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        }
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c * 32, v);
+    tmem_ld_wait();
+    const int col0 = n0 + c * 32;
+    if (row_ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = col0 + g * 8;
+        if (col < p.N) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+          epi_add_bias8(pr.bias, col, f);
+          epi_store8(p, pr, f, row, col, crow, col_shift, rrow);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace utx

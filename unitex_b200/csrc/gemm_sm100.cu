@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "common.h"
+#include "gemm_epilogue.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -28,28 +29,10 @@ constexpr int BK = 64;
 constexpr int GROUP_M = 16;
 constexpr int kThreads = 256;
 
-struct DevProblem {
-  int M;
-  int tiles_m;
-  bf16* C;
-  long ldc;
-  const bf16* bias;
-  const float* gate;
-  const bf16* res;
-  long ldres;
-  int split_col;
-  bf16* C2;
-  long ldc2;
-};
 struct DevParams {
-  int N, K;
-  int tiles_n;
-  int nprob;
-  int epi;
-  int gelu_col_start;
-  float out_scale;
-  int total_tiles;
-  DevProblem prob[2];
+  int K, tiles_n, nprob, total_tiles;
+  EpiParams e;
+  EpiProblem prob[2];
 };
 
 struct TileCoord {
@@ -183,70 +166,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     uint32_t aph = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(p, t);
-      const DevProblem& pr = p.prob[tc.pi];
+      const EpiProblem& pr = p.prob[tc.pi];
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const int row = tc.m_blk * BM + ew * 32 + lane;
-      const bool row_ok = row < pr.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-      bf16* crow;
-      int col_shift = 0;
-      if (pr.split_col > 0 && tc.n_blk * BN >= pr.split_col) {
-        crow = pr.C2 + static_cast<long>(row) * pr.ldc2;
-        col_shift = pr.split_col;
-      } else {
-        crow = pr.C + static_cast<long>(row) * pr.ldc;
-      }
-      const bf16* rrow = pr.res ? pr.res + static_cast<long>(row) * pr.ldres : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = tc.n_blk * BN + c * 32;
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < p.N) {
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-              if (pr.bias) {
-                const uint4 b = *reinterpret_cast<const uint4*>(pr.bias + col);
-                f[0] += bf16lo(b.x); f[1] += bf16hi(b.x); f[2] += bf16lo(b.y); f[3] += bf16hi(b.y);
-                f[4] += bf16lo(b.z); f[5] += bf16hi(b.z); f[6] += bf16lo(b.w); f[7] += bf16hi(b.w);
-              }
-              if (p.epi == EPI_BIAS_GELU) {
-                if (col >= p.gelu_col_start) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = gelu_tanh(f[j]);
-                }
-              } else if (p.epi == EPI_GATE_RES) {
-                const float4 g0 = *reinterpret_cast<const float4*>(pr.gate + col);
-                const float4 g1 = *reinterpret_cast<const float4*>(pr.gate + col + 4);
-                const uint4 r = *reinterpret_cast<const uint4*>(rrow + col);
-                f[0] = fmaf(g0.x, f[0], bf16lo(r.x)); f[1] = fmaf(g0.y, f[1], bf16hi(r.x));
-                f[2] = fmaf(g0.z, f[2], bf16lo(r.y)); f[3] = fmaf(g0.w, f[3], bf16hi(r.y));
-                f[4] = fmaf(g1.x, f[4], bf16lo(r.z)); f[5] = fmaf(g1.y, f[5], bf16hi(r.z));
-                f[6] = fmaf(g1.z, f[6], bf16lo(r.w)); f[7] = fmaf(g1.w, f[7], bf16hi(r.w));
-              }
-              if (p.epi == EPI_BIAS_F32) {   // fp32 output (attention scores of the VAE mid block): C is float*, ldc in floats
-                float* crow32 = reinterpret_cast<float*>(pr.C) + static_cast<long>(row) * pr.ldc + (col - col_shift);
-                *reinterpret_cast<float4*>(crow32) = make_float4(f[0] * p.out_scale, f[1] * p.out_scale, f[2] * p.out_scale, f[3] * p.out_scale);
-                *reinterpret_cast<float4*>(crow32 + 4) = make_float4(f[4] * p.out_scale, f[5] * p.out_scale, f[6] * p.out_scale, f[7] * p.out_scale);
-                continue;
-              }
-              uint4 o;
-              o.x = pack_bf16x2(f[0], f[1]);
-              o.y = pack_bf16x2(f[2], f[3]);
-              o.z = pack_bf16x2(f[4], f[5]);
-              o.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(crow + (col - col_shift)) = o;
-            }
-          }
-        }
-      }
+      epilogue_tile<BN>(p.e, pr, taddr, row, tc.n_blk * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -267,22 +192,17 @@ template <int BN, int STAGES>
 int launch(const GemmArgs& a, cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES>;
   DevParams p{};
-  p.N = a.N;
   p.K = a.K;
   p.tiles_n = (a.N + BN - 1) / BN;
   p.nprob = a.nprob;
-  p.epi = a.epi;
-  p.gelu_col_start = a.gelu_col_start;
-  p.out_scale = a.out_scale;
+  p.e = EpiParams{a.N, a.epi, a.gelu_col_start, a.out_scale, a.qk_cols, a.cos_t, a.sin_t};
   CUtensorMap tm[4];
   int total = 0;
   for (int i = 0; i < a.nprob; ++i) {
     const GemmProblem& g = a.prob[i];
-    DevProblem& d = p.prob[i];
-    d.M = g.M;
-    d.tiles_m = (g.M + BM - 1) / BM;
-    d.C = g.C; d.ldc = g.ldc; d.bias = g.bias; d.gate = g.gate; d.res = g.res; d.ldres = g.ldres;
-    d.split_col = g.split_col; d.C2 = g.C2; d.ldc2 = g.ldc2;
+    EpiProblem& d = p.prob[i];
+    d = EpiProblem{g.M, (g.M + BM - 1) / BM, g.C, g.ldc, g.bias, g.gate, g.res, g.ldres, g.split_col, g.C2, g.ldc2, g.wq, g.wk,
+                   g.row_offset};
     total += d.tiles_m * p.tiles_n;
     UTX_TRY(make_tmap_2d_bf16(&tm[2 * i], g.A, g.M, a.K, g.lda, BM, BK));
     UTX_TRY(make_tmap_2d_bf16(&tm[2 * i + 1], g.W, a.N, a.K, g.ldw, BN, BK));
@@ -318,6 +238,7 @@ int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
     UTX_CHECK(g.M >= 0, "gemm: negative M");
     UTX_CHECK(g.ldc % 8 == 0 && (g.res == nullptr || g.ldres % 8 == 0), "gemm: ldc/ldres must be multiples of 8");
     UTX_CHECK(a.epi != EPI_BIAS_F32 || g.split_col == 0, "gemm: fp32 output cannot be combined with a column split");
+    UTX_CHECK(a.qk_cols == 0 || (g.wq && g.wk), "gemm: qk_cols needs RMSNorm weights");
     UTX_CHECK(a.epi != EPI_GATE_RES || (g.gate && g.res), "gemm: EPI_GATE_RES needs gate and res");
     UTX_CHECK(g.split_col == 0 || (g.split_col % 256 == 0 && g.C2 && g.ldc2 % 8 == 0), "gemm: bad column split");
   }
@@ -328,6 +249,9 @@ int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
     const int r = gemm2_bf16_tn(a, stream);
     if (r >= 0) return r;
   }
+  UTX_CHECK(a.qk_cols == 0 || (a.qk_cols % 256 == 0 && a.N % 128 == 0 && a.cos_t && a.sin_t && a.epi != EPI_BIAS_F32 &&
+                               a.epi != EPI_GATE_RES),
+            "gemm: bad fused q/k norm-rope configuration");
   if (a.N % 256 == 0) return launch<256, 4>(a, stream);
   if (a.N % 128 == 0) return launch<128, 6>(a, stream);
   return launch<64, 8>(a, stream);

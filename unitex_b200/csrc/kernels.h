@@ -34,12 +34,20 @@ struct GemmProblem {
   int split_col;      // 0 = no split
   bf16* C2;
   long ldc2;
+  // fused per-head RMSNorm + RoPE on the q|k columns (GemmArgs::qk_cols > 0): this problem's norm weights [128] and the
+  // token index of its row 0 in the cos/sin tables
+  const bf16* wq;
+  const bf16* wk;
+  int row_offset;
 };
 struct GemmArgs {
   int N, K;
   int epi;
   int gelu_col_start;
   float out_scale;       // EPI_BIAS_F32 only
+  int qk_cols;           // 0 = off; 2*D: columns [0,D) are q heads, [D,2D) k heads (128 per head) -> RMSNorm + RoPE in the epilogue
+  const float* cos_t;    // [S,128] fp32 tables for qk_cols > 0
+  const float* sin_t;
   int nprob;             // 1 or 2 problems sharing N, K and the epilogue (txt + img streams)
   GemmProblem prob[2];
 };
@@ -86,6 +94,8 @@ size_t bvh_workspace_bytes(int F);
 int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, void* workspace, size_t ws_bytes,
               cudaStream_t stream);
 int point_bvh_build(const float* pts, int n, void* nodes_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
+int knn1(const float* src, int n_src, const float* dst, long long M, long long* index, float* score, void* nodes, void* workspace,
+         size_t ws_bytes, cudaStream_t stream);
 int bvh_export(const void* nodes, int F, int* info, float* aabb, cudaStream_t stream);
 int bvh_intersect(const void* nodes, const float* vert, const int* tri, const float* rays_o, const float* rays_d,
                   long long N, unsigned char* hit, int* tid, float* pos, float* uv, cudaStream_t stream);

@@ -40,6 +40,18 @@ def gemm(A, W, bias=None, epi=EPI_BIAS, gate=None, res=None, out=None):
     return out
 
 
+def gemm_qkv(A, W, bias, heads, wq, wk, cos, sin, row_offset=0, out=None):
+    """QKV projection with per-head RMSNorm + RoPE fused into the epilogue for q and k."""
+    _req(A, torch.bfloat16, "A"); _req(W, torch.bfloat16, "W")
+    M, K = A.shape
+    if out is None:
+        out = torch.empty(M, 3 * heads * 128, device=A.device, dtype=torch.bfloat16)
+    L = _lib.load()
+    _lib.check(L.utx_gemm_bf16_qkv(_p(A), A.stride(0), _p(W), _p(bias), _p(out), out.stride(0), M, heads, K, _p(wq), _p(wk),
+                                   _p(cos), _p(sin), row_offset, _stream()), "utx_gemm_bf16_qkv")
+    return out
+
+
 def gemm_grouped2(A0, W0, b0, C0, A1, W1, b1, C1, epi=EPI_BIAS, gate0=None, gate1=None):
     L = _lib.load()
     N, K = W0.shape
