@@ -39,7 +39,7 @@ enum Bar { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL 
 
 __global__ void __launch_bounds__(kThreads, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, long ld_out, int S, int H,
-                  float scale_log2, int n_qblocks, int n_full, int n_splits, float* __restrict__ partial) {
+                  float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -47,22 +47,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // Work items: the first n_full (q-block, head) units run over all keys; the units of the last, partial wave are cut into
-  // n_splits key ranges each so that the tail wave fills the machine, and merged by attn2_merge_kernel.
-  const int item = blockIdx.x;
-  int unit = item, split = 0;
-  if (item >= n_full) {
-    unit = n_full + (item - n_full) / n_splits;
-    split = (item - n_full) % n_splits;
-  }
-  const bool is_split = item >= n_full && n_splits > 1;
-  const int q0 = (unit % n_qblocks) * (2 * BQ);
-  const int head = unit / n_qblocks;
+  const int q0 = blockIdx.x * (2 * BQ);
+  const int head = blockIdx.y;
   const int D = H * HD;
-  const int n_kv_all = (S + BKV - 1) / BKV;
-  const int kv_begin = is_split ? static_cast<int>(static_cast<long>(split) * n_kv_all / n_splits) : 0;
-  const int kv_end = is_split ? static_cast<int>(static_cast<long>(split + 1) * n_kv_all / n_splits) : n_kv_all;
-  const int n_kv = kv_end - kv_begin;      // local tile count; barriers/stages use the local index, addresses the global one
+  const int n_kv = (S + BKV - 1) / BKV;
 
   if (warp == 0 && lane == 0) prefetch_tmap(&tm_qkv);
   if (warp == 1 && lane == 0) {
@@ -87,13 +75,13 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
       mbar_wait(&bar[K_EMPTY + s], ph ^ 1);
       mbar_arrive_expect_tx(&bar[K_FULL + s], TILE_BYTES);
       uint8_t* kd = smem + OFF_K + s * TILE_BYTES;
-      tma_load_2d(kd, &tm_qkv, &bar[K_FULL + s], D + head * HD, (kv_begin + j) * BKV);
-      tma_load_2d(kd + HALF_BYTES, &tm_qkv, &bar[K_FULL + s], D + head * HD + 64, (kv_begin + j) * BKV);
+      tma_load_2d(kd, &tm_qkv, &bar[K_FULL + s], D + head * HD, j * BKV);
+      tma_load_2d(kd + HALF_BYTES, &tm_qkv, &bar[K_FULL + s], D + head * HD + 64, j * BKV);
       mbar_wait(&bar[V_EMPTY + s], ph ^ 1);
       mbar_arrive_expect_tx(&bar[V_FULL + s], TILE_BYTES);
       uint8_t* vd = smem + OFF_V + s * TILE_BYTES;
-      tma_load_2d(vd, &tm_qkv, &bar[V_FULL + s], 2 * D + head * HD, (kv_begin + j) * BKV);
-      tma_load_2d(vd + HALF_BYTES, &tm_qkv, &bar[V_FULL + s], 2 * D + head * HD + 64, (kv_begin + j) * BKV);
+      tma_load_2d(vd, &tm_qkv, &bar[V_FULL + s], 2 * D + head * HD, j * BKV);
+      tma_load_2d(vd + HALF_BYTES, &tm_qkv, &bar[V_FULL + s], 2 * D + head * HD + 64, j * BKV);
     }
   } else if (warp == 1 && lane == 0) {
     // ---------------------------------------------------------------- MMA issuer
@@ -156,7 +144,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&bar[S_FULL + x], j & 1);
       tc_fence_after();
-      const int kv_valid = S - (kv_begin + j) * BKV;
+      const int kv_valid = S - j * BKV;
       const bool ragged = kv_valid < BKV;
       // row max: four tcgen05.ld in flight, one wait (the first version paid the TMEM round trip eight times per tile and
       // was latency bound: tensor pipe 44 %, r01_attention2_kernel profile)
@@ -243,24 +231,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
     // ---------------------------------------------------------------- epilogue
     mbar_wait(&bar[O_FULL], 0);
     tc_fence_after();
-    const int row = q0 + x * BQ + r;
-    if (is_split) {
-      // un-normalised O (fp32), running max and row sum of this key range -> workspace [tail unit][split][256 rows][132]
-      float* prow = partial + ((static_cast<long>(unit - n_full) * n_splits + split) * (2 * BQ) + x * BQ + r) * 132;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t ov[32];
-        tmem_ld32(tO + c * 32, ov);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<float4*>(prow + c * 32 + g * 4) =
-              make_float4(__uint_as_float(ov[g * 4]), __uint_as_float(ov[g * 4 + 1]), __uint_as_float(ov[g * 4 + 2]), __uint_as_float(ov[g * 4 + 3]));
-      }
-      prow[128] = m_used;
-      prow[129] = l;
-    } else {
     const float inv = 1.0f / l;
+    const int row = q0 + x * BQ + r;
     bf16* orow = out + static_cast<long>(row) * ld_out + head * HD;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
@@ -279,7 +251,6 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
         }
       }
     }
-    }
   }
 
   tc_fence_before();
@@ -290,36 +261,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
   }
 }
 
-// merges the key-range partials of the tail units: out = sum_s 2^(m_s - m*) O_s / sum_s 2^(m_s - m*) l_s
-__global__ void __launch_bounds__(128) attn2_merge_kernel(const float* __restrict__ partial, bf16* __restrict__ out, long ld_out,
-                                                          int S, int n_qblocks, int n_full, int n_splits) {
-  const int tail_unit = blockIdx.x / (2 * BQ), rr = blockIdx.x % (2 * BQ);
-  const int unit = n_full + tail_unit;
-  const int row = (unit % n_qblocks) * (2 * BQ) + rr, head = unit / n_qblocks;
-  if (row >= S) return;
-  const float* base = partial + (static_cast<long>(tail_unit) * n_splits * (2 * BQ) + rr) * 132;
-  const long sstride = static_cast<long>(2 * BQ) * 132;
-  float mstar = -INFINITY;
-  for (int s = 0; s < n_splits; ++s) mstar = fmaxf(mstar, base[s * sstride + 128]);
-  float num = 0.f, den = 0.f;
-  for (int s = 0; s < n_splits; ++s) {
-    const float w = ex2_approx(base[s * sstride + 128] - mstar);
-    num = fmaf(w, base[s * sstride + threadIdx.x], num);
-    den = fmaf(w, base[s * sstride + 129], den);
-  }
-  out[static_cast<long>(row) * ld_out + head * HD + threadIdx.x] = __float2bfloat16(num / den);
-}
-
 }  // namespace
-
-size_t attention2_workspace_bytes(int S, int H) {
-  const int units = ((S + 2 * BQ - 1) / (2 * BQ)) * H;
-  const int sms = num_sms();
-  const int rem = units % sms;
-  const int n_splits = rem > 0 ? sms / rem : 1;
-  if (rem == 0 || n_splits < 2) return 0;
-  return static_cast<size_t>(rem) * n_splits * (2 * BQ) * 132 * sizeof(float);
-}
 
 int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream) {
   UTX_CHECK(S > 0 && H > 0, "attention: empty problem");
@@ -332,28 +274,8 @@ int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S,
     attr_set = true;
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
-  const int n_qblocks = (S + 2 * BQ - 1) / (2 * BQ);
-  const int units = n_qblocks * H;
-  const int sms = num_sms();
-  int rem = units % sms, n_full = units - rem, n_splits = rem > 0 ? sms / rem : 1;
-  const int n_kv = (S + BKV - 1) / BKV;
-  if (n_splits > n_kv) n_splits = n_kv;
-  // the partial buffer lives for the whole process (one per device; sized for the largest tail seen)
-  static float* partial = nullptr;
-  static size_t partial_bytes = 0;
-  if (rem == 0 || n_splits < 2) {
-    n_full = units; rem = 0; n_splits = 1;
-  } else {
-    const size_t need = static_cast<size_t>(rem) * n_splits * (2 * BQ) * 132 * sizeof(float);
-    if (need > partial_bytes) {
-      if (partial) UTX_CUDA(cudaFree(partial));
-      UTX_CUDA(cudaMalloc(&partial, need));
-      partial_bytes = need;
-    }
-  }
-  const int grid = n_full + rem * n_splits;
-  attention2_kernel<<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2, n_qblocks, n_full, n_splits, partial);
-  if (rem > 0) attn2_merge_kernel<<<rem * 2 * BQ, 128, 0, stream>>>(partial, out, ld_out, S, n_qblocks, n_full, n_splits);
+  dim3 grid((S + 2 * BQ - 1) / (2 * BQ), H);
+  attention2_kernel<<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2);
   UTX_CUDA(cudaGetLastError());
   return 0;
 }
