@@ -94,3 +94,37 @@ def test_denoise_matches_committed_golden(lib):
     torch.cuda.synchronize()
     db = fs.psnr(lat[:64].float().cpu(), torch.from_numpy(z["out"])[0])
     assert db >= PSNR_MIN_DB, db
+
+
+def test_ragged_token_counts_and_empty_calls(lib):
+    """Token counts that are not multiples of the 128-row tiles (txt 77, img 333) and degenerate calls through the C ABI."""
+    from oracle import flux_dit as fd
+    from oracle import flux_sampler as fs
+    from unitex_b200 import ops
+    from unitex_b200.flux import FluxConfig, FluxTransformer
+    ocfg = fd.FluxConfig.tiny(1, 1)
+    P = {k: v.to(torch.bfloat16).float() for k, v in fd.init_params(ocfg, 7, norm_weight_std=0.1).items()}
+    eng = FluxTransformer(FluxConfig(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=256,
+                                     pooled_projection_dim=64)).load_state_dict(P)
+    s_txt, s_img = 77, 333
+    g = torch.Generator().manual_seed(1)
+    img_ids = torch.stack([torch.zeros(s_img), torch.randint(0, 40, (s_img,), generator=g).float(),
+                           torch.randint(0, 40, (s_img,), generator=g).float()], -1)
+    enc = (torch.randn(s_txt, 256, generator=g) * 0.3).to(torch.bfloat16)
+    lat = torch.randn(s_img, 64, generator=g).to(torch.bfloat16).cuda()
+    eng.prepare(torch.cat([torch.zeros(s_txt, 3), img_ids]), enc, None, s_txt=s_txt)
+    v = eng.forward(lat, 0.5, 3.5)
+    torch.cuda.synchronize()
+    Pg = {k: w.cuda() for k, w in P.items()}
+    ref = fd.flux_forward(Pg, ocfg, lat[None].float(), torch.tensor([0.5]).cuda(), torch.tensor([3.5]).cuda(),
+                          torch.zeros(1, 64).cuda(), enc[None].float().cuda(), torch.zeros(s_txt, 3).cuda(), img_ids.cuda())[0]
+    assert fs.psnr(v.float(), ref) >= PSNR_MIN_DB
+    # zero steps is a no-op; zero-row GEMM / Euler calls succeed without launching
+    before = lat.clone()
+    eng.denoise_(lat, 100, [1.0], 3.5)
+    torch.cuda.synchronize()
+    assert torch.equal(lat, before)
+    ops.gemm(torch.empty(0, 256, device="cuda", dtype=torch.bfloat16), torch.zeros(256, 256, device="cuda", dtype=torch.bfloat16))
+    ops.euler_update_(lat, lat, 0, 0.1)
+    torch.cuda.synchronize()
+    assert torch.equal(lat, before)
