@@ -137,7 +137,7 @@ int utx_euler_update(void* latents, const void* v, int rows, int cols, float dsi
  * ------------------------------------------------------------------------------------------------------------------ */
 /* dr.rasterize (renderer_inverse.py:183,273; renderer_base.py:142): pos [B or 1, V, 4] clip space fp32, tri [F,3] int32
  * -> rast [B,H,W,4] = (u, v, z/w, triangle_id + 1), 0 = background.  workspace: utx_rasterize_workspace_bytes. */
-size_t utx_rasterize_workspace_bytes(int B, int H, int W);
+size_t utx_rasterize_workspace_bytes(int B, int H, int W, int F);
 int utx_rasterize(const float* pos, int pos_batched, int V, const int32_t* tri, int F, int B, int H, int W,
                   float* rast_out, void* workspace, void* stream);
 /* dr.interpolate (renderer_inverse.py:188,277,288): out[b,y,x,:] = u a0 + v a1 + (1-u-v) a2 */

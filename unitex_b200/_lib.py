@@ -62,7 +62,7 @@ _SIGS = {
     "utx_gemv_bf16": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "utx_rope_table": (i32, [vp, i32, vp, vp, vp]),
     "utx_euler_update": (i32, [vp, vp, i32, i32, f32, vp]),
-    "utx_rasterize_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
+    "utx_rasterize_workspace_bytes": (C.c_size_t, [i32, i32, i32, i32]),
     "utx_rasterize": (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]),
     "utx_interpolate": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, i32, vp, vp]),
     "utx_transform_points": (i32, [vp, i32, vp, i32, vp, vp]),

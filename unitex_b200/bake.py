@@ -85,7 +85,7 @@ def rasterize(pos: torch.Tensor, tri: torch.Tensor, resolution: Tuple[int, int])
     B, V = pos.shape[0], pos.shape[1]
     tri = tri.to(torch.int32).contiguous()
     out = torch.empty(B, H, W, 4, device=pos.device, dtype=torch.float32)
-    ws = torch.empty(L.utx_rasterize_workspace_bytes(B, H, W), device=pos.device, dtype=torch.uint8)
+    ws = torch.empty(L.utx_rasterize_workspace_bytes(B, H, W, tri.shape[0]), device=pos.device, dtype=torch.uint8)
     _lib.check(L.utx_rasterize(_p(pos), 1, V, _p(tri), tri.shape[0], B, H, W, _p(out), _p(ws), _stream()), "utx_rasterize")
     return out
 

@@ -5,9 +5,9 @@
 //
 // Coverage is decided in integers (8 sub-pixel bits, pixel centres, top-left rule), depth by an order-preserving
 // 64-bit key (depth bits << 32 | triangle id) and atomicMin, so the result does not depend on thread scheduling:
-// nearest z/w wins, ties go to the lowest triangle id.  One warp per triangle: lanes stride over the pixel centres of
-// the bounding box (most bake triangles cover a handful of texels); a resolve pass then recomputes (u, v, z/w) of the
-// winner per pixel with fully coalesced float4 stores.  Built with -fmad=false: every fp32 op is separately rounded, so
+// nearest z/w wins, ties go to the lowest triangle id.  Small triangles (<= 8 pixel centres in the box) are drawn by the
+// thread that set them up, the rest by persistent warps whose lanes stride over the bounding box; a resolve pass then
+// recomputes (u, v, z/w) of the winner per pixel with fully coalesced float4 stores.  Built with -fmad=false: every fp32 op is separately rounded, so
 // the CPU oracle reproduces ids AND barycentrics bit for bit.
 #include "common.h"
 #include "kernels.h"
@@ -62,42 +62,88 @@ __global__ void __launch_bounds__(256) raster_clear_kernel(unsigned long long* z
   if (i < n) zbuf[i] = ~0ull;
 }
 
-__global__ void __launch_bounds__(256) raster_tri_kernel(const float* __restrict__ pos, int pos_batched, int V,
-                                                         const int* __restrict__ tri, int F, int B, int H, int W,
-                                                         unsigned long long* __restrict__ zbuf) {
-  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (gw >= static_cast<long long>(F) * B) return;
-  const int b = static_cast<int>(gw / F), f = static_cast<int>(gw % F);
-  const float* P = pos + (pos_batched ? static_cast<size_t>(b) * V * 4 : 0);
-  const TriSetup t = setup_tri(P, tri, f, H, W);
-  if (!t.ok) return;
-  const long long sgn = t.area > 0 ? 1 : -1;
+// Pass 1, one THREAD per (view, triangle): set-up; triangles whose bounding box holds <= kSmallBox pixel centres (the common
+// case of the 6 x 512^2 view pass: ~0.5 pixel per triangle) are drawn right here, the others are appended to a work list.
+// Pass 2, persistent WARPS over that list: lanes stride over the bounding box.
+constexpr int kSmallBox = 8;
+
+struct TriDraw {
+  TriSetup t;
+  long long sgn;
+  int x0, y0, bw;
+  long long npix;
+  bool t0, t1, t2;
+  float fa;
+};
+__device__ __forceinline__ bool prepare_draw(const float* P, const int* tri, int f, int H, int W, TriDraw& d) {
+  d.t = setup_tri(P, tri, f, H, W);
+  if (!d.t.ok) return false;
+  const TriSetup& t = d.t;
+  d.sgn = t.area > 0 ? 1 : -1;
   const int minx = min(t.X[0], min(t.X[1], t.X[2])), maxx = max(t.X[0], max(t.X[1], t.X[2]));
   const int miny = min(t.Y[0], min(t.Y[1], t.Y[2])), maxy = max(t.Y[0], max(t.Y[1], t.Y[2]));
   int x0 = (minx - SUBPIX / 2 + SUBPIX - 1) >> 8, x1 = (maxx - SUBPIX / 2) >> 8;
   int y0 = (miny - SUBPIX / 2 + SUBPIX - 1) >> 8, y1 = (maxy - SUBPIX / 2) >> 8;
   x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, W - 1); y1 = min(y1, H - 1);
-  if (x1 < x0 || y1 < y0) return;
-  const bool t0 = sgn > 0 ? tie_ok(t.X[1], t.Y[1], t.X[2], t.Y[2]) : tie_ok(t.X[2], t.Y[2], t.X[1], t.Y[1]);
-  const bool t1 = sgn > 0 ? tie_ok(t.X[2], t.Y[2], t.X[0], t.Y[0]) : tie_ok(t.X[0], t.Y[0], t.X[2], t.Y[2]);
-  const bool t2 = sgn > 0 ? tie_ok(t.X[0], t.Y[0], t.X[1], t.Y[1]) : tie_ok(t.X[1], t.Y[1], t.X[0], t.Y[0]);
-  const float fa = static_cast<float>(t.area * sgn);
-  const int bw = x1 - x0 + 1;
-  const long long npix = static_cast<long long>(bw) * (y1 - y0 + 1);
-  unsigned long long* zb = zbuf + static_cast<size_t>(b) * H * W;
-  for (long long i = lane; i < npix; i += 32) {
-    const int x = x0 + static_cast<int>(i % bw), y = y0 + static_cast<int>(i / bw);
+  if (x1 < x0 || y1 < y0) return false;
+  const long long sgn = d.sgn;
+  d.t0 = sgn > 0 ? tie_ok(t.X[1], t.Y[1], t.X[2], t.Y[2]) : tie_ok(t.X[2], t.Y[2], t.X[1], t.Y[1]);
+  d.t1 = sgn > 0 ? tie_ok(t.X[2], t.Y[2], t.X[0], t.Y[0]) : tie_ok(t.X[0], t.Y[0], t.X[2], t.Y[2]);
+  d.t2 = sgn > 0 ? tie_ok(t.X[0], t.Y[0], t.X[1], t.Y[1]) : tie_ok(t.X[1], t.Y[1], t.X[0], t.Y[0]);
+  d.fa = static_cast<float>(t.area * sgn);
+  d.x0 = x0; d.y0 = y0; d.bw = x1 - x0 + 1;
+  d.npix = static_cast<long long>(d.bw) * (y1 - y0 + 1);
+  return true;
+}
+__device__ __forceinline__ void draw_pixels(const TriDraw& d, int f, int W, unsigned long long* zb, int first, int step) {
+  const TriSetup& t = d.t;
+  for (long long i = first; i < d.npix; i += step) {
+    const int x = d.x0 + static_cast<int>(i % d.bw), y = d.y0 + static_cast<int>(i / d.bw);
     const long long px = static_cast<long long>(x) * SUBPIX + SUBPIX / 2, py = static_cast<long long>(y) * SUBPIX + SUBPIX / 2;
-    const long long e0 = edge_fn(t.X[1], t.Y[1], t.X[2], t.Y[2], px, py) * sgn;
-    const long long e1 = edge_fn(t.X[2], t.Y[2], t.X[0], t.Y[0], px, py) * sgn;
-    const long long e2 = edge_fn(t.X[0], t.Y[0], t.X[1], t.Y[1], px, py) * sgn;
+    const long long e0 = edge_fn(t.X[1], t.Y[1], t.X[2], t.Y[2], px, py) * d.sgn;
+    const long long e1 = edge_fn(t.X[2], t.Y[2], t.X[0], t.Y[0], px, py) * d.sgn;
+    const long long e2 = edge_fn(t.X[0], t.Y[0], t.X[1], t.Y[1], px, py) * d.sgn;
     if (e0 < 0 || e1 < 0 || e2 < 0) continue;
-    if ((e0 == 0 && !t0) || (e1 == 0 && !t1) || (e2 == 0 && !t2)) continue;
-    const float u = static_cast<float>(e0) / fa, v = static_cast<float>(e1) / fa, w2 = static_cast<float>(e2) / fa;
+    if ((e0 == 0 && !d.t0) || (e1 == 0 && !d.t1) || (e2 == 0 && !d.t2)) continue;
+    const float u = static_cast<float>(e0) / d.fa, v = static_cast<float>(e1) / d.fa, w2 = static_cast<float>(e2) / d.fa;
     const float zw = (u * t.zn[0] + v * t.zn[1]) + w2 * t.zn[2];
     const unsigned long long key = (static_cast<unsigned long long>(ordered_bits(zw)) << 32) | static_cast<unsigned>(f);
     atomicMin(zb + static_cast<size_t>(y) * W + x, key);
+  }
+}
+
+__global__ void __launch_bounds__(256) raster_small_kernel(const float* __restrict__ pos, int pos_batched, int V,
+                                                           const int* __restrict__ tri, int F, int B, int H, int W,
+                                                           unsigned long long* __restrict__ zbuf, unsigned* __restrict__ list,
+                                                           unsigned* __restrict__ count) {
+  const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= static_cast<long long>(F) * B) return;
+  const int b = static_cast<int>(g / F), f = static_cast<int>(g % F);
+  const float* P = pos + (pos_batched ? static_cast<size_t>(b) * V * 4 : 0);
+  TriDraw d;
+  if (!prepare_draw(P, tri, f, H, W, d)) return;
+  if (d.npix > kSmallBox) {
+    list[atomicAdd(count, 1u)] = static_cast<unsigned>(g);
+    return;
+  }
+  draw_pixels(d, f, W, zbuf + static_cast<size_t>(b) * H * W, 0, 1);
+}
+
+__global__ void __launch_bounds__(256) raster_large_kernel(const float* __restrict__ pos, int pos_batched, int V,
+                                                           const int* __restrict__ tri, int F, int H, int W,
+                                                           unsigned long long* __restrict__ zbuf,
+                                                           const unsigned* __restrict__ list,
+                                                           const unsigned* __restrict__ count) {
+  const unsigned n = *count;
+  const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const unsigned g = list[i];
+    const int b = static_cast<int>(g / F), f = static_cast<int>(g % F);
+    const float* P = pos + (pos_batched ? static_cast<size_t>(b) * V * 4 : 0);
+    TriDraw d;
+    if (!prepare_draw(P, tri, f, H, W, d)) continue;
+    draw_pixels(d, f, W, zbuf + static_cast<size_t>(b) * H * W, lane, 32);
   }
 }
 
@@ -150,7 +196,9 @@ __global__ void __launch_bounds__(256) interpolate_kernel(const float* __restric
 
 }  // namespace
 
-size_t rasterize_workspace_bytes(int B, int H, int W) { return static_cast<size_t>(B) * H * W * 8; }
+size_t rasterize_workspace_bytes(int B, int H, int W, int F) {
+  return static_cast<size_t>(B) * H * W * 8 + static_cast<size_t>(B) * F * 4 + 256;   // depth/id keys + large-triangle list + counter
+}
 
 int rasterize(const float* pos, int pos_batched, int V, const int* tri, int F, int B, int H, int W, float* rast_out,
               void* workspace, cudaStream_t stream) {
@@ -161,9 +209,14 @@ int rasterize(const float* pos, int pos_batched, int V, const int* tri, int F, i
   const size_t n = static_cast<size_t>(B) * H * W;
   raster_clear_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(zbuf, n);
   if (F > 0) {
-    const long long warps = static_cast<long long>(F) * B;
-    raster_tri_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(pos, pos_batched, V, tri, F, B,
-                                                                                           H, W, zbuf);
+    const long long tris = static_cast<long long>(F) * B;
+    UTX_CHECK(tris < (1ll << 32), "rasterize: too many (view, triangle) pairs");
+    unsigned* list = reinterpret_cast<unsigned*>(static_cast<uint8_t*>(workspace) + n * 8);
+    unsigned* count = list + tris;
+    UTX_CUDA(cudaMemsetAsync(count, 0, 4, stream));
+    raster_small_kernel<<<static_cast<unsigned>((tris + 255) / 256), 256, 0, stream>>>(pos, pos_batched, V, tri, F, B, H, W, zbuf,
+                                                                                      list, count);
+    raster_large_kernel<<<num_sms() * 8, 256, 0, stream>>>(pos, pos_batched, V, tri, F, H, W, zbuf, list, count);
   }
   raster_resolve_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
       pos, pos_batched, V, tri, B, H, W, zbuf, reinterpret_cast<float4*>(rast_out));

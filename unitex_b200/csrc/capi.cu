@@ -94,7 +94,7 @@ int utx_lora_merge(void* W, long ldw, const float* A, const float* B, int out_fe
                     static_cast<cudaStream_t>(stream));
 }
 
-size_t utx_rasterize_workspace_bytes(int B, int H, int W) { return rasterize_workspace_bytes(B, H, W); }
+size_t utx_rasterize_workspace_bytes(int B, int H, int W, int F) { return rasterize_workspace_bytes(B, H, W, F); }
 int utx_rasterize(const float* pos, int pos_batched, int V, const int32_t* tri, int F, int B, int H, int W,
                   float* rast_out, void* workspace, void* stream) {
   UTX_CHECK(pos && tri && rast_out && workspace, "utx_rasterize: null pointer");

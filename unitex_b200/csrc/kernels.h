@@ -81,7 +81,7 @@ int lora_merge(bf16* W, long ldw, const float* A, const float* B, int out_f, int
 
 
 // ------------------------------------------------------------------ bake: rasterise / interpolate / LBVH / fused UV bake
-size_t rasterize_workspace_bytes(int B, int H, int W);
+size_t rasterize_workspace_bytes(int B, int H, int W, int F);
 // pos [B or 1, V, 4] clip space, tri [F,3] -> rast [B,H,W,4] = (u, v, z/w, id+1)
 int rasterize(const float* pos, int pos_batched, int V, const int* tri, int F, int B, int H, int W, float* rast_out,
               void* workspace, cudaStream_t stream);
