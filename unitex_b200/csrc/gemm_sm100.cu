@@ -229,8 +229,13 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
 
 int gemm2_bf16_tn(const GemmArgs& a, cudaStream_t stream);   // 2-CTA pairs, gemm2_sm100.cu; -1 = shape not supported
 
-int gemm_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
-  UTX_CHECK(a.nprob == 1 || a.nprob == 2, "gemm: nprob must be 1 or 2");
+int gemm_bf16_tn(const GemmArgs& a_in, cudaStream_t stream) {
+  UTX_CHECK(a_in.nprob == 1 || a_in.nprob == 2, "gemm: nprob must be 1 or 2");
+  // empty problems (no text tokens, zero-row calls) are dropped here: a TMA descriptor cannot describe a 0-row tensor
+  GemmArgs a = a_in;
+  if (a.nprob == 2 && a.prob[1].M == 0) a.nprob = 1;
+  if (a.nprob == 2 && a.prob[0].M == 0) { a.prob[0] = a.prob[1]; a.nprob = 1; }
+  if (a.nprob == 1 && a.prob[0].M == 0) return 0;
   UTX_CHECK(a.K % BK == 0 && a.K > 0, "gemm: K must be a positive multiple of 64");
   UTX_CHECK(a.N % 8 == 0 && a.N > 0, "gemm: N must be a positive multiple of 8");
   for (int i = 0; i < a.nprob; ++i) {
