@@ -124,7 +124,10 @@ def test_ragged_token_counts_and_empty_calls(lib):
     eng.denoise_(lat, 100, [1.0], 3.5)
     torch.cuda.synchronize()
     assert torch.equal(lat, before)
-    ops.gemm(torch.empty(0, 256, device="cuda", dtype=torch.bfloat16), torch.zeros(256, 256, device="cuda", dtype=torch.bfloat16))
+    X = torch.zeros(4, 256, device="cuda", dtype=torch.bfloat16)
+    Y = torch.ones(4, 256, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(X[:0], torch.zeros(256, 256, device="cuda", dtype=torch.bfloat16), out=Y[:0])     # M = 0: nothing launched
+    assert (Y == 1).all()
     ops.euler_update_(lat, lat, 0, 0.1)
     torch.cuda.synchronize()
     assert torch.equal(lat, before)
