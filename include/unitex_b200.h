@@ -146,7 +146,7 @@ int utx_interpolate(const float* attr, int attr_batched, int V, int C, const flo
 /* vertices_homo @ (P @ W2C)^T (renderer_inverse.py:178,263): out [n, V, 4] */
 int utx_transform_points(const float* vert, int V, const float* mats, int n, float* out, void* stream);
 /* RayTracing(vertices, faces) / update_raw (raytracing/__init__.py:12-80; rt_aprmis/bvhhelpers.py:20-83): builds the
- * same LBVH the reference builds into `nodes` (utx_bvh_nodes_bytes(F) bytes, 48 B per node). */
+ * same LBVH the reference builds into `nodes` (utx_bvh_nodes_bytes(F) bytes: 48 B per node + packed triangle vertices). */
 size_t utx_bvh_nodes_bytes(int F);
 size_t utx_bvh_workspace_bytes(int F);
 int utx_bvh_build(const float* vert, int V, const int32_t* tri, int F, void* nodes, void* workspace, size_t workspace_bytes,
@@ -154,7 +154,7 @@ int utx_bvh_build(const float* vert, int V, const int32_t* tri, int F, void* nod
 /* reference node layout for inspection: info [2F-1, 3] (left, right, prim), aabb [2F-1, 6] */
 int utx_bvh_export(const void* nodes, int F, int32_t* info, float* aabb, void* stream);
 /* intersects_closest (rt_aprmis/__init__.py:36-86): hit u8 [N], tri_idx i32 [N] (-1 = miss), loc [N,3], uv [N,2] */
-int utx_bvh_intersect(const void* nodes, const float* vert, const int32_t* tri, const float* rays_o, const float* rays_d,
+int utx_bvh_intersect(const void* nodes, const float* vert, const int32_t* tri, int F, const float* rays_o, const float* rays_d,
                       long long N, unsigned char* hit, int32_t* tri_idx, float* loc, float* uv, void* stream);
 /* knn(src, dst, k=1) (pcd/knn/__init__.py:104-114, default backend torch_kdtree): exact nearest source point of every
  * dst point, lowest index on ties.  index int64 [M], score fp32 [M] = Euclidean distance.  nodes: utx_bvh_nodes_bytes(n_src),

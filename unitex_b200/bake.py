@@ -153,7 +153,7 @@ class RayTracing:
         tid = torch.empty(N, device=self.device, dtype=torch.int32)
         loc = torch.empty(N, 3, device=self.device, dtype=torch.float32)
         uv = torch.empty(N, 2, device=self.device, dtype=torch.float32)
-        _lib.check(L.utx_bvh_intersect(_p(self.nodes), _p(self.vertices), _p(self.faces), _p(o), _p(d), N, _p(hit), _p(tid),
+        _lib.check(L.utx_bvh_intersect(_p(self.nodes), _p(self.vertices), _p(self.faces), self.faces.shape[0], _p(o), _p(d), N, _p(hit), _p(tid),
                                        _p(loc), _p(uv), _stream()), "utx_bvh_intersect")
         return hit.bool().reshape(shape), None, tid.to(torch.int64).reshape(shape), loc.reshape(*shape, 3), uv.reshape(*shape, 2)
 

@@ -216,6 +216,18 @@ __global__ void __launch_bounds__(256) refit_kernel(int F, Node* __restrict__ no
   }
 }
 
+// packed triangle vertices behind the nodes: [F][3] float4 (xyz, 0)
+__global__ void __launch_bounds__(256) pack_tris_kernel(const float* __restrict__ vert, const int* __restrict__ tri, int F,
+                                                        float4* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float* v = vert + static_cast<size_t>(tri[f * 3 + k]) * 3;
+    out[static_cast<size_t>(f) * 3 + k] = make_float4(v[0], v[1], v[2], 0.f);
+  }
+}
+
 __global__ void __launch_bounds__(256) export_kernel(const Node* __restrict__ nodes, int n, int* __restrict__ info,
                                                      float* __restrict__ aabb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(256) export_kernel(const Node* __restrict__ no
 
 namespace {
 __global__ void __launch_bounds__(128) intersect_kernel(const void* __restrict__ nodes, const float* __restrict__ vert,
-                                                        const int* __restrict__ tri, const float* __restrict__ rays_o,
+                                                        const int* __restrict__ tri, int F, const float* __restrict__ rays_o,
                                                         const float* __restrict__ rays_d, long long N,
                                                         unsigned char* __restrict__ hit, int* __restrict__ tid,
                                                         float* __restrict__ pos, float* __restrict__ uv) {
@@ -240,7 +252,7 @@ __global__ void __launch_bounds__(128) intersect_kernel(const void* __restrict__
   float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
   const float len = sqrtf(dot3f(d[0], d[1], d[2], d[0], d[1], d[2]));
   d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
-  const RayHit h = bvh_trace(nodes, vert, tri, o, d);
+  const RayHit h = bvh_trace(nodes, vert, tri, o, d, static_cast<const float4*>(nodes) + static_cast<size_t>(2 * F - 1) * 3);
   hit[r] = static_cast<unsigned char>(h.any);
   tid[r] = h.any ? h.tid : -1;
   pos[r * 3] = h.any ? o[0] + h.t * d[0] : 0.f;
@@ -253,7 +265,8 @@ __global__ void __launch_bounds__(128) intersect_kernel(const void* __restrict__
 
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
-size_t bvh_nodes_bytes(int F) { return static_cast<size_t>(2 * F - 1) * sizeof(Node); }
+// nodes [2F-1] followed by the packed triangle vertices [F][3] float4 (unused by the point tree)
+size_t bvh_nodes_bytes(int F) { return static_cast<size_t>(2 * F - 1) * sizeof(Node) + static_cast<size_t>(F) * 48; }
 
 size_t bvh_workspace_bytes(int F) {
   size_t cub_bytes = 0;
@@ -294,7 +307,11 @@ static int build_tree(const float* vert, const int* tri, const float* pts, int F
 int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, void* workspace, size_t ws_bytes,
               cudaStream_t stream) {
   (void)V;
-  return build_tree(vert, tri, nullptr, F, nodes_out, workspace, ws_bytes, stream);
+  UTX_TRY(build_tree(vert, tri, nullptr, F, nodes_out, workspace, ws_bytes, stream));
+  pack_tris_kernel<<<(F + 255) / 256, 256, 0, stream>>>(vert, tri, F,
+                                                       reinterpret_cast<float4*>(static_cast<Node*>(nodes_out) + (2 * F - 1)));
+  UTX_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // LBVH over n points (leaf prim = point index): the search structure of the bake's exact 1-NN fill
@@ -340,10 +357,10 @@ int bvh_export(const void* nodes, int F, int* info, float* aabb, cudaStream_t st
   return 0;
 }
 
-int bvh_intersect(const void* nodes, const float* vert, const int* tri, const float* rays_o, const float* rays_d,
+int bvh_intersect(const void* nodes, const float* vert, const int* tri, int F, const float* rays_o, const float* rays_d,
                   long long N, unsigned char* hit, int* tid, float* pos, float* uv, cudaStream_t stream) {
   if (N == 0) return 0;
-  intersect_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, stream>>>(nodes, vert, tri, rays_o, rays_d, N, hit, tid,
+  intersect_kernel<<<static_cast<unsigned>((N + 127) / 128), 128, 0, stream>>>(nodes, vert, tri, F, rays_o, rays_d, N, hit, tid,
                                                                                pos, uv);
   UTX_CUDA(cudaGetLastError());
   return 0;

@@ -120,10 +120,10 @@ int utx_bvh_export(const void* nodes, int F, int32_t* info, float* aabb, void* s
   UTX_CHECK(nodes && info && aabb, "utx_bvh_export: null pointer");
   return bvh_export(nodes, F, info, aabb, static_cast<cudaStream_t>(stream));
 }
-int utx_bvh_intersect(const void* nodes, const float* vert, const int32_t* tri, const float* rays_o, const float* rays_d,
+int utx_bvh_intersect(const void* nodes, const float* vert, const int32_t* tri, int F, const float* rays_o, const float* rays_d,
                       long long N, unsigned char* hit, int32_t* tri_idx, float* loc, float* uv, void* stream) {
   UTX_CHECK(nodes && vert && tri && rays_o && rays_d && hit && tri_idx && loc && uv, "utx_bvh_intersect: null pointer");
-  return bvh_intersect(nodes, vert, tri, rays_o, rays_d, N, hit, tri_idx, loc, uv, static_cast<cudaStream_t>(stream));
+  return bvh_intersect(nodes, vert, tri, F, rays_o, rays_d, N, hit, tri_idx, loc, uv, static_cast<cudaStream_t>(stream));
 }
 int utx_knn1(const float* src, int n_src, const float* dst, long long M, long long* index, float* score, void* nodes,
              void* workspace, size_t workspace_bytes, void* stream) {

@@ -97,7 +97,7 @@ int point_bvh_build(const float* pts, int n, void* nodes_out, void* workspace, s
 int knn1(const float* src, int n_src, const float* dst, long long M, long long* index, float* score, void* nodes, void* workspace,
          size_t ws_bytes, cudaStream_t stream);
 int bvh_export(const void* nodes, int F, int* info, float* aabb, cudaStream_t stream);
-int bvh_intersect(const void* nodes, const float* vert, const int* tri, const float* rays_o, const float* rays_d,
+int bvh_intersect(const void* nodes, const float* vert, const int* tri, int F, const float* rays_o, const float* rays_d,
                   long long N, unsigned char* hit, int* tid, float* pos, float* uv, cudaStream_t stream);
 size_t uv_bake_workspace_bytes(int H2, int W2);
 int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
