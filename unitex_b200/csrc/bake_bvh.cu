@@ -252,7 +252,8 @@ __global__ void __launch_bounds__(128) intersect_kernel(const void* __restrict__
   float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
   const float len = sqrtf(dot3f(d[0], d[1], d[2], d[0], d[1], d[2]));
   d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
-  const RayHit h = bvh_trace(nodes, vert, tri, o, d, static_cast<const float4*>(nodes) + static_cast<size_t>(2 * F - 1) * 3);
+  (void)F;
+  const RayHit h = bvh_trace(nodes, vert, tri, o, d, nullptr);
   hit[r] = static_cast<unsigned char>(h.any);
   tid[r] = h.any ? h.tid : -1;
   pos[r * 3] = h.any ? o[0] + h.t * d[0] : 0.f;
