@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_error_reporting_no_fallback(lib):
     assert lib.utx_version() >= 100
-    rc = lib.utx_gemm_bf16(None, 0, None, 0, None, None, 0, 0, 0, 0, 0, None, None, 0, None)
+    rc = lib.utx_gemm_bf16(None, 0, None, 0, None, None, 0, 128, 128, 64, 0, None, None, 0, None)
     assert rc != 0 and b"null pointer" in lib.utx_last_error()
     from unitex_b200 import _lib
     with pytest.raises(_lib.UtxError):

@@ -12,6 +12,8 @@ int utx_version(void) { return 100; }
 
 int utx_gemm_bf16(const void* A, long lda, const void* W, long ldw, const void* bias, void* C, long ldc, int M, int N,
                   int K, int epi, const float* gate, const void* res, long ldres, void* stream) {
+  UTX_CHECK(M >= 0 && N > 0 && K > 0, "utx_gemm_bf16: bad shape");
+  if (M == 0) return 0;   // empty batch (torch hands out null data pointers for empty tensors): nothing to launch
   UTX_CHECK(A && W && C, "utx_gemm_bf16: null pointer");
   GemmArgs a{};
   a.N = N; a.K = K; a.epi = epi; a.gelu_col_start = 0; a.nprob = 1;
