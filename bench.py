@@ -88,48 +88,58 @@ class ClockSampler:
 CPU_FRAC = 4   # the bounded CPU sample is exactly 1/CPU_FRAC of one block's work
 
 
-def cpu_block_seconds(repeats: int = 1):
-    """Times a 1/4 sample of ONE single-stream FLUX block at the full S=9728 on the host cores, with the oracle's
-    eager op sequence (= diffusers' CPU path restated, bf16 weights like the reference): LayerNorm-modulate, proj_mlp,
-    GELU and proj_out on a quarter of the token rows (rows are independent), q/k/v projection + RMSNorm + RoPE + SDPA
-    for a quarter of the heads over ALL 9728 keys (heads are independent).  All 57 blocks touch the same 113 246 208
-    params per token and do the same attention, so one step ~ 57 x 4 x this."""
+def cpu_block_seconds(repeats: int = 1, device="cpu", frac: int = CPU_FRAC):
+    """Times a 1/frac sample of ONE single-stream FLUX block at the full S=9728 with the oracle's eager op sequence
+    (= diffusers' eager path restated, bf16 weights like the reference): LayerNorm-modulate, proj_mlp, GELU and proj_out
+    on 1/frac of the token rows (rows are independent), q/k/v projection + RMSNorm + RoPE + SDPA for 1/frac of the heads
+    over ALL 9728 keys (heads are independent).  All 57 blocks touch the same 113 246 208 params per token and do the same
+    attention (SURVEY 8d), so one step ~ 57 x frac x this.  device='cpu': the host-core baseline (frac 4);
+    device=cuda, frac=1: the same eager sequence on the B200 through cuBLAS + torch SDPA ("the reference on B200" stand-in,
+    SURVEY 8d) -- a reported baseline, never the product path."""
     import torch
     import torch.nn.functional as F
     from oracle import flux_dit as fd
     torch.manual_seed(0)
     cfg = fd.FluxConfig()
     D, H = cfg.inner_dim, cfg.num_attention_heads
-    Hs, Sr = H // CPU_FRAC, S_TOT // CPU_FRAC
+    Hs, Sr = H // frac, S_TOT // frac
     bf = torch.bfloat16
-    w_mod, b_mod = (torch.randn(3 * D, D) * 0.02).to(bf), (torch.randn(3 * D) * 0.02).to(bf)
-    w_qkv = [(torch.randn(Hs * 128, D) * 0.02).to(bf) for _ in range(3)]
-    b_qkv = [(torch.randn(Hs * 128) * 0.02).to(bf) for _ in range(3)]
-    w_mlp, b_mlp = (torch.randn(4 * D, D) * 0.02).to(bf), (torch.randn(4 * D) * 0.02).to(bf)
-    w_out, b_out = (torch.randn(D, 5 * D) * 0.02).to(bf), (torch.randn(D) * 0.02).to(bf)
-    rq, rk = torch.ones(128, dtype=bf), torch.ones(128, dtype=bf)
-    x = torch.randn(1, S_TOT, D).to(bf)
-    temb = torch.randn(1, D).to(bf)
+    dev = torch.device(device)
+    on_gpu = dev.type == "cuda"
+    def rnd(*shape):
+        return (torch.randn(*shape) * 0.02).to(bf).to(dev)
+    w_mod, b_mod = rnd(3 * D, D), rnd(3 * D)
+    w_qkv = [rnd(Hs * 128, D) for _ in range(3)]
+    b_qkv = [rnd(Hs * 128) for _ in range(3)]
+    w_mlp, b_mlp = rnd(4 * D, D), rnd(4 * D)
+    w_out, b_out = rnd(D, 5 * D), rnd(D)
+    rq, rk = torch.ones(128, dtype=bf, device=dev), torch.ones(128, dtype=bf, device=dev)
+    x = torch.randn(1, S_TOT, D).to(bf).to(dev)
+    temb = torch.randn(1, D).to(bf).to(dev)
     ids = torch.zeros(S_TOT, 3)
     ids[:, 1] = torch.arange(S_TOT) % 96
     ids[:, 2] = torch.arange(S_TOT) // 96
-    cos, sin = fd.rope_table(ids, cfg)
+    cos, sin = (t.to(dev) for t in fd.rope_table(ids, cfg))
     best = None
     with torch.no_grad():
         for _ in range(repeats):
+            if on_gpu:
+                torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             sh, sc, gate = F.linear(F.silu(temb), w_mod, b_mod).chunk(3, dim=1)
             nx = fd.layer_norm(x) * (1 + sc[:, None]) + sh[:, None]          # full rows: attention needs every key
             q, k, v = (F.linear(nx, w, b).view(1, S_TOT, Hs, 128).transpose(1, 2) for w, b in zip(w_qkv, b_qkv))
             q, k = fd.apply_rope(fd.rms_norm(q, rq), cos, sin), fd.apply_rope(fd.rms_norm(k, rk), cos, sin)
-            ao = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(1, S_TOT, Hs * 128)
+            ao = F.scaled_dot_product_attention(q.to(bf), k.to(bf), v).transpose(1, 2).reshape(1, S_TOT, Hs * 128)
             mlp = F.gelu(F.linear(nx[:, :Sr], w_mlp, b_mlp), approximate="tanh")
-            cat = torch.cat([ao[:, :Sr].repeat(1, 1, CPU_FRAC), mlp], dim=2)
+            cat = torch.cat([ao[:, :Sr].repeat(1, 1, frac), mlp], dim=2)
             y = x[:, :Sr] + gate.unsqueeze(1) * F.linear(cat, w_out, b_out)
+            if on_gpu:
+                torch.cuda.synchronize(dev)
             dt = time.perf_counter() - t0
             assert torch.isfinite(y.float()).all()
             best = dt if best is None else min(best, dt)
-    return best * CPU_FRAC, torch.get_num_threads()
+    return best * frac, torch.get_num_threads()
 
 
 def run_reference(args, rank, world):
@@ -270,13 +280,52 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_bake:
         out["uv_bake"] = bench_uv_bake(dev)
         out["vae_decode"] = bench_vae_decode(dev)
+    if world == 1 and not args.no_bake:
+        out["delight"] = bench_delight(eng, dev, sig)
     if world == 1 and not args.no_cpu_baseline:
+        del eng
+        torch.cuda.empty_cache()
+        cpu_block_seconds(2, device=dev, frac=1)                       # warm-up (cuBLAS heuristics, SDPA backend choice)
+        dt_gpu, _ = cpu_block_seconds(5, device=dev, frac=1)
+        out["gpu_eager_baseline"] = {"value": 1.0 / (57.0 * dt_gpu), "unit": UNIT, "kind": "port",
+                                     "sample": "ONE full single-stream block at S=9728 through torch eager on this B200 (cuBLAS bf16 "
+                                               "linears + torch SDPA, the oracle's op sequence); step = 57 x sample. The closest "
+                                               "stand-in for 'the reference on B200' (SURVEY 8d); reported, not a target"}
         dt, cores = cpu_block_seconds(1)
         out["cpu_baseline"] = {"value": 1.0 / (57.0 * dt), "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": "1/4 of one single-stream block (of 57 equal-cost blocks) at S=9728 (quarter of the "
                                          "rows for LN/MLP/proj_out, quarter of the heads for attention over all keys), "
                                          "eager oracle port of the diffusers CPU path, bf16 weights; step = 57 x 4 x sample"}
     print(json.dumps(out), flush=True)
+
+
+def bench_delight(eng, dev, sig):
+    """BASELINE config 3 side measurement: the delight call's shape, S = 512 txt + 4096 noise + 4096 control = 8704
+    (no reference-image tokens), same engine and weights, CUDA events over 3 steps after 2 warm-up steps."""
+    import torch
+    s_img = S_NOISE + 4096
+    ids = torch.zeros(S_TXT + s_img, 3)
+    yy, xx = torch.meshgrid(torch.arange(64), torch.arange(64), indexing="ij")
+    g = torch.stack([torch.zeros(64, 64), yy.float(), xx.float()], -1).reshape(-1, 3)
+    g2 = g.clone()
+    g2[:, 1] += 64
+    ids[S_TXT:] = torch.cat([g, g2])
+    eng.prepare(ids, None, None, s_txt=S_TXT)
+    lat = torch.randn(s_img, 64, device=dev, generator=torch.Generator(device=dev).manual_seed(5)).to(torch.bfloat16)
+    for i in range(2):
+        eng.denoise_(lat, S_NOISE, sig[i:i + 2], 3.5)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(3):
+        eng.denoise_(lat, S_NOISE, sig[i:i + 2], 3.5)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    S = S_TXT + s_img
+    flops = 57 * 2 * 113246208 * S + 57 * 4 * 3072 * S * S
+    return {"metric": METRIC, "workload": "delight 1024x1024 4-view: S=8704 = 512 txt + 4096 noise + 4096 control", "value": 1e3 / ms,
+            "unit": UNIT, "ms_per_step": ms, "tflops": flops / (ms * 1e-3) / 1e12, "finite": bool(torch.isfinite(lat.float()).all())}
 
 
 def bench_vae_decode(dev):
