@@ -15,6 +15,8 @@
 // O / l are rescaled lazily (running max grows by > 8).
 // `tcgen05.commit` of S_X(j+1) retires every earlier MMA of the issuing thread, so "S_X(j+1) ready" also means
 // "PV_X(j) done": no separate barrier guards the O rescale or the P overwrite.
+#include <type_traits>
+
 #include "common.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -34,8 +36,21 @@ constexpr int OFF_V = 4 * TILE_BYTES;      // 2 stages
 constexpr int OFF_BAR = 6 * TILE_BYTES;
 constexpr int SMEM_TOTAL = OFF_BAR + 32 * 8 + 1024;
 constexpr float kRescaleThreshold = 8.0f;
+constexpr int kPolyOf8 = 3;         // exponential pairs per 8 evaluated by the FMA-pipe polynomial instead of MUFU
+constexpr int kRegsSoftmax = 208, kRegsOther = 88;   // 256 x 208 + 128 x 88 = 64512 = 384 x 168
 
-enum Bar { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, P_FULL = 11, O_FULL = 13, NUM_BARS = 14 };
+// scripts/attn_trace.cu compiles this file with -DUTX_ATTN_TRACE to record SM-clock stamps of one CTA's roles
+#ifdef UTX_ATTN_TRACE
+__device__ long long* g_attn_trace = nullptr;   // [3 roles][n_kv][8 points]
+#define UTX_TR(role, j, pt)                                                                                   \
+  do {                                                                                                        \
+    if (blockIdx.x == 1 && blockIdx.y == 0 && g_attn_trace) g_attn_trace[((role) * 128 + (j)) * 8 + (pt)] = clock64(); \
+  } while (0)
+#else
+#define UTX_TR(role, j, pt) do { } while (0)
+#endif
+
+enum Bar { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, P_FULL = 11, O_FULL = 13, PH_FULL = 14, NUM_BARS = 16 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, long ld_out, int S, int H,
@@ -45,7 +60,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + NUM_BARS);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (2 * BQ);
   const int head = blockIdx.y;
@@ -54,7 +69,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
 
   if (warp == 0 && lane == 0) prefetch_tmap(&tm_qkv);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NUM_BARS; ++i) mbar_init(&bar[i], (i == P_FULL || i == P_FULL + 1) ? 4 : 1);
+    for (int i = 0; i < NUM_BARS; ++i)
+      mbar_init(&bar[i], (i == P_FULL || i == P_FULL + 1 || i == PH_FULL || i == PH_FULL + 1) ? 4 : 1);   // 4 softmax warps each
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -62,6 +78,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // register re-balancing: the softmax warpgroups keep a whole 128-column S row per thread
+  // (ptxas only honours the new budget for code nested under the branch that executes the setmaxnreg)
+  if (warp < 4) {
+  setmaxnreg_dec<kRegsOther>();
   if (warp == 0 && lane == 0) {
     // ---------------------------------------------------------------- TMA producer
     mbar_arrive_expect_tx(&bar[Q_FULL], 2 * TILE_BYTES);
@@ -83,56 +103,86 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
       tma_load_2d(vd, &tm_qkv, &bar[V_FULL + s], 2 * D + head * HD, j * BKV);
       tma_load_2d(vd + HALF_BYTES, &tm_qkv, &bar[V_FULL + s], 2 * D + head * HD + 64, j * BKV);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ---------------------------------------------------------------- MMA issuer
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer: the whole warp runs the loop (waits and
+    // descriptor arithmetic stay warp-uniform), one elected lane issues.  With a single divergent thread owning the loop
+    // every UTCHMMA cost ~19 SASS instructions (R2UR + elect loop) = ~91 clk against the 64 clk the 128x128x16 MMA takes:
+    // the tensor pipe was issue-starved (scripts/attn_trace.cu timeline, profiles/r01_summary.md).
+    const bool leader = elect_one();
+    const uint32_t sb = __shfl_sync(0xffffffffu, smem_u32(smem), 0);   // warp-uniform shared-window base
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);   // warp-uniform copy: TMEM operands stay in uniform registers
     constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);   // Q (smem, K-major) x K (smem, K-major)
     constexpr uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);    // P (TMEM)          x V (smem, MN-major)
     auto issue_S = [&](int x, int j) {   // S_x = Q_x K_j^T
-      const uint32_t q_addr = smem_u32(smem + OFF_Q + x * TILE_BYTES);
-      const uint32_t k_addr = smem_u32(smem + OFF_K + (j & 1) * TILE_BYTES);
+      const uint32_t q_addr = sb + OFF_Q + x * TILE_BYTES;
+      const uint32_t k_addr = sb + OFF_K + (j & 1) * TILE_BYTES;
+      if (leader) {
 #pragma unroll
-      for (int kk = 0; kk < HD / 16; ++kk) {
-        const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
-        umma_ss(tmem_base + x * 128, make_sdesc(q_addr + off, 16, 1024), make_sdesc(k_addr + off, 16, 1024), idesc_s, kk != 0);
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
+          umma_ss(tmem_u + x * 128, make_sdesc(q_addr + off, 16, 1024), make_sdesc(k_addr + off, 16, 1024), idesc_s, kk != 0);
+        }
+        umma_commit_a(sb + OFF_BAR + (S_FULL + x) * 8);
       }
-      umma_commit(&bar[S_FULL + x]);
+      __syncwarp();
     };
-    auto issue_PV = [&](int x, int j) {  // O_x += P_x V_j, P_x bf16 in the first 64 columns of S_x
-      const uint32_t v_addr = smem_u32(smem + OFF_V + (j & 1) * TILE_BYTES);
+    auto issue_PV = [&](int x, int j, int half) {  // O_x += P_x[:, 64*half : 64*half+64] V_j[64*half : ...], P_x bf16 over S_x
+      const uint32_t v_addr = sb + OFF_V + (j & 1) * TILE_BYTES;
+      if (leader) {
 #pragma unroll
-      for (int kk = 0; kk < BKV / 16; ++kk)
-        umma_ts(tmem_base + 256 + x * 128, tmem_base + x * 128 + kk * 8, make_sdesc(v_addr + kk * 16 * 128, HALF_BYTES, 1024),
-                idesc_o, (j | kk) != 0);
+        for (int kk = 4 * half; kk < 4 * half + 4; ++kk)
+          umma_ts(tmem_u + 256 + x * 128, tmem_u + x * 128 + kk * 8, make_sdesc(v_addr + kk * 16 * 128, HALF_BYTES, 1024),
+                  idesc_o, (j | kk) != 0);
+      }
+      __syncwarp();
     };
-    mbar_wait(&bar[Q_FULL], 0);
-    mbar_wait(&bar[K_FULL], 0);
+    auto commit = [&](int b) {
+      if (leader) umma_commit_a(sb + OFF_BAR + (b) * 8);
+      __syncwarp();
+    };
+    mbar_wait_a(sb + OFF_BAR + (Q_FULL) * 8, 0);
+    mbar_wait_a(sb + OFF_BAR + (K_FULL) * 8, 0);
     tc_fence_after();
     issue_S(0, 0);
     issue_S(1, 0);
-    umma_commit(&bar[K_EMPTY]);
+    commit(K_EMPTY);
     for (int j = 0; j < n_kv; ++j) {
       const int s = j & 1, sn = (j + 1) & 1;
       const bool more = j + 1 < n_kv;
-      mbar_wait(&bar[V_FULL + s], (j >> 1) & 1);
-      mbar_wait(&bar[P_FULL], j & 1);
+      if (leader) UTX_TR(2, j, 0);
+      mbar_wait_a(sb + OFF_BAR + (V_FULL + s) * 8, (j >> 1) & 1);
+      if (leader) UTX_TR(2, j, 1);
+      mbar_wait_a(sb + OFF_BAR + (PH_FULL) * 8, j & 1);
+      if (leader) UTX_TR(2, j, 2);
       tc_fence_after();
-      issue_PV(0, j);
+      issue_PV(0, j, 0);
+      mbar_wait_a(sb + OFF_BAR + (P_FULL) * 8, j & 1);
+      tc_fence_after();
+      issue_PV(0, j, 1);
       if (more) {
-        mbar_wait(&bar[K_FULL + sn], ((j + 1) >> 1) & 1);
+        mbar_wait_a(sb + OFF_BAR + (K_FULL + sn) * 8, ((j + 1) >> 1) & 1);
         tc_fence_after();
         issue_S(0, j + 1);
       }
-      mbar_wait(&bar[P_FULL + 1], j & 1);
+      if (leader) UTX_TR(2, j, 3);
+      mbar_wait_a(sb + OFF_BAR + (PH_FULL + 1) * 8, j & 1);
+      if (leader) UTX_TR(2, j, 4);
       tc_fence_after();
-      issue_PV(1, j);
-      umma_commit(&bar[V_EMPTY + s]);
+      issue_PV(1, j, 0);
+      mbar_wait_a(sb + OFF_BAR + (P_FULL + 1) * 8, j & 1);
+      tc_fence_after();
+      issue_PV(1, j, 1);
+      commit(V_EMPTY + s);
       if (more) {
         issue_S(1, j + 1);
-        umma_commit(&bar[K_EMPTY + sn]);
+        commit(K_EMPTY + sn);
       }
+      if (leader) UTX_TR(2, j, 5);
     }
-    umma_commit(&bar[O_FULL]);
-  } else if (warp >= 4) {
+    commit(O_FULL);
+  }
+  } else {
+    setmaxnreg_inc<kRegsSoftmax>();
     // ---------------------------------------------------------------- softmax warpgroups: thread == query row
     const int x = (warp - 4) >> 2;                 // 0 = tile A, 1 = tile B
     const int ew = (warp - 4) & 3;                 // == warp % 4: the TMEM lane quarter this warp may touch
@@ -141,30 +191,26 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
     const uint32_t tS = tmem_base + lane_off + x * 128;
     const uint32_t tO = tmem_base + lane_off + 256 + x * 128;
     float m_used = -INFINITY, l = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
+    // one KV tile of the online softmax; RAGGED only for a last tile with fewer than 128 keys
+    auto tile = [&](int j, auto ragged_c) {
+      constexpr bool RAGGED = decltype(ragged_c)::value;
+      if (lane == 0 && ew == 0) UTX_TR(x, j, 0);
       mbar_wait(&bar[S_FULL + x], j & 1);
+      if (lane == 0 && ew == 0) UTX_TR(x, j, 1);
       tc_fence_after();
       const int kv_valid = S - j * BKV;
-      const bool ragged = kv_valid < BKV;
-      // row max: four tcgen05.ld in flight, one wait (the first version paid the TMEM round trip eight times per tile and
-      // was latency bound: tensor pipe 44 %, r01_attention2_kernel profile)
+      // the whole 128-column S row lives in registers (setmaxnreg gives the softmax warpgroups 232): one TMEM read per tile
       uint32_t sv[4][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, sv[c]);
       tmem_ld_wait();
+      if (lane == 0 && ew == 0) UTX_TR(x, j, 2);
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (!ragged) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[c][i]));
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < kv_valid) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[c][i]));
-      }
+        for (int i = 0; i < 32; ++i)
+          if (!RAGGED || c * 32 + i < kv_valid) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[c][i]));
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = mx * scale_log2;
       const bool upd = m_new > m_used + kRescaleThreshold;
@@ -173,39 +219,36 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
       m_used = m_next;
       if (j > 0 && __any_sync(0xffffffffu, upd)) {     // PV_x(j-1) has retired (see header): O_x is consistent
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t ov[32];
-          tmem_ld32(tO + c * 32, ov);
+        for (int c = 0; c < 8; ++c) {
+          uint32_t ov[16];
+          tmem_ld16(tO + c * 16, ov);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-          tmem_st32(tO + c * 32, ov);
+          for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st16(tO + c * 16, ov);
         }
       }
-      // exponentials: S re-read in 32-column chunks with the next chunk's load in flight behind the current chunk's math;
-      // packed fp32x2 scale/sum, every 4th pair on the FMA pipe; P written back over S (16 packed columns per chunk)
+      if (lane == 0 && ew == 0) UTX_TR(x, j, 3);
+      // exponentials in place: packed fp32x2 scale/sum, kPolyOf8 of every 8 pairs on the FMA pipe instead of MUFU;
+      // P (bf16) is written back over S in four 16-column stores; the first half is announced early so the PV MMAs
+      // of keys 0-63 start while keys 64-127 are still being exponentiated
       uint64_t lsum2 = pack2(0.f, 0.f);
       const uint64_t sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_next, -m_next);
-      uint32_t buf[2][32];
-      tmem_ld32(tS, buf[0]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        tmem_ld_wait();
-        if (c + 1 < 4) tmem_ld32(tS + (c + 1) * 32, buf[(c + 1) & 1]);
-        const uint32_t* cur = buf[c & 1];
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const uint64_t x2 = fma2(pack2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])), sc2, nm2);
+          const uint64_t x2 = fma2(pack2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
           uint64_t p2;
-          if ((i & 3) == 3) {
+          if ((i & 7) < kPolyOf8) {
             p2 = exp2_poly2(x2);
           } else {
             float x0, x1;
             unpack2(x2, x0, x1);
             p2 = pack2(ex2_approx(x0), ex2_approx(x1));
           }
-          if (ragged) {
+          if (RAGGED) {
             float p0, p1;
             unpack2(p2, p0, p1);
             if (c * 32 + 2 * i >= kv_valid) p0 = 0.f;
@@ -217,17 +260,27 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
           unpack2(p2, p0, p1);
           pk[i] = pack_bf16x2(p0, p1);
         }
+        if (c == 2) {   // stores of chunks 0-1 (keys 0-63) have had this chunk's arithmetic to land
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[PH_FULL + x]);
+        }
         tmem_st16(tS + c * 16, pk);
       }
       float ls0, ls1;
       unpack2(lsum2, ls0, ls1);
-      const float lsum = ls0 + ls1;
-      l = l * alpha + lsum;
+      l = l * alpha + (ls0 + ls1);
+      if (lane == 0 && ew == 0) UTX_TR(x, j, 4);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[P_FULL + x]);
-    }
+      if (lane == 0 && ew == 0) UTX_TR(x, j, 5);
+    };
+    const int n_full = S / BKV;
+    for (int j = 0; j < n_full; ++j) tile(j, std::false_type{});
+    if (n_full < n_kv) tile(n_full, std::true_type{});
     // ---------------------------------------------------------------- epilogue
     mbar_wait(&bar[O_FULL], 0);
     tc_fence_after();
