@@ -15,6 +15,7 @@
 // O / l are rescaled lazily (running max grows by > 8).
 // `tcgen05.commit` of S_X(j+1) retires every earlier MMA of the issuing thread, so "S_X(j+1) ready" also means
 // "PV_X(j) done": no separate barrier guards the O rescale or the P overwrite.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.h"
@@ -36,7 +37,6 @@ constexpr int OFF_V = 4 * TILE_BYTES;      // 2 stages
 constexpr int OFF_BAR = 6 * TILE_BYTES;
 constexpr int SMEM_TOTAL = OFF_BAR + 32 * 8 + 1024;
 constexpr float kRescaleThreshold = 8.0f;
-constexpr int kPolyOf8 = 3;         // exponential pairs per 8 evaluated by the FMA-pipe polynomial instead of MUFU
 constexpr int kRegsSoftmax = 208, kRegsOther = 88;   // 256 x 208 + 128 x 88 = 64512 = 384 x 168
 
 // scripts/attn_trace.cu compiles this file with -DUTX_ATTN_TRACE to record SM-clock stamps of one CTA's roles
@@ -52,6 +52,8 @@ __device__ long long* g_attn_trace = nullptr;   // [3 roles][n_kv][8 points]
 
 enum Bar { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, P_FULL = 11, O_FULL = 13, PH_FULL = 14, NUM_BARS = 16 };
 
+// kPolyOf8: exponential pairs per 8 evaluated by the FMA-pipe polynomial instead of MUFU
+template <int kPolyOf8>
 __global__ void __launch_bounds__(kThreads, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, long ld_out, int S, int H,
                   float scale_log2) {
@@ -205,13 +207,15 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
       for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, sv[c]);
       tmem_ld_wait();
       if (lane == 0 && ew == 0) UTX_TR(x, j, 2);
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      float mx8[8];      // eight independent chains: four left every FMNMX3 waiting on its predecessor
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mx8[k] = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (!RAGGED || c * 32 + i < kv_valid) mx4[c] = fmaxf(mx4[c], __uint_as_float(sv[c][i]));
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+          if (!RAGGED || c * 32 + i < kv_valid) mx8[c * 2 + ((i >> 1) & 1)] = fmaxf(mx8[c * 2 + ((i >> 1) & 1)], __uint_as_float(sv[c][i]));
+      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       const float m_new = mx * scale_log2;
       const bool upd = m_new > m_used + kRescaleThreshold;
       const float m_next = upd ? m_new : m_used;
@@ -321,14 +325,24 @@ int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S,
   UTX_CHECK(ld_qkv >= 3L * H * HD && ld_out % 8 == 0, "attention: bad leading dimensions");
   CUtensorMap tm;
   UTX_TRY(make_tmap_2d_bf16(&tm, qkv, S, 3L * H * HD, ld_qkv, 128, 64));
-  static bool attr_set = false;
-  if (!attr_set) {
-    UTX_CUDA(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    attr_set = true;
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = std::getenv("UTX_ATTN_POLY");   // tuning knob; default measured best at S = 9728
+    poly = e ? std::atoi(e) : 2;
+    if (poly < 0 || poly > 3) poly = 2;
+    UTX_CUDA(cudaFuncSetAttribute(attention2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    UTX_CUDA(cudaFuncSetAttribute(attention2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    UTX_CUDA(cudaFuncSetAttribute(attention2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    UTX_CUDA(cudaFuncSetAttribute(attention2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   dim3 grid((S + 2 * BQ - 1) / (2 * BQ), H);
-  attention2_kernel<<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2);
+  switch (poly) {
+    case 0: attention2_kernel<0><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2); break;
+    case 1: attention2_kernel<1><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2); break;
+    case 3: attention2_kernel<3><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2); break;
+    default: attention2_kernel<2><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2); break;
+  }
   UTX_CUDA(cudaGetLastError());
   return 0;
 }
