@@ -90,9 +90,10 @@ def test_gemm_grouped_two_streams(lib, gemm_impl):
     _check_bf16(C[M0:], X[M0:].float() @ W1.float().T + b1.float(), name="grouped img")
 
 
-@pytest.fixture(params=["1", "2"])
+@pytest.fixture(params=["1", "2", "3"])
 def attn_impl(request, monkeypatch):
-    """Both attention kernels stay under test: 1 = one query tile per CTA, P via smem; 2 = two-tile ping-pong, P in TMEM."""
+    """All attention kernels stay under test: 1 = one query tile per CTA, P via smem; 2 = two-tile ping-pong, P in TMEM;
+    3 = one query tile, S and P double-buffered in TMEM, two softmax threads per row."""
     monkeypatch.setenv("UTX_ATTN_IMPL", request.param)
     return request.param
 

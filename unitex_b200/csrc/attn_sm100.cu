@@ -245,11 +245,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ 
 }  // namespace
 
 int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream);
+int attention3_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream);
 
 int attention_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream) {
   // UTX_ATTN_IMPL=1: one query tile per CTA, P through smem (this file).  =2 (default): two-tile ping-pong, P in TMEM
-  // (attn2_sm100.cu).  Both stay built so the parity tests can run either.
+  // (attn2_sm100.cu).  =3: one query tile, S and P double-buffered in TMEM (attn3_sm100.cu).  All stay built so the
+  // parity tests can run each.
   const char* impl = getenv("UTX_ATTN_IMPL");
+  if (impl != nullptr && impl[0] == '3') return attention3_bf16(qkv, ld_qkv, out, ld_out, S, H, stream);
   if (impl == nullptr || impl[0] != '1') return attention2_bf16(qkv, ld_qkv, out, ld_out, S, H, stream);
   UTX_CHECK(S > 0 && H > 0, "attention: empty problem");
   UTX_CHECK(ld_qkv >= 3L * H * HD && ld_out % 8 == 0, "attention: bad leading dimensions");
