@@ -116,6 +116,27 @@ def test_attention(lib, attn_impl, S, H, qscale):
     assert (out.float() - ref).abs().max().item() < 0.05 * ref.abs().max().item() + 2e-2
 
 
+@pytest.mark.parametrize("S,slope", [(640, 0.02), (1000, 0.05), (384, -0.03)])
+def test_attention_growing_logits(lib, attn_impl, S, slope):
+    """Logits that climb (or fall) steadily along the key axis: every key tile outgrows the running reference, in both of
+    its halves -- the lazy-reference fast path must fall back to the exact maximum and rescale O / l each time."""
+    from unitex_b200 import ops
+    H = 2
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q = torch.ones(S, H * 128, device="cuda") + 0.1 * torch.randn(S, H * 128, device="cuda", generator=g)
+    ramp = (torch.arange(S, device="cuda", dtype=torch.float32) * slope)[:, None]
+    k = ramp * torch.ones(S, H * 128, device="cuda") + 0.1 * torch.randn(S, H * 128, device="cuda", generator=g)
+    v = torch.randn(S, H * 128, device="cuda", generator=g)
+    qkv = _bf(torch.cat([q, k, v], dim=1))
+    out = ops.attention(qkv, H)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().view(S, H, 128).transpose(0, 1) for t in qkv.split(H * 128, dim=1))
+    ref = torch.nn.functional.scaled_dot_product_attention(qf[None], kf[None], vf[None])[0].transpose(0, 1).reshape(S, -1)
+    assert torch.isfinite(out.float()).all()
+    rel = _rel_err(out, ref)
+    assert rel < 1.5e-2, f"attention rel err {rel}"
+
+
 def test_attention_matches_explicit_bf16_p(lib, attn_impl):
     """Tighter: emulate the kernel's one deliberate rounding (P -> bf16 before PV) in fp32 torch."""
     from unitex_b200 import ops
