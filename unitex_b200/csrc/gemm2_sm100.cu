@@ -65,7 +65,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -105,25 +105,33 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA): warp-uniform loop, one elected
+    // lane issues (a loop owned by a single divergent thread costs ~19 SASS instructions per tcgen05.mma, attn2_sm100.cu)
+    const bool leader = elect_one();
+    const uint32_t sb = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    const uint32_t bar0 = sb + BAR_OFF;                                   // full[STAGES] | empty[STAGES] | tfull[2] | tempty[2]
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
     int s = 0, as = 0;
     uint32_t ph = 0, aph = 0;
     for (int t = pair; t < p.total_tiles; t += npairs) {
-      mbar_wait(&tempty[as], aph ^ 1);
+      mbar_wait_a(bar0 + (2 * STAGES + 2 + as) * 8, aph ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * BN;
+      const uint32_t d_tmem = tmem_u + as * BN;
       for (int kb = 0; kb < nk; ++kb) {
-        mbar_wait(&full[s], ph);
+        mbar_wait_a(bar0 + s * 8, ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t a_addr = sb + s * STAGE_BYTES;
         const uint32_t b_addr = a_addr + A_BYTES;
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_ss_2sm(d_tmem, make_sdesc(a_addr + k * 32, 16, 1024), make_sdesc(b_addr + k * 32, 16, 1024), idesc, (kb | k) != 0);
-        umma_commit_2sm(&empty[s]);
-        if (kb == nk - 1) umma_commit_2sm(&tfull[as]);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss_2sm(d_tmem, make_sdesc(a_addr + k * 32, 16, 1024), make_sdesc(b_addr + k * 32, 16, 1024), idesc, (kb | k) != 0);
+          umma_commit_2sm_a(bar0 + (STAGES + s) * 8);
+          if (kb == nk - 1) umma_commit_2sm_a(bar0 + (2 * STAGES + as) * 8);
+        }
+        __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       as ^= 1;

@@ -80,7 +80,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();
   const int lane = threadIdx.x & 31;
   const int nk = p.K / BK;
 
@@ -129,28 +129,37 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer (single thread)
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer: the whole warp runs the loop (waits and
+    // descriptor arithmetic stay warp-uniform), one elected lane issues -- a loop owned by a single divergent thread costs
+    // ~19 SASS instructions per tcgen05.mma (see attn2_sm100.cu)
+    const bool leader = elect_one();
+    const uint32_t sb = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    const uint32_t bar0 = __shfl_sync(0xffffffffu, smem_u32(full), 0);   // full[STAGES] | empty[STAGES] | tfull[2] | tempty[2]
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
     int s = 0, as = 0;
     uint32_t ph = 0, aph = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      mbar_wait(&tempty[as], aph ^ 1);   // epilogue drained this accumulator stage
+      mbar_wait_a(bar0 + (2 * STAGES + 2 + as) * 8, aph ^ 1);   // epilogue drained this accumulator stage
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * BN;
+      const uint32_t d_tmem = tmem_u + as * BN;
       for (int kb = 0; kb < nk; ++kb) {
-        mbar_wait(&full[s], ph);
+        mbar_wait_a(bar0 + s * 8, ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t a_addr = sb + s * L::STAGE_BYTES;
         const uint32_t b_addr = a_addr + L::A_BYTES;
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = make_sdesc(a_addr + k * 32, 16, 1024);
-          const uint64_t db = make_sdesc(b_addr + k * 32, 16, 1024);
-          umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_sdesc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = make_sdesc(b_addr + k * 32, 16, 1024);
+            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit_a(bar0 + (STAGES + s) * 8);                                 // smem stage reusable once these MMAs retire
+          if (kb == nk - 1) umma_commit_a(bar0 + (2 * STAGES + as) * 8);          // accumulator complete
         }
-        umma_commit(&empty[s]);                    // smem stage reusable once these MMAs retire
-        if (kb == nk - 1) umma_commit(&tfull[as]); // accumulator complete
+        __syncwarp();
         if (++s == STAGES) {
           s = 0;
           ph ^= 1;

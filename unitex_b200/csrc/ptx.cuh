@@ -294,6 +294,11 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                "h"(static_cast<uint16_t>(3))
                : "memory");
 }
+__device__ __forceinline__ void umma_commit_2sm_a(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
 // arrive on the barrier at the same smem offset in CTA `rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   asm volatile(
