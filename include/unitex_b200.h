@@ -146,7 +146,8 @@ int utx_interpolate(const float* attr, int attr_batched, int V, int C, const flo
 /* vertices_homo @ (P @ W2C)^T (renderer_inverse.py:178,263): out [n, V, 4] */
 int utx_transform_points(const float* vert, int V, const float* mats, int n, float* out, void* stream);
 /* RayTracing(vertices, faces) / update_raw (raytracing/__init__.py:12-80; rt_aprmis/bvhhelpers.py:20-83): builds the
- * same LBVH the reference builds into `nodes` (utx_bvh_nodes_bytes(F) bytes: 48 B per node + packed triangle vertices). */
+ * same LBVH the reference builds into `nodes` (utx_bvh_nodes_bytes(F) bytes: the reference-layout nodes, 48 B each, followed by the
+ * traversal layout the intersect / bake kernels walk). */
 size_t utx_bvh_nodes_bytes(int F);
 size_t utx_bvh_workspace_bytes(int F);
 int utx_bvh_build(const float* vert, int V, const int32_t* tri, int F, void* nodes, void* workspace, size_t workspace_bytes,

@@ -8,7 +8,9 @@
 //     single-workgroup sort on ONE SM -- its slowest stage); stable, so ties keep element order exactly like its LSD sort
 //   * Karras-2012 hierarchy, identical delta / range / split rules incl. the duplicate-code tie-break on sorted index
 //   * ONE bottom-up refit pass with per-node arrival counters instead of one launch per tree level + host sync
-//   * nodes packed in 48 B (aabb[6], left, right, prim) = three 16 B loads, instead of two strided arrays
+//   * nodes packed in 48 B (aabb[6], left, right, prim) instead of two strided arrays (export / 1-NN search), plus a
+//     traversal layout with both children's boxes in the parent (64 B per internal node, leaves folded in): one fetch and
+//     two slab tests per visited node, children that fail are never pushed (bake_trace.cuh proves the visit order is kept)
 // The traversal keeps the reference's order and quirks (intersect_test2.slang:63-146), because they decide which
 // triangle id a ray reports and `rays_tid == tid_2d` is the bake's visibility test (renderer_inverse.py:321-323).
 // Built with -fmad=false (see bake_raster.cu).
@@ -216,16 +218,26 @@ __global__ void __launch_bounds__(256) refit_kernel(int F, Node* __restrict__ no
   }
 }
 
-// packed triangle vertices behind the nodes: [F][3] float4 (xyz, 0)
-__global__ void __launch_bounds__(256) pack_tris_kernel(const float* __restrict__ vert, const int* __restrict__ tri, int F,
-                                                        float4* __restrict__ out) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float* v = vert + static_cast<size_t>(tri[f * 3 + k]) * 3;
-    out[static_cast<size_t>(f) * 3 + k] = make_float4(v[0], v[1], v[2], 0.f);
+// traversal layout behind the reference-layout nodes (bake_trace.cuh): header (root box, root reference) + 64 B per
+// internal node holding both children's boxes and references (child >= 0: internal node index, < 0: ~prim of a leaf)
+__global__ void __launch_bounds__(256) pack_wide_kernel(const Node* __restrict__ nodes, int F, float4* __restrict__ W) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int LEAF = F - 1;
+  if (n == 0) {
+    const Node r = nodes[0];
+    const int ref = (F == 1) ? ~r.prim : 0;
+    W[0] = make_float4(r.bb[0], r.bb[1], r.bb[2], r.bb[3]);
+    W[1] = make_float4(r.bb[4], r.bb[5], __int_as_float(ref), 0.f);
   }
+  if (n >= F - 1) return;
+  const int ca = nodes[n].left, cb = nodes[n].right;
+  const Node A = nodes[ca], B = nodes[cb];
+  const int ra = ca >= LEAF ? ~A.prim : ca, rb = cb >= LEAF ? ~B.prim : cb;
+  float4* o = W + 2 + static_cast<size_t>(n) * 4;
+  o[0] = make_float4(A.bb[0], A.bb[1], A.bb[2], A.bb[3]);
+  o[1] = make_float4(A.bb[4], A.bb[5], B.bb[0], B.bb[1]);
+  o[2] = make_float4(B.bb[2], B.bb[3], B.bb[4], B.bb[5]);
+  o[3] = make_float4(__int_as_float(ra), __int_as_float(rb), 0.f, 0.f);
 }
 
 __global__ void __launch_bounds__(256) export_kernel(const Node* __restrict__ nodes, int n, int* __restrict__ info,
@@ -252,8 +264,7 @@ __global__ void __launch_bounds__(128) intersect_kernel(const void* __restrict__
   float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
   const float len = sqrtf(dot3f(d[0], d[1], d[2], d[0], d[1], d[2]));
   d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
-  (void)F;
-  const RayHit h = bvh_trace(nodes, vert, tri, o, d, nullptr);
+  const RayHit h = bvh_trace(static_cast<const float4*>(nodes) + static_cast<size_t>(2 * F - 1) * 3, vert, tri, o, d);
   hit[r] = static_cast<unsigned char>(h.any);
   tid[r] = h.any ? h.tid : -1;
   pos[r * 3] = h.any ? o[0] + h.t * d[0] : 0.f;
@@ -267,7 +278,8 @@ __global__ void __launch_bounds__(128) intersect_kernel(const void* __restrict__
 static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
 // nodes [2F-1] followed by the packed triangle vertices [F][3] float4 (unused by the point tree)
-size_t bvh_nodes_bytes(int F) { return static_cast<size_t>(2 * F - 1) * sizeof(Node) + static_cast<size_t>(F) * 48; }
+// reference-layout nodes (48 B each) + the traversal layout (32 B header + 64 B per internal node)
+size_t bvh_nodes_bytes(int F) { return static_cast<size_t>(2 * F - 1) * sizeof(Node) + static_cast<size_t>(F) * 64; }
 
 size_t bvh_workspace_bytes(int F) {
   size_t cub_bytes = 0;
@@ -309,7 +321,7 @@ int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, 
               cudaStream_t stream) {
   (void)V;
   UTX_TRY(build_tree(vert, tri, nullptr, F, nodes_out, workspace, ws_bytes, stream));
-  pack_tris_kernel<<<(F + 255) / 256, 256, 0, stream>>>(vert, tri, F,
+  pack_wide_kernel<<<(F + 255) / 256, 256, 0, stream>>>(static_cast<const Node*>(nodes_out), F,
                                                        reinterpret_cast<float4*>(static_cast<Node*>(nodes_out) + (2 * F - 1)));
   UTX_CUDA(cudaGetLastError());
   return 0;

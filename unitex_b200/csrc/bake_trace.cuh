@@ -1,5 +1,5 @@
-// Closest-hit traversal of the packed LBVH (48 B nodes: aabb[6], left, right, prim), shared by the standalone
-// intersect kernel and the fused UV-bake texel kernel.  Order and quirks follow the reference's bvh_hit
+// Closest-hit traversal of the LBVH, shared by the standalone intersect kernel and the fused UV-bake texel kernel.
+// Order and quirks follow the reference's bvh_hit
 // (TextureTools/texturetools/raytracing/rt_aprmis/bvhworkers/intersect_test2.slang:63-146): push left, push right, pop
 // right first; slab test against the running closest t; Moller-Trumbore without a t-range test; the reported triangle is
 // the LAST accepted leaf.  Translation units including this are built with -fmad=false.
@@ -29,49 +29,83 @@ __device__ __forceinline__ bool aabb_hit_dev(const float* o, const float* inv, f
   }
   return true;
 }
-// `d` must already be normalised exactly like the reference does (d / |d|).  `tris`: optional packed triangle vertices
-// ([F][3] float4, written by bvh_build behind the nodes): one contiguous 48-byte read per leaf instead of an index triple
-// plus three scattered vertex reads.
-__device__ __forceinline__ RayHit bvh_trace(const void* __restrict__ nodes_v, const float* __restrict__ vert, const int* __restrict__ tri,
-                            const float* o, const float* d, const float4* __restrict__ tris = nullptr) {
-  const float4* nodes = static_cast<const float4*>(nodes_v);
+// Entry / exit parameters of the slab test without the running closest-t: te = max(0, near_x, near_y, near_z),
+// tx = min(far_x, far_y, far_z), built with the reference's own compare-and-select chain (a NaN operand is skipped, exactly
+// as in aabb_hit_dev).  The reference's test `tmax < tmin` after the last axis, with tmax seeded by the closest t, is then
+//   fail  <=>  min(closest, tx) < te
+// (its per-axis early exits cannot fail earlier than the final comparison: tmin only grows, tmax only shrinks).
+__device__ __forceinline__ void slab_params(const float* o, const float* inv, const float* bb, float& te, float& tx) {
+  te = 0.0f;
+  tx = INFINITY;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float t0 = (bb[i] - o[i]) * inv[i], t1 = (bb[3 + i] - o[i]) * inv[i];
+    if (inv[i] < 0.0f) { const float t = t1; t1 = t0; t0 = t; }
+    te = t0 > te ? t0 : te;
+    tx = t1 < tx ? t1 : tx;
+  }
+}
+__device__ __forceinline__ bool slab_pass(float te, float tx, float closest) {
+  const float m = tx < closest ? tx : closest;
+  return !(m < te);
+}
+
+// Closest-hit query on the traversal layout bvh_build writes behind the reference-layout nodes ("wide" nodes, 64 B per
+// INTERNAL node: both children's boxes + both child references, leaves folded into their parents as ~prim):
+//   W[0..1]            root box (6 floats), root reference, pad
+//   W[2 + 4 n ..]      internal node n:  L.min xyz, L.max xyz, R.min xyz, R.max xyz, refL, refR, pad, pad
+// One 64 B fetch per visited internal node yields both children's slab tests; a child that already fails is never pushed,
+// one that passes is pushed with its entry distance te and re-checked against the closest t of the moment it is popped.
+// This visits exactly the leaves the reference's loop visits, in the same order, with the same closest t at each visit:
+// the reference tests a node's own box when it pops it (closest = value at pop time); a box fails iff
+// min(closest_pop, tx) < te; closest only shrinks, so "fails at push time" implies "fails at pop time", and for the rest
+// the pop-time comparison `closest < te` completes the identical predicate (tx >= te is already known).  Push order
+// (left, then right; right popped first), Moller-Trumbore without a t-range test and "last accepted leaf wins" are the
+// reference's (intersect_test2.slang:63-146).  `d` must already be normalised exactly like the reference does (d / |d|).
+__device__ __forceinline__ RayHit bvh_trace(const float4* __restrict__ W, const float* __restrict__ vert, const int* __restrict__ tri,
+                                            const float* o, const float* d) {
   float inv[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     float di = d[i];
-    if (di == 0.0f) di = 0.000001f;
+    if (di == 0.0f) di = 0.000001f;      // intersect_test2.slang:18-21; the quotient is the same IEEE value at every node
     inv[i] = 1.0f / di;
   }
-  int stack[64];
+  int sref[64];
+  float ste[64];
   int count = 0;
-  stack[count++] = 0;
   float closest = 1e9f;
   RayHit h;
   h.any = 0; h.tid = -1; h.t = 0.f; h.u = 0.f; h.v = 0.f;
+  {
+    const float4 r0 = __ldg(W), r1 = __ldg(W + 1);
+    const float bb[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+    float te, tx;
+    slab_params(o, inv, bb, te, tx);
+    if (slab_pass(te, tx, closest)) { sref[0] = __float_as_int(r1.z); ste[0] = te; count = 1; }
+  }
   while (count > 0) {
-    const int n = stack[--count];
-    const float4 q0 = __ldg(nodes + static_cast<size_t>(n) * 3), q1 = __ldg(nodes + static_cast<size_t>(n) * 3 + 1);
-    const float bb[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
-    if (!aabb_hit_dev(o, inv, 0.0f, closest, bb)) continue;
-    const int l = __float_as_int(q1.z), r = __float_as_int(q1.w);
-    if (l != 0 && r != 0) {
+    --count;
+    const int ref = sref[count];
+    if (closest < ste[count]) continue;
+    if (ref >= 0) {
+      const float4* nd = W + 2 + static_cast<size_t>(ref) * 4;
+      const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+      const float bl[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y}, br[6] = {q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+      float tel, txl, ter, txr;
+      slab_params(o, inv, bl, tel, txl);
+      slab_params(o, inv, br, ter, txr);
       if (count + 2 <= 64) {
-        stack[count++] = l;
-        stack[count++] = r;
+        if (slab_pass(tel, txl, closest)) { sref[count] = __float_as_int(q3.x); ste[count] = tel; ++count; }
+        if (slab_pass(ter, txr, closest)) { sref[count] = __float_as_int(q3.y); ste[count] = ter; ++count; }
       }
-    } else if (l == 0 && r == 0) {
-      const int p = __float_as_int(__ldg(nodes + static_cast<size_t>(n) * 3 + 2).x);
+    } else {
+      const int p = ~ref;
+      const float *pa = vert + static_cast<size_t>(tri[p * 3]) * 3, *pb = vert + static_cast<size_t>(tri[p * 3 + 1]) * 3,
+                  *pc = vert + static_cast<size_t>(tri[p * 3 + 2]) * 3;
       float a[3], b[3], c[3];
-      if (tris) {
-        const float4 ta = __ldg(tris + static_cast<size_t>(p) * 3), tb = __ldg(tris + static_cast<size_t>(p) * 3 + 1),
-                     tc = __ldg(tris + static_cast<size_t>(p) * 3 + 2);
-        a[0] = ta.x; a[1] = ta.y; a[2] = ta.z; b[0] = tb.x; b[1] = tb.y; b[2] = tb.z; c[0] = tc.x; c[1] = tc.y; c[2] = tc.z;
-      } else {
-        const float *pa = vert + static_cast<size_t>(tri[p * 3]) * 3, *pb = vert + static_cast<size_t>(tri[p * 3 + 1]) * 3,
-                    *pc = vert + static_cast<size_t>(tri[p * 3 + 2]) * 3;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { a[k] = pa[k]; b[k] = pb[k]; c[k] = pc[k]; }
-      }
+      for (int k = 0; k < 3; ++k) { a[k] = pa[k]; b[k] = pb[k]; c[k] = pc[k]; }
       const float e1x = b[0] - a[0], e1y = b[1] - a[1], e1z = b[2] - a[2];
       const float e2x = c[0] - a[0], e2y = c[1] - a[1], e2z = c[2] - a[2];
       const float px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;

@@ -81,7 +81,7 @@ __device__ __forceinline__ void texel_ndc(const float* m, const float* p0, const
 
 __global__ void __launch_bounds__(128) texel_kernel(const float4* __restrict__ rast, int T, const float* __restrict__ vert,
                                                     const int* __restrict__ tri, const void* __restrict__ nodes,
-                                                    const float4* __restrict__ tris, const Views vw, const float* __restrict__ images /*[n,H,W,4] rgba*/,
+                                                    const float4* __restrict__ wide /* traversal layout, bake_trace.cuh */, const Views vw, const float* __restrict__ images /*[n,H,W,4] rgba*/,
                                                     int H, int W, float cos_thresh, unsigned char* __restrict__ raw_vis,
                                                     unsigned char* __restrict__ alpha_ok, float* __restrict__ pos_out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128) texel_kernel(const float4* __restrict__ r
     if (cosv < cos_thresh) {
       const float len = norm3(d[0], d[1], d[2]);                        // the tracer normalises again (intersect_test2.slang:283)
       d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
-      const RayHit h = bvh_trace(nodes, vert, tri, o, d, tris);
+      const RayHit h = bvh_trace(wide, vert, tri, o, d);
       if (h.any && h.tid == f) vis |= 1u << i;
     }
   }
@@ -422,10 +422,7 @@ int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, 
 
   const unsigned g128 = (T + 127) / 128, g256 = (T + 255) / 256;
   const float4* rast = reinterpret_cast<const float4*>(rast2d);
-  // packed triangle vertices (behind the nodes) measured SLOWER here than the indexed vertex array: neighbouring leaves share
-  // vertices, 3 MB of vertices stay cache resident where 24 MB of packed triangles do not -> pass nullptr
-  (void)F;
-  texel_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, nodes, nullptr, vw, images_rgba, H, W, cos_thresh, raw, aok, pos);
+  texel_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, nodes, static_cast<const float4*>(nodes) + static_cast<size_t>(2 * F - 1) * 3, vw, images_rgba, H, W, cos_thresh, raw, aok, pos);
   repair3_kernel<<<g256, 256, 0, stream>>>(raw, rep3, H2, W2);
   repair5_kernel<<<g256, 256, 0, stream>>>(rep3, rep5, H2, W2, n_views);
   compose_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, vw, images_rgba, H, W, rep5, aok, mask2d, mask_vis, owner, col_a);
