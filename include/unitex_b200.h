@@ -178,6 +178,12 @@ int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void*
  * Activations NHWC bf16; a 3x3 conv = utx_im2col3x3 + utx_gemm_bf16 with W arranged [Cout, ky, kx, Cin].
  * ------------------------------------------------------------------------------------------------------------------ */
 /* out [N*Ho*Wo, Kpad] (zero padded beyond 9*C); up = 1|2 nearest upsample folded in; pad = top/left padding */
+/* Implicit-GEMM 3x3 convolution, stride 1, zero padding 1 (the ResnetBlock2D / mid-block convolutions of AutoencoderKL [ext]):
+ * y[N*H*W, Cout] = conv(x) + bias, or gate[c] * (conv(x) + bias) + res when gate / res are given (fused residual add).  No
+ * im2col buffer: the A tiles are TMA boxes of the activation shifted by the tap.  Cin % 64 == 0, Cout % 8 == 0,
+ * W % 128 == 0 or (128 % W == 0 and H % (128 / W) == 0); other convolutions go through utx_im2col3x3 + utx_gemm_bf16. */
+int utx_conv3x3_nhwc(const void* x, int N, int H, int W, int C, const void* w, const void* bias, int Cout, void* y, long ldy,
+                     const float* gate, const void* res, long ldres, void* stream);
 int utx_im2col3x3(const void* x, int N, int Hin, int Win, int C, int up, int stride, int pad, int Ho, int Wo, int Kpad,
                   void* out, void* stream);
 /* GroupNorm(G, eps 1e-6, affine fp32) [+ SiLU]; stats_ws: N*G*2 doubles */

@@ -76,3 +76,30 @@ def test_pipeline_with_images_end_to_end(lib):
     assert len(out) == 1 and out[0].size == (128, 128)
     a = np.asarray(out[0])
     assert a.dtype == np.uint8 and a.std() > 1.0
+
+
+@pytest.mark.parametrize("N,H,W,C,Co,with_res", [(1, 16, 128, 64, 128, False), (2, 8, 32, 128, 64, True), (1, 4, 256, 64, 256, True),
+                                                 (1, 16, 16, 64, 64, False), (3, 2, 64, 192, 128, False)])
+def test_implicit_conv3x3_matches_conv2d(lib, N, H, W, C, Co, with_res):
+    """The implicit-GEMM convolution (TMA boxes shifted by the tap, zero fill as padding) against torch conv2d in fp32 on the
+    same bf16-rounded operands; M = N*H*W is not always a multiple of the 128-row tile (tail boxes past the last image)."""
+    from unitex_b200 import _lib
+    L = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(N * 1000 + W)
+    x = torch.randn(N, H, W, C, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(Co, 3, 3, C, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    b = torch.randn(Co, device="cuda", generator=g).to(torch.bfloat16)
+    res = torch.randn(N * H * W, Co, device="cuda", generator=g).to(torch.bfloat16) if with_res else None
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b.float(), padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(N * H * W, Co)
+    y = res.clone() if with_res else torch.empty(N * H * W, Co, device="cuda", dtype=torch.bfloat16)
+    one = torch.ones(Co, device="cuda")
+    if with_res:
+        ref = ref + res.float()
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.utx_conv3x3_nhwc(x.data_ptr(), N, H, W, C, w.data_ptr(), b.data_ptr(), Co, y.data_ptr(), Co,
+                                  one.data_ptr() if with_res else None, y.data_ptr() if with_res else None, Co if with_res else 0, st),
+               "utx_conv3x3_nhwc")
+    torch.cuda.synchronize()
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-2, f"max abs err {err}"

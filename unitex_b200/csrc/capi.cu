@@ -146,6 +146,12 @@ int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void*
                  workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int utx_conv3x3_nhwc(const void* x, int N, int H, int W, int C, const void* w, const void* bias, int Cout, void* y, long ldy,
+                     const float* gate, const void* res, long ldres, void* stream) {
+  UTX_CHECK(x && w && y, "utx_conv3x3_nhwc: null pointer");
+  return conv3x3_nhwc(static_cast<const bf16*>(x), N, H, W, C, static_cast<const bf16*>(w), static_cast<const bf16*>(bias), Cout,
+                      static_cast<bf16*>(y), ldy, gate, static_cast<const bf16*>(res), ldres, static_cast<cudaStream_t>(stream));
+}
 int utx_im2col3x3(const void* x, int N, int Hin, int Win, int C, int up, int stride, int pad, int Ho, int Wo, int Kpad,
                   void* out, void* stream) {
   UTX_CHECK(x && out, "utx_im2col3x3: null pointer");

@@ -46,6 +46,23 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+int make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t box_w,
+                        uint32_t box_h) {
+  EncodeTiledFn fn = encode_fn();
+  UTX_CHECK(fn != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+  UTX_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
+  UTX_CHECK(C % 64 == 0 && box_w <= 256 && box_h <= 256, "NHWC TMA map: C must be a multiple of 64, box dims <= 256");
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {64, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UTX_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (NHWC) failed with CUresult " + std::to_string((int)r));
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

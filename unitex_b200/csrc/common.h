@@ -43,6 +43,11 @@ const char* get_error();
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
 
+// 4-D NHWC bf16 activation map for implicit-GEMM 3x3 convolutions: dims (C, W, H, N), box (64 channels, box_w, box_h, 1),
+// 128B swizzle; out-of-range coordinates (the padding ring, the tail past the last image) read as zeros.
+int make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t box_w,
+                        uint32_t box_h);
+
 int num_sms();
 
 }  // namespace utx

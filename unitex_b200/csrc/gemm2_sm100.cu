@@ -23,7 +23,7 @@ constexpr int BM = 128;        // rows per CTA (256 per pair)
 constexpr int BN = 256;        // tile columns; each CTA stages BN/2 rows of W
 constexpr int BK = 64;
 constexpr int STAGES = 6;
-constexpr int GROUP_M = 8;     // bands of 8 pair-row-blocks (2048 rows)
+constexpr int GROUP_M_DEFAULT = 8;   // bands of 8 pair-row-blocks (2048 rows); UTX_GEMM_GROUP_M overrides (tuning knob)
 constexpr int kThreads = 256;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = (BN / 2) * BK * 2;
@@ -32,7 +32,7 @@ constexpr int BAR_OFF = STAGES * STAGE_BYTES;
 constexpr int SMEM_TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
 
 struct DevParams {
-  int K, tiles_n, nprob, total_tiles;
+  int K, tiles_n, nprob, total_tiles, group_m;
   EpiParams e;
   EpiProblem prob[2];
 };
@@ -45,6 +45,7 @@ __device__ __forceinline__ TileCoord decode_tile(const DevParams& p, int t) {
   const int t0 = p.prob[0].tiles_m * p.tiles_n;
   if (p.nprob > 1 && t >= t0) { tc.pi = 1; t -= t0; }
   const int tiles_m = p.prob[tc.pi].tiles_m;
+  const int GROUP_M = p.group_m;
   const int band_sz = GROUP_M * p.tiles_n;
   const int band = t / band_sz;
   const int r = t - band * band_sz;
@@ -175,6 +176,13 @@ int gemm2_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
   p.K = a.K;
   p.tiles_n = a.N / BN;
   p.nprob = a.nprob;
+  static int group_m = 0;
+  if (group_m == 0) {
+    const char* e = std::getenv("UTX_GEMM_GROUP_M");
+    group_m = e ? std::atoi(e) : GROUP_M_DEFAULT;
+    if (group_m < 1) group_m = GROUP_M_DEFAULT;
+  }
+  p.group_m = group_m;
   p.e = EpiParams{a.N, a.epi, a.gelu_col_start, a.out_scale, a.qk_cols, a.cos_t, a.sin_t};
   CUtensorMap tm[4];
   int total = 0;

@@ -31,6 +31,7 @@ constexpr int kThreads = 256;
 
 struct DevParams {
   int K, tiles_n, nprob, total_tiles;
+  int conv_cblk, conv_w, conv_hw;   // implicit 3x3 convolution: channel blocks per tap (0 = plain GEMM), image width, pixels per image
   EpiParams e;
   EpiProblem prob[2];
 };
@@ -117,11 +118,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const TileCoord tc = decode_tile(p, t);
       const CUtensorMap* ta = tc.pi ? &tmA1 : &tmA0;
       const CUtensorMap* tb = tc.pi ? &tmB1 : &tmB0;
+      // implicit convolution: the tile's 128 output pixels start at (img, y0, x0); tap (ky, kx) reads the same box of the
+      // activation shifted by (ky - 1, kx - 1), out-of-range rows / columns arrive as zeros (= the padding ring)
+      int img = 0, y0 = 0, x0 = 0;
+      if (p.conv_cblk > 0) {
+        const int p0 = tc.m_blk * BM;
+        img = p0 / p.conv_hw;
+        const int rem = p0 - img * p.conv_hw;
+        y0 = rem / p.conv_w;
+        x0 = rem - y0 * p.conv_w;
+      }
+      int tap = 0, cb = 0;
       for (int kb = 0; kb < nk; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], L::STAGE_BYTES);
         uint8_t* st = smem + s * L::STAGE_BYTES;
-        tma_load_2d(st, ta, &full[s], kb * BK, tc.m_blk * BM);
+        if (p.conv_cblk > 0) {
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          tma_load_4d(st, ta, &full[s], cb * BK, x0 + kx - 1, y0 + ky - 1, img);
+          if (++cb == p.conv_cblk) { cb = 0; ++tap; }
+        } else {
+          tma_load_2d(st, ta, &full[s], kb * BK, tc.m_blk * BM);
+        }
         tma_load_2d(st + L::A_BYTES, tb, &full[s], kb * BK, tc.n_blk * BN);
         if (++s == STAGES) {
           s = 0;
@@ -204,6 +222,9 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
   p.K = a.K;
   p.tiles_n = (a.N + BN - 1) / BN;
   p.nprob = a.nprob;
+  p.conv_cblk = a.conv_c / BK;
+  p.conv_w = a.conv_w;
+  p.conv_hw = a.conv_h * a.conv_w;
   p.e = EpiParams{a.N, a.epi, a.gelu_col_start, a.out_scale, a.qk_cols, a.cos_t, a.sin_t};
   CUtensorMap tm[4];
   int total = 0;
@@ -213,7 +234,12 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
     d = EpiProblem{g.M, (g.M + BM - 1) / BM, g.C, g.ldc, g.bias, g.gate, g.res, g.ldres, g.split_col, g.C2, g.ldc2, g.wq, g.wk,
                    g.row_offset};
     total += d.tiles_m * p.tiles_n;
-    UTX_TRY(make_tmap_2d_bf16(&tm[2 * i], g.A, g.M, a.K, g.lda, BM, BK));
+    if (a.conv_c > 0) {
+      const int bw = a.conv_w < BM ? a.conv_w : BM;
+      UTX_TRY(make_tmap_nhwc_bf16(&tm[2 * i], g.A, a.conv_n, a.conv_h, a.conv_w, a.conv_c, bw, BM / bw));
+    } else {
+      UTX_TRY(make_tmap_2d_bf16(&tm[2 * i], g.A, g.M, a.K, g.lda, BM, BK));
+    }
     UTX_TRY(make_tmap_2d_bf16(&tm[2 * i + 1], g.W, a.N, a.K, g.ldw, BN, BK));
   }
   if (a.nprob == 1) {
@@ -259,7 +285,7 @@ int gemm_bf16_tn(const GemmArgs& a_in, cudaStream_t stream) {
   // Default: cta_group::2 kernel (256x256 tiles per CTA pair, gemm2_sm100.cu) whenever N % 256 == 0 -- 2-3 % faster at the
   // DiT shapes (profiles/r01_microbench_gemm.json).  UTX_GEMM_IMPL=1 forces the 1-CTA kernel of this file.
   const char* impl = getenv("UTX_GEMM_IMPL");
-  if ((impl == nullptr || impl[0] != '1') && a.N % 256 == 0) {
+  if ((impl == nullptr || impl[0] != '1') && a.N % 256 == 0 && a.conv_c == 0) {
     const int r = gemm2_bf16_tn(a, stream);
     if (r >= 0) return r;
   }
@@ -269,6 +295,20 @@ int gemm_bf16_tn(const GemmArgs& a_in, cudaStream_t stream) {
   if (a.N % 256 == 0) return launch<256, 4>(a, stream);
   if (a.N % 128 == 0) return launch<128, 6>(a, stream);
   return launch<64, 8>(a, stream);
+}
+
+int conv3x3_nhwc(const bf16* x, int N, int H, int W, int C, const bf16* w, const bf16* bias, int Cout, bf16* y, long ldy,
+                 const float* gate, const bf16* res, long ldres, cudaStream_t stream) {
+  UTX_CHECK(N > 0 && H > 0 && W > 0, "conv3x3: empty input");
+  UTX_CHECK(C % 64 == 0 && C > 0, "conv3x3: Cin must be a multiple of 64");
+  UTX_CHECK(W % BM == 0 || (BM % W == 0 && H % (BM / W) == 0), "conv3x3: image width must tile 128-pixel row blocks");
+  UTX_CHECK((res == nullptr) == (gate == nullptr), "conv3x3: the residual epilogue needs both gate and res");
+  GemmArgs a{};
+  a.N = Cout; a.K = 9 * C; a.epi = res ? EPI_GATE_RES : EPI_BIAS; a.nprob = 1;
+  a.conv_n = N; a.conv_h = H; a.conv_w = W; a.conv_c = C;
+  a.prob[0] = GemmProblem{x, static_cast<long>(C), w, 9L * C, N * H * W, y, ldy, bias, gate, res, ldres, 0, nullptr, 0,
+                          nullptr, nullptr, 0};
+  return gemm_bf16_tn(a, stream);
 }
 
 }  // namespace utx

@@ -49,6 +49,9 @@ struct GemmArgs {
   const float* cos_t;    // [S,128] fp32 tables for qk_cols > 0
   const float* sin_t;
   int nprob;             // 1 or 2 problems sharing N, K and the epilogue (txt + img streams)
+  // implicit-GEMM 3x3 convolution (stride 1, pad 1): prob[0].A is the NHWC activation [conv_n, conv_h, conv_w, conv_c],
+  // M = conv_n*conv_h*conv_w output pixels, K = 9*conv_c with W arranged [Cout][ky][kx][Cin]; 0 = plain GEMM
+  int conv_n, conv_h, conv_w, conv_c;
   GemmProblem prob[2];
 };
 int gemm_bf16_tn(const GemmArgs& args, cudaStream_t stream);
@@ -108,6 +111,11 @@ int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, 
 
 
 // ------------------------------------------------------------------ VAE (NHWC bf16; convs = im2col + gemm_bf16_tn)
+// y[N*H*W, Cout] = conv3x3(x NHWC [N,H,W,C], w [Cout][3][3][C]) + bias, or gate * (conv + bias) + res: no im2col buffer, the A tiles are TMA boxes of
+// the activation shifted by the tap, zero padding comes from TMA's out-of-bounds fill.  C % 64 == 0; W % 128 == 0 or
+// (128 % W == 0 and H % (128 / W) == 0)
+int conv3x3_nhwc(const bf16* x, int N, int H, int W, int C, const bf16* w, const bf16* bias, int Cout, bf16* y, long ldy,
+                 const float* gate, const bf16* res, long ldres, cudaStream_t stream);
 int im2col3x3(const bf16* x, int N, int Hin, int Win, int C, int up, int stride, int pad, int Ho, int Wo, int Kpad, bf16* out,
               cudaStream_t stream);
 int groupnorm_nhwc(const bf16* x, bf16* y, int N, int HW, int C, int G, const float* gamma, const float* beta, int silu,

@@ -33,6 +33,7 @@ class AutoencoderKLB200:
         self.scaling_factor, self.shift_factor = scaling_factor, shift_factor
         self.dtype = torch.bfloat16
         self.lib = _lib.load()
+        self.implicit_conv = os.environ.get("UTX_VAE_IM2COL", "0") != "1"   # debug knob: force the im2col path
         self.W: Dict[str, torch.Tensor] = {}
         for k, v in state_dict.items():
             if not k.endswith(".weight"):
@@ -121,6 +122,15 @@ class AutoencoderKLB200:
         else:                                                   # Downsample2D: pad (0,1,0,1), stride 2
             Ho, Wo = (Hs + 1 - 3) // 2 + 1, (Ws + 1 - 3) // 2 + 1
         Kp = w.shape[1]
+        if (self.implicit_conv and up == 1 and stride == 1 and pad == 1 and C % 64 == 0 and Kp == 9 * C and
+                (W % 128 == 0 or (128 % W == 0 and H % (128 // W) == 0))):
+            # implicit GEMM: TMA boxes of the activation shifted by the tap are the A tiles, no im2col buffer
+            Co = w.shape[0]
+            y = res if res is not None else torch.empty(N * H * W, Co, device=self.device, dtype=torch.bfloat16)
+            _lib.check(self.lib.utx_conv3x3_nhwc(_p(x), N, H, W, C, _p(w), _p(b), Co, _p(y), y.stride(0),
+                                                 _p(self._one(Co)) if res is not None else None, _p(res), 0 if res is None else res.stride(0),
+                                                 _stream()), "utx_conv3x3_nhwc")
+            return y, H, W
         col = torch.empty(N * Ho * Wo, Kp, device=self.device, dtype=torch.bfloat16)
         _lib.check(self.lib.utx_im2col3x3(_p(x), N, H, W, C, up, stride, pad, Ho, Wo, Kp, _p(col), _stream()), "utx_im2col3x3")
         if res is None:
