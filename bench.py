@@ -265,7 +265,7 @@ def run_ours(args, rank, world, local_rank):
                    "timing": "CUDA events on the launching stream, max over ranks"},
         "roofline": {"bound": "tensor", "kernel": "gemm2_bf16_tn_kernel (tcgen05 cta_group::2; 1-CTA gemm_bf16_tn_kernel for narrow N)",
                      "achieved": gemm_tf, "peak": peak_sus, "unit": "TFLOP/s", "frac": gemm_tf / peak_sus,
-                     "traffic": 1.024e9, "traffic_note": "dram read+write of ONE qkv-shaped launch (M 9728, N 9216, K 3072) from profiles/r01_gemm_bf16_tn.ncu-rep; algorithmic 296 MB",
+                     "traffic": 5.20e8, "traffic_note": "dram read+write of ONE qkv-shaped launch (M 9728, N 9216, K 3072), warm L2 as inside the step (ncu --cache-control none, profiles/r01_gemm_groupm_sweep.txt: 335 MB read + 185 MB written); 1046 MB with ncu's cache flush (profiles/r01_gemm2_bf16_tn_final.ncu-rep); algorithmic 296 MB",
                      "peak_source": peak_src,
                      "launches_per_step": n_gemm, "flops_per_step": f_gemm, "ms_per_step": cat_ms["gemm"] / args.steps,
                      "attention": {"kernel": "attention2_kernel (tcgen05, P in TMEM)", "achieved": attn_tf, "frac": attn_tf / peak_sus,
@@ -348,7 +348,7 @@ def bench_vae_decode(dev):
     del vae
     torch.cuda.empty_cache()
     return {"metric": "VAE decode ms @1024^2", "ms": ms, "tflops": 10.47e12 / (ms * 1e-3) / 1e12, "finite": bool(torch.isfinite(img.float()).all()),
-            "note": "im2col + tcgen05 GEMM convolutions, NHWC bf16; implicit-GEMM fusion is the next step (DESIGN 6)"}
+            "note": "implicit-GEMM 3x3 convolutions (TMA boxes shifted by the tap) on the tcgen05 GEMM, NHWC bf16, deterministic GroupNorm+SiLU"}
 
 
 def bench_uv_bake(dev):

@@ -186,7 +186,10 @@ int utx_conv3x3_nhwc(const void* x, int N, int H, int W, int C, const void* w, c
                      const float* gate, const void* res, long ldres, void* stream);
 int utx_im2col3x3(const void* x, int N, int Hin, int Win, int C, int up, int stride, int pad, int Ho, int Wo, int Kpad,
                   void* out, void* stream);
-/* GroupNorm(G, eps 1e-6, affine fp32) [+ SiLU]; stats_ws: N*G*2 doubles */
+/* nearest-neighbour 2x upsampling NHWC [N,H,W,C] -> [N,2H,2W,C] (Upsample2D [ext], ahead of its implicit-GEMM convolution) */
+int utx_upsample2x_nhwc(const void* x, int N, int H, int W, int C, void* y, void* stream);
+/* GroupNorm(G, eps 1e-6, affine fp32) [+ SiLU], deterministic; stats_ws: utx_groupnorm_workspace_bytes(N, HW, C, G) bytes, 8B aligned */
+size_t utx_groupnorm_workspace_bytes(int N, int HW, int C, int G);
 int utx_groupnorm_nhwc(const void* x, void* y, int N, int HW, int C, int G, const float* gamma, const float* beta, int silu,
                        void* stats_ws, void* stream);
 /* C fp32 [M,N] = scale * (A @ W^T + bias) */

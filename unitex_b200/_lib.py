@@ -73,6 +73,8 @@ _SIGS = {
     "utx_bvh_intersect": (i32, [vp, vp, vp, i32, vp, vp, C.c_longlong, vp, vp, vp, vp, vp]),
     "utx_conv3x3_nhwc": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, C.c_long, vp, vp, C.c_long, vp]),
     "utx_im2col3x3": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "utx_upsample2x_nhwc": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "utx_groupnorm_workspace_bytes": (C.c_size_t, [i32, i32, i32, i32]),
     "utx_groupnorm_nhwc": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
     "utx_gemm_bf16_f32out": (i32, [vp, lng, vp, lng, vp, vp, lng, i32, i32, i32, f32, vp]),
     "utx_softmax_rows": (i32, [vp, lng, vp, lng, i32, i32, vp]),

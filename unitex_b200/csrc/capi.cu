@@ -158,6 +158,11 @@ int utx_im2col3x3(const void* x, int N, int Hin, int Win, int C, int up, int str
   return im2col3x3(static_cast<const bf16*>(x), N, Hin, Win, C, up, stride, pad, Ho, Wo, Kpad, static_cast<bf16*>(out),
                    static_cast<cudaStream_t>(stream));
 }
+int utx_upsample2x_nhwc(const void* x, int N, int H, int W, int C, void* y, void* stream) {
+  UTX_CHECK(x && y, "utx_upsample2x_nhwc: null pointer");
+  return upsample2x_nhwc(static_cast<const bf16*>(x), N, H, W, C, static_cast<bf16*>(y), static_cast<cudaStream_t>(stream));
+}
+size_t utx_groupnorm_workspace_bytes(int N, int HW, int C, int G) { return groupnorm_workspace_bytes(N, HW, C, G); }
 int utx_groupnorm_nhwc(const void* x, void* y, int N, int HW, int C, int G, const float* gamma, const float* beta, int silu,
                        void* stats_ws, void* stream) {
   UTX_CHECK(x && y && gamma && beta && stats_ws, "utx_groupnorm_nhwc: null pointer");

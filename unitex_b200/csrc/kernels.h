@@ -118,6 +118,8 @@ int conv3x3_nhwc(const bf16* x, int N, int H, int W, int C, const bf16* w, const
                  const float* gate, const bf16* res, long ldres, cudaStream_t stream);
 int im2col3x3(const bf16* x, int N, int Hin, int Win, int C, int up, int stride, int pad, int Ho, int Wo, int Kpad, bf16* out,
               cudaStream_t stream);
+int upsample2x_nhwc(const bf16* x, int N, int H, int W, int C, bf16* y, cudaStream_t stream);
+size_t groupnorm_workspace_bytes(int N, int HW, int C, int G);
 int groupnorm_nhwc(const bf16* x, bf16* y, int N, int HW, int C, int G, const float* gamma, const float* beta, int silu,
                    double* stats_ws, cudaStream_t stream);
 int softmax_rows(const float* S, long lds, bf16* P, long ldp, int M, int N, cudaStream_t stream);

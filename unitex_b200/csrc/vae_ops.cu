@@ -52,60 +52,111 @@ __global__ void __launch_bounds__(256) im2col_kernel(const bf16* __restrict__ x,
   *reinterpret_cast<uint4*>(out + pix * Kpad + k0) = val;
 }
 
-// statistics: grid (chunks, groups, N); each block reduces `rows_per_block` pixels of one group
-__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, int HW, int C, int G, int rows_per_block,
-                                                       double* __restrict__ stats /*[N,G,2]*/) {
-  const int g = blockIdx.y, n = blockIdx.z;
-  const int cpg = C / G;
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
-  float s = 0.f, ss = 0.f;
-  const long long base = static_cast<long long>(n) * HW * C + g * cpg;
-  const int per_row = cpg;   // contiguous channels of the group within a pixel
-  for (long long idx = static_cast<long long>(r0) * per_row + threadIdx.x; idx < static_cast<long long>(r1) * per_row; idx += blockDim.x) {
-    const int r = static_cast<int>(idx / per_row), c = static_cast<int>(idx % per_row);
-    const float v = __bfloat162float(x[base + static_cast<long long>(r) * C + c]);
-    s += v;
-    ss = fmaf(v, v, ss);
-  }
-  __shared__ float sh[2][8];
+// GroupNorm statistics, NHWC: grid (pixel chunks, N), blockDim = a multiple of the C/8 vectors of one pixel, so a thread
+// always owns the same 8 channels and a warp reads whole pixels contiguously (16-byte vectors).  Deterministic: per-thread
+// fp32 partials are folded per channel in a fixed order, per group in double, and every block writes its own slot of
+// `partial` [N][chunks][G][2]; gn_coef_kernel adds the chunks in order.  HBM-bound: the tensor is read once.
+constexpr int kGnRowsPerBlock = 2048;
+__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, int HW, int C, int G,
+                                                       double* __restrict__ partial) {
+  extern __shared__ float sm[];                       // [blockDim][16] partials, then [2][C] channel sums
+  const int n = blockIdx.y, nchunks = gridDim.x;
+  const int nv = C >> 3;                              // vectors per pixel
+  const int lanes = blockDim.x / nv;                  // pixels in flight per block step
+  const int cv = threadIdx.x % nv;
+  const int r0 = blockIdx.x * kGnRowsPerBlock, r1 = min(r0 + kGnRowsPerBlock, HW);
+  const uint4* xv = reinterpret_cast<const uint4*>(x + static_cast<long long>(n) * HW * C);
+  float s[8], ss[8];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+  for (long long v = static_cast<long long>(r0) * nv + threadIdx.x; v < static_cast<long long>(r1) * nv; v += blockDim.x) {
+    const uint4 raw = xv[v];
+    const float f[8] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y), bf16lo(raw.z), bf16hi(raw.z), bf16lo(raw.w), bf16hi(raw.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
   }
-  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+  float* part = sm + threadIdx.x * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { part[j] = s[j]; part[8 + j] = ss[j]; }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  float* ch = sm + blockDim.x * 16;                   // [2][C]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int v = c >> 3, j = c & 7;
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < lanes; ++k) { a += sm[(v + k * nv) * 16 + j]; b += sm[(v + k * nv) * 16 + 8 + j]; }
+    ch[c] = a; ch[C + c] = b;
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double a = 0, b = 0;
-    for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
-    atomicAdd(stats + (static_cast<long long>(n) * G + g) * 2, a);
-    atomicAdd(stats + (static_cast<long long>(n) * G + g) * 2 + 1, b);
+    for (int c = 0; c < cpg; ++c) { a += ch[g * cpg + c]; b += ch[C + g * cpg + c]; }
+    double* o = partial + ((static_cast<long long>(n) * nchunks + blockIdx.x) * G + g) * 2;
+    o[0] = a; o[1] = b;
+  }
+  (void)cv;
+}
+
+// per (image, channel) affine of the normalisation: y = x * a + b with a = rstd * gamma, b = beta - mean * rstd * gamma
+__global__ void __launch_bounds__(256) gn_coef_kernel(const double* __restrict__ partial, int nchunks, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, int HW, int C, int G, int N,
+                                                      float* __restrict__ coef /*[N][2][C]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  const int cpg = C / G, g = c / cpg;
+  double sa = 0, sb = 0;
+  for (int k = 0; k < nchunks; ++k) {
+    const double* o = partial + ((static_cast<long long>(n) * nchunks + k) * G + g) * 2;
+    sa += o[0]; sb += o[1];
+  }
+  const double cnt = static_cast<double>(HW) * cpg;
+  const double m = sa / cnt;
+  const double var = sb / cnt - m * m;
+  const float rstd = rsqrtf(static_cast<float>(var > 0 ? var : 0) + 1e-6f);
+  const float a = rstd * gamma[c];
+  coef[(static_cast<long long>(n) * 2) * C + c] = a;
+  coef[(static_cast<long long>(n) * 2 + 1) * C + c] = beta[c] - static_cast<float>(m) * a;
+}
+
+// y = [silu](x * a + b): one 16-byte vector per thread per step, grid-stride; HBM-bound (read + write once)
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int HW, int C,
+                                                       const float* __restrict__ coef, int silu, long long total8) {
+  const int nv = C >> 3;
+  const long long per_img = static_cast<long long>(HW) * nv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / per_img);
+    const int c0 = static_cast<int>(i % nv) * 8;
+    const float* ca = coef + static_cast<long long>(n) * 2 * C + c0;
+    const float4 a0 = *reinterpret_cast<const float4*>(ca), a1 = *reinterpret_cast<const float4*>(ca + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(ca + C), b1 = *reinterpret_cast<const float4*>(ca + C + 4);
+    const uint4 raw = reinterpret_cast<const uint4*>(x)[i];
+    float f[8] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y), bf16lo(raw.z), bf16hi(raw.z), bf16lo(raw.w), bf16hi(raw.w)};
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = fmaf(f[j], av[j], bv[j]);
+      if (silu) v = v / (1.0f + __expf(-v));
+      f[j] = v;
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int HW, int C, int G,
-                                                       const double* __restrict__ stats, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, int silu, long long total8) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const long long e0 = i * 8;
-  const int c0 = static_cast<int>(e0 % C);
-  const int n = static_cast<int>(e0 / (static_cast<long long>(HW) * C));
-  const int cpg = C / G;
-  const uint4 raw = *reinterpret_cast<const uint4*>(x + e0);
-  float f[8] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y), bf16lo(raw.z), bf16hi(raw.z), bf16lo(raw.w), bf16hi(raw.w)};
-  const double cnt = static_cast<double>(HW) * cpg;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = c0 + j, g = c / cpg;
-    const double m = stats[(static_cast<long long>(n) * G + g) * 2] / cnt;
-    const double var = stats[(static_cast<long long>(n) * G + g) * 2 + 1] / cnt - m * m;
-    const float rstd = rsqrtf(static_cast<float>(var > 0 ? var : 0) + 1e-6f);
-    float v = (f[j] - static_cast<float>(m)) * rstd * gamma[c] + beta[c];
-    if (silu) v = v / (1.0f + __expf(-v));
-    f[j] = v;
+// nearest-neighbour 2x upsampling, NHWC (Upsample2D [ext] before its 3x3 convolution): one 16-byte vector per thread
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int nv,
+                                                         long long total) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % nv);
+    long long p = i / nv;
+    const int xo = static_cast<int>(p % (2 * W));
+    p /= 2 * W;
+    const int yo = static_cast<int>(p % (2 * H));
+    const long long n = p / (2 * H);
+    y[i] = x[((n * H + (yo >> 1)) * W + (xo >> 1)) * nv + v];
   }
-  *reinterpret_cast<uint4*>(y + e0) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
 // one block per row: softmax over N fp32 scores -> bf16
@@ -163,16 +214,41 @@ int im2col3x3(const bf16* x, int N, int Hin, int Win, int C, int up, int stride,
   return 0;
 }
 
+size_t groupnorm_workspace_bytes(int N, int HW, int C, int G) {
+  const size_t nchunks = (static_cast<size_t>(HW) + kGnRowsPerBlock - 1) / kGnRowsPerBlock;
+  return static_cast<size_t>(N) * nchunks * G * 2 * sizeof(double) + static_cast<size_t>(N) * 2 * C * sizeof(float);
+}
+
 int groupnorm_nhwc(const bf16* x, bf16* y, int N, int HW, int C, int G, const float* gamma, const float* beta, int silu,
                    double* stats_ws, cudaStream_t stream) {
-  UTX_CHECK(C % G == 0 && C % 8 == 0, "groupnorm: C must be a multiple of G and of 8");
-  UTX_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * N * G * 2, stream));
-  const int rows_per_block = 4096;
-  dim3 grid((HW + rows_per_block - 1) / rows_per_block, G, N);
-  gn_stats_kernel<<<grid, 256, 0, stream>>>(x, HW, C, G, rows_per_block, stats_ws);
+  UTX_CHECK(C % G == 0 && C % 8 == 0 && C <= 2048, "groupnorm: C must be a multiple of G and of 8, <= 2048");
+  if (N == 0 || HW == 0) return 0;
+  const int nchunks = (HW + kGnRowsPerBlock - 1) / kGnRowsPerBlock;
+  // workspace (groupnorm_workspace_bytes): per-block moments [N][chunks][G][2] doubles, then [N][2][C] fp32 coefficients
+  float* coef = reinterpret_cast<float*>(stats_ws + static_cast<size_t>(N) * nchunks * G * 2);
+  const int nv = C / 8;
+  const int threads = (256 / nv) * nv;
+  dim3 grid(nchunks, N);
+  gn_stats_kernel<<<grid, threads, (threads * 16 + 2 * C) * sizeof(float), stream>>>(x, HW, C, G, stats_ws);
+  gn_coef_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>(stats_ws, nchunks, gamma, beta, HW, C, G, N, coef);
   const long long total8 = static_cast<long long>(N) * HW * C / 8;
-  gn_apply_kernel<<<static_cast<unsigned>((total8 + 255) / 256), 256, 0, stream>>>(x, y, HW, C, G, stats_ws, gamma, beta, silu,
-                                                                                  total8);
+  long long blocks = (total8 + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  gn_apply_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, y, HW, C, coef, silu, total8);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int upsample2x_nhwc(const bf16* x, int N, int H, int W, int C, bf16* y, cudaStream_t stream) {
+  UTX_CHECK(C % 8 == 0, "upsample2x: C must be a multiple of 8");
+  const long long total = static_cast<long long>(N) * 4 * H * W * (C / 8);
+  if (total == 0) return 0;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  upsample2x_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W,
+                                                                       C / 8, total);
   UTX_CUDA(cudaGetLastError());
   return 0;
 }

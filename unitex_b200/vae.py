@@ -122,6 +122,12 @@ class AutoencoderKLB200:
         else:                                                   # Downsample2D: pad (0,1,0,1), stride 2
             Ho, Wo = (Hs + 1 - 3) // 2 + 1, (Ws + 1 - 3) // 2 + 1
         Kp = w.shape[1]
+        if (self.implicit_conv and up == 2 and stride == 1 and pad == 1 and C % 64 == 0 and Kp == 9 * C and
+                (Ws % 128 == 0 or (128 % Ws == 0 and Hs % (128 // Ws) == 0))):
+            # Upsample2D: materialise the nearest-neighbour upsampling (4x the input, not the 36x of an im2col buffer)
+            xu = torch.empty(N * Hs * Ws, C, device=self.device, dtype=torch.bfloat16)
+            _lib.check(self.lib.utx_upsample2x_nhwc(_p(x), N, H, W, C, _p(xu), _stream()), "utx_upsample2x_nhwc")
+            x, H, W, up = xu, Hs, Ws, 1
         if (self.implicit_conv and up == 1 and stride == 1 and pad == 1 and C % 64 == 0 and Kp == 9 * C and
                 (W % 128 == 0 or (128 % W == 0 and H % (128 // W) == 0))):
             # implicit GEMM: TMA boxes of the activation shifted by the tap are the A tiles, no im2col buffer
@@ -154,6 +160,9 @@ class AutoencoderKLB200:
 
     def _gn(self, name, x, N, HW, C, silu=True):
         y = torch.empty_like(x)
+        need = (self.lib.utx_groupnorm_workspace_bytes(N, HW, C, self.groups) + 7) // 8     # in doubles
+        if self._stats.numel() < need:
+            self._stats = torch.zeros(need, device=self.device, dtype=torch.float64)
         _lib.check(self.lib.utx_groupnorm_nhwc(_p(x), _p(y), N, HW, C, self.groups, _p(self.W[name + ".w"]), _p(self.W[name + ".b"]),
                                                int(silu), _p(self._stats), _stream()), "utx_groupnorm_nhwc")
         return y
