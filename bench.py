@@ -282,6 +282,7 @@ def run_ours(args, rank, world, local_rank):
         out["vae_decode"] = bench_vae_decode(dev)
     if world == 1 and not args.no_bake:
         out["delight"] = bench_delight(eng, dev, sig)
+        out["pipeline_call"] = bench_pipeline_call(eng, dev)
     if world == 1 and not args.no_cpu_baseline:
         del eng
         torch.cuda.empty_cache()
@@ -326,6 +327,34 @@ def bench_delight(eng, dev, sig):
     flops = 57 * 2 * 113246208 * S + 57 * 4 * 3072 * S * S
     return {"metric": METRIC, "workload": "delight 1024x1024 4-view: S=8704 = 512 txt + 4096 noise + 4096 control", "value": 1e3 / ms,
             "unit": UNIT, "ms_per_step": ms, "tflops": flops / (ms * 1e-3) / 1e12, "finite": bool(torch.isfinite(lat.float()).all())}
+
+
+def bench_pipeline_call(eng, dev):
+    """The whole public call of the sampler, as the reference makes it (pipeline.py:245-262): PIL control image 1024^2 + PIL
+    reference image 512^2 in, VAE encode, 28 denoise steps at S = 9728, VAE decode, PIL image out.  Wall clock around the
+    call with a device synchronize on both sides; random-init VAE weights."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from unitex_b200.flux_pipeline import PBRFluxPipeline
+    from unitex_b200.vae import AutoencoderKLB200
+    vae = AutoencoderKLB200.from_random(seed=1, device=dev)
+    pipe = PBRFluxPipeline(eng, vae=vae)
+    rng = np.random.default_rng(0)
+    control = Image.fromarray(rng.integers(0, 255, (1024, 1024, 3), dtype=np.uint8))
+    dual = Image.fromarray(rng.integers(0, 255, (512, 512, 3), dtype=np.uint8))
+    kw = dict(prompt="", prompt_2="", dual_image=dual, control_image=control, height=1024, width=1024, n_rows=2, n_cols=2,
+              num_inference_steps=28, guidance_scale=3.5, generator=torch.Generator().manual_seed(63))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    img = pipe(**kw).images[0]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ok = bool(np.isfinite(np.asarray(img, dtype=np.float32)).all()) and img.size == (1024, 1024)
+    del pipe, vae
+    torch.cuda.empty_cache()
+    return {"what": "PBRFluxPipeline.__call__: PIL in -> VAE encode -> 28 steps at S=9728 -> VAE decode -> PIL out", "seconds": dt,
+            "steps": 28, "steps_per_s_whole_call": 28 / dt, "ok": ok}
 
 
 def bench_vae_decode(dev):
