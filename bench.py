@@ -99,6 +99,12 @@ def cpu_block_seconds(repeats: int = 1, device="cpu", frac: int = CPU_FRAC):
     import torch
     import torch.nn.functional as F
     from oracle import flux_dit as fd
+    if str(device) == "cpu":
+        # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would time one core)
+        try:
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+        except (AttributeError, RuntimeError):
+            pass
     torch.manual_seed(0)
     cfg = fd.FluxConfig()
     D, H = cfg.inner_dim, cfg.num_attention_heads
