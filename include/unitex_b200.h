@@ -162,6 +162,11 @@ int utx_bvh_intersect(const void* nodes, const float* vert, const int32_t* tri, 
  * workspace: utx_bvh_workspace_bytes(n_src). */
 int utx_knn1(const float* src, int n_src, const float* dst, long long M, long long* index, float* score, void* nodes,
              void* workspace, size_t workspace_bytes, void* stream);
+/* knn(src, dst, k) for 1 <= k <= min(32, n_src) (pcd/knn/__init__.py:104-114; k = 8+1 / 32 in renderer_inverse.py:377,382,
+ * 429,464): index int64 [M,k], score fp32 [M,k] = Euclidean distance, each row ascending by (distance, index).  Buffers as
+ * for utx_knn1. */
+int utx_knn(const float* src, int n_src, const float* dst, long long M, int k, long long* index, float* score, void* nodes,
+            void* workspace, size_t workspace_bytes, void* stream);
 /* uv_to_pcd + bake_mv_to_uv_reproject_blur (renderer_inverse.py:243-365,574-633) fused.  rast2d: UV raster [H2,W2,4];
  * view_mats/view_dirs/priority/grid_lo: HOST arrays ([n,16] P@W2C row-major, [n,3] = -c2w[:3,2], [n], [3]);
  * images_rgba: device [n,H,W,4] = view colour + visible alpha; blur_k2d: device [49].  Outputs: mask2d u8 [H2*W2],
@@ -172,6 +177,35 @@ int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void*
                 const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
                 const float* grid_lo, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color,
                 int32_t* nn_index, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Staged form of utx_uv_bake over the SAME workspace, for the bake variants that differ between the stages
+ * (`method='kdtree'`, renderer_inverse.py:367-433; `*_inpainting=True` with a registered query field, :93-103,:427-432,:609-614):
+ *   utx_uv_bake_visibility   uv_to_pcd (:243-365) + priority composite + seam mask (:591-605): writes mask2d, mask_vis and
+ *                            leaves owner i8 [T] (winning view, -1 = none), pos fp32 [T,3], colour fp32 [T,3], seam u8 [T] in
+ *                            the workspace at the byte offsets utx_uv_bake_layout reports
+ *   utx_uv_bake_views_knn    kdtree variant, visible part: merge = 0 `order_mean` -- texels owned by view i take the mean colour
+ *                            of their k nearest points of view i's pixel cloud (:406-417); merge = 1 `mean` -- every covered texel
+ *                            from the union cloud (:385-389).  pix_pos [n,H,W,3] = vertex positions interpolated at the pixels
+ *                            (:188), images_rgba as for utx_uv_bake (alpha = mask_visiable); scratch:
+ *                            utx_uv_bake_views_workspace_bytes(n, H, W)
+ *   utx_uv_bake_fill         covered-but-unowned texels <- mean colour of their k nearest owned texels; k = 1 reproject
+ *                            (:606-615), k = 32 kdtree (:427-431).  A caller with a query field writes those colours itself
+ *                            (through the layout offsets) and skips this stage.
+ *   utx_uv_bake_finish       blur != 0: lens blur on the seam texels (:617-624); then pull-push (:627, :423) -> color [T,3]
+ * utx_uv_bake == visibility; fill(k = 1); finish(blur = 1). */
+int utx_uv_bake_layout(int H2, int W2, size_t* off_owner, size_t* off_pos, size_t* off_color, size_t* off_seam);
+int utx_uv_bake_visibility(const float* vert, int V, const int32_t* tri, int F, const void* nodes, const float* rast2d, int H2,
+                           int W2, int n_views, const float* view_mats, const float* view_dirs, const int32_t* priority,
+                           const float* images_rgba, int H, int W, float cos_thresh, unsigned char* mask2d,
+                           unsigned char* mask_vis, void* workspace, size_t workspace_bytes, void* stream);
+size_t utx_uv_bake_views_workspace_bytes(int n_views, int H, int W);
+int utx_uv_bake_views_knn(const float* pix_pos, const float* images_rgba, int n_views, int H, int W, int k, int merge,
+                          const unsigned char* mask2d, int H2, int W2, void* workspace, size_t workspace_bytes, void* scratch,
+                          size_t scratch_bytes, void* stream);
+int utx_uv_bake_fill(const unsigned char* mask2d, int H2, int W2, int k, int32_t* nn_index, void* workspace,
+                     size_t workspace_bytes, void* stream);
+int utx_uv_bake_finish(const unsigned char* mask2d, int H2, int W2, int blur, const float* blur_k2d, float blur_gamma,
+                       float* color, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * FLUX VAE building blocks (AutoencoderKL; flux_piplines/texturing/pipeline.py:226-238 encode, :688-692 decode).

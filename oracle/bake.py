@@ -6,6 +6,8 @@ after them restates the reference's torch code with the same torch calls, on the
   get_boundary_mask                :435-444
   bake_mv_to_uv_reproject_blur     :574-633   (k=1 nearest neighbour restated as exact brute force, lowest index on ties;
                                                torch_kdtree@86961f7d [ext] leaves ties unspecified)
+  bake_mv_to_uv_kdtree             :367-433   (`order_mean` and `mean`; k nearest neighbours = exact brute force, ascending by
+                                               (distance, index)), query_field hook :93-103,:139-154
   lens_blur_torch                  texturetools/image/lens_blur.py:82-93,109-121,172-195,260-280
   pull_push                        texturetools/texture/stitching/mip.py:9-96
 PARITY UNPINNED (no golden vectors in the reference); pinned here by analytic tests in tests/test_oracle_bake.py.
@@ -200,10 +202,34 @@ def nearest_index(src: torch.Tensor, dst: torch.Tensor, chunk: int = 2048) -> to
     return out
 
 
+def nearest_k(src: torch.Tensor, dst: torch.Tensor, k: int, chunk: int = 512):
+    """Exact k nearest src points of each dst point, ascending by (fp32 squared distance ((dx^2+dy^2)+dz^2), index):
+    -> (distance [M,k] fp32, index [M,k] int64), the `knn(src, dst, k)` contract of pcd/knn/__init__.py:104-114."""
+    M = dst.shape[0]
+    idx = torch.empty(M, k, dtype=torch.int64)
+    dist = torch.empty(M, k, dtype=torch.float32)
+    for i in range(0, M, chunk):
+        d = src[None, :, :] - dst[i:i + chunk, None, :]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        v, j = torch.sort(d2, dim=1, stable=True)            # stable: equal distances keep ascending index order
+        idx[i:i + chunk] = j[:, :k]
+        dist[i:i + chunk] = v[:, :k].sqrt()
+    return dist, idx
+
+
 @torch.no_grad()
-def infer_reproject(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, image_attrs: torch.Tensor,
-                    H: int, W: int, H2: int, W2: int, angle_deg: float = 100.0, index=(0, 3, 4, 1, 2, 5)) -> Dict[str, torch.Tensor]:
-    """NVDiffRendererInverse.infer(method='reproject', perspective=False, filt_gradient_points=False) (:635-726)."""
+def infer_reproject(*a, **kw):
+    return infer(*a, **kw)
+
+
+@torch.no_grad()
+def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, image_attrs: torch.Tensor,
+                    H: int, W: int, H2: int, W2: int, angle_deg: float = 100.0, index=(0, 3, 4, 1, 2, 5), method: str = "reproject",
+                    kdtree_method: str = "order_mean", k_all: int = 32, k_vis: int = 1, k_invis: int = 32,
+                    query_field=None) -> Dict[str, torch.Tensor]:
+    """NVDiffRendererInverse.infer(perspective=False, filt_gradient_points=False) (:635-726) for method='reproject'
+    (reproject_method='lens') and method='kdtree' (kdtree_method 'order_mean' | 'mean'); `query_field` set = the
+    *_inpainting=True branches (:387-389, :427-432, :609-614)."""
     vert = np.ascontiguousarray(vert, np.float32)
     tri = np.ascontiguousarray(tri, np.int32)
     tri_uv = np.ascontiguousarray(tri_uv, np.int32)
@@ -251,6 +277,38 @@ def infer_reproject(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch
         conv = F.conv2d(vis.float().permute(0, 3, 1, 2), ker, stride=1, padding=k // 2).permute(0, 2, 3, 1)
         vis = vis | (conv >= ((k - 1) ** 2 - 1) * ((k - 2) ** 2))
     vis = vis & mask_2d & (alpha_2d > 0.999)
+    if method == "kdtree":
+        # mv_to_pcd point clouds (:188, :227-231): positions interpolated at the pixels, one cloud per view
+        attrs_mv = torch.from_numpy(interpolate(vert, rast_mv.numpy(), tri))                 # [n,H,W,3]
+        mmv = rast_mv[..., 3] > 0
+        clouds = [(attrs_mv[i][mmv[i]], image_attrs[i][mmv[i]]) for i in range(n)]
+        P2 = pos_2d[0][m]                                                                    # point_cloud_2d.vertices
+        wc = torch.zeros(P2.shape[0], 3)
+        cur = torch.zeros(1, H2, W2, 1, dtype=torch.bool)
+        if kdtree_method == "mean":                                                          # :385-389
+            allp, allc = torch.cat([c[0] for c in clouds]), torch.cat([c[1] for c in clouds])
+            wc = query_field(allp, allc, P2) if query_field is not None else allc[nearest_k(allp, P2, k_all)[1]].mean(dim=-2)
+        else:                                                                                # order_mean :406-432
+            for i in index:
+                extra = (~cur) & vis[i:i + 1]
+                sel = extra[0, ..., 0][m]
+                if sel.any():
+                    _, idx = nearest_k(clouds[i][0], P2[sel], k_vis)
+                    wc[sel] = clouds[i][1][idx].mean(dim=-2)
+                cur = cur | extra
+            vsel = cur[0, ..., 0][m]
+            if (~vsel).any():
+                if query_field is not None:
+                    wc[~vsel] = query_field(P2[vsel], wc[vsel], P2[~vsel])
+                else:
+                    kk = min(k_invis, int(vsel.sum()))
+                    _, idx = nearest_k(P2[vsel], P2[~vsel], kk)
+                    wc[~vsel] = wc[vsel][idx].mean(dim=-2)
+        color = torch.zeros(1, H2, W2, 3)
+        color[0][m] = wc
+        color_2d = pull_push(color.permute(0, 3, 1, 2), mask_2d.permute(0, 3, 1, 2))[0].permute(0, 2, 3, 1)
+        return {"mask_2d": mask_2d, "mask_2d_visiable": vis, "color_2d": color_2d, "pre_pull_push": color,
+                "rast_2d": torch.from_numpy(rast2)}
     # bake_mv_to_uv_reproject_blur
     color = torch.zeros(1, H2, W2, 3)
     cur = torch.zeros(1, H2, W2, 1, dtype=torch.bool)
@@ -268,10 +326,13 @@ def infer_reproject(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch
     inv_m = (~cur[0, ..., 0]) & m
     nn_index = torch.full((H2 * W2,), -1, dtype=torch.int64)
     if inv_m.any() and vis_m.any():
-        src_idx = torch.nonzero(vis_m.reshape(-1))[:, 0]
-        idx = nearest_index(pos_2d[0][vis_m], pos_2d[0][inv_m])
-        color[0][inv_m] = color[0][vis_m][idx]
-        nn_index[inv_m.reshape(-1)] = src_idx[idx]
+        if query_field is not None:                                                          # inpainting=True (:612-613)
+            color[0][inv_m] = query_field(pos_2d[0][vis_m], color[0][vis_m], pos_2d[0][inv_m])
+        else:
+            src_idx = torch.nonzero(vis_m.reshape(-1))[:, 0]
+            idx = nearest_index(pos_2d[0][vis_m], pos_2d[0][inv_m])
+            color[0][inv_m] = color[0][vis_m][idx]
+            nn_index[inv_m.reshape(-1)] = src_idx[idx]
     pre_blur = color.clone()
     blur = lens_blur_torch(color.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
     color = torch.where(bnd, blur, color)

@@ -136,3 +136,95 @@ def test_knn_plugin_exact(lib):
     assert index.shape == (3001, 1) and index.dtype == torch.int64
     assert torch.equal(index[:, 0].cpu(), ref) and index[-1, 0] == 7
     assert torch.allclose(score[:, 0].cpu(), (src[ref] - dst).norm(dim=-1), atol=1e-6)
+
+
+@pytest.mark.parametrize("k", [2, 9, 32])
+def test_knn_k_exact(lib, k):
+    """knn(src, dst, k) for the kdtree bake's k (renderer_inverse.py:385,413,427): rows ascending by (distance, index)."""
+    from oracle import bake as ob
+    from unitex_b200.bake import knn
+    g = torch.Generator().manual_seed(k)
+    src = torch.rand(6000, 3, generator=g)
+    src[100] = src[7]
+    src[4000:4004] = src[9]                              # a run of duplicates: must come out in index order
+    dst = torch.cat([torch.rand(1500, 3, generator=g), src[100:101], src[4001:4002]])
+    score, index = knn(src, dst, k=k)
+    torch.cuda.synchronize()
+    rd, ri = ob.nearest_k(src, dst, k)
+    assert index.shape == (1502, k) and index.dtype == torch.int64 and score.dtype == torch.float32
+    assert torch.equal(index.cpu(), ri)
+    assert torch.equal(score.cpu(), rd)                   # sqrt of the same fp32 squared distance
+    assert index[-2, :2].tolist() == [7, 100]
+    with pytest.raises(ValueError):
+        knn(src[:4], dst, k=5)
+
+
+def _bake_case(rows=16):
+    from oracle import bake as ob
+    v, f, uv, fuv = two_spheres(rows, 2 * rows)
+    c2ws, intr = _views()
+    H = W = 96
+    mats = torch.matmul(ob.intr_to_proj_ortho(intr), ob.c2w_to_w2c(c2ws))
+    vh = torch.cat([torch.from_numpy(v), torch.ones(len(v), 1)], -1)
+    rast = ob.rasterize(torch.matmul(vh, mats.permute(0, 2, 1)).numpy(), f, H, W)
+    img = torch.from_numpy(analytic_color(ob.interpolate(v, rast, f)) * (rast[..., 3:4] > 0)).float()
+    return v, f, uv, fuv, c2ws, intr, img, H, W
+
+
+@pytest.mark.parametrize("kdtree_method,k_vis", [("order_mean", 1), ("order_mean", 9), ("mean", 32)])
+def test_uv_bake_kdtree_matches_oracle(lib, kdtree_method, k_vis):
+    """infer(method='kdtree') (bake_mv_to_uv_kdtree, renderer_inverse.py:367-433) vs the oracle restatement."""
+    from oracle import bake as ob
+    from unitex_b200 import bake as ub
+    v, f, uv, fuv, c2ws, intr, img, H, W = _bake_case()
+    H2 = W2 = 128
+    ref = ob.infer(v, f, uv, fuv, c2ws, intr, img, H, W, H2, W2, method="kdtree", kdtree_method=kdtree_method,
+                   k_all=32, k_vis=k_vis, k_invis=32)
+    r = ub.NVDiffRendererInverse(pbr_mesh=ub.BakeMesh(v, f, uv, fuv))
+    _, vis, m2, col = r.infer(r.pbr_mesh, c2ws, intr, img, H=H, W=W, H2D=H2, W2D=W2, perspective=False,
+                              ray_normal_angle_threhold=100.0, method="kdtree", kdtree_method=kdtree_method,
+                              kdtree_n_neighbors=32, kdtree_n_neighbors_visiable=k_vis, kdtree_n_neighbors_invisiable=32,
+                              filt_gradient_points=False)
+    torch.cuda.synchronize()
+    assert torch.equal(m2.cpu(), ref["mask_2d"]) and torch.equal(vis.cpu(), ref["mask_2d_visiable"])
+    err = (col.cpu() - ref["color_2d"]).abs()
+    assert err.max().item() < COLOR_ATOL, err.max().item()
+    # the bake reproduces the analytic colour field on the texels the views see (the reference's test_gt idea, :732-774)
+    seen = ref["mask_2d_visiable"].any(dim=0)[..., 0]
+    pos = torch.from_numpy(ob.interpolate(v, ref["rast_2d"].numpy(), f))[0]
+    gt = torch.from_numpy(analytic_color(pos.numpy())).float()
+    assert (col.cpu()[0][seen] - gt[seen]).abs().mean().item() < 0.03
+
+
+@pytest.mark.parametrize("method,kdtree_method", [("reproject", "order_mean"), ("kdtree", "order_mean"), ("kdtree", "mean")])
+def test_uv_bake_query_field_hook(lib, method, kdtree_method):
+    """`*_inpainting=True`: the registered query field supplies the colours (register_query_field :93-103; call sites
+    :387-389, :427-432, :609-614) -- same arguments, in the same order, as the oracle hands its field."""
+    from oracle import bake as ob
+    from unitex_b200 import bake as ub
+    v, f, uv, fuv, c2ws, intr, img, H, W = _bake_case(12)
+    H2 = W2 = 64
+    calls = []
+
+    def field(vv, cv, vi):
+        calls.append((vv.detach().cpu(), cv.detach().cpu(), vi.detach().cpu()))
+        return (0.25 + 0.5 * torch.sigmoid(vi * 3.0)).to(vi)      # a colour that depends only on the query position
+
+    ref = ob.infer(v, f, uv, fuv, c2ws, intr, img, H, W, H2, W2, method=method, kdtree_method=kdtree_method, query_field=field)
+    ref_call = calls.pop()
+    r = ub.NVDiffRendererInverse(pbr_mesh=ub.BakeMesh(v, f, uv, fuv))
+    with pytest.raises(NotImplementedError):
+        r.infer(r.pbr_mesh, c2ws, intr, img, H=H, W=W, H2D=H2, W2D=W2, perspective=False, method=method,
+                kdtree_method=kdtree_method, kdtree_inpainting=True, reproject_inpainting=True, filt_gradient_points=False)
+    r.register_query_field(field)
+    _, vis, m2, col = r.infer(r.pbr_mesh, c2ws, intr, img, H=H, W=W, H2D=H2, W2D=W2, perspective=False,
+                              ray_normal_angle_threhold=100.0, method=method, kdtree_method=kdtree_method,
+                              kdtree_inpainting=True, reproject_inpainting=True, filt_gradient_points=False)
+    torch.cuda.synchronize()
+    assert len(calls) == 1
+    for got, want in zip(calls[0], ref_call):
+        assert got.shape == want.shape and (got - want).abs().max().item() < COLOR_ATOL
+    assert torch.equal(calls[0][2], ref_call[2])                  # query positions: bit-exact, same (row-major) order
+    assert torch.equal(vis.cpu(), ref["mask_2d_visiable"])
+    err = (col.cpu() - ref["color_2d"]).abs()
+    assert err.max().item() < COLOR_ATOL, err.max().item()

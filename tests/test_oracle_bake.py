@@ -135,3 +135,73 @@ def test_bake_roundtrip_recovers_analytic_colour():
     assert err.mean() < 0.02 and torch.quantile(err, 0.99) < 0.08               # bilinear resampling of a smooth field
     assert (out["color_2d"][0][~m2] >= 0).all()                                  # pull-push filled outside the charts
     assert ((out["nn_index"] >= 0).reshape(128, 128) == (m2 & (out["owner"] < 0))).all()
+
+
+def test_nearest_k_known_answers():
+    """knn contract (pcd/knn/__init__.py:104-114): k nearest, ascending distance; ties by index (our pinned rule)."""
+    src = torch.tensor([[0.0, 0, 0], [1.0, 0, 0], [2.0, 0, 0], [1.0, 0, 0], [5.0, 0, 0]])
+    dst = torch.tensor([[0.9, 0, 0], [10.0, 0, 0]])
+    d, i = ob.nearest_k(src, dst, 3)
+    assert i.tolist() == [[1, 3, 0], [4, 2, 1]]
+    assert torch.allclose(d, torch.tensor([[0.1, 0.1, 0.9], [5.0, 8.0, 9.0]]), atol=1e-6)
+    assert torch.equal(ob.nearest_k(src, dst, 1)[1][:, 0], ob.nearest_index(src, dst))
+
+
+def _kd_case():
+    from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics
+    v, f, uv, fuv = two_spheres(12, 24)
+    c2ws = generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]]
+    intr = generate_intrinsics(1.0, 1.0, fov=False)
+    H = W = 64
+    mats = torch.matmul(ob.intr_to_proj_ortho(intr), ob.c2w_to_w2c(c2ws))
+    vh = torch.cat([torch.from_numpy(v), torch.ones(len(v), 1)], -1)
+    rast = ob.rasterize(torch.matmul(vh, mats.permute(0, 2, 1)).numpy(), f, H, W)
+    img = torch.from_numpy(analytic_color(ob.interpolate(v, rast, f)) * (rast[..., 3:4] > 0)).float()
+    return v, f, uv, fuv, c2ws, intr, img, H, W
+
+
+def test_kdtree_bake_recovers_analytic_colour():
+    """bake_mv_to_uv_kdtree (renderer_inverse.py:367-433): nearest pixel-cloud points carry the analytic colour of their own
+    position, so the baked atlas approximates the field for both merge rules."""
+    v, f, uv, fuv, c2ws, intr, img, H, W = _kd_case()
+    pos2d = None
+    errs = {}
+    for km in ("order_mean", "mean"):
+        out = ob.infer(v, f, uv, fuv, c2ws, intr, img, H, W, 64, 64, method="kdtree", kdtree_method=km)
+        m2 = out["mask_2d"][0, ..., 0]
+        if pos2d is None:
+            pos2d = ob.interpolate(v, out["rast_2d"].numpy(), f)[0]
+        want = torch.from_numpy(analytic_color(pos2d)).float()
+        seen = out["mask_2d_visiable"].any(dim=0)[..., 0]
+        errs[km] = (out["color_2d"][0] - want).abs().max(-1).values[seen].mean().item()
+        assert torch.equal(out["color_2d"][0][m2], out["pre_pull_push"][0][m2])          # pull-push leaves the charts alone
+        assert (out["color_2d"][0][~m2] >= 0).all()
+    assert errs["order_mean"] < 0.03 and errs["mean"] < 0.03
+
+
+def test_query_field_hook_contract():
+    """register_query_field (:93-103): f(vertices_visiable [Nv,3], colors_visiable [Nv,C], vertices_invisiable [Ni,3]) ->
+    [Ni,C]; the reproject bake hands it the owned / unowned texels (:609-614), `order_mean` the same split (:427-432),
+    `mean` the union pixel cloud and every covered texel (:387-389)."""
+    v, f, uv, fuv, c2ws, intr, img, H, W = _kd_case()
+    seen_args = {}
+
+    def field(vv, cv, vi):
+        seen_args["shapes"] = (tuple(vv.shape), tuple(cv.shape), tuple(vi.shape))
+        return torch.full((vi.shape[0], 3), 0.125)
+
+    base = ob.infer(v, f, uv, fuv, c2ws, intr, img, H, W, 64, 64)
+    owned, m2 = base["owner"] >= 0, base["mask_2d"][0, ..., 0]
+    n_own, n_un = int((owned & m2).sum()), int((~owned & m2).sum())
+    assert n_un > 0
+    out = ob.infer(v, f, uv, fuv, c2ws, intr, img, H, W, 64, 64, query_field=field)
+    assert seen_args["shapes"] == ((n_own, 3), (n_own, 3), (n_un, 3))
+    unowned_inner = ~owned & m2 & ~base["seam"][0, ..., 0]
+    assert (out["pre_blur"][0][~owned & m2] == 0.125).all() and unowned_inner.any()
+    out = ob.infer(v, f, uv, fuv, c2ws, intr, img, H, W, 64, 64, method="kdtree", query_field=field)
+    assert seen_args["shapes"] == ((n_own, 3), (n_own, 3), (n_un, 3))
+    assert (out["pre_pull_push"][0][~owned & m2] == 0.125).all()
+    out = ob.infer(v, f, uv, fuv, c2ws, intr, img, H, W, 64, 64, method="kdtree", kdtree_method="mean", query_field=field)
+    n_cloud = int((img.abs().sum(-1) > 0).sum())
+    assert seen_args["shapes"][2] == (int(m2.sum()), 3) and seen_args["shapes"][0][0] >= n_cloud
+    assert (out["pre_pull_push"][0][m2] == 0.125).all()

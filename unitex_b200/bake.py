@@ -160,20 +160,23 @@ class RayTracing:
 
 def knn(src: torch.Tensor, dst: torch.Tensor, k: int = 1, backend: Optional[str] = None, batch_size: Optional[int] = None,
         device="cuda"):
-    """Drop-in for texturetools.pcd.knn (pcd/knn/__init__.py:104-114) for the k=1 case the bake uses
-    (renderer_inverse.py:611): -> (score [M,1] fp32 distance, index [M,1] int64), exact, lowest index on ties."""
-    if k != 1:
-        raise NotImplementedError("only k=1 is on the UniTEX hot path")
+    """Drop-in for texturetools.pcd.knn (pcd/knn/__init__.py:104-114): -> (score [M,k] fp32 distance, index [M,k] int64),
+    exact, rows ascending by (distance, index).  k = 1 is the reproject fill (renderer_inverse.py:611); k = 32 / 8+1 the
+    kdtree bake (:385,:413,:427).  `backend` / `batch_size` are accepted and ignored (one backend, no batching needed)."""
     L = _lib.load()
     dev = torch.device(device)
     s, d = _f32(src, dev), _f32(dst, dev)
     n, M = s.shape[0], d.shape[0]
-    index = torch.empty(M, device=dev, dtype=torch.int64)
-    score = torch.empty(M, device=dev, dtype=torch.float32)
+    if not 1 <= k <= 32:
+        raise ValueError("knn: k must be in 1..32")
+    if k > n:
+        raise ValueError("knn: k exceeds the number of source points")
+    index = torch.empty(M, k, device=dev, dtype=torch.int64)
+    score = torch.empty(M, k, device=dev, dtype=torch.float32)
     nodes = torch.empty(max(L.utx_bvh_nodes_bytes(max(n, 2)), 64), device=dev, dtype=torch.uint8)
     ws = torch.empty(L.utx_bvh_workspace_bytes(max(n, 2)), device=dev, dtype=torch.uint8)
-    _lib.check(L.utx_knn1(_p(s), n, _p(d), M, _p(index), _p(score), _p(nodes), _p(ws), ws.numel(), _stream()), "utx_knn1")
-    return score[:, None], index[:, None]
+    _lib.check(L.utx_knn(_p(s), n, _p(d), M, k, _p(index), _p(score), _p(nodes), _p(ws), ws.numel(), _stream()), "utx_knn")
+    return score, index
 
 
 # ------------------------------------------------------------------------------------------------ lens-blur kernel (b9)
@@ -280,16 +283,33 @@ class NVDiffRendererInverse:
         mask = rast[..., 3:4] > 0
         return {"mask": mask, "alpha": mask.float(), "mask_visiable": mask, "alpha_visiable": mask.float(), "rast": rast}
 
+    def query_field(self, vertices_visiable, colors_visiable, vertices_invisiable):
+        """:139-154."""
+        if self.query_field_function is None:
+            raise NotImplementedError("using register_query_field before query")
+        return self.query_field_function(vertices_visiable, colors_visiable, vertices_invisiable)
+
     def infer(self, blank_mesh, c2ws: torch.Tensor, intrinsics: torch.Tensor, image_attrs: torch.Tensor, H=512, W=512,
               H2D=2048, W2D=2048, perspective=True, grad_norm_threhold=0.20, ray_normal_angle_threhold=115.0,
-              grid_interpolate_mode="torch", method="reproject", reproject_method="lens", reproject_inpainting=False,
-              return_mv_reproject_uv=False, filt_gradient_points=True, **kw):
+              grid_interpolate_mode="torch", method="reproject", kdtree_n_neighbors=32, kdtree_n_neighbors_visiable=1,
+              kdtree_n_neighbors_invisiable=32, kdtree_method="order_mean", kdtree_inpainting=False,
+              reproject_method="lens", reproject_kernel_size_boundary=3, reproject_kernel_size_boundary_blur=3,
+              reproject_kernel_size_blur=5, reproject_inpainting=False, return_mv_reproject_uv=False,
+              filt_gradient_points=True):
         """:635-726.  Returns (textured_mesh, mask_2d_visiable [n,H2D,W2D,1] bool, mask_2d [1,H2D,W2D,1] bool,
-        color_2d [1,H2D,W2D,3] fp32).  textured_mesh is left to the caller's exporter (io layer)."""
-        if method != "reproject" or reproject_method != "lens" or reproject_inpainting or perspective or filt_gradient_points:
-            raise NotImplementedError("B200 bake implements the path CustomRGBTextureFullPipeline uses: orthographic, "
-                                      "method='reproject', lens blur, no inpainting, filt_gradient_points=False "
-                                      "(pipeline.py:335-348)")
+        color_2d [1,H2D,W2D,3] fp32).  textured_mesh is left to the caller's exporter (io layer).
+        method='reproject' (reproject_method='lens') is the path CustomRGBTextureFullPipeline uses (pipeline.py:335-348);
+        method='kdtree' (kdtree_method 'order_mean' | 'mean') is bake_mv_to_uv_kdtree (:367-433); `*_inpainting=True` routes the
+        uncovered texels through the registered query field (:387-389, :427-432, :609-614)."""
+        assert method in ("kdtree", "reproject")
+        assert image_attrs.shape[-1] in (3, 9)
+        if perspective or filt_gradient_points or image_attrs.shape[-1] != 3:
+            raise NotImplementedError("B200 bake implements what CustomRGBTextureFullPipeline passes: orthographic views, "
+                                      "RGB attributes, filt_gradient_points=False (pipeline.py:335-348)")
+        if method == "reproject" and (reproject_method != "lens" or (reproject_kernel_size_boundary, reproject_kernel_size_boundary_blur) != (3, 3)):
+            raise NotImplementedError("reproject bake: only reproject_method='lens' with the 3x3 boundary kernels")
+        if method == "kdtree" and kdtree_method not in ("order_mean", "mean"):
+            raise NotImplementedError("kdtree bake: kdtree_method 'order_mean' or 'mean' ('mvpaint' needs per-point normals)")
         if isinstance(blank_mesh, str):
             self.update_from_file(blank_mesh)
         elif isinstance(blank_mesh, BakeMesh):
@@ -305,9 +325,6 @@ class NVDiffRendererInverse:
         mats = self._view_mats(c2ws, intrinsics, perspective).contiguous()
         dirs = (-c2ws[:, :3, 2]).float().cpu().contiguous()
         prio = (C.c_int32 * n)(*self.index)
-        lo = m.vertices.min(dim=0).values.cpu()
-        ext = float((m.vertices.max(dim=0).values.cpu() - lo).max()) * 1.0001 + 1e-6
-        lo_arr = (C.c_float * 3)(*[float(x) for x in lo])
         T = H2D * W2D
         mask2d = torch.empty(T, device=self.device, dtype=torch.uint8)
         mask_vis = torch.empty(n, T, device=self.device, dtype=torch.uint8)
@@ -315,11 +332,66 @@ class NVDiffRendererInverse:
         nn_index = torch.empty(T, device=self.device, dtype=torch.int32)
         ws = torch.empty(L.utx_uv_bake_workspace_bytes(H2D, W2D), device=self.device, dtype=torch.uint8)
         cos_t = float(np.float32(math.cos(math.radians(ray_normal_angle_threhold))))
-        _lib.check(L.utx_uv_bake(_p(m.vertices), m.vertices.shape[0], _p(m.faces), m.faces.shape[0], _p(m.optix.nodes),
-                                 _p(rast2d), H2D, W2D, n, mats.numpy().ctypes.data_as(_lib.fp), dirs.numpy().ctypes.data_as(_lib.fp),
-                                 prio, _p(rgba), H, W, cos_t, _p(self._k2d), 5.0, lo_arr, ext, _p(mask2d), _p(mask_vis), _p(color),
-                                 _p(nn_index), _p(ws), ws.numel(), _stream()), "utx_uv_bake")
-        self.last_nn_index = nn_index
         self.last_rast2d = rast2d
-        return (None, mask_vis.bool().reshape(n, H2D, W2D, 1), mask2d.bool().reshape(1, H2D, W2D, 1),
-                color.reshape(1, H2D, W2D, 3))
+        out = (None, mask_vis.bool().reshape(n, H2D, W2D, 1), mask2d.bool().reshape(1, H2D, W2D, 1),
+               color.reshape(1, H2D, W2D, 3))
+        vis_args = (_p(m.vertices), m.vertices.shape[0], _p(m.faces), m.faces.shape[0], _p(m.optix.nodes), _p(rast2d), H2D, W2D,
+                    n, mats.numpy().ctypes.data_as(_lib.fp), dirs.numpy().ctypes.data_as(_lib.fp), prio, _p(rgba), H, W, cos_t)
+        if method == "reproject" and not reproject_inpainting:
+            lo_arr = (C.c_float * 3)(0.0, 0.0, 0.0)
+            _lib.check(L.utx_uv_bake(*vis_args, _p(self._k2d), 5.0, lo_arr, 1.0, _p(mask2d), _p(mask_vis), _p(color),
+                                     _p(nn_index), _p(ws), ws.numel(), _stream()), "utx_uv_bake")
+            self.last_nn_index = nn_index
+            return out
+        # staged form: visibility -> [per-view k-NN colours] -> fill (k-NN or the caller's query field) -> finish
+        _lib.check(L.utx_uv_bake_visibility(*vis_args, _p(mask2d), _p(mask_vis), _p(ws), ws.numel(), _stream()),
+                   "utx_uv_bake_visibility")
+        self.last_nn_index = None
+        skip_fill = False
+        if method == "kdtree":
+            if kdtree_method == "mean" and kdtree_inpainting:
+                self._field_fill(ws, mask2d, rgba, mv["rast"], H2D, W2D, union_cloud=True)
+            else:
+                merge = int(kdtree_method == "mean")
+                k = kdtree_n_neighbors if merge else kdtree_n_neighbors_visiable
+                pix_pos = interpolate(m.vertices, mv["rast"], m.faces)
+                scratch = torch.empty(L.utx_uv_bake_views_workspace_bytes(n, H, W), device=self.device, dtype=torch.uint8)
+                _lib.check(L.utx_uv_bake_views_knn(_p(pix_pos), _p(rgba), n, H, W, k, merge, _p(mask2d), H2D, W2D, _p(ws),
+                                                   ws.numel(), _p(scratch), scratch.numel(), _stream()), "utx_uv_bake_views_knn")
+            skip_fill = kdtree_method == "mean"
+            inpaint, k_fill, blur = kdtree_inpainting, kdtree_n_neighbors_invisiable, 0
+        else:
+            inpaint, k_fill, blur = True, 1, 1
+        if not skip_fill:
+            if inpaint:
+                self._field_fill(ws, mask2d, rgba, mv["rast"], H2D, W2D, union_cloud=False)
+            else:
+                _lib.check(L.utx_uv_bake_fill(_p(mask2d), H2D, W2D, k_fill, _p(nn_index), _p(ws), ws.numel(), _stream()),
+                           "utx_uv_bake_fill")
+                self.last_nn_index = nn_index
+        _lib.check(L.utx_uv_bake_finish(_p(mask2d), H2D, W2D, blur, _p(self._k2d), 5.0, _p(color), _p(ws), ws.numel(), _stream()),
+                   "utx_uv_bake_finish")
+        return out
+
+    def _field_fill(self, ws, mask2d, rgba, rast_mv, H2D, W2D, union_cloud: bool):
+        """The `*_inpainting=True` branches: the registered query field colours the texels the views do not own
+        (:427-432, :609-614), or every covered texel from the union pixel cloud (`mean`, :387-389).  Reads and writes the
+        staged bake's owner / position / colour planes in place (utx_uv_bake_layout)."""
+        L = _lib.load()
+        off = [C.c_size_t() for _ in range(4)]
+        _lib.check(L.utx_uv_bake_layout(H2D, W2D, *[C.byref(o) for o in off]), "utx_uv_bake_layout")
+        T = H2D * W2D
+        owner = ws[off[0].value:off[0].value + T].view(torch.int8)
+        pos = ws[off[1].value:off[1].value + T * 12].view(torch.float32).reshape(T, 3)
+        col = ws[off[2].value:off[2].value + T * 12].view(torch.float32).reshape(T, 3)
+        covered = mask2d.bool()
+        if union_cloud:
+            m = self.pbr_mesh
+            sel = rgba[..., 3] > 0.5
+            pix_pos = interpolate(m.vertices, rast_mv, m.faces)
+            col[covered] = self.query_field(pix_pos[sel], rgba[..., :3][sel], pos[covered]).to(torch.float32)
+            return
+        seen = covered & (owner >= 0)
+        unseen = covered & (owner < 0)
+        if bool(unseen.any()) and bool(seen.any()):
+            col[unseen] = self.query_field(pos[seen], col[seen], pos[unseen]).to(torch.float32)

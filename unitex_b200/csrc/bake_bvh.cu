@@ -363,6 +363,45 @@ int knn1(const float* src, int n_src, const float* dst, long long M, long long* 
   return 0;
 }
 
+namespace {
+// one thread per query; the k candidates live in the thread's local arrays (k <= KNN_MAX)
+__global__ void __launch_bounds__(128) knn_kernel(const void* __restrict__ nodes, const float* __restrict__ src, int n_src,
+                                                  const float* __restrict__ dst, long long M, int k,
+                                                  long long* __restrict__ index, float* __restrict__ score) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float q[3] = {dst[i * 3], dst[i * 3 + 1], dst[i * 3 + 2]};
+  float bd[KNN_MAX];
+  int bi[KNN_MAX];
+  if (n_src == 1) {
+    const float dx = src[0] - q[0], dy = src[1] - q[1], dz = src[2] - q[2];
+    bd[0] = (dx * dx + dy * dy) + dz * dz;
+    bi[0] = 0;
+  } else {
+    knn_trace(nodes, src, nullptr, q, k, bd, bi);
+  }
+  for (int j = 0; j < k; ++j) {
+    index[i * k + j] = bi[j];
+    score[i * k + j] = sqrtf(bd[j]);
+  }
+}
+}  // namespace
+
+// knn(src, dst, k) of pcd/knn/__init__.py:104-114 for 1 <= k <= min(32, n_src): index int64 [M,k], score = distance [M,k],
+// each row ascending by (distance, index)
+int knn(const float* src, int n_src, const float* dst, long long M, int k, long long* index, float* score, void* nodes,
+        void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  UTX_CHECK(n_src >= 1, "knn: empty source set");
+  UTX_CHECK(k >= 1 && k <= KNN_MAX, "knn: k must be in 1..32");
+  UTX_CHECK(k <= n_src, "knn: k exceeds the number of source points");
+  if (k == 1) return knn1(src, n_src, dst, M, index, score, nodes, workspace, ws_bytes, stream);
+  UTX_TRY(point_bvh_build(src, n_src, nodes, workspace, ws_bytes, stream));
+  if (M == 0) return 0;
+  knn_kernel<<<static_cast<unsigned>((M + 127) / 128), 128, 0, stream>>>(nodes, src, n_src, dst, M, k, index, score);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int bvh_export(const void* nodes, int F, int* info, float* aabb, cudaStream_t stream) {
   const int n = 2 * F - 1;
   export_kernel<<<(n + 255) / 256, 256, 0, stream>>>(static_cast<const Node*>(nodes), n, info, aabb);

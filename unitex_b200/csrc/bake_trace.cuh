@@ -170,4 +170,56 @@ __device__ __forceinline__ int nn_trace(const void* __restrict__ nodes_v, const 
   return best_id;
 }
 
+// Exact k nearest neighbours (k <= KNN_MAX) of q among the points of a point-LBVH, ascending by (fp32 squared distance,
+// point id) -- the order `knn(src, dst, k)` of the reference returns (pcd/knn/__init__.py:85-95, sorted by distance; ties by
+// lowest id here, torch_kdtree@86961f7d [ext] leaves them unspecified).  bd / bi: caller's arrays of k entries; entries
+// beyond the number of points found keep (INFINITY, -1).  Same conservative pruning as nn_trace, against the current
+// k-th best distance, so the result does not depend on the visit order.
+constexpr int KNN_MAX = 32;
+__device__ __forceinline__ void knn_trace(const void* __restrict__ nodes_v, const float* __restrict__ pts,
+                                          const int* __restrict__ ids, const float* q, int k, float* bd, int* bi) {
+  const float4* nodes = static_cast<const float4*>(nodes_v);
+  for (int j = 0; j < k; ++j) { bd[j] = INFINITY; bi[j] = -1; }
+  int stack[64];
+  int count = 0;
+  stack[count++] = 0;
+  while (count > 0) {
+    const int n = stack[--count];
+    const float4 q0 = __ldg(nodes + static_cast<size_t>(n) * 3), q1 = __ldg(nodes + static_cast<size_t>(n) * 3 + 1);
+    const float bx = fmaxf(fmaxf(q0.x - q[0], q[0] - q0.w), 0.f), by = fmaxf(fmaxf(q0.y - q[1], q[1] - q1.x), 0.f),
+                bz = fmaxf(fmaxf(q0.z - q[2], q[2] - q1.y), 0.f);
+    const float bound = ((bx * bx + by * by) + bz * bz) * 0.999999f;
+    if (bound > bd[k - 1]) continue;
+    const int l = __float_as_int(q1.z), r = __float_as_int(q1.w);
+    if (l == 0 && r == 0) {
+      const int pidx = __float_as_int(__ldg(nodes + static_cast<size_t>(n) * 3 + 2).x);
+      const float dx = pts[static_cast<size_t>(pidx) * 3] - q[0], dy = pts[static_cast<size_t>(pidx) * 3 + 1] - q[1],
+                  dz = pts[static_cast<size_t>(pidx) * 3 + 2] - q[2];
+      const float d2 = (dx * dx + dy * dy) + dz * dz;
+      const int id = ids ? ids[pidx] : pidx;
+      const bool better = d2 < bd[k - 1] || (d2 == bd[k - 1] && (bi[k - 1] < 0 || id < bi[k - 1]));
+      if (better) {
+        int j = k - 1;
+        while (j > 0 && (bd[j - 1] > d2 || (bd[j - 1] == d2 && (bi[j - 1] < 0 || bi[j - 1] > id)))) {
+          bd[j] = bd[j - 1];
+          bi[j] = bi[j - 1];
+          --j;
+        }
+        bd[j] = d2;
+        bi[j] = id;
+      }
+    } else if (count + 2 <= 64) {
+      const float4 a0 = __ldg(nodes + static_cast<size_t>(l) * 3), a1 = __ldg(nodes + static_cast<size_t>(l) * 3 + 1);
+      const float ax = fmaxf(fmaxf(a0.x - q[0], q[0] - a0.w), 0.f), ay = fmaxf(fmaxf(a0.y - q[1], q[1] - a1.x), 0.f),
+                  az = fmaxf(fmaxf(a0.z - q[2], q[2] - a1.y), 0.f);
+      const float4 c0 = __ldg(nodes + static_cast<size_t>(r) * 3), c1 = __ldg(nodes + static_cast<size_t>(r) * 3 + 1);
+      const float cx = fmaxf(fmaxf(c0.x - q[0], q[0] - c0.w), 0.f), cy = fmaxf(fmaxf(c0.y - q[1], q[1] - c1.x), 0.f),
+                  cz = fmaxf(fmaxf(c0.z - q[2], q[2] - c1.y), 0.f);
+      const float dl = (ax * ax + ay * ay) + az * az, dr = (cx * cx + cy * cy) + cz * cz;
+      if (dl <= dr) { stack[count++] = r; stack[count++] = l; }
+      else { stack[count++] = l; stack[count++] = r; }
+    }
+  }
+}
+
 }  // namespace utx

@@ -361,7 +361,101 @@ __global__ void __launch_bounds__(256) transform_points_kernel(const float* __re
   out[i] = make_float4(o[0], o[1], o[2], o[3]);
 }
 
+// ------------------------------------------------------------------------------------------------ k-NN colour fills
+// (bake_mv_to_uv_kdtree, renderer_inverse.py:367-433).  `want`: texels with owner == want are recoloured (want >= 0), or
+// every covered texel (want == -2), or the covered-but-unowned ones (want == -1).  The colour is the mean of the k nearest
+// source points' colours, summed in ascending (distance, id) order: `colors[index, :].mean(dim=-2)` (:421, :431).
+__global__ void __launch_bounds__(128) knn_mean_kernel(const unsigned char* __restrict__ mask2d,
+                                                       const signed char* __restrict__ owner, int want,
+                                                       const float* __restrict__ pos, int T, const void* __restrict__ nodes,
+                                                       const float* __restrict__ pts, const int* __restrict__ ids, int n_pts,
+                                                       int k, const float* src_col, float* dst_col, int* __restrict__ nn_index) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  if (nn_index) nn_index[t] = -1;
+  if (!mask2d[t] || n_pts == 0) return;
+  const int o = owner[t];
+  if (want >= 0 ? o != want : (want == -1 && o >= 0)) return;
+  const float q[3] = {pos[static_cast<size_t>(t) * 3], pos[static_cast<size_t>(t) * 3 + 1], pos[static_cast<size_t>(t) * 3 + 2]};
+  float bd[KNN_MAX];
+  int bi[KNN_MAX];
+  const int kk = k < n_pts ? k : n_pts;
+  if (n_pts == 1) { bi[0] = ids ? ids[0] : 0; }
+  else knn_trace(nodes, pts, ids, q, kk, bd, bi);
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int j = 0; j < kk; ++j) {
+    const float* c = src_col + static_cast<size_t>(bi[j]) * 3;
+    acc[0] = acc[0] + c[0]; acc[1] = acc[1] + c[1]; acc[2] = acc[2] + c[2];
+  }
+  const float kf = static_cast<float>(kk);
+  dst_col[t * 3] = acc[0] / kf; dst_col[t * 3 + 1] = acc[1] / kf; dst_col[t * 3 + 2] = acc[2] / kf;
+  if (nn_index) nn_index[t] = bi[0];
+}
+
+// per-view pixel clouds of mv_to_pcd (:227-231): a pixel belongs to its view's cloud when its visible alpha is set
+__global__ void __launch_bounds__(256) pix_flag_kernel(const float4* __restrict__ rgba, long long N, int* __restrict__ flags) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < N) flags[i] = rgba[i].w > 0.5f;
+}
+__global__ void __launch_bounds__(256) pix_compact_kernel(const float4* __restrict__ rgba, const float* __restrict__ pix_pos,
+                                                          const int* __restrict__ flags, const int* __restrict__ offs,
+                                                          long long N, float* __restrict__ pts, float* __restrict__ cols) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= N || !flags[i]) return;
+  const size_t k = static_cast<size_t>(offs[i]) * 3;
+  const float4 c = rgba[i];
+  pts[k] = pix_pos[i * 3]; pts[k + 1] = pix_pos[i * 3 + 1]; pts[k + 2] = pix_pos[i * 3 + 2];
+  cols[k] = c.x; cols[k + 1] = c.y; cols[k + 2] = c.z;
+}
 inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
+
+// fixed carve-up of the caller's workspace for an H2 x W2 atlas; the staged entry points find each other's results here
+struct BakeWs {
+  unsigned char *raw, *aok, *rep3, *rep5, *b0, *seam;
+  float *pos, *col_a, *col_b;
+  signed char* owner;
+  int *ids, *flags, *offs;
+  float* pts;
+  void* scan_tmp;
+  size_t scan_bytes;
+  uint8_t* rest;   // nearest-neighbour tree + builder scratch during the fill, the pull-push pyramid afterwards
+};
+BakeWs carve(void* workspace, int T) {
+  BakeWs w{};
+  uint8_t* p = static_cast<uint8_t*>(workspace);
+  auto take = [&](size_t b) { uint8_t* q = p; p += al(b); return q; };
+  w.raw = take(T); w.aok = take(T); w.rep3 = take(T); w.rep5 = take(T); w.b0 = take(T); w.seam = take(T);
+  w.pos = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
+  w.col_a = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
+  w.col_b = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
+  w.owner = reinterpret_cast<signed char*>(take(static_cast<size_t>(T) * 4));
+  w.ids = reinterpret_cast<int*>(take(static_cast<size_t>(T) * 4));
+  w.flags = reinterpret_cast<int*>(take(static_cast<size_t>(T) * 4));
+  w.offs = reinterpret_cast<int*>(take(static_cast<size_t>(T) * 4 + 4));
+  w.pts = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
+  cub::DeviceScan::ExclusiveSum(nullptr, w.scan_bytes, w.flags, w.offs, T);
+  w.scan_tmp = take(w.scan_bytes);
+  w.rest = p;
+  return w;
+}
+
+int check_atlas(int H2, int W2, size_t ws_bytes, const char* who) {
+  UTX_CHECK(H2 >= 8 && W2 >= 8 && (H2 & (H2 - 1)) == 0 && (W2 & (W2 - 1)) == 0, "uv_bake: atlas must be a power of two >= 8");
+  UTX_CHECK(ws_bytes >= uv_bake_workspace_bytes(H2, W2), "uv_bake: workspace too small");
+  (void)who;
+  return 0;
+}
+
+// flags -> exclusive scan -> total on the host (the tree builder needs the point count: one sync)
+int count_flags(const int* flags, int* offs, long long N, void* scan_tmp, size_t scan_bytes, int* total, cudaStream_t stream) {
+  UTX_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, flags, offs, static_cast<int>(N), stream));
+  int last_off = 0, last_flag = 0;
+  UTX_CUDA(cudaMemcpyAsync(&last_off, offs + (N - 1), 4, cudaMemcpyDeviceToHost, stream));
+  UTX_CUDA(cudaMemcpyAsync(&last_flag, flags + (N - 1), 4, cudaMemcpyDeviceToHost, stream));
+  UTX_CUDA(cudaStreamSynchronize(stream));
+  *total = last_off + last_flag;
+  return 0;
+}
 
 }  // namespace
 
@@ -387,15 +481,25 @@ size_t uv_bake_workspace_bytes(int H2, int W2) {
          al(bvh_workspace_bytes(static_cast<int>(T))) + pyr_c + pyr_m + 8192;
 }
 
-int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
-            int n_views, const float* view_mats_host, const float* view_dirs_host, const int* priority_host,
-            const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
-            const float* grid_lo_host, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color_out,
-            int* nn_index_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+void uv_bake_layout(int H2, int W2, size_t* off_owner, size_t* off_pos, size_t* off_color, size_t* off_seam) {
+  uint8_t* base = reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(256));
+  const BakeWs w = carve(base, H2 * W2);
+  *off_owner = reinterpret_cast<uint8_t*>(w.owner) - base;
+  *off_pos = reinterpret_cast<uint8_t*>(w.pos) - base;
+  *off_color = reinterpret_cast<uint8_t*>(w.col_a) - base;
+  *off_seam = w.seam - base;
+}
+
+// Stage 1 -- uv_to_pcd (:243-365) + the priority composite and seam mask of bake_mv_to_uv_reproject_blur (:591-605).
+// Leaves in the workspace: owner i8 [T] (winning view or -1), pos fp32 [T,3], colour fp32 [T,3] (the owner's reprojected
+// colour, 0 elsewhere), seam u8 [T].
+int uv_bake_visibility(const float* vert, int V, const int* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
+                       int n_views, const float* view_mats_host, const float* view_dirs_host, const int* priority_host,
+                       const float* images_rgba, int H, int W, float cos_thresh, unsigned char* mask2d,
+                       unsigned char* mask_vis, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   (void)V;
   UTX_CHECK(n_views >= 1 && n_views <= MAXV, "uv_bake: 1..8 views");
-  UTX_CHECK(H2 >= 8 && W2 >= 8 && (H2 & (H2 - 1)) == 0 && (W2 & (W2 - 1)) == 0, "uv_bake: atlas must be a power of two >= 8");
-  UTX_CHECK(ws_bytes >= uv_bake_workspace_bytes(H2, W2), "uv_bake: workspace too small");
+  UTX_TRY(check_atlas(H2, W2, ws_bytes, "uv_bake_visibility"));
   const int T = H2 * W2;
   Views vw;
   vw.n = n_views;
@@ -404,77 +508,167 @@ int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, 
     for (int k = 0; k < 3; ++k) vw.dir[i][k] = view_dirs_host[i * 3 + k];
     vw.priority[i] = priority_host[i];
   }
-  uint8_t* p = static_cast<uint8_t*>(workspace);
-  auto take = [&](size_t b) { uint8_t* q = p; p += al(b); return q; };
-  unsigned char* raw = take(T); unsigned char* aok = take(T); unsigned char* rep3 = take(T); unsigned char* rep5 = take(T);
-  unsigned char* b0 = take(T); unsigned char* seam = take(T);
-  float* pos = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
-  float* col_a = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
-  float* col_b = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
-  signed char* owner = reinterpret_cast<signed char*>(take(static_cast<size_t>(T) * 4));
-  int* ids = reinterpret_cast<int*>(take(static_cast<size_t>(T) * 4));
-  int* flags = reinterpret_cast<int*>(take(static_cast<size_t>(T) * 4));
-  int* offs = reinterpret_cast<int*>(take(static_cast<size_t>(T) * 4 + 4));
-  float* pts = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
-  size_t scan_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flags, offs, T);
-  void* scan_tmp = take(scan_bytes);
-
+  const BakeWs w = carve(workspace, T);
   const unsigned g128 = (T + 127) / 128, g256 = (T + 255) / 256;
   const float4* rast = reinterpret_cast<const float4*>(rast2d);
-  texel_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, nodes, static_cast<const float4*>(nodes) + static_cast<size_t>(2 * F - 1) * 3, vw, images_rgba, H, W, cos_thresh, raw, aok, pos);
-  repair3_kernel<<<g256, 256, 0, stream>>>(raw, rep3, H2, W2);
-  repair5_kernel<<<g256, 256, 0, stream>>>(rep3, rep5, H2, W2, n_views);
-  compose_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, vw, images_rgba, H, W, rep5, aok, mask2d, mask_vis, owner, col_a);
-  seam0_kernel<<<g256, 256, 0, stream>>>(owner, b0, H2, W2);
-  seam1_kernel<<<g256, 256, 0, stream>>>(b0, mask2d, seam, H2, W2);
-  // exact 1-NN fill of covered-but-invisible texels
-  (void)grid_lo_host; (void)grid_extent;
-  nn_flag_kernel<<<g256, 256, 0, stream>>>(owner, T, flags);
-  UTX_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, flags, offs, T, stream));
-  nn_compact_kernel<<<g256, 256, 0, stream>>>(owner, offs, pos, T, ids, pts);
-  int last_off = 0, last_flag = 0;   // number of visible texels: the tree builder needs it on the host (one sync per bake)
-  UTX_CUDA(cudaMemcpyAsync(&last_off, offs + (T - 1), 4, cudaMemcpyDeviceToHost, stream));
-  UTX_CUDA(cudaMemcpyAsync(&last_flag, flags + (T - 1), 4, cudaMemcpyDeviceToHost, stream));
-  UTX_CUDA(cudaStreamSynchronize(stream));
-  const int n_pts = last_off + last_flag;
+  texel_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, nodes, static_cast<const float4*>(nodes) + static_cast<size_t>(2 * F - 1) * 3, vw, images_rgba, H, W, cos_thresh, w.raw, w.aok, w.pos);
+  repair3_kernel<<<g256, 256, 0, stream>>>(w.raw, w.rep3, H2, W2);
+  repair5_kernel<<<g256, 256, 0, stream>>>(w.rep3, w.rep5, H2, W2, n_views);
+  compose_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, vw, images_rgba, H, W, w.rep5, w.aok, mask2d, mask_vis, w.owner, w.col_a);
+  seam0_kernel<<<g256, 256, 0, stream>>>(w.owner, w.b0, H2, W2);
+  seam1_kernel<<<g256, 256, 0, stream>>>(w.b0, mask2d, w.seam, H2, W2);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Stage 2 -- covered-but-unowned texels take the mean colour of their k nearest owned texels (3-D distance, exact):
+// k = 1 is the fill of bake_mv_to_uv_reproject_blur (:606-615), k = 32 the `order_mean` tail of bake_mv_to_uv_kdtree (:427-432).
+int uv_bake_fill(const unsigned char* mask2d, int H2, int W2, int k, int* nn_index_out, void* workspace, size_t ws_bytes,
+                 cudaStream_t stream) {
+  UTX_TRY(check_atlas(H2, W2, ws_bytes, "uv_bake_fill"));
+  UTX_CHECK(k >= 1 && k <= KNN_MAX, "uv_bake_fill: k must be in 1..32");
+  const int T = H2 * W2;
+  const BakeWs w = carve(workspace, T);
+  const unsigned g128 = (T + 127) / 128, g256 = (T + 255) / 256;
+  nn_flag_kernel<<<g256, 256, 0, stream>>>(w.owner, T, w.flags);
+  int n_pts = 0;
+  UTX_TRY(count_flags(w.flags, w.offs, T, w.scan_tmp, w.scan_bytes, &n_pts, stream));
+  nn_compact_kernel<<<g256, 256, 0, stream>>>(w.owner, w.offs, w.pos, T, w.ids, w.pts);
   void* nn_nodes = nullptr;
   if (n_pts >= 2) {
-    nn_nodes = take(bvh_nodes_bytes(n_pts));
+    nn_nodes = w.rest;
     const size_t wsb = bvh_workspace_bytes(n_pts);
-    void* nn_ws = take(wsb);
-    UTX_TRY(point_bvh_build(pts, n_pts, nn_nodes, nn_ws, wsb, stream));
+    void* nn_ws = w.rest + al(bvh_nodes_bytes(n_pts));
+    UTX_TRY(point_bvh_build(w.pts, n_pts, nn_nodes, nn_ws, wsb, stream));
   }
-  nn_query_kernel<<<g128, 128, 0, stream>>>(mask2d, owner, pos, T, nn_nodes, pts, ids, n_pts, col_a, col_a, nn_index_out);
-  // seam blur (reads col_a, writes col_b)
-  lens_blur_kernel<<<g256, 256, 0, stream>>>(col_a, seam, blur_k2d, blur_gamma, H2, W2, col_b);
-  // pull-push
+  if (k == 1)
+    nn_query_kernel<<<g128, 128, 0, stream>>>(mask2d, w.owner, w.pos, T, nn_nodes, w.pts, w.ids, n_pts, w.col_a, w.col_a, nn_index_out);
+  else
+    knn_mean_kernel<<<g128, 128, 0, stream>>>(mask2d, w.owner, -1, w.pos, T, nn_nodes, w.pts, w.ids, n_pts, k, w.col_a, w.col_a, nn_index_out);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t uv_bake_views_workspace_bytes(int n_views, int H, int W) {
+  const size_t N = static_cast<size_t>(n_views) * H * W;
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, static_cast<int*>(nullptr), static_cast<int*>(nullptr), static_cast<int>(N));
+  return al(N * 4) + al(N * 4 + 4) + 2 * al(N * 12) + al(scan_bytes) + al(bvh_nodes_bytes(static_cast<int>(N))) +
+         al(bvh_workspace_bytes(static_cast<int>(N))) + 4096;
+}
+
+// Stage 2' -- the visible part of bake_mv_to_uv_kdtree: texels are coloured from the multi-view POINT CLOUD instead of the
+// bilinear reprojection.  merge = 0 (`order_mean`, :406-417): every texel owned by view i takes the mean colour of its k nearest
+// points of view i's pixel cloud.  merge = 1 (`mean`, :385-389): every covered texel takes the mean of its k nearest points of
+// the union cloud (the caller skips the fill stage).  pix_pos [n,H,W,3]: vertex positions interpolated at the
+// pixels (dr.interpolate, :188); images_rgba [n,H,W,4]: colour + visible alpha, pixels with alpha set form the clouds (:227-231).
+int uv_bake_views_knn(const float* pix_pos, const float* images_rgba, int n_views, int H, int W, int k, int merge,
+                      const unsigned char* mask2d, int H2, int W2, void* workspace, size_t ws_bytes, void* scratch,
+                      size_t scratch_bytes, cudaStream_t stream) {
+  UTX_TRY(check_atlas(H2, W2, ws_bytes, "uv_bake_views_knn"));
+  UTX_CHECK(n_views >= 1 && n_views <= MAXV, "uv_bake_views_knn: 1..8 views");
+  UTX_CHECK(k >= 1 && k <= KNN_MAX, "uv_bake_views_knn: k must be in 1..32");
+  UTX_CHECK(scratch_bytes >= uv_bake_views_workspace_bytes(n_views, H, W), "uv_bake_views_knn: scratch too small");
+  const int T = H2 * W2;
+  const long long HW = static_cast<long long>(H) * W, N = HW * n_views;
+  UTX_CHECK(N < (1LL << 31), "uv_bake_views_knn: too many pixels");
+  const BakeWs w = carve(workspace, T);
+  uint8_t* p = static_cast<uint8_t*>(scratch);
+  auto take = [&](size_t b) { uint8_t* q = p; p += al(b); return q; };
+  int* flags = reinterpret_cast<int*>(take(N * 4));
+  int* offs = reinterpret_cast<int*>(take(N * 4 + 4));
+  float* pts = reinterpret_cast<float*>(take(N * 12));
+  float* cols = reinterpret_cast<float*>(take(N * 12));
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, flags, offs, static_cast<int>(N));
+  void* scan_tmp = take(scan_bytes);
+  void* nodes = take(bvh_nodes_bytes(static_cast<int>(N)));
+  const size_t tree_ws_bytes = bvh_workspace_bytes(static_cast<int>(N));
+  void* tree_ws = take(tree_ws_bytes);
+  const float4* rgba = reinterpret_cast<const float4*>(images_rgba);
+  const unsigned gN = static_cast<unsigned>((N + 255) / 256);
+  pix_flag_kernel<<<gN, 256, 0, stream>>>(rgba, N, flags);
+  int total = 0;
+  UTX_TRY(count_flags(flags, offs, N, scan_tmp, scan_bytes, &total, stream));
+  pix_compact_kernel<<<gN, 256, 0, stream>>>(rgba, pix_pos, flags, offs, N, pts, cols);
+  int start[MAXV + 1];
+  start[0] = 0;
+  start[n_views] = total;
+  for (int v = 1; v < n_views; ++v)
+    UTX_CUDA(cudaMemcpyAsync(&start[v], offs + v * HW, 4, cudaMemcpyDeviceToHost, stream));
+  UTX_CUDA(cudaStreamSynchronize(stream));
+  const unsigned g128 = (T + 127) / 128;
+  if (merge) {
+    UTX_CHECK(total >= 1, "uv_bake_views_knn: the views hold no visible pixel");
+    if (total >= 2) UTX_TRY(point_bvh_build(pts, total, nodes, tree_ws, tree_ws_bytes, stream));
+    knn_mean_kernel<<<g128, 128, 0, stream>>>(mask2d, w.owner, -2, w.pos, T, nodes, pts, nullptr, total, k, cols, w.col_a, nullptr);
+  } else {
+    for (int v = 0; v < n_views; ++v) {
+      const int cnt = start[v + 1] - start[v];
+      if (cnt == 0) continue;                              // an empty view owns no texel (ownership needs alpha > 0.999)
+      const float* vp = pts + static_cast<size_t>(start[v]) * 3;
+      if (cnt >= 2) UTX_TRY(point_bvh_build(vp, cnt, nodes, tree_ws, tree_ws_bytes, stream));
+      knn_mean_kernel<<<g128, 128, 0, stream>>>(mask2d, w.owner, v, w.pos, T, nodes, vp, nullptr, cnt, k,
+                                                cols + static_cast<size_t>(start[v]) * 3, w.col_a, nullptr);
+    }
+  }
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Stage 3 -- seam blur (reproject only, :617-624) and pull-push into the texels outside the charts (:627, :423).
+int uv_bake_finish(const unsigned char* mask2d, int H2, int W2, int blur, const float* blur_k2d, float blur_gamma,
+                   float* color_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  UTX_TRY(check_atlas(H2, W2, ws_bytes, "uv_bake_finish"));
+  const int T = H2 * W2;
+  const BakeWs w = carve(workspace, T);
+  const unsigned g256 = (T + 255) / 256;
+  const float* src = w.col_a;
+  if (blur) {
+    lens_blur_kernel<<<g256, 256, 0, stream>>>(w.col_a, w.seam, blur_k2d, blur_gamma, H2, W2, w.col_b);
+    src = w.col_b;
+  }
   int levels = 0;
   for (int s = (H2 < W2 ? H2 : W2); s > 1; s >>= 1) ++levels;
   levels = levels - 2 > 0 ? levels - 2 : 0;
   if (levels == 0) {
-    UTX_CUDA(cudaMemcpyAsync(color_out, col_b, static_cast<size_t>(T) * 12, cudaMemcpyDeviceToDevice, stream));
+    UTX_CUDA(cudaMemcpyAsync(color_out, src, static_cast<size_t>(T) * 12, cudaMemcpyDeviceToDevice, stream));
   } else {
+    uint8_t* p = w.rest;
+    auto take = [&](size_t b) { uint8_t* q = p; p += al(b); return q; };
     std::vector<float*> pc(levels + 1);
     std::vector<unsigned char*> pm(levels + 1);
     pc[0] = color_out;
     pm[0] = take(T);
-    pp_init_kernel<<<g256, 256, 0, stream>>>(col_b, mask2d, T, pc[0], pm[0]);
-    int h = H2, w = W2;
+    pp_init_kernel<<<g256, 256, 0, stream>>>(src, mask2d, T, pc[0], pm[0]);
+    int h = H2, ww = W2;
     for (int l = 1; l <= levels; ++l) {
-      pc[l] = reinterpret_cast<float*>(take(static_cast<size_t>(h / 2) * (w / 2) * 12));
-      pm[l] = take(static_cast<size_t>(h / 2) * (w / 2));
-      pp_down_kernel<<<((h / 2) * (w / 2) + 255) / 256, 256, 0, stream>>>(pc[l - 1], pm[l - 1], h, w, pc[l], pm[l]);
-      h /= 2; w /= 2;
+      pc[l] = reinterpret_cast<float*>(take(static_cast<size_t>(h / 2) * (ww / 2) * 12));
+      pm[l] = take(static_cast<size_t>(h / 2) * (ww / 2));
+      pp_down_kernel<<<((h / 2) * (ww / 2) + 255) / 256, 256, 0, stream>>>(pc[l - 1], pm[l - 1], h, ww, pc[l], pm[l]);
+      h /= 2; ww /= 2;
     }
     for (int l = levels; l >= 1; --l) {
-      const int hh = H2 >> (l - 1), ww = W2 >> (l - 1);
-      pp_up_kernel<<<(hh * ww + 255) / 256, 256, 0, stream>>>(pc[l - 1], pm[l - 1], hh, ww, pc[l]);
+      const int hh = H2 >> (l - 1), wl = W2 >> (l - 1);
+      pp_up_kernel<<<(hh * wl + 255) / 256, 256, 0, stream>>>(pc[l - 1], pm[l - 1], hh, wl, pc[l]);
     }
+    UTX_CHECK(static_cast<size_t>(p - static_cast<uint8_t*>(workspace)) <= ws_bytes, "uv_bake: workspace overrun");
   }
-  UTX_CHECK(static_cast<size_t>(p - static_cast<uint8_t*>(workspace)) <= ws_bytes, "uv_bake: workspace overrun");
   UTX_CUDA(cudaGetLastError());
   return 0;
+}
+
+// The three stages back to back = NVDiffRendererInverse.infer(method='reproject', reproject_method='lens') (:635-726)
+int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
+            int n_views, const float* view_mats_host, const float* view_dirs_host, const int* priority_host,
+            const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
+            const float* grid_lo_host, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color_out,
+            int* nn_index_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  (void)grid_lo_host; (void)grid_extent;
+  UTX_TRY(uv_bake_visibility(vert, V, tri, F, nodes, rast2d, H2, W2, n_views, view_mats_host, view_dirs_host, priority_host,
+                             images_rgba, H, W, cos_thresh, mask2d, mask_vis, workspace, ws_bytes, stream));
+  UTX_TRY(uv_bake_fill(mask2d, H2, W2, 1, nn_index_out, workspace, ws_bytes, stream));
+  return uv_bake_finish(mask2d, H2, W2, 1, blur_k2d, blur_gamma, color_out, workspace, ws_bytes, stream);
 }
 
 }  // namespace utx

@@ -132,7 +132,46 @@ int utx_knn1(const float* src, int n_src, const float* dst, long long M, long lo
   UTX_CHECK(src && dst && index && score && nodes && workspace, "utx_knn1: null pointer");
   return knn1(src, n_src, dst, M, index, score, nodes, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
+int utx_knn(const float* src, int n_src, const float* dst, long long M, int k, long long* index, float* score, void* nodes,
+            void* workspace, size_t workspace_bytes, void* stream) {
+  UTX_CHECK(src && dst && index && score && nodes && workspace, "utx_knn: null pointer");
+  return knn(src, n_src, dst, M, k, index, score, nodes, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
 size_t utx_uv_bake_workspace_bytes(int H2, int W2) { return uv_bake_workspace_bytes(H2, W2); }
+int utx_uv_bake_layout(int H2, int W2, size_t* off_owner, size_t* off_pos, size_t* off_color, size_t* off_seam) {
+  UTX_CHECK(off_owner && off_pos && off_color && off_seam, "utx_uv_bake_layout: null pointer");
+  UTX_CHECK(H2 >= 8 && W2 >= 8, "utx_uv_bake_layout: atlas too small");
+  uv_bake_layout(H2, W2, off_owner, off_pos, off_color, off_seam);
+  return 0;
+}
+int utx_uv_bake_visibility(const float* vert, int V, const int32_t* tri, int F, const void* nodes, const float* rast2d, int H2,
+                           int W2, int n_views, const float* view_mats, const float* view_dirs, const int32_t* priority,
+                           const float* images_rgba, int H, int W, float cos_thresh, unsigned char* mask2d,
+                           unsigned char* mask_vis, void* workspace, size_t workspace_bytes, void* stream) {
+  UTX_CHECK(vert && tri && nodes && rast2d && view_mats && view_dirs && priority && images_rgba && mask2d && mask_vis && workspace,
+            "utx_uv_bake_visibility: null pointer");
+  return uv_bake_visibility(vert, V, tri, F, nodes, rast2d, H2, W2, n_views, view_mats, view_dirs, priority, images_rgba, H, W,
+                            cos_thresh, mask2d, mask_vis, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+int utx_uv_bake_fill(const unsigned char* mask2d, int H2, int W2, int k, int32_t* nn_index, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  UTX_CHECK(mask2d && workspace, "utx_uv_bake_fill: null pointer");
+  return uv_bake_fill(mask2d, H2, W2, k, nn_index, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+size_t utx_uv_bake_views_workspace_bytes(int n_views, int H, int W) { return uv_bake_views_workspace_bytes(n_views, H, W); }
+int utx_uv_bake_views_knn(const float* pix_pos, const float* images_rgba, int n_views, int H, int W, int k, int merge,
+                          const unsigned char* mask2d, int H2, int W2, void* workspace, size_t workspace_bytes, void* scratch,
+                          size_t scratch_bytes, void* stream) {
+  UTX_CHECK(pix_pos && images_rgba && mask2d && workspace && scratch, "utx_uv_bake_views_knn: null pointer");
+  return uv_bake_views_knn(pix_pos, images_rgba, n_views, H, W, k, merge, mask2d, H2, W2, workspace, workspace_bytes, scratch,
+                           scratch_bytes, static_cast<cudaStream_t>(stream));
+}
+int utx_uv_bake_finish(const unsigned char* mask2d, int H2, int W2, int blur, const float* blur_k2d, float blur_gamma,
+                       float* color, void* workspace, size_t workspace_bytes, void* stream) {
+  UTX_CHECK(mask2d && color && workspace && (!blur || blur_k2d), "utx_uv_bake_finish: null pointer");
+  return uv_bake_finish(mask2d, H2, W2, blur, blur_k2d, blur_gamma, color, workspace, workspace_bytes,
+                        static_cast<cudaStream_t>(stream));
+}
 int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
                 int n_views, const float* view_mats, const float* view_dirs, const int32_t* priority,
                 const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
