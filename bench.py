@@ -386,7 +386,7 @@ def bench_vae_decode(dev):
             "note": "implicit-GEMM 3x3 convolutions (TMA boxes shifted by the tap) on the tcgen05 GEMM, NHWC bf16, deterministic GroupNorm+SiLU"}
 
 
-def bench_uv_bake(dev):
+def bench_uv_bake(dev, return_tensors=False):
     """Second metric of BASELINE.json: UV-bake Mpix/s = atlas texels / time of NVDiffRendererInverse.infer(method=
     'reproject') with the mesh resident on the GPU (SURVEY 8d metric 2), on a synthetic teaser-robot-sized mesh
     (two UV-mapped spheres, ~500k faces; the reference fixture is not available on the GPU box), 6 box views of 512^2
@@ -444,7 +444,8 @@ def bench_uv_bake(dev):
     algo = V * 24 + len(uv) * 8 + F * 24 + (2 * F - 1) * 36 + 6 * H * W * 16 + T * 12 + T + 6 * T
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6589.6) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     covered = int(m2.sum())
-    return {"metric": "UV-bake Mpix/s", "value": T / 1e6 / (wall_ms * 1e-3), "unit": "Mpix/s", "ms_per_bake": wall_ms,
+    extra = {"tensors": (vis, m2, col, r.last_nn_index)} if return_tensors else {}
+    return {**extra, "metric": "UV-bake Mpix/s", "value": T / 1e6 / (wall_ms * 1e-3), "unit": "Mpix/s", "ms_per_bake": wall_ms,
             "gpu_ms_per_bake": gpu_ms, "bvh_build_ms": build_ms,
             "config": {"workload": f"synthetic 2-sphere mesh V={V} F={F}, 6 box views 512^2, atlas 2048^2, method=reproject",
                        "covered_texels": covered, "rays": 6 * covered, "visible_texels": int(vis.any(dim=0).sum())},

@@ -213,7 +213,7 @@ def nearest_k(src: torch.Tensor, dst: torch.Tensor, k: int, chunk: int = 512):
         d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
         v, j = torch.sort(d2, dim=1, stable=True)            # stable: equal distances keep ascending index order
         idx[i:i + chunk] = j[:, :k]
-        dist[i:i + chunk] = v[:, :k].sqrt()
+        dist[i:i + chunk] = torch.from_numpy(np.sqrt(v[:, :k].contiguous().numpy()))   # IEEE sqrt; torch's vectorised CPU sqrt is not correctly rounded
     return dist, idx
 
 

@@ -333,8 +333,11 @@ class NVDiffRendererInverse:
         ws = torch.empty(L.utx_uv_bake_workspace_bytes(H2D, W2D), device=self.device, dtype=torch.uint8)
         cos_t = float(np.float32(math.cos(math.radians(ray_normal_angle_threhold))))
         self.last_rast2d = rast2d
-        out = (None, mask_vis.bool().reshape(n, H2D, W2D, 1), mask2d.bool().reshape(1, H2D, W2D, 1),
-               color.reshape(1, H2D, W2D, 3))
+
+        def out():      # built AFTER the launches: .bool() copies
+            return (None, mask_vis.bool().reshape(n, H2D, W2D, 1), mask2d.bool().reshape(1, H2D, W2D, 1),
+                    color.reshape(1, H2D, W2D, 3))
+
         vis_args = (_p(m.vertices), m.vertices.shape[0], _p(m.faces), m.faces.shape[0], _p(m.optix.nodes), _p(rast2d), H2D, W2D,
                     n, mats.numpy().ctypes.data_as(_lib.fp), dirs.numpy().ctypes.data_as(_lib.fp), prio, _p(rgba), H, W, cos_t)
         if method == "reproject" and not reproject_inpainting:
@@ -342,7 +345,7 @@ class NVDiffRendererInverse:
             _lib.check(L.utx_uv_bake(*vis_args, _p(self._k2d), 5.0, lo_arr, 1.0, _p(mask2d), _p(mask_vis), _p(color),
                                      _p(nn_index), _p(ws), ws.numel(), _stream()), "utx_uv_bake")
             self.last_nn_index = nn_index
-            return out
+            return out()
         # staged form: visibility -> [per-view k-NN colours] -> fill (k-NN or the caller's query field) -> finish
         _lib.check(L.utx_uv_bake_visibility(*vis_args, _p(mask2d), _p(mask_vis), _p(ws), ws.numel(), _stream()),
                    "utx_uv_bake_visibility")
@@ -371,7 +374,7 @@ class NVDiffRendererInverse:
                 self.last_nn_index = nn_index
         _lib.check(L.utx_uv_bake_finish(_p(mask2d), H2D, W2D, blur, _p(self._k2d), 5.0, _p(color), _p(ws), ws.numel(), _stream()),
                    "utx_uv_bake_finish")
-        return out
+        return out()
 
     def _field_fill(self, ws, mask2d, rgba, rast_mv, H2D, W2D, union_cloud: bool):
         """The `*_inpainting=True` branches: the registered query field colours the texels the views do not own

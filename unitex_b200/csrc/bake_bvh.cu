@@ -21,6 +21,7 @@
 #include "kernels.h"
 
 namespace utx {
+static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 namespace {
 
 struct __align__(16) Node {
@@ -39,6 +40,32 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 __global__ void bounds_init_kernel(int* bounds) {
   if (threadIdx.x < 3) bounds[threadIdx.x] = 0x7fffffff;
   else if (threadIdx.x < 6) bounds[threadIdx.x] = static_cast<int>(0x80000000u);
+}
+
+// scene AABB: warp shuffle, then one atomic per BLOCK per component (one per warp put 6 x F/32 atomics on six addresses --
+// 0.47 ms of the 3.5 M-point tree build, profiles/r01_bake_launches_final.csv)
+__device__ __forceinline__ void block_bounds(const float* mn, const float* mx, bool valid, int* __restrict__ bounds) {
+  __shared__ float red[6][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float lo = valid ? mn[a] : INFINITY, hi = valid ? mx[a] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { red[a][warp] = lo; red[3 + a][warp] = hi; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const int a = threadIdx.x;
+    float v = red[a][0];
+    const int nw = blockDim.x >> 5;
+    for (int w = 1; w < nw; ++w) v = a < 3 ? fminf(v, red[a][w]) : fmaxf(v, red[a][w]);
+    if (a < 3) atomicMin(bounds + a, f2ord(v));
+    else atomicMax(bounds + a, f2ord(v));
+  }
 }
 
 // get_elements.slang:1-40
@@ -65,20 +92,7 @@ __global__ void __launch_bounds__(256) elements_kernel(const float* __restrict__
       mx[a] = hi;
     }
   }
-  // scene AABB: warp reduce, one atomic per warp per component
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    float lo = f < F ? mn[a] : INFINITY, hi = f < F ? mx[a] : -INFINITY;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(bounds + a, f2ord(lo));
-      atomicMax(bounds + 3 + a, f2ord(hi));
-    }
-  }
+  block_bounds(mn, mx, f < F, bounds);
 }
 
 // points as degenerate boxes (nearest-neighbour tree over the visible texels, bake_uv.cu)
@@ -94,19 +108,7 @@ __global__ void __launch_bounds__(256) point_elements_kernel(const float* __rest
       eab[static_cast<size_t>(f) * 6 + 3 + a] = p[a];
     }
   }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    float lo = f < n ? p[a] : INFINITY, hi = f < n ? p[a] : -INFINITY;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(bounds + a, f2ord(lo));
-      atomicMax(bounds + 3 + a, f2ord(hi));
-    }
-  }
+  block_bounds(p, p, f < n, bounds);
 }
 
 __device__ __forceinline__ unsigned expand_bits(unsigned v) {
@@ -218,8 +220,8 @@ __global__ void __launch_bounds__(256) refit_kernel(int F, Node* __restrict__ no
   }
 }
 
-// traversal layout behind the reference-layout nodes (bake_trace.cuh): header (root box, root reference) + 64 B per
-// internal node holding both children's boxes and references (child >= 0: internal node index, < 0: ~prim of a leaf)
+// traversal layout behind the reference-layout nodes (bake_trace.cuh): 128 B header (root box, root reference) + 128 B per
+// internal node holding the boxes and references of its up to four grandchildren, [left part, right part]
 __global__ void __launch_bounds__(256) pack_wide_kernel(const Node* __restrict__ nodes, int F, float4* __restrict__ W) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int LEAF = F - 1;
@@ -230,14 +232,28 @@ __global__ void __launch_bounds__(256) pack_wide_kernel(const Node* __restrict__
     W[1] = make_float4(r.bb[4], r.bb[5], __int_as_float(ref), 0.f);
   }
   if (n >= F - 1) return;
-  const int ca = nodes[n].left, cb = nodes[n].right;
-  const Node A = nodes[ca], B = nodes[cb];
-  const int ra = ca >= LEAF ? ~A.prim : ca, rb = cb >= LEAF ? ~B.prim : cb;
-  float4* o = W + 2 + static_cast<size_t>(n) * 4;
-  o[0] = make_float4(A.bb[0], A.bb[1], A.bb[2], A.bb[3]);
-  o[1] = make_float4(A.bb[4], A.bb[5], B.bb[0], B.bb[1]);
-  o[2] = make_float4(B.bb[2], B.bb[3], B.bb[4], B.bb[5]);
-  o[3] = make_float4(__int_as_float(ra), __int_as_float(rb), 0.f, 0.f);
+  int ent[4];
+  int cnt = 0;
+  const int ch[2] = {nodes[n].left, nodes[n].right};
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (ch[s] >= LEAF) ent[cnt++] = ch[s];
+    else { ent[cnt++] = nodes[ch[s]].left; ent[cnt++] = nodes[ch[s]].right; }
+  }
+  float v[28];
+  for (int k = 0; k < 4; ++k) {
+    if (k < cnt) {
+      const Node c = nodes[ent[k]];
+      for (int a = 0; a < 6; ++a) v[6 * k + a] = c.bb[a];
+      v[24 + k] = __int_as_float(ent[k] >= LEAF ? ~c.prim : ent[k]);
+    } else {
+      for (int a = 0; a < 3; ++a) { v[6 * k + a] = INFINITY; v[6 * k + 3 + a] = -INFINITY; }
+      v[24 + k] = __int_as_float(WIDE_EMPTY);
+    }
+  }
+  float4* o = W + 8 + static_cast<size_t>(n) * 8;
+  for (int k = 0; k < 7; ++k) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  o[7] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 __global__ void __launch_bounds__(256) export_kernel(const Node* __restrict__ nodes, int n, int* __restrict__ info,
@@ -264,7 +280,7 @@ __global__ void __launch_bounds__(128) intersect_kernel(const void* __restrict__
   float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
   const float len = sqrtf(dot3f(d[0], d[1], d[2], d[0], d[1], d[2]));
   d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
-  const RayHit h = bvh_trace(static_cast<const float4*>(nodes) + static_cast<size_t>(2 * F - 1) * 3, vert, tri, o, d);
+  const RayHit h = bvh_trace(reinterpret_cast<const float4*>(static_cast<const uint8_t*>(nodes) + wide_offset_bytes(F)), vert, tri, o, d);
   hit[r] = static_cast<unsigned char>(h.any);
   tid[r] = h.any ? h.tid : -1;
   pos[r * 3] = h.any ? o[0] + h.t * d[0] : 0.f;
@@ -275,11 +291,9 @@ __global__ void __launch_bounds__(128) intersect_kernel(const void* __restrict__
 }
 }  // namespace
 
-static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
-// nodes [2F-1] followed by the packed triangle vertices [F][3] float4 (unused by the point tree)
-// reference-layout nodes (48 B each) + the traversal layout (32 B header + 64 B per internal node)
-size_t bvh_nodes_bytes(int F) { return static_cast<size_t>(2 * F - 1) * sizeof(Node) + static_cast<size_t>(F) * 64; }
+// reference-layout nodes (48 B each) + the traversal layout (128 B header + 128 B per internal node), 128 B aligned
+size_t bvh_nodes_bytes(int F) { return wide_offset_bytes(F) + 128 + static_cast<size_t>(F) * 128; }
 
 size_t bvh_workspace_bytes(int F) {
   size_t cub_bytes = 0;
@@ -322,70 +336,131 @@ int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, 
   (void)V;
   UTX_TRY(build_tree(vert, tri, nullptr, F, nodes_out, workspace, ws_bytes, stream));
   pack_wide_kernel<<<(F + 255) / 256, 256, 0, stream>>>(static_cast<const Node*>(nodes_out), F,
-                                                       reinterpret_cast<float4*>(static_cast<Node*>(nodes_out) + (2 * F - 1)));
+                                                       reinterpret_cast<float4*>(static_cast<uint8_t*>(nodes_out) + wide_offset_bytes(F)));
   UTX_CUDA(cudaGetLastError());
   return 0;
 }
 
-// LBVH over n points (leaf prim = point index): the search structure of the bake's exact 1-NN fill
-int point_bvh_build(const float* pts, int n, void* nodes_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
-  return build_tree(nullptr, nullptr, pts, n, nodes_out, workspace, ws_bytes, stream);
+// ---------------------------------------------------------------------------------------------- point search tree
+namespace {
+// one thread per cluster of PT_CLUSTER Morton-consecutive points: gathers them into `spts` (x, y, z, id), their box becomes the
+// cluster's element box, the first point's code its Morton code (non-decreasing along the clusters; the hierarchy kernel breaks
+// ties on the index exactly as for duplicate triangle codes)
+__global__ void __launch_bounds__(256) cluster_kernel(const float* __restrict__ pts, const int* __restrict__ ids, int n, int n_c,
+                                                      const unsigned* __restrict__ codes_sorted,
+                                                      const unsigned* __restrict__ elem_sorted, float4* __restrict__ spts,
+                                                      float* __restrict__ ceab, unsigned* __restrict__ ccodes,
+                                                      unsigned* __restrict__ celem) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_c) return;
+  const int j0 = c * PT_CLUSTER, j1 = min(j0 + PT_CLUSTER, n);
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int j = j0; j < j1; ++j) {
+    const int e = static_cast<int>(elem_sorted[j]);
+    const float x = pts[static_cast<size_t>(e) * 3], y = pts[static_cast<size_t>(e) * 3 + 1], z = pts[static_cast<size_t>(e) * 3 + 2];
+    spts[j] = make_float4(x, y, z, __int_as_float(ids ? ids[e] : e));
+    lo[0] = fminf(lo[0], x); lo[1] = fminf(lo[1], y); lo[2] = fminf(lo[2], z);
+    hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    ceab[static_cast<size_t>(c) * 6 + a] = lo[a];
+    ceab[static_cast<size_t>(c) * 6 + 3 + a] = hi[a];
+  }
+  ccodes[c] = codes_sorted[j0];
+  celem[c] = static_cast<unsigned>(c);
+}
+}  // namespace
+
+PointTree point_tree_view(const void* nodes, int n) {
+  PointTree pt;
+  pt.n = n;
+  pt.n_c = (n + PT_CLUSTER - 1) / PT_CLUSTER;
+  const uint8_t* base = static_cast<const uint8_t*>(nodes);
+  size_t off = 0;
+  pt.wide = nullptr;
+  if (pt.n_c >= 2) {
+    off = wide_offset_bytes(pt.n_c);
+    pt.wide = reinterpret_cast<const float4*>(base + off);
+    off += 128 + static_cast<size_t>(pt.n_c) * 128;
+  }
+  pt.spts = reinterpret_cast<const float4*>(base + off);
+  return pt;
+}
+
+// Search tree over n >= 1 points (`ids`: optional caller ids, default = point index).  nodes_out: bvh_nodes_bytes(max(n, 2))
+// bytes, workspace: bvh_workspace_bytes(max(n, 2)).  Read it back with point_tree_view(nodes_out, n).
+int point_bvh_build(const float* pts, const int* ids, int n, void* nodes_out, void* workspace, size_t ws_bytes,
+                    cudaStream_t stream) {
+  UTX_CHECK(n >= 1, "point_bvh_build: empty point set");
+  UTX_CHECK(ws_bytes >= bvh_workspace_bytes(n < 2 ? 2 : n), "point_bvh_build: workspace too small");
+  UTX_CHECK((reinterpret_cast<uintptr_t>(nodes_out) & 15) == 0, "point_bvh_build: nodes must be 16B aligned");
+  const PointTree pt = point_tree_view(nodes_out, n);
+  uint8_t* p = static_cast<uint8_t*>(workspace);
+  const size_t F = n < 2 ? 2 : n;                       // same carve-up as build_tree (the sizes were computed for it)
+  float* eab = reinterpret_cast<float*>(p); p += al256(F * 24);
+  unsigned* codes = reinterpret_cast<unsigned*>(p); p += al256(F * 4);
+  unsigned* codes2 = reinterpret_cast<unsigned*>(p); p += al256(F * 4);
+  unsigned* elem = reinterpret_cast<unsigned*>(p); p += al256(F * 4);
+  unsigned* elem2 = reinterpret_cast<unsigned*>(p); p += al256(F * 4);
+  int* parent = reinterpret_cast<int*>(p); p += al256(2 * F * 4);
+  int* arrivals = reinterpret_cast<int*>(p); p += al256(F * 4);
+  int* bounds = reinterpret_cast<int*>(p); p += 256;
+  size_t cub_bytes = ws_bytes - static_cast<size_t>(p - static_cast<uint8_t*>(workspace));
+  const unsigned grid = (n + 255) / 256;
+  bounds_init_kernel<<<1, 32, 0, stream>>>(bounds);
+  point_elements_kernel<<<grid, 256, 0, stream>>>(pts, n, eab, bounds);
+  morton_kernel<<<grid, 256, 0, stream>>>(eab, bounds, n, codes, elem);
+  UTX_CUDA(cub::DeviceRadixSort::SortPairs(p, cub_bytes, codes, codes2, elem, elem2, n, 0, 32, stream));
+  // the unsorted code / element arrays and the per-point boxes are dead now: the clusters' go there
+  const unsigned cgrid = (pt.n_c + 255) / 256;
+  cluster_kernel<<<cgrid, 256, 0, stream>>>(pts, ids, n, pt.n_c, codes2, elem2, const_cast<float4*>(pt.spts), eab, codes, elem);
+  if (pt.n_c >= 2) {
+    Node* nodes = static_cast<Node*>(nodes_out);
+    hierarchy_kernel<<<cgrid, 256, 0, stream>>>(pt.n_c, codes, elem, eab, nodes, parent, arrivals);
+    refit_kernel<<<cgrid, 256, 0, stream>>>(pt.n_c, nodes, parent, arrivals);
+    pack_wide_kernel<<<cgrid, 256, 0, stream>>>(nodes, pt.n_c, const_cast<float4*>(pt.wide));
+  }
+  UTX_CUDA(cudaGetLastError());
+  return 0;
 }
 
 namespace {
-__global__ void __launch_bounds__(128) knn1_kernel(const void* __restrict__ nodes, const float* __restrict__ src, int n_src,
-                                                   const float* __restrict__ dst, long long M, long long* __restrict__ index,
-                                                   float* __restrict__ score) {
+__global__ void __launch_bounds__(128) knn1_kernel(const PointTree pt, const float* __restrict__ dst, long long M,
+                                                   long long* __restrict__ index, float* __restrict__ score) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= M) return;
   const float q[3] = {dst[i * 3], dst[i * 3 + 1], dst[i * 3 + 2]};
   float d2 = 0.f;
-  int best = 0;
-  if (n_src == 1) {
-    const float dx = src[0] - q[0], dy = src[1] - q[1], dz = src[2] - q[2];
-    d2 = (dx * dx + dy * dy) + dz * dz;
-  } else {
-    best = nn_trace(nodes, src, nullptr, q, &d2);
-  }
-  index[i] = best;
+  index[i] = nn_trace(pt, q, &d2);
   score[i] = sqrtf(d2);
 }
-}  // namespace
-
-// knn(src, dst, k=1) of pcd/knn/__init__.py:104-114 (exact, lowest index on ties): index int64 [M], score = distance [M]
-int knn1(const float* src, int n_src, const float* dst, long long M, long long* index, float* score, void* nodes, void* workspace,
-         size_t ws_bytes, cudaStream_t stream) {
-  UTX_CHECK(n_src >= 1, "knn1: empty source set");
-  if (n_src >= 2) UTX_TRY(point_bvh_build(src, n_src, nodes, workspace, ws_bytes, stream));
-  if (M == 0) return 0;
-  knn1_kernel<<<static_cast<unsigned>((M + 127) / 128), 128, 0, stream>>>(nodes, src, n_src, dst, M, index, score);
-  UTX_CUDA(cudaGetLastError());
-  return 0;
-}
-
-namespace {
 // one thread per query; the k candidates live in the thread's local arrays (k <= KNN_MAX)
-__global__ void __launch_bounds__(128) knn_kernel(const void* __restrict__ nodes, const float* __restrict__ src, int n_src,
-                                                  const float* __restrict__ dst, long long M, int k,
+__global__ void __launch_bounds__(128) knn_kernel(const PointTree pt, const float* __restrict__ dst, long long M, int k,
                                                   long long* __restrict__ index, float* __restrict__ score) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= M) return;
   const float q[3] = {dst[i * 3], dst[i * 3 + 1], dst[i * 3 + 2]};
   float bd[KNN_MAX];
   int bi[KNN_MAX];
-  if (n_src == 1) {
-    const float dx = src[0] - q[0], dy = src[1] - q[1], dz = src[2] - q[2];
-    bd[0] = (dx * dx + dy * dy) + dz * dz;
-    bi[0] = 0;
-  } else {
-    knn_trace(nodes, src, nullptr, q, k, bd, bi);
-  }
+  knn_trace(pt, q, k, bd, bi);
   for (int j = 0; j < k; ++j) {
     index[i * k + j] = bi[j];
     score[i * k + j] = sqrtf(bd[j]);
   }
 }
 }  // namespace
+
+// knn(src, dst, 1) of pcd/knn/__init__.py:104-114: index int64 [M], score = distance [M]; lowest index on ties
+int knn1(const float* src, int n_src, const float* dst, long long M, long long* index, float* score, void* nodes, void* workspace,
+         size_t ws_bytes, cudaStream_t stream) {
+  UTX_CHECK(n_src >= 1, "knn: empty source set");
+  UTX_TRY(point_bvh_build(src, nullptr, n_src, nodes, workspace, ws_bytes, stream));
+  if (M == 0) return 0;
+  knn1_kernel<<<static_cast<unsigned>((M + 127) / 128), 128, 0, stream>>>(point_tree_view(nodes, n_src), dst, M, index, score);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // knn(src, dst, k) of pcd/knn/__init__.py:104-114 for 1 <= k <= min(32, n_src): index int64 [M,k], score = distance [M,k],
 // each row ascending by (distance, index)
@@ -395,9 +470,9 @@ int knn(const float* src, int n_src, const float* dst, long long M, int k, long 
   UTX_CHECK(k >= 1 && k <= KNN_MAX, "knn: k must be in 1..32");
   UTX_CHECK(k <= n_src, "knn: k exceeds the number of source points");
   if (k == 1) return knn1(src, n_src, dst, M, index, score, nodes, workspace, ws_bytes, stream);
-  UTX_TRY(point_bvh_build(src, n_src, nodes, workspace, ws_bytes, stream));
+  UTX_TRY(point_bvh_build(src, nullptr, n_src, nodes, workspace, ws_bytes, stream));
   if (M == 0) return 0;
-  knn_kernel<<<static_cast<unsigned>((M + 127) / 128), 128, 0, stream>>>(nodes, src, n_src, dst, M, k, index, score);
+  knn_kernel<<<static_cast<unsigned>((M + 127) / 128), 128, 0, stream>>>(point_tree_view(nodes, n_src), dst, M, k, index, score);
   UTX_CUDA(cudaGetLastError());
   return 0;
 }

@@ -50,18 +50,49 @@ __device__ __forceinline__ bool slab_pass(float te, float tx, float closest) {
   return !(m < te);
 }
 
-// Closest-hit query on the traversal layout bvh_build writes behind the reference-layout nodes ("wide" nodes, 64 B per
-// INTERNAL node: both children's boxes + both child references, leaves folded into their parents as ~prim):
-//   W[0..1]            root box (6 floats), root reference, pad
-//   W[2 + 4 n ..]      internal node n:  L.min xyz, L.max xyz, R.min xyz, R.max xyz, refL, refR, pad, pad
-// One 64 B fetch per visited internal node yields both children's slab tests; a child that already fails is never pushed,
-// one that passes is pushed with its entry distance te and re-checked against the closest t of the moment it is popped.
-// This visits exactly the leaves the reference's loop visits, in the same order, with the same closest t at each visit:
-// the reference tests a node's own box when it pops it (closest = value at pop time); a box fails iff
-// min(closest_pop, tx) < te; closest only shrinks, so "fails at push time" implies "fails at pop time", and for the rest
-// the pop-time comparison `closest < te` completes the identical predicate (tx >= te is already known).  Push order
-// (left, then right; right popped first), Moller-Trumbore without a t-range test and "last accepted leaf wins" are the
-// reference's (intersect_test2.slang:63-146).  `d` must already be normalised exactly like the reference does (d / |d|).
+// Traversal layout ("wide" records) written behind the reference-layout nodes by bvh_build / point_bvh_build: one 128 B
+// record per INTERNAL binary node n holding the boxes and references of its (up to) four grandchildren -- a child that is a leaf
+// stays as one entry -- in the order [left part, right part]:
+//   W[0..7]              header: root box (6 floats), root reference, pad            (128 B, so records are 128 B aligned)
+//   W[8 + 8 n ..]        24 floats = 4 boxes (min xyz, max xyz), 4 int references, pad
+// reference >= 0: internal node index, < 0: ~prim of a leaf, WIDE_EMPTY: unused slot (its box is inverted and fails every test).
+constexpr int WIDE_EMPTY = static_cast<int>(0x80000000u);
+__host__ __device__ __forceinline__ size_t wide_offset_bytes(int F) {      // from the start of the nodes buffer
+  return (static_cast<size_t>(2 * F - 1) * 48 + 127) / 128 * 128;
+}
+struct WideRec {
+  float bb[24];
+  int ref[4];
+};
+__device__ __forceinline__ WideRec wide_load(const float4* __restrict__ W, int n) {
+  const float4* nd = W + 8 + static_cast<size_t>(n) * 8;
+  WideRec r;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float4 q = __ldg(nd + k);
+    r.bb[4 * k] = q.x; r.bb[4 * k + 1] = q.y; r.bb[4 * k + 2] = q.z; r.bb[4 * k + 3] = q.w;
+  }
+  const float4 q = __ldg(nd + 6);
+  r.ref[0] = __float_as_int(q.x); r.ref[1] = __float_as_int(q.y); r.ref[2] = __float_as_int(q.z); r.ref[3] = __float_as_int(q.w);
+  return r;
+}
+
+// Closest-hit query.  One 128 B fetch per visited record yields four slab tests: two levels of the reference's binary walk per
+// dependent memory round trip (the walk is latency-bound: ~150 dependent visits per ray, profiles/r01_summary.md).  An entry
+// that already fails is never pushed, one that passes is pushed with its entry distance te and re-checked against the closest t
+// of the moment it is popped.
+// This visits exactly the leaves the reference's loop (intersect_test2.slang:63-146) visits, in the same order, with the same
+// closest t at each visit:
+//  * the reference tests a node's own box when it pops it (closest = value at pop time); a box fails iff
+//    min(closest_pop, tx) < te; closest only shrinks, so "fails at push time" implies "fails at pop time", and for the rest the
+//    pop-time comparison `closest < te` completes the identical predicate (tx >= te is already known);
+//  * skipping the intermediate child's own test is exact: a grandchild's box lies inside the child's box (refit takes exact
+//    min / max), the slab arithmetic is monotone in the box coordinates, so te_grandchild >= te_child and
+//    tx_grandchild <= tx_child: whenever the child's box fails, both grandchildren fail on their own;
+//  * order: the reference pushes left, right and pops right first, i.e. a depth-first walk that takes the right subtree
+//    before the left one; pushing the entries [LL, LR, RL, RR] in that order and popping from the top is the same walk.
+// Moller-Trumbore without a t-range test and "last accepted leaf wins" are the reference's quirks.  `d` must already be
+// normalised exactly like the reference does (d / |d|).
 __device__ __forceinline__ RayHit bvh_trace(const float4* __restrict__ W, const float* __restrict__ vert, const int* __restrict__ tri,
                                             const float* o, const float* d) {
   float inv[3];
@@ -89,15 +120,14 @@ __device__ __forceinline__ RayHit bvh_trace(const float4* __restrict__ W, const 
     const int ref = sref[count];
     if (closest < ste[count]) continue;
     if (ref >= 0) {
-      const float4* nd = W + 2 + static_cast<size_t>(ref) * 4;
-      const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
-      const float bl[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y}, br[6] = {q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-      float tel, txl, ter, txr;
-      slab_params(o, inv, bl, tel, txl);
-      slab_params(o, inv, br, ter, txr);
-      if (count + 2 <= 64) {
-        if (slab_pass(tel, txl, closest)) { sref[count] = __float_as_int(q3.x); ste[count] = tel; ++count; }
-        if (slab_pass(ter, txr, closest)) { sref[count] = __float_as_int(q3.y); ste[count] = ter; ++count; }
+      const WideRec r = wide_load(W, ref);
+      if (count + 4 <= 64) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float te, tx;
+          slab_params(o, inv, r.bb + 6 * k, te, tx);
+          if (r.ref[k] != WIDE_EMPTY && slab_pass(te, tx, closest)) { sref[count] = r.ref[k]; ste[count] = te; ++count; }
+        }
       }
     } else {
       const int p = ~ref;
@@ -127,99 +157,99 @@ __device__ __forceinline__ RayHit bvh_trace(const float4* __restrict__ W, const 
   return h;
 }
 
-// Exact nearest neighbour of q among the points of a point-LBVH: fp32 squared distance ((dx^2+dy^2)+dz^2), lowest point id on
-// ties (`ids` maps the tree's point index to the caller's id).  Boxes are pruned only when their (slightly deflated)
-// distance bound exceeds the best distance, so rounding can never drop the true nearest point.
-__device__ __forceinline__ int nn_trace(const void* __restrict__ nodes_v, const float* __restrict__ pts,
-                                        const int* __restrict__ ids, const float* q, float* best_d2_out) {
-  const float4* nodes = static_cast<const float4*>(nodes_v);
-  int stack[64];
-  int count = 0;
-  stack[count++] = 0;
-  float best = INFINITY;
-  int best_id = -1;
+// ---------------------------------------------------------------------------------------------- point search tree
+// The exact nearest-neighbour structure of the bake (torch_kdtree's role, pcd/knn/__init__.py:36-39,93-95): points sorted by
+// Morton code, cut into clusters of PT_CLUSTER consecutive points, and a Karras LBVH over the CLUSTER boxes (same hierarchy /
+// refit kernels as the triangle tree).  A leaf is scored by reading its points from one contiguous 128 B run of `spts`
+// (x, y, z, caller's id) -- an eighth of the nodes to build and to walk compared with one leaf per point.
+//   nodes  [2 n_c - 1] x 48 B (box, left, right, prim = cluster), absent when n_c == 1
+//   spts   [n] float4, Morton order
+// Results do not depend on the tree: fp32 squared distance ((dx^2+dy^2)+dz^2), ties by lowest id; a box is pruned only when
+// its slightly deflated distance bound exceeds the current worst kept distance, so rounding can never drop a true neighbour.
+constexpr int PT_CLUSTER = 8;
+struct PointTree {
+  const float4* wide;   // traversal records of the cluster tree (layout as above; leaf reference = ~cluster), unused when n_c == 1
+  const float4* spts;
+  int n_c, n;
+};
+__device__ __forceinline__ float box_dist2(const float* bb, const float* q) {
+  const float ax = fmaxf(fmaxf(bb[0] - q[0], q[0] - bb[3]), 0.f), ay = fmaxf(fmaxf(bb[1] - q[1], q[1] - bb[4]), 0.f),
+              az = fmaxf(fmaxf(bb[2] - q[2], q[2] - bb[5]), 0.f);
+  return (ax * ax + ay * ay) + az * az;
+}
+// Generic walk: `worst()` = current pruning distance, `offer(d2, id)` = score one point.  Entries carry their bound and are
+// re-checked against worst() when popped; of a record's entries the nearest is pushed last (popped first).
+template <typename Worst, typename Offer>
+__device__ __forceinline__ void point_tree_walk(const PointTree& pt, const float* q, Worst worst, Offer offer) {
+  auto leaf = [&](int c) {
+    const int j0 = c * PT_CLUSTER, j1 = min(j0 + PT_CLUSTER, pt.n);
+    for (int j = j0; j < j1; ++j) {
+      const float4 p = __ldg(pt.spts + j);
+      const float dx = p.x - q[0], dy = p.y - q[1], dz = p.z - q[2];
+      offer((dx * dx + dy * dy) + dz * dz, __float_as_int(p.w));
+    }
+  };
+  if (pt.n_c <= 1) {
+    if (pt.n > 0) leaf(0);
+    return;
+  }
+  int sn[64];
+  float sb[64];
+  int count = 1;
+  sn[0] = 0; sb[0] = 0.f;
   while (count > 0) {
-    const int n = stack[--count];
-    const float4 q0 = __ldg(nodes + static_cast<size_t>(n) * 3), q1 = __ldg(nodes + static_cast<size_t>(n) * 3 + 1);
-    const float bx = fmaxf(fmaxf(q0.x - q[0], q[0] - q0.w), 0.f), by = fmaxf(fmaxf(q0.y - q[1], q[1] - q1.x), 0.f),
-                bz = fmaxf(fmaxf(q0.z - q[2], q[2] - q1.y), 0.f);
-    const float bd = ((bx * bx + by * by) + bz * bz) * 0.999999f;
-    if (bd > best) continue;
-    const int l = __float_as_int(q1.z), r = __float_as_int(q1.w);
-    if (l == 0 && r == 0) {
-      const int pidx = __float_as_int(__ldg(nodes + static_cast<size_t>(n) * 3 + 2).x);
-      const float dx = pts[static_cast<size_t>(pidx) * 3] - q[0], dy = pts[static_cast<size_t>(pidx) * 3 + 1] - q[1],
-                  dz = pts[static_cast<size_t>(pidx) * 3 + 2] - q[2];
-      const float d2 = (dx * dx + dy * dy) + dz * dz;
-      const int id = ids ? ids[pidx] : pidx;
-      if (d2 < best || (d2 == best && id < best_id)) { best = d2; best_id = id; }
-    } else if (count + 2 <= 64) {
-      // visit the nearer child first: push the farther one below it
-      const float4 a0 = __ldg(nodes + static_cast<size_t>(l) * 3), a1 = __ldg(nodes + static_cast<size_t>(l) * 3 + 1);
-      const float ax = fmaxf(fmaxf(a0.x - q[0], q[0] - a0.w), 0.f), ay = fmaxf(fmaxf(a0.y - q[1], q[1] - a1.x), 0.f),
-                  az = fmaxf(fmaxf(a0.z - q[2], q[2] - a1.y), 0.f);
-      const float4 c0 = __ldg(nodes + static_cast<size_t>(r) * 3), c1 = __ldg(nodes + static_cast<size_t>(r) * 3 + 1);
-      const float cx = fmaxf(fmaxf(c0.x - q[0], q[0] - c0.w), 0.f), cy = fmaxf(fmaxf(c0.y - q[1], q[1] - c1.x), 0.f),
-                  cz = fmaxf(fmaxf(c0.z - q[2], q[2] - c1.y), 0.f);
-      const float dl = (ax * ax + ay * ay) + az * az, dr = (cx * cx + cy * cy) + cz * cz;
-      if (dl <= dr) { stack[count++] = r; stack[count++] = l; }
-      else { stack[count++] = l; stack[count++] = r; }
+    --count;
+    if (sb[count] > worst()) continue;
+    const int ref = sn[count];
+    if (ref < 0) { leaf(~ref); continue; }
+    const WideRec r = wide_load(pt.wide, ref);
+    float bd[4];
+    int nearest = 0, nref = r.ref[0];
+    float nb = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bd[k] = r.ref[k] == WIDE_EMPTY ? INFINITY : box_dist2(r.bb + 6 * k, q) * 0.999999f;   // (an inverted box is not "far" here)
+      if (bd[k] < nb) { nb = bd[k]; nearest = k; nref = r.ref[k]; }
+    }
+    const float w = worst();
+    if (count + 4 <= 64) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k != nearest && r.ref[k] != WIDE_EMPTY && bd[k] <= w) { sn[count] = r.ref[k]; sb[count] = bd[k]; ++count; }
+      if (nb <= w) { sn[count] = nref; sb[count] = nb; ++count; }
     }
   }
+}
+// exact 1-NN: returns the id (-1 when the tree is empty), *best_d2_out = squared distance
+__device__ __forceinline__ int nn_trace(const PointTree& pt, const float* q, float* best_d2_out) {
+  float best = INFINITY;
+  int best_id = -1;
+  point_tree_walk(pt, q, [&]() { return best; },
+                  [&](float d2, int id) {
+                    if (d2 < best || (d2 == best && id < best_id) || best_id < 0) { best = d2; best_id = id; }
+                  });
   if (best_d2_out) *best_d2_out = best;
   return best_id;
 }
-
-// Exact k nearest neighbours (k <= KNN_MAX) of q among the points of a point-LBVH, ascending by (fp32 squared distance,
-// point id) -- the order `knn(src, dst, k)` of the reference returns (pcd/knn/__init__.py:85-95, sorted by distance; ties by
-// lowest id here, torch_kdtree@86961f7d [ext] leaves them unspecified).  bd / bi: caller's arrays of k entries; entries
-// beyond the number of points found keep (INFINITY, -1).  Same conservative pruning as nn_trace, against the current
-// k-th best distance, so the result does not depend on the visit order.
+// exact k-NN (k <= KNN_MAX), ascending by (squared distance, id) -- the order `knn(src, dst, k)` of the reference returns
+// (pcd/knn/__init__.py:85-95, sorted by distance; ties by lowest id here, torch_kdtree@86961f7d [ext] leaves them unspecified).
+// bd / bi: caller's arrays of k entries; entries beyond the number of points keep (INFINITY, -1).
 constexpr int KNN_MAX = 32;
-__device__ __forceinline__ void knn_trace(const void* __restrict__ nodes_v, const float* __restrict__ pts,
-                                          const int* __restrict__ ids, const float* q, int k, float* bd, int* bi) {
-  const float4* nodes = static_cast<const float4*>(nodes_v);
+__device__ __forceinline__ void knn_trace(const PointTree& pt, const float* q, int k, float* bd, int* bi) {
   for (int j = 0; j < k; ++j) { bd[j] = INFINITY; bi[j] = -1; }
-  int stack[64];
-  int count = 0;
-  stack[count++] = 0;
-  while (count > 0) {
-    const int n = stack[--count];
-    const float4 q0 = __ldg(nodes + static_cast<size_t>(n) * 3), q1 = __ldg(nodes + static_cast<size_t>(n) * 3 + 1);
-    const float bx = fmaxf(fmaxf(q0.x - q[0], q[0] - q0.w), 0.f), by = fmaxf(fmaxf(q0.y - q[1], q[1] - q1.x), 0.f),
-                bz = fmaxf(fmaxf(q0.z - q[2], q[2] - q1.y), 0.f);
-    const float bound = ((bx * bx + by * by) + bz * bz) * 0.999999f;
-    if (bound > bd[k - 1]) continue;
-    const int l = __float_as_int(q1.z), r = __float_as_int(q1.w);
-    if (l == 0 && r == 0) {
-      const int pidx = __float_as_int(__ldg(nodes + static_cast<size_t>(n) * 3 + 2).x);
-      const float dx = pts[static_cast<size_t>(pidx) * 3] - q[0], dy = pts[static_cast<size_t>(pidx) * 3 + 1] - q[1],
-                  dz = pts[static_cast<size_t>(pidx) * 3 + 2] - q[2];
-      const float d2 = (dx * dx + dy * dy) + dz * dz;
-      const int id = ids ? ids[pidx] : pidx;
-      const bool better = d2 < bd[k - 1] || (d2 == bd[k - 1] && (bi[k - 1] < 0 || id < bi[k - 1]));
-      if (better) {
-        int j = k - 1;
-        while (j > 0 && (bd[j - 1] > d2 || (bd[j - 1] == d2 && (bi[j - 1] < 0 || bi[j - 1] > id)))) {
-          bd[j] = bd[j - 1];
-          bi[j] = bi[j - 1];
-          --j;
-        }
-        bd[j] = d2;
-        bi[j] = id;
-      }
-    } else if (count + 2 <= 64) {
-      const float4 a0 = __ldg(nodes + static_cast<size_t>(l) * 3), a1 = __ldg(nodes + static_cast<size_t>(l) * 3 + 1);
-      const float ax = fmaxf(fmaxf(a0.x - q[0], q[0] - a0.w), 0.f), ay = fmaxf(fmaxf(a0.y - q[1], q[1] - a1.x), 0.f),
-                  az = fmaxf(fmaxf(a0.z - q[2], q[2] - a1.y), 0.f);
-      const float4 c0 = __ldg(nodes + static_cast<size_t>(r) * 3), c1 = __ldg(nodes + static_cast<size_t>(r) * 3 + 1);
-      const float cx = fmaxf(fmaxf(c0.x - q[0], q[0] - c0.w), 0.f), cy = fmaxf(fmaxf(c0.y - q[1], q[1] - c1.x), 0.f),
-                  cz = fmaxf(fmaxf(c0.z - q[2], q[2] - c1.y), 0.f);
-      const float dl = (ax * ax + ay * ay) + az * az, dr = (cx * cx + cy * cy) + cz * cz;
-      if (dl <= dr) { stack[count++] = r; stack[count++] = l; }
-      else { stack[count++] = l; stack[count++] = r; }
-    }
-  }
+  point_tree_walk(pt, q, [&]() { return bd[k - 1]; },
+                  [&](float d2, int id) {
+                    const bool better = d2 < bd[k - 1] || (d2 == bd[k - 1] && (bi[k - 1] < 0 || id < bi[k - 1]));
+                    if (!better) return;
+                    int j = k - 1;
+                    while (j > 0 && (bd[j - 1] > d2 || (bd[j - 1] == d2 && (bi[j - 1] < 0 || bi[j - 1] > id)))) {
+                      bd[j] = bd[j - 1];
+                      bi[j] = bi[j - 1];
+                      --j;
+                    }
+                    bd[j] = d2;
+                    bi[j] = id;
+                  });
 }
 
 }  // namespace utx

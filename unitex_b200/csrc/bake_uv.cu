@@ -19,6 +19,7 @@
 // Built with -fmad=false.
 #include <cub/device/device_scan.cuh>
 
+#include <cstdlib>
 #include <vector>
 
 #include "bake_trace.cuh"
@@ -133,6 +134,109 @@ __global__ void __launch_bounds__(128) texel_kernel(const float4* __restrict__ r
   alpha_ok[t] = static_cast<unsigned char>(aok);
 }
 
+// ---- the same texel pass split in two so that the ray tracing runs on DENSE, coherent warps -----------------------
+// texel_prep_kernel: everything of texel_kernel except the trace; a texel that faces view i (the angle test) appends itself
+// to view i's ray list.  Threads map to texels in 16x8 tiles (one 8x4 sub-tile per warp) and every block appends its rays
+// with ONE atomicAdd per view, so a list is a sequence of per-tile runs: 32 consecutive entries are rays of one direction
+// through neighbouring texels.  ray_kernel walks the lists, one thread per ray, and ORs the view's bit into raw_vis.
+// The per-ray arithmetic is texel_kernel's, so the bits are identical; only the order in which rays run differs (the
+// block order inside a list depends on the atomics, the result does not).  In the fused kernel 15 of 32 lanes were active on
+// average (profiles/r01_texel_kernel.metrics.csv): lanes not facing the view idled through every trace.
+__device__ __forceinline__ int tile_texel(int H2, int W2, int block, int thread) {
+  if (W2 < 16 || H2 < 8) return block * 128 + thread;
+  const int tiles_x = W2 >> 4, ty = block / tiles_x, tx = block - ty * tiles_x;
+  const int warp = thread >> 5, lane = thread & 31;
+  const int x = (tx << 4) + ((warp & 1) << 3) + (lane & 7), y = (ty << 3) + ((warp >> 1) << 2) + (lane >> 3);
+  return y * W2 + x;
+}
+__global__ void __launch_bounds__(128) texel_prep_kernel(const float4* __restrict__ rast, int H2, int W2,
+                                                         const float* __restrict__ vert, const int* __restrict__ tri,
+                                                         const Views vw, const float* __restrict__ images, int H, int W,
+                                                         float cos_thresh, unsigned char* __restrict__ raw_vis,
+                                                         unsigned char* __restrict__ alpha_ok, float* __restrict__ pos_out,
+                                                         int* __restrict__ lists, int* __restrict__ counts) {
+  __shared__ int wcount[MAXV][4];
+  __shared__ int base[MAXV];
+  const int T = H2 * W2;
+  const int t = tile_texel(H2, W2, blockIdx.x, threadIdx.x);
+  unsigned face = 0, aok = 0;
+  if (t < T) {
+    const float4 r = rast[t];
+    const int f = static_cast<int>(r.w) - 1;
+    float pos[3] = {0.f, 0.f, 0.f};
+    if (f >= 0) {
+      const float *p0 = vert + static_cast<size_t>(tri[f * 3]) * 3, *p1 = vert + static_cast<size_t>(tri[f * 3 + 1]) * 3,
+                  *p2 = vert + static_cast<size_t>(tri[f * 3 + 2]) * 3;
+      const float u = r.x, v = r.y, w = (1.0f - u) - v;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) pos[a] = (u * p0[a] + v * p1[a]) + w * p2[a];
+      const float e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+      float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+      const float nl = fmaxf(norm3(n[0], n[1], n[2]), 1e-12f);
+      n[0] = n[0] / nl; n[1] = n[1] / nl; n[2] = n[2] / nl;
+      const float nn = fmaxf(norm3(n[0], n[1], n[2]), 1e-8f);
+      for (int i = 0; i < vw.n; ++i) {
+        const float* dr = vw.dir[i];
+        const float dl = fmaxf(norm3(dr[0], dr[1], dr[2]), 1e-12f);
+        const float d[3] = {dr[0] / dl, dr[1] / dl, dr[2] / dl};
+        const float dn = fmaxf(norm3(d[0], d[1], d[2]), 1e-8f);
+        const float cosv = ((d[0] / dn) * (n[0] / nn) + (d[1] / dn) * (n[1] / nn)) + (d[2] / dn) * (n[2] / nn);
+        float gx, gy;
+        texel_ndc(vw.mat[i], p0, p1, p2, u, v, &gx, &gy);
+        float rgba[4];
+        bilinear<4>(images + static_cast<size_t>(i) * H * W * 4, H, W, gx, gy, rgba);
+        if (rgba[3] > 0.999f) aok |= 1u << i;
+        if (cosv < cos_thresh) face |= 1u << i;
+      }
+    }
+    raw_vis[t] = 0;
+    alpha_ok[t] = static_cast<unsigned char>(aok);
+    pos_out[t * 3] = pos[0]; pos_out[t * 3 + 1] = pos[1]; pos_out[t * 3 + 2] = pos[2];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned ballots[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    ballots[i] = __ballot_sync(0xffffffffu, (face >> i) & 1u);
+    if (lane == 0) wcount[i][warp] = __popc(ballots[i]);
+  }
+  __syncthreads();
+  if (threadIdx.x < vw.n) {
+    const int i = threadIdx.x;
+    const int total = ((wcount[i][0] + wcount[i][1]) + wcount[i][2]) + wcount[i][3];
+    base[i] = total ? atomicAdd(counts + i, total) : 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if ((face >> i) & 1u) {
+      int off = base[i] + __popc(ballots[i] & ((1u << lane) - 1u));
+      for (int w = 0; w < warp; ++w) off += wcount[i][w];
+      lists[static_cast<size_t>(i) * T + off] = t;
+    }
+  }
+}
+__global__ void __launch_bounds__(128) ray_kernel(const int* __restrict__ lists, const int* __restrict__ counts, int T,
+                                                  const float4* __restrict__ rast, const float* __restrict__ pos_in,
+                                                  const float* __restrict__ vert, const int* __restrict__ tri,
+                                                  const float4* __restrict__ wide, const Views vw, unsigned* raw_vis_words) {
+  const int view = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= counts[view]) return;
+  const int t = lists[static_cast<size_t>(view) * T + i];
+  const int f = static_cast<int>(rast[t].w) - 1;
+  const float pos[3] = {pos_in[static_cast<size_t>(t) * 3], pos_in[static_cast<size_t>(t) * 3 + 1], pos_in[static_cast<size_t>(t) * 3 + 2]};
+  const float k2s3 = 3.4641016151377544f;   // float32(2 * sqrt(3)), renderer_inverse.py:284
+  const float* dr = vw.dir[view];
+  const float o[3] = {pos[0] - k2s3 * dr[0], pos[1] - k2s3 * dr[1], pos[2] - k2s3 * dr[2]};
+  const float dl = fmaxf(norm3(dr[0], dr[1], dr[2]), 1e-12f);
+  float d[3] = {dr[0] / dl, dr[1] / dl, dr[2] / dl};                    // F.normalize (:285)
+  const float len = norm3(d[0], d[1], d[2]);                            // the tracer normalises again (intersect_test2.slang:283)
+  d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
+  const RayHit h = bvh_trace(wide, vert, tri, o, d);
+  if (h.any && h.tid == f) atomicOr(raw_vis_words + (t >> 2), (1u << view) << ((t & 3) * 8));
+}
+
 // k = 3: conv >= 3  <=>  at least one of the 8 ring texels set (9 r - c >= 3, c <= 1)
 __global__ void __launch_bounds__(256) repair3_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out,
                                                       int H, int W) {
@@ -240,9 +344,37 @@ __global__ void __launch_bounds__(256) seam1_kernel(const unsigned char* __restr
 // positions (same builder as the triangle tree, bake_bvh.cu) and every covered-but-invisible texel walks it for its exact
 // nearest neighbour.  Cost is logarithmic in the number of visible texels and independent of how far the hidden region is
 // from the nearest visible one (the first version used a uniform grid whose ring search was 88 % of the bake).
-__global__ void __launch_bounds__(256) nn_flag_kernel(const signed char* __restrict__ owner, int T, int* __restrict__ flags) {
+// flags the owned texels (the source points) and appends the covered-but-unowned ones (the queries) to `qlist`, one atomicAdd
+// per block: the query kernels then run on dense warps of neighbouring texels instead of the ~10 % of a full-atlas launch
+__global__ void __launch_bounds__(256) nn_flag_kernel(const unsigned char* __restrict__ mask2d,
+                                                      const signed char* __restrict__ owner, int T, int* __restrict__ flags,
+                                                      int* __restrict__ nn_index, int* __restrict__ qlist,
+                                                      int* __restrict__ qcount) {
+  __shared__ int wcount[8];
+  __shared__ int base;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < T) flags[t] = owner[t] >= 0;
+  bool query = false;
+  if (t < T) {
+    const int o = owner[t];
+    flags[t] = o >= 0;
+    if (nn_index) nn_index[t] = -1;
+    query = mask2d[t] && o < 0;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned b = __ballot_sync(0xffffffffu, query);
+  if (lane == 0) wcount[warp] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int w = 0; w < 8; ++w) total += wcount[w];
+    base = total ? atomicAdd(qcount, total) : 0;
+  }
+  __syncthreads();
+  if (query) {
+    int off = base + __popc(b & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) off += wcount[w];
+    qlist[off] = t;
+  }
 }
 __global__ void __launch_bounds__(256) nn_compact_kernel(const signed char* __restrict__ owner, const int* __restrict__ offs,
                                                          const float* __restrict__ pos, int T, int* __restrict__ ids,
@@ -255,17 +387,14 @@ __global__ void __launch_bounds__(256) nn_compact_kernel(const signed char* __re
   pts[static_cast<size_t>(k) * 3 + 1] = pos[static_cast<size_t>(t) * 3 + 1];
   pts[static_cast<size_t>(k) * 3 + 2] = pos[static_cast<size_t>(t) * 3 + 2];
 }
-__global__ void __launch_bounds__(128) nn_query_kernel(const unsigned char* __restrict__ mask2d,
-                                                       const signed char* __restrict__ owner, const float* __restrict__ pos,
-                                                       int T, const void* __restrict__ nodes, const float* __restrict__ pts,
-                                                       const int* __restrict__ ids, int n_pts, const float* color_in,
-                                                       float* color_out, int* __restrict__ nn_index) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  if (nn_index) nn_index[t] = -1;
-  if (!mask2d[t] || owner[t] >= 0 || n_pts == 0) return;
+__global__ void __launch_bounds__(128) nn_query_kernel(const int* __restrict__ qlist, int n_q, const float* __restrict__ pos,
+                                                       const PointTree pt, const float* color_in, float* color_out,
+                                                       int* __restrict__ nn_index) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_q) return;
+  const int t = qlist[i];
   const float q[3] = {pos[static_cast<size_t>(t) * 3], pos[static_cast<size_t>(t) * 3 + 1], pos[static_cast<size_t>(t) * 3 + 2]};
-  const int best = n_pts == 1 ? ids[0] : nn_trace(nodes, pts, ids, q, nullptr);
+  const int best = nn_trace(pt, q, nullptr);
   if (nn_index) nn_index[t] = best;
   if (best >= 0) {
     color_out[t * 3] = color_in[static_cast<size_t>(best) * 3];
@@ -367,21 +496,25 @@ __global__ void __launch_bounds__(256) transform_points_kernel(const float* __re
 // source points' colours, summed in ascending (distance, id) order: `colors[index, :].mean(dim=-2)` (:421, :431).
 __global__ void __launch_bounds__(128) knn_mean_kernel(const unsigned char* __restrict__ mask2d,
                                                        const signed char* __restrict__ owner, int want,
-                                                       const float* __restrict__ pos, int T, const void* __restrict__ nodes,
-                                                       const float* __restrict__ pts, const int* __restrict__ ids, int n_pts,
-                                                       int k, const float* src_col, float* dst_col, int* __restrict__ nn_index) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  if (nn_index) nn_index[t] = -1;
-  if (!mask2d[t] || n_pts == 0) return;
-  const int o = owner[t];
-  if (want >= 0 ? o != want : (want == -1 && o >= 0)) return;
+                                                       const float* __restrict__ pos, int T, const PointTree pt, int k,
+                                                       const float* src_col, float* dst_col, int* __restrict__ nn_index,
+                                                       const int* __restrict__ list = nullptr, int n_list = 0) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (list) {                                   // the fill stage's compacted query list (its flag kernel reset nn_index)
+    if (t >= n_list) return;
+    t = list[t];
+  } else {
+    if (t >= T) return;
+    if (nn_index) nn_index[t] = -1;
+    if (!mask2d[t] || pt.n == 0) return;
+    const int o = owner[t];
+    if (want >= 0 ? o != want : (want == -1 && o >= 0)) return;
+  }
   const float q[3] = {pos[static_cast<size_t>(t) * 3], pos[static_cast<size_t>(t) * 3 + 1], pos[static_cast<size_t>(t) * 3 + 2]};
   float bd[KNN_MAX];
   int bi[KNN_MAX];
-  const int kk = k < n_pts ? k : n_pts;
-  if (n_pts == 1) { bi[0] = ids ? ids[0] : 0; }
-  else knn_trace(nodes, pts, ids, q, kk, bd, bi);
+  const int kk = k < pt.n ? k : pt.n;
+  knn_trace(pt, q, kk, bd, bi);
   float acc[3] = {0.f, 0.f, 0.f};
   for (int j = 0; j < kk; ++j) {
     const float* c = src_col + static_cast<size_t>(bi[j]) * 3;
@@ -418,6 +551,7 @@ struct BakeWs {
   float* pts;
   void* scan_tmp;
   size_t scan_bytes;
+  int* counters;   // [0..MAXV) ray-list lengths, [MAXV] query-list length
   uint8_t* rest;   // nearest-neighbour tree + builder scratch during the fill, the pull-push pyramid afterwards
 };
 BakeWs carve(void* workspace, int T) {
@@ -435,6 +569,7 @@ BakeWs carve(void* workspace, int T) {
   w.pts = reinterpret_cast<float*>(take(static_cast<size_t>(T) * 12));
   cub::DeviceScan::ExclusiveSum(nullptr, w.scan_bytes, w.flags, w.offs, T);
   w.scan_tmp = take(w.scan_bytes);
+  w.counters = reinterpret_cast<int*>(take(256));
   w.rest = p;
   return w;
 }
@@ -447,11 +582,13 @@ int check_atlas(int H2, int W2, size_t ws_bytes, const char* who) {
 }
 
 // flags -> exclusive scan -> total on the host (the tree builder needs the point count: one sync)
-int count_flags(const int* flags, int* offs, long long N, void* scan_tmp, size_t scan_bytes, int* total, cudaStream_t stream) {
+int count_flags(const int* flags, int* offs, long long N, void* scan_tmp, size_t scan_bytes, int* total, cudaStream_t stream,
+                const int* extra_dev = nullptr, int* extra = nullptr) {
   UTX_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, flags, offs, static_cast<int>(N), stream));
   int last_off = 0, last_flag = 0;
   UTX_CUDA(cudaMemcpyAsync(&last_off, offs + (N - 1), 4, cudaMemcpyDeviceToHost, stream));
   UTX_CUDA(cudaMemcpyAsync(&last_flag, flags + (N - 1), 4, cudaMemcpyDeviceToHost, stream));
+  if (extra_dev) UTX_CUDA(cudaMemcpyAsync(extra, extra_dev, 4, cudaMemcpyDeviceToHost, stream));
   UTX_CUDA(cudaStreamSynchronize(stream));
   *total = last_off + last_flag;
   return 0;
@@ -478,7 +615,7 @@ size_t uv_bake_workspace_bytes(int H2, int W2) {
   size_t scan_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, static_cast<int*>(nullptr), static_cast<int*>(nullptr), static_cast<int>(T));
   return 6 * al(T) + al(T * 12) * 4 + al(T * 4) * 4 + al(scan_bytes) + al(bvh_nodes_bytes(static_cast<int>(T))) +
-         al(bvh_workspace_bytes(static_cast<int>(T))) + pyr_c + pyr_m + 8192;
+         al(bvh_workspace_bytes(static_cast<int>(T))) + pyr_c + pyr_m + 8192 + 256;
 }
 
 void uv_bake_layout(int H2, int W2, size_t* off_owner, size_t* off_pos, size_t* off_color, size_t* off_seam) {
@@ -511,7 +648,19 @@ int uv_bake_visibility(const float* vert, int V, const int* tri, int F, const vo
   const BakeWs w = carve(workspace, T);
   const unsigned g128 = (T + 127) / 128, g256 = (T + 255) / 256;
   const float4* rast = reinterpret_cast<const float4*>(rast2d);
-  texel_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, nodes, static_cast<const float4*>(nodes) + static_cast<size_t>(2 * F - 1) * 3, vw, images_rgba, H, W, cos_thresh, w.raw, w.aok, w.pos);
+  const float4* wide = reinterpret_cast<const float4*>(static_cast<const uint8_t*>(nodes) + wide_offset_bytes(F));
+  static const bool fused = std::getenv("UTX_BAKE_FUSED_TEXEL") != nullptr;   // the r01 one-kernel form, kept for A/B timing
+  if (fused) {
+    texel_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, nodes, wide, vw, images_rgba, H, W, cos_thresh, w.raw, w.aok, w.pos);
+  } else {
+    // ray lists [n_views][T] live in the region the nearest-neighbour tree / pull-push pyramid use later (160 T bytes >= 32 T)
+    int* lists = reinterpret_cast<int*>(w.rest);
+    UTX_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
+    texel_prep_kernel<<<g128, 128, 0, stream>>>(rast, H2, W2, vert, tri, vw, images_rgba, H, W, cos_thresh, w.raw, w.aok, w.pos,
+                                                lists, w.counters);
+    ray_kernel<<<dim3(g128, n_views), 128, 0, stream>>>(lists, w.counters, T, rast, w.pos, vert, tri, wide, vw,
+                                                        reinterpret_cast<unsigned*>(w.raw));
+  }
   repair3_kernel<<<g256, 256, 0, stream>>>(w.raw, w.rep3, H2, W2);
   repair5_kernel<<<g256, 256, 0, stream>>>(w.rep3, w.rep5, H2, W2, n_views);
   compose_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, vw, images_rgba, H, W, w.rep5, w.aok, mask2d, mask_vis, w.owner, w.col_a);
@@ -529,22 +678,26 @@ int uv_bake_fill(const unsigned char* mask2d, int H2, int W2, int k, int* nn_ind
   UTX_CHECK(k >= 1 && k <= KNN_MAX, "uv_bake_fill: k must be in 1..32");
   const int T = H2 * W2;
   const BakeWs w = carve(workspace, T);
-  const unsigned g128 = (T + 127) / 128, g256 = (T + 255) / 256;
-  nn_flag_kernel<<<g256, 256, 0, stream>>>(w.owner, T, w.flags);
-  int n_pts = 0;
-  UTX_TRY(count_flags(w.flags, w.offs, T, w.scan_tmp, w.scan_bytes, &n_pts, stream));
+  const unsigned g256 = (T + 255) / 256;
+  // query list: T ints over the four visibility byte planes (raw | aok | rep3 | rep5), dead after stage 1
+  int* qlist = reinterpret_cast<int*>(w.raw);
+  int* qcount = w.counters + MAXV;
+  UTX_CUDA(cudaMemsetAsync(qcount, 0, 4, stream));
+  nn_flag_kernel<<<g256, 256, 0, stream>>>(mask2d, w.owner, T, w.flags, nn_index_out, qlist, qcount);
+  int n_pts = 0, n_q = 0;
+  UTX_TRY(count_flags(w.flags, w.offs, T, w.scan_tmp, w.scan_bytes, &n_pts, stream, qcount, &n_q));
+  if (n_q == 0 || n_pts == 0) return 0;
   nn_compact_kernel<<<g256, 256, 0, stream>>>(w.owner, w.offs, w.pos, T, w.ids, w.pts);
-  void* nn_nodes = nullptr;
-  if (n_pts >= 2) {
-    nn_nodes = w.rest;
-    const size_t wsb = bvh_workspace_bytes(n_pts);
-    void* nn_ws = w.rest + al(bvh_nodes_bytes(n_pts));
-    UTX_TRY(point_bvh_build(w.pts, n_pts, nn_nodes, nn_ws, wsb, stream));
-  }
+  void* nn_nodes = w.rest;
+  const size_t wsb = bvh_workspace_bytes(n_pts < 2 ? 2 : n_pts);
+  void* nn_ws = w.rest + al(bvh_nodes_bytes(n_pts < 2 ? 2 : n_pts));
+  UTX_TRY(point_bvh_build(w.pts, w.ids, n_pts, nn_nodes, nn_ws, wsb, stream));
+  const PointTree pt = point_tree_view(nn_nodes, n_pts);
+  const unsigned gq = (n_q + 127) / 128;
   if (k == 1)
-    nn_query_kernel<<<g128, 128, 0, stream>>>(mask2d, w.owner, w.pos, T, nn_nodes, w.pts, w.ids, n_pts, w.col_a, w.col_a, nn_index_out);
+    nn_query_kernel<<<gq, 128, 0, stream>>>(qlist, n_q, w.pos, pt, w.col_a, w.col_a, nn_index_out);
   else
-    knn_mean_kernel<<<g128, 128, 0, stream>>>(mask2d, w.owner, -1, w.pos, T, nn_nodes, w.pts, w.ids, n_pts, k, w.col_a, w.col_a, nn_index_out);
+    knn_mean_kernel<<<gq, 128, 0, stream>>>(mask2d, w.owner, -1, w.pos, T, pt, k, w.col_a, w.col_a, nn_index_out, qlist, n_q);
   UTX_CUDA(cudaGetLastError());
   return 0;
 }
@@ -600,15 +753,15 @@ int uv_bake_views_knn(const float* pix_pos, const float* images_rgba, int n_view
   const unsigned g128 = (T + 127) / 128;
   if (merge) {
     UTX_CHECK(total >= 1, "uv_bake_views_knn: the views hold no visible pixel");
-    if (total >= 2) UTX_TRY(point_bvh_build(pts, total, nodes, tree_ws, tree_ws_bytes, stream));
-    knn_mean_kernel<<<g128, 128, 0, stream>>>(mask2d, w.owner, -2, w.pos, T, nodes, pts, nullptr, total, k, cols, w.col_a, nullptr);
+    UTX_TRY(point_bvh_build(pts, nullptr, total, nodes, tree_ws, tree_ws_bytes, stream));
+    knn_mean_kernel<<<g128, 128, 0, stream>>>(mask2d, w.owner, -2, w.pos, T, point_tree_view(nodes, total), k, cols, w.col_a, nullptr);
   } else {
     for (int v = 0; v < n_views; ++v) {
       const int cnt = start[v + 1] - start[v];
       if (cnt == 0) continue;                              // an empty view owns no texel (ownership needs alpha > 0.999)
       const float* vp = pts + static_cast<size_t>(start[v]) * 3;
-      if (cnt >= 2) UTX_TRY(point_bvh_build(vp, cnt, nodes, tree_ws, tree_ws_bytes, stream));
-      knn_mean_kernel<<<g128, 128, 0, stream>>>(mask2d, w.owner, v, w.pos, T, nodes, vp, nullptr, cnt, k,
+      UTX_TRY(point_bvh_build(vp, nullptr, cnt, nodes, tree_ws, tree_ws_bytes, stream));
+      knn_mean_kernel<<<g128, 128, 0, stream>>>(mask2d, w.owner, v, w.pos, T, point_tree_view(nodes, cnt), k,
                                                 cols + static_cast<size_t>(start[v]) * 3, w.col_a, nullptr);
     }
   }

@@ -96,7 +96,10 @@ size_t bvh_nodes_bytes(int F);
 size_t bvh_workspace_bytes(int F);
 int bvh_build(const float* vert, int V, const int* tri, int F, void* nodes_out, void* workspace, size_t ws_bytes,
               cudaStream_t stream);
-int point_bvh_build(const float* pts, int n, void* nodes_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
+struct PointTree;   // bake_trace.cuh
+int point_bvh_build(const float* pts, const int* ids, int n, void* nodes_out, void* workspace, size_t ws_bytes,
+                    cudaStream_t stream);
+PointTree point_tree_view(const void* nodes, int n);
 int knn1(const float* src, int n_src, const float* dst, long long M, long long* index, float* score, void* nodes, void* workspace,
          size_t ws_bytes, cudaStream_t stream);
 int bvh_export(const void* nodes, int F, int* info, float* aabb, cudaStream_t stream);
