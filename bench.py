@@ -430,7 +430,7 @@ def bench_uv_bake(dev, return_tensors=False):
               filt_gradient_points=False)
     r.infer(mesh, c2ws, intr, img, **kw)
     torch.cuda.synchronize()
-    reps = 3
+    reps = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()

@@ -115,20 +115,37 @@ __device__ __forceinline__ RayHit bvh_trace(const float4* __restrict__ W, const 
     slab_params(o, inv, bb, te, tx);
     if (slab_pass(te, tx, closest)) { sref[0] = __float_as_int(r1.z); ste[0] = te; count = 1; }
   }
-  while (count > 0) {
-    --count;
-    const int ref = sref[count];
-    if (closest < ste[count]) continue;
+  // The entry that would be popped next is kept in registers (cur / cur_te) instead of being pushed and popped straight
+  // away: of a record's passing entries all but the last go to the stack, the last becomes `cur`.  Same order, ~half the
+  // local-memory traffic (the stack was 41 % of the L1 wavefronts of this L1-bound kernel, profiles/r01_bake_ray_nn.ncu-rep).
+  bool have = false;
+  int ref = 0;
+  float cur_te = 0.f;
+  if (count > 0) { have = true; ref = sref[0]; cur_te = ste[0]; count = 0; }
+  for (;;) {
+    if (!have) {
+      if (count == 0) break;
+      --count;
+      ref = sref[count];
+      cur_te = ste[count];
+    }
+    have = false;
+    if (closest < cur_te) continue;
     if (ref >= 0) {
       const WideRec r = wide_load(W, ref);
-      if (count + 4 <= 64) {
+      int pend_ref = 0;
+      float pend_te = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float te, tx;
-          slab_params(o, inv, r.bb + 6 * k, te, tx);
-          if (r.ref[k] != WIDE_EMPTY && slab_pass(te, tx, closest)) { sref[count] = r.ref[k]; ste[count] = te; ++count; }
+      for (int k = 0; k < 4; ++k) {
+        float te, tx;
+        slab_params(o, inv, r.bb + 6 * k, te, tx);
+        if (r.ref[k] != WIDE_EMPTY && slab_pass(te, tx, closest)) {
+          if (have && count < 64) { sref[count] = pend_ref; ste[count] = pend_te; ++count; }
+          pend_ref = r.ref[k]; pend_te = te; have = true;
         }
       }
+      ref = pend_ref;
+      cur_te = pend_te;
     } else {
       const int p = ~ref;
       const float *pa = vert + static_cast<size_t>(tri[p * 3]) * 3, *pb = vert + static_cast<size_t>(tri[p * 3 + 1]) * 3,
@@ -180,7 +197,8 @@ __device__ __forceinline__ float box_dist2(const float* bb, const float* q) {
 // Generic walk: `worst()` = current pruning distance, `offer(d2, id)` = score one point.  Entries carry their bound and are
 // re-checked against worst() when popped; of a record's entries the nearest is pushed last (popped first).
 template <typename Worst, typename Offer>
-__device__ __forceinline__ void point_tree_walk(const PointTree& pt, const float* q, Worst worst, Offer offer) {
+__device__ __forceinline__ void point_tree_walk(const PointTree& pt, const float* q, Worst worst, Offer offer,
+                                                const float* order_q = nullptr) {
   auto leaf = [&](int c) {
     const int j0 = c * PT_CLUSTER, j1 = min(j0 + PT_CLUSTER, pt.n);
     for (int j = j0; j < j1; ++j) {
@@ -193,41 +211,54 @@ __device__ __forceinline__ void point_tree_walk(const PointTree& pt, const float
     if (pt.n > 0) leaf(0);
     return;
   }
+  // `order_q` (default: q itself) decides which entry of a record is visited first; a warp of neighbouring queries passes ONE
+  // common point so that its lanes walk the tree in the same order and stay converged (the result does not depend on the
+  // order).  The entry to visit next stays in registers, the others go to the local-memory stack.
+  const float* oq = order_q ? order_q : q;
   int sn[64];
   float sb[64];
-  int count = 1;
-  sn[0] = 0; sb[0] = 0.f;
-  while (count > 0) {
-    --count;
-    if (sb[count] > worst()) continue;
-    const int ref = sn[count];
+  int count = 0;
+  bool have = true;
+  int ref = 0;
+  float bound = 0.f;
+  for (;;) {
+    if (!have) {
+      if (count == 0) break;
+      --count;
+      ref = sn[count];
+      bound = sb[count];
+    }
+    have = false;
+    if (bound > worst()) continue;
     if (ref < 0) { leaf(~ref); continue; }
     const WideRec r = wide_load(pt.wide, ref);
     float bd[4];
-    int nearest = 0, nref = r.ref[0];
-    float nb = INFINITY;
+    int nearest = 0;
+    float nkey = INFINITY;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      bd[k] = r.ref[k] == WIDE_EMPTY ? INFINITY : box_dist2(r.bb + 6 * k, q) * 0.999999f;   // (an inverted box is not "far" here)
-      if (bd[k] < nb) { nb = bd[k]; nearest = k; nref = r.ref[k]; }
+      const bool used = r.ref[k] != WIDE_EMPTY;                       // (an inverted box is not "far" for box_dist2)
+      bd[k] = used ? box_dist2(r.bb + 6 * k, q) * 0.999999f : INFINITY;
+      const float key = used ? (order_q ? box_dist2(r.bb + 6 * k, oq) : bd[k]) : INFINITY;
+      if (key < nkey) { nkey = key; nearest = k; }
     }
     const float w = worst();
-    if (count + 4 <= 64) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k != nearest && r.ref[k] != WIDE_EMPTY && bd[k] <= w) { sn[count] = r.ref[k]; sb[count] = bd[k]; ++count; }
-      if (nb <= w) { sn[count] = nref; sb[count] = nb; ++count; }
+    for (int k = 0; k < 4; ++k) {
+      if (r.ref[k] == WIDE_EMPTY || !(bd[k] <= w)) continue;
+      if (k == nearest) { have = true; ref = r.ref[k]; bound = bd[k]; }
+      else if (count < 64) { sn[count] = r.ref[k]; sb[count] = bd[k]; ++count; }
     }
   }
 }
 // exact 1-NN: returns the id (-1 when the tree is empty), *best_d2_out = squared distance
-__device__ __forceinline__ int nn_trace(const PointTree& pt, const float* q, float* best_d2_out) {
+__device__ __forceinline__ int nn_trace(const PointTree& pt, const float* q, float* best_d2_out, const float* order_q = nullptr) {
   float best = INFINITY;
   int best_id = -1;
   point_tree_walk(pt, q, [&]() { return best; },
                   [&](float d2, int id) {
                     if (d2 < best || (d2 == best && id < best_id) || best_id < 0) { best = d2; best_id = id; }
-                  });
+                  }, order_q);
   if (best_d2_out) *best_d2_out = best;
   return best_id;
 }

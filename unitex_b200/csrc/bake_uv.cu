@@ -2,23 +2,27 @@
 // (TextureTools/texturetools/render/nvdiffrast/renderer_inverse.py:243-365, 574-633) without the per-view
 // [n, H2D, W2D, *] rays / ndc / colour tensors and the ~40 masked_select / masked_scatter compactions of the reference.
 //
-//   texel pass      per covered texel: position + face normal from the UV raster, then per view: orthographic ray,
-//                   ray/normal angle test, projected bilinear fetch of (rgb, alpha), LBVH closest-hit, `tid == raster tid`
-//                   -> one visibility bit and one alpha bit per view                                   (:277-325, :343)
+//   texel pass      per covered texel: position + face normal from the UV raster, then per view: ray/normal angle test and
+//                   projected bilinear fetch of alpha (texel_prep_kernel, which also appends the texel to the ray list of every
+//                   view it faces); then one thread per listed ray: orthographic ray, LBVH closest hit, `tid == raster tid`
+//                   (ray_kernel) -> one visibility bit and one alpha bit per view                      (:277-325, :343)
 //   repair          the "misjudgment repair" convolutions as exact integer stencils on the 6-bit planes: k=3 ORs in a
 //                   texel when any 8-neighbour is visible, k=5 when >= 6 of the 16 ring texels are      (:329-339)
 //   compose         and-with-coverage/alpha, first-visible-view-wins in priority order, winning colour re-fetched (:591-603)
 //   seam mask       3x3 boundary of every view's claim = "a 3x3 neighbour has a different owner", dilated 3x3, kept where
 //                   the 7x7 erosion of the chart mask holds                                              (:435-444, :603-605)
-//   nn fill         invisible covered texels take the colour of the 3-D nearest visible texel (exact 1-NN, uniform grid,
-//                   lowest index on ties)                                                                (:606-615)
+//   nn fill         invisible covered texels take the colour of the 3-D nearest visible texel (exact 1-NN through the clustered
+//                   point tree of bake_trace.cuh, lowest index on ties; queries compacted into a tile-ordered list) (:606-615)
 //   lens blur       7x7 effective kernel of the 5-component complex separable blur, evaluated ONLY on seam texels
 //                   (image/lens_blur.py:260-280; the reference blurs the whole atlas, then keeps seam texels) (:621-624)
 //   pull-push       alpha-weighted 2x2 pyramid + bilinear up-fill of texels outside the charts (texture/stitching/mip.py:51-96)
-// HBM-bound by contract: one thread per texel, row-major so a warp reads/writes 32 consecutive texels.
+// HBM-bound by contract for the streaming stages: one thread per texel, row-major so a warp reads/writes 32
+// consecutive texels; the two tree walks (rays, nearest neighbour) run over compacted, tile-ordered work lists.
 // Built with -fmad=false.
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -80,68 +84,14 @@ __device__ __forceinline__ void texel_ndc(const float* m, const float* p0, const
   *gy = (u * ny[0] + v * ny[1]) + w * ny[2];
 }
 
-__global__ void __launch_bounds__(128) texel_kernel(const float4* __restrict__ rast, int T, const float* __restrict__ vert,
-                                                    const int* __restrict__ tri, const void* __restrict__ nodes,
-                                                    const float4* __restrict__ wide /* traversal layout, bake_trace.cuh */, const Views vw, const float* __restrict__ images /*[n,H,W,4] rgba*/,
-                                                    int H, int W, float cos_thresh, unsigned char* __restrict__ raw_vis,
-                                                    unsigned char* __restrict__ alpha_ok, float* __restrict__ pos_out) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  const float4 r = rast[t];
-  const int f = static_cast<int>(r.w) - 1;
-  if (f < 0) {
-    raw_vis[t] = 0;
-    alpha_ok[t] = 0;
-    pos_out[t * 3] = pos_out[t * 3 + 1] = pos_out[t * 3 + 2] = 0.f;
-    return;
-  }
-  const float *p0 = vert + static_cast<size_t>(tri[f * 3]) * 3, *p1 = vert + static_cast<size_t>(tri[f * 3 + 1]) * 3,
-              *p2 = vert + static_cast<size_t>(tri[f * 3 + 2]) * 3;
-  const float u = r.x, v = r.y, w = (1.0f - u) - v;
-  float pos[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) pos[a] = (u * p0[a] + v * p1[a]) + w * p2[a];
-  pos_out[t * 3] = pos[0]; pos_out[t * 3 + 1] = pos[1]; pos_out[t * 3 + 2] = pos[2];
-  // face normal = normalize(cross(v1 - v0, v2 - v0))   (structure_v2.py:49-50; F.normalize eps 1e-12)
-  const float e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, e2[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
-  float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-  const float nl = fmaxf(norm3(n[0], n[1], n[2]), 1e-12f);
-  n[0] = n[0] / nl; n[1] = n[1] / nl; n[2] = n[2] / nl;
-  const float nn = fmaxf(norm3(n[0], n[1], n[2]), 1e-8f);
-  unsigned vis = 0, aok = 0;
-  const float k2s3 = 3.4641016151377544f;   // float32(2 * sqrt(3)), renderer_inverse.py:284
-  for (int i = 0; i < vw.n; ++i) {
-    const float* dr = vw.dir[i];
-    const float o[3] = {pos[0] - k2s3 * dr[0], pos[1] - k2s3 * dr[1], pos[2] - k2s3 * dr[2]};
-    const float dl = fmaxf(norm3(dr[0], dr[1], dr[2]), 1e-12f);
-    float d[3] = {dr[0] / dl, dr[1] / dl, dr[2] / dl};                  // F.normalize (:285)
-    // cosine_similarity(d, n) with torch's normalise-first formulation, eps 1e-8
-    const float dn = fmaxf(norm3(d[0], d[1], d[2]), 1e-8f);
-    const float cosv = ((d[0] / dn) * (n[0] / nn) + (d[1] / dn) * (n[1] / nn)) + (d[2] / dn) * (n[2] / nn);
-    float gx, gy;
-    texel_ndc(vw.mat[i], p0, p1, p2, u, v, &gx, &gy);
-    float rgba[4];
-    bilinear<4>(images + static_cast<size_t>(i) * H * W * 4, H, W, gx, gy, rgba);
-    if (rgba[3] > 0.999f) aok |= 1u << i;
-    if (cosv < cos_thresh) {
-      const float len = norm3(d[0], d[1], d[2]);                        // the tracer normalises again (intersect_test2.slang:283)
-      d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
-      const RayHit h = bvh_trace(wide, vert, tri, o, d);
-      if (h.any && h.tid == f) vis |= 1u << i;
-    }
-  }
-  raw_vis[t] = static_cast<unsigned char>(vis);
-  alpha_ok[t] = static_cast<unsigned char>(aok);
-}
-
-// ---- the same texel pass split in two so that the ray tracing runs on DENSE, coherent warps -----------------------
-// texel_prep_kernel: everything of texel_kernel except the trace; a texel that faces view i (the angle test) appends itself
-// to view i's ray list.  Threads map to texels in 16x8 tiles (one 8x4 sub-tile per warp) and every block appends its rays
+// ---- texel pass, in two kernels so that the ray tracing runs on DENSE, coherent warps ------------------------------
+// texel_prep_kernel: position + face normal from the UV raster, then per view the angle test and the projected bilinear fetch of
+// alpha; a texel that faces view i (the angle test) appends itself to view i's ray list.  Threads map to texels in 16x8 tiles (one 8x4 sub-tile per warp) and every block appends its rays
 // with ONE atomicAdd per view, so a list is a sequence of per-tile runs: 32 consecutive entries are rays of one direction
 // through neighbouring texels.  ray_kernel walks the lists, one thread per ray, and ORs the view's bit into raw_vis.
-// The per-ray arithmetic is texel_kernel's, so the bits are identical; only the order in which rays run differs (the
-// block order inside a list depends on the atomics, the result does not).  In the fused kernel 15 of 32 lanes were active on
-// average (profiles/r01_texel_kernel.metrics.csv): lanes not facing the view idled through every trace.
+// Only the order in which rays run depends on the atomics, the result does not (checked bit for bit against the one-kernel
+// form of r01, where 15 of 32 lanes were active on average -- profiles/r01_texel_kernel.metrics.csv -- because lanes not facing
+// the view idled through every trace).
 __device__ __forceinline__ int tile_texel(int H2, int W2, int block, int thread) {
   if (W2 < 16 || H2 < 8) return block * 128 + thread;
   const int tiles_x = W2 >> 4, ty = block / tiles_x, tx = block - ty * tiles_x;
@@ -349,10 +299,11 @@ __global__ void __launch_bounds__(256) seam1_kernel(const unsigned char* __restr
 __global__ void __launch_bounds__(256) nn_flag_kernel(const unsigned char* __restrict__ mask2d,
                                                       const signed char* __restrict__ owner, int T, int* __restrict__ flags,
                                                       int* __restrict__ nn_index, int* __restrict__ qlist,
-                                                      int* __restrict__ qcount) {
+                                                      int* __restrict__ qcount, int H2, int W2) {
   __shared__ int wcount[8];
   __shared__ int base;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  // 16x8 texel tiles, one 8x4 sub-tile per warp (as in texel_prep_kernel): 32 consecutive queries are spatial neighbours
+  const int t = tile_texel(H2, W2, blockIdx.x * 2 + (threadIdx.x >> 7), threadIdx.x & 127);
   bool query = false;
   if (t < T) {
     const int o = owner[t];
@@ -389,12 +340,22 @@ __global__ void __launch_bounds__(256) nn_compact_kernel(const signed char* __re
 }
 __global__ void __launch_bounds__(128) nn_query_kernel(const int* __restrict__ qlist, int n_q, const float* __restrict__ pos,
                                                        const PointTree pt, const float* color_in, float* color_out,
-                                                       int* __restrict__ nn_index) {
+                                                       int* __restrict__ nn_index, int W2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_q) return;
   const int t = qlist[i];
   const float q[3] = {pos[static_cast<size_t>(t) * 3], pos[static_cast<size_t>(t) * 3 + 1], pos[static_cast<size_t>(t) * 3 + 2]};
-  const int best = nn_trace(pt, q, nullptr);
+  // When the warp's queries are neighbours (texels within 16 rows / columns of the first live lane's) its lanes order their
+  // walks by ONE common point (that lane's query) and so stay converged: 2.86 -> 2.52 ms on the bench bake.  Applied to every
+  // warp it doubles the time (5.4 ms): lanes far from the common point descend into the wrong subtree first.
+  const unsigned live = __activemask();
+  const int lead = __ffs(live) - 1;
+  const float oq[3] = {__shfl_sync(live, q[0], lead), __shfl_sync(live, q[1], lead), __shfl_sync(live, q[2], lead)};
+  const int tl = __shfl_sync(live, t, lead);
+  const int dy = t / W2 - tl / W2, dx = t % W2 - tl % W2;
+  const bool near_lead = dy > -16 && dy < 16 && dx > -16 && dx < 16;
+  const bool common = __all_sync(live, near_lead);
+  const int best = nn_trace(pt, q, nullptr, common ? oq : nullptr);
   if (nn_index) nn_index[t] = best;
   if (best >= 0) {
     color_out[t * 3] = color_in[static_cast<size_t>(best) * 3];
@@ -649,18 +610,13 @@ int uv_bake_visibility(const float* vert, int V, const int* tri, int F, const vo
   const unsigned g128 = (T + 127) / 128, g256 = (T + 255) / 256;
   const float4* rast = reinterpret_cast<const float4*>(rast2d);
   const float4* wide = reinterpret_cast<const float4*>(static_cast<const uint8_t*>(nodes) + wide_offset_bytes(F));
-  static const bool fused = std::getenv("UTX_BAKE_FUSED_TEXEL") != nullptr;   // the r01 one-kernel form, kept for A/B timing
-  if (fused) {
-    texel_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, nodes, wide, vw, images_rgba, H, W, cos_thresh, w.raw, w.aok, w.pos);
-  } else {
-    // ray lists [n_views][T] live in the region the nearest-neighbour tree / pull-push pyramid use later (160 T bytes >= 32 T)
-    int* lists = reinterpret_cast<int*>(w.rest);
-    UTX_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
-    texel_prep_kernel<<<g128, 128, 0, stream>>>(rast, H2, W2, vert, tri, vw, images_rgba, H, W, cos_thresh, w.raw, w.aok, w.pos,
-                                                lists, w.counters);
-    ray_kernel<<<dim3(g128, n_views), 128, 0, stream>>>(lists, w.counters, T, rast, w.pos, vert, tri, wide, vw,
-                                                        reinterpret_cast<unsigned*>(w.raw));
-  }
+  // ray lists [n_views][T] live in the region the nearest-neighbour tree / pull-push pyramid use later (>= 160 T bytes >= 32 T)
+  int* lists = reinterpret_cast<int*>(w.rest);
+  UTX_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
+  texel_prep_kernel<<<g128, 128, 0, stream>>>(rast, H2, W2, vert, tri, vw, images_rgba, H, W, cos_thresh, w.raw, w.aok, w.pos,
+                                              lists, w.counters);
+  ray_kernel<<<dim3(g128, n_views), 128, 0, stream>>>(lists, w.counters, T, rast, w.pos, vert, tri, wide, vw,
+                                                      reinterpret_cast<unsigned*>(w.raw));
   repair3_kernel<<<g256, 256, 0, stream>>>(w.raw, w.rep3, H2, W2);
   repair5_kernel<<<g256, 256, 0, stream>>>(w.rep3, w.rep5, H2, W2, n_views);
   compose_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, vw, images_rgba, H, W, w.rep5, w.aok, mask2d, mask_vis, w.owner, w.col_a);
@@ -683,7 +639,7 @@ int uv_bake_fill(const unsigned char* mask2d, int H2, int W2, int k, int* nn_ind
   int* qlist = reinterpret_cast<int*>(w.raw);
   int* qcount = w.counters + MAXV;
   UTX_CUDA(cudaMemsetAsync(qcount, 0, 4, stream));
-  nn_flag_kernel<<<g256, 256, 0, stream>>>(mask2d, w.owner, T, w.flags, nn_index_out, qlist, qcount);
+  nn_flag_kernel<<<g256, 256, 0, stream>>>(mask2d, w.owner, T, w.flags, nn_index_out, qlist, qcount, H2, W2);
   int n_pts = 0, n_q = 0;
   UTX_TRY(count_flags(w.flags, w.offs, T, w.scan_tmp, w.scan_bytes, &n_pts, stream, qcount, &n_q));
   if (n_q == 0 || n_pts == 0) return 0;
@@ -695,7 +651,7 @@ int uv_bake_fill(const unsigned char* mask2d, int H2, int W2, int k, int* nn_ind
   const PointTree pt = point_tree_view(nn_nodes, n_pts);
   const unsigned gq = (n_q + 127) / 128;
   if (k == 1)
-    nn_query_kernel<<<gq, 128, 0, stream>>>(qlist, n_q, w.pos, pt, w.col_a, w.col_a, nn_index_out);
+    nn_query_kernel<<<gq, 128, 0, stream>>>(qlist, n_q, w.pos, pt, w.col_a, w.col_a, nn_index_out, W2);
   else
     knn_mean_kernel<<<gq, 128, 0, stream>>>(mask2d, w.owner, -1, w.pos, T, pt, k, w.col_a, w.col_a, nn_index_out, qlist, n_q);
   UTX_CUDA(cudaGetLastError());
