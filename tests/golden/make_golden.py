@@ -47,7 +47,25 @@ def bake():
                         lbvh_info=info, rast_mv_id=rast[..., 3].astype(np.int32))
 
 
+def bake_kdtree():
+    """bake_mv_to_uv_kdtree (`order_mean`, k = 9 visible / 32 invisible) on the same case + a k-NN table."""
+    from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics
+    z = np.load(os.path.join(HERE, "bake_two_spheres.npz"))
+    v, f, uv, fuv = two_spheres(10, 20)
+    c2ws = generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]]
+    intr = generate_intrinsics(1.0, 1.0, fov=False)
+    out = ob.infer(v, f, uv, fuv, c2ws, intr, torch.from_numpy(z["image"]), 48, 48, 64, 64, method="kdtree",
+                   kdtree_method="order_mean", k_vis=9, k_invis=32)
+    g = torch.Generator().manual_seed(5)
+    src, dst = torch.rand(500, 3, generator=g), torch.rand(64, 3, generator=g)
+    src[17] = src[3]
+    dist, idx = ob.nearest_k(src, dst, 8)
+    np.savez_compressed(os.path.join(HERE, "bake_kdtree.npz"), color_2d=out["color_2d"].numpy().astype(np.float16),
+                        knn_src=src.numpy(), knn_dst=dst.numpy(), knn_index=idx.numpy().astype(np.int32), knn_dist=dist.numpy())
+
+
 if __name__ == "__main__":
     dit()
     bake()
+    bake_kdtree()
     print(sorted(os.listdir(HERE)))

@@ -36,3 +36,16 @@ def test_bake_golden_integers_exact():
     assert np.abs(out["color_2d"].numpy() - z["color_2d"].astype(np.float32)).max() < 2e-3
     info, _, _ = ob.lbvh_build(v, f)
     assert np.array_equal(info, z["lbvh_info"])
+
+
+def test_bake_kdtree_golden():
+    from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics
+    z, zk = np.load(os.path.join(G, "bake_two_spheres.npz")), np.load(os.path.join(G, "bake_kdtree.npz"))
+    v, f, uv, fuv = two_spheres(10, 20)
+    c2ws = generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]]
+    intr = generate_intrinsics(1.0, 1.0, fov=False)
+    out = ob.infer(v, f, uv, fuv, c2ws, intr, torch.from_numpy(z["image"]), 48, 48, 64, 64, method="kdtree",
+                   kdtree_method="order_mean", k_vis=9, k_invis=32)
+    assert np.abs(out["color_2d"].numpy() - zk["color_2d"].astype(np.float32)).max() < 2e-3
+    dist, idx = ob.nearest_k(torch.from_numpy(zk["knn_src"]), torch.from_numpy(zk["knn_dst"]), 8)
+    assert np.array_equal(idx.numpy().astype(np.int32), zk["knn_index"]) and np.array_equal(dist.numpy(), zk["knn_dist"])

@@ -228,3 +228,22 @@ def test_uv_bake_query_field_hook(lib, method, kdtree_method):
     assert torch.equal(vis.cpu(), ref["mask_2d_visiable"])
     err = (col.cpu() - ref["color_2d"]).abs()
     assert err.max().item() < COLOR_ATOL, err.max().item()
+
+
+def test_kdtree_bake_matches_committed_golden(lib):
+    """CUDA path vs tests/golden/bake_kdtree.npz: k-NN indices and distances exact, kdtree-baked colours within fp16 storage."""
+    import os
+    from unitex_b200 import bake as ub
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    z, zk = np.load(os.path.join(G, "bake_two_spheres.npz")), np.load(os.path.join(G, "bake_kdtree.npz"))
+    score, index = ub.knn(torch.from_numpy(zk["knn_src"]), torch.from_numpy(zk["knn_dst"]), k=8)
+    assert np.array_equal(index.cpu().numpy().astype(np.int32), zk["knn_index"])
+    assert np.array_equal(score.cpu().numpy(), zk["knn_dist"])
+    v, f, uv, fuv = two_spheres(10, 20)
+    c2ws, intr = _views()
+    r = ub.NVDiffRendererInverse(pbr_mesh=ub.BakeMesh(v, f, uv, fuv))
+    _, _, _, col = r.infer(r.pbr_mesh, c2ws, intr, torch.from_numpy(z["image"]), H=48, W=48, H2D=64, W2D=64, perspective=False,
+                           ray_normal_angle_threhold=100.0, method="kdtree", kdtree_n_neighbors_visiable=9,
+                           kdtree_n_neighbors_invisiable=32, filt_gradient_points=False)
+    torch.cuda.synchronize()
+    assert np.abs(col.cpu().numpy() - zk["color_2d"].astype(np.float32)).max() < 2e-3
