@@ -122,11 +122,14 @@ def lens_blur_torch(img: torch.Tensor, radius: float = 3.0, exposure_gamma: floa
         k.real = torch.exp(-a * ax ** 2) * torch.cos(b * ax ** 2)
         k.imag = torch.exp(-a * ax ** 2) * torch.sin(b * ax ** 2)
         comps.append(k.reshape(1, size))
-    total = 0.0
+    total = 0.0                                     # :109-121 -- the reference's sequential fp32 accumulation order, kept
     for k, (_, _, A, B) in zip(comps, params):
-        kr, ki = k[0].real, k[0].imag
-        total = total + (A * (kr[:, None] * kr[None] - ki[:, None] * ki[None]) + B * (kr[:, None] * ki[None] + ki[:, None] * kr[None])).sum()
-    comps = [k / total.sqrt() for k in comps]
+        for i in range(size):
+            for j in range(size):
+                total += A * (k[0, i].real * k[0, j].real - k[0, i].imag * k[0, j].imag) + \
+                         B * (k[0, i].real * k[0, j].imag + k[0, i].imag * k[0, j].real)
+    total = total.sqrt()
+    comps = [k / total for k in comps]
     img = torch.pow(img, exposure_gamma)
     Cn = img.shape[1]
     acc = 0.0

@@ -28,9 +28,9 @@ def calculate_shift(image_seq_len, base_seq_len=256, max_seq_len=4096, base_shif
 def flow_match_sigmas(num_steps: int, image_seq_len: int) -> np.ndarray:
     """sigmas = linspace(1, 1/N, N) (:594) -> time shift exp(mu)/(exp(mu)+(1/s-1)) [ext
     set_timesteps, use_dynamic_shifting] -> float32, with the terminal 0 appended."""
-    sig = np.linspace(1.0, 1.0 / num_steps, num_steps)
+    sig = np.linspace(1.0, 1.0 / num_steps, num_steps).astype(np.float32)     # [ext] set_timesteps: np.array(sigmas).astype(np.float32)
     mu = calculate_shift(image_seq_len)
-    sig = math.exp(mu) / (math.exp(mu) + (1.0 / sig - 1.0))
+    sig = math.exp(mu) / (math.exp(mu) + (1 / sig - 1) ** 1.0)                # [ext] time_shift(mu, 1.0, sigmas): evaluated in fp32
     return np.concatenate([sig.astype(np.float32), np.zeros(1, np.float32)])
 
 
@@ -73,8 +73,13 @@ def build_ids(HL: int, WL: int, control_hw=None, dual_hw=None, dtype=torch.float
 
 
 def euler_step(latents: torch.Tensor, v: torch.Tensor, sigma: float, sigma_next: float) -> torch.Tensor:
-    """FlowMatchEulerDiscreteScheduler.step [ext]: fp32 x + (s' - s) v, cast to v.dtype."""
-    x = latents.to(torch.float32) + (np.float32(sigma_next) - np.float32(sigma)) * v.to(torch.float32)
+    """FlowMatchEulerDiscreteScheduler.step [ext]: `sample.float() + (sigma_next - sigma) * model_output`, cast to
+    model_output.dtype.  The sigmas are 0-dim fp32 tensors there, so by torch's promotion rules the product
+    `(sigma_next - sigma) * model_output` is formed in model_output's dtype: with the bf16 transformer of the reference the
+    sigma difference is cast to bf16, multiplied, and the increment rounded to bf16 BEFORE the fp32 add.  Kept (0-dim tensors
+    here too), so an fp32 `v` sees no extra rounding."""
+    dt = torch.tensor(np.float32(sigma_next)) - torch.tensor(np.float32(sigma))
+    x = latents.to(torch.float32) + dt.to(v.device) * v
     return x.to(v.dtype)
 
 
@@ -152,3 +157,38 @@ def psnr(x: torch.Tensor, ref: torch.Tensor) -> float:
     if mse == 0:
         return float("inf")
     return 10.0 * math.log10(peak * peak / mse)
+
+
+@torch.no_grad()
+def pipeline_call(P, cfg: FluxConfig, VP, vcfg, control_image, dual_image, height: int, width: int, num_steps: int,
+                  generator: torch.Generator, guidance_scale: float = 3.5, S_txt: int = 512, output_type: str = "latent"):
+    """`PBRFluxPipeline.__call__` :502-700 from PIL images, with the VAE on both ends (pinned against the reference's own
+    `__call__` by tests/golden/ref_flux_call.npz).  Order of generator draws: noise (:292), dual sample (:308), control
+    sample (:364).  `control_image` / `dual_image`: PIL (sizes multiples of 16) or None.  P / VP in the run dtype (the
+    reference runs everything in bf16: pipeline.py:102)."""
+    from . import vae as ov
+    dt = P["x_embedder.weight"].dtype
+
+    def prep(img):                                   # VaeImageProcessor.preprocess [ext]: uint8 -> [-1, 1], no resize (:301, :357)
+        a = torch.from_numpy(np.asarray(img.convert("RGB")).astype(np.float32) / 255.0)
+        return (a.permute(2, 0, 1)[None] * 2.0 - 1.0).to(dt)
+
+    def encode(img):                                 # _encode_vae_image :226-238
+        mean, logvar = ov.encode_moments(VP, vcfg, prep(img))
+        z = ov.sample(mean, logvar, torch.randn(mean.shape, generator=generator, dtype=mean.dtype))
+        return ((z - vcfg.shift_factor) * vcfg.scaling_factor).to(dt)
+
+    HL, WL = 2 * (height // 16), 2 * (width // 16)
+    noise = pack_latents(torch.randn((1, 16, HL, WL), generator=generator, dtype=dt))
+    dual = encode(dual_image) if dual_image is not None else None
+    control = encode(control_image) if control_image is not None else None
+    cond = [pack_latents(z) for z in (control, dual) if z is not None]                       # condition = cat[control, dual] :575-577
+    ids = build_ids(HL, WL, tuple(control.shape[-2:]) if control is not None else None,
+                    tuple(dual.shape[-2:]) if dual is not None else None, dtype=dt)
+    lat = denoise(P, cfg, noise, torch.cat(cond, 1) if cond else None, ids, num_steps, guidance_scale, S_txt)
+    if output_type == "latent":
+        return lat
+    z = unpack_latents(lat, height, width) / vcfg.scaling_factor + vcfg.shift_factor         # :688-689
+    img = ov.decode(VP, vcfg, z.to(dt))
+    img = (img.float() / 2 + 0.5).clamp(0, 1)                                                # VaeImageProcessor.postprocess [ext]
+    return (img.permute(0, 2, 3, 1).numpy() * 255).round().astype("uint8")

@@ -1,0 +1,221 @@
+"""Golden fixtures produced by the REFERENCE'S OWN Python, run in the build container through `ref_harness.py`
+(absent third-party packages stubbed; their arithmetic supplied by the oracle's restatements -- see the harness header
+for exactly what is real and what is substituted).       python tests/golden/make_reference_golden.py
+
+Writes tests/golden/ref_*.npz.  tests/test_reference_golden_cpu.py pins the oracle against them (bit-exact where the code
+path is torch on both sides); tests/test_gpu_reference_golden.py compares the CUDA path with them on the GPU box.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+import ref_harness as rh                                      # noqa: E402
+from oracle import flux_dit as fd                             # noqa: E402
+from oracle import vae as ov                                  # noqa: E402
+from tests.bake_meshes import two_spheres                     # noqa: E402
+
+
+def bake():
+    """NVDiffRendererInverse.infer (renderer_inverse.py:635-726) -- the reference class, its PBRMesh / PointCloud / knn /
+    pull_push / lens_blur_torch / camera code -- on the two-sphere case of bake_two_spheres.npz, every variant the path has."""
+    ri = rh.texturetools()
+    from texturetools.camera.conversion import c2w_to_w2c, intr_to_proj
+    from texturetools.camera.generator import generate_box_views_c2ws, generate_intrinsics
+    from texturetools.image.lens_blur import lens_blur_torch
+    from texturetools.mesh.structure_v2 import PBRMesh
+    from texturetools.pcd.knn import knn
+    from texturetools.texture.stitching.mip import pull_push
+
+    v, f, uv, fuv = two_spheres(10, 20)
+    z = np.load(os.path.join(HERE, "bake_two_spheres.npz"))
+    img = torch.from_numpy(z["image"])
+    c2ws_all = generate_box_views_c2ws(radius=2.8)                       # generator.py:153-185
+    c2ws = c2ws_all[[0, 1, 4, 2, 3, 5]]
+    intr = generate_intrinsics(1.0, 1.0, fov=False)                      # generator.py:93-114
+    out = {"c2ws_all": c2ws_all.numpy(), "intrinsics": intr.numpy(),
+           "proj": intr_to_proj(intr, perspective=False).numpy(), "w2c": c2w_to_w2c(c2ws).numpy()}
+    mesh = PBRMesh(torch.from_numpy(v), torch.from_numpy(f).long(), torch.from_numpy(uv), torch.from_numpy(fuv).long())
+    out["face_normals"] = mesh.normals.numpy()
+    out["vertex_normals"] = mesh.vertex_normals.numpy()                  # structure_v2.py:63-71
+    r = ri.NVDiffRendererInverse(device="cpu", pbr_mesh=mesh)
+    common = dict(H=48, W=48, H2D=64, W2D=64, perspective=False, ray_normal_angle_threhold=100.0, filt_gradient_points=False)
+
+    def field(vertices_visiable, colors_visiable, vertices_invisiable):  # register_query_field contract :93-103
+        field.calls.append((vertices_visiable.clone(), colors_visiable.clone(), vertices_invisiable.clone()))
+        return 0.25 + 0.5 * torch.sigmoid(vertices_invisiable * 3.0)
+    field.calls = []
+
+    variants = {
+        "reproject": dict(method="reproject"),
+        "kdtree_order_mean": dict(method="kdtree", kdtree_method="order_mean", kdtree_n_neighbors_visiable=9, kdtree_n_neighbors_invisiable=32),
+        "kdtree_mean": dict(method="kdtree", kdtree_method="mean", kdtree_n_neighbors=32),
+        "reproject_inpaint": dict(method="reproject", reproject_inpainting=True),
+        "kdtree_inpaint": dict(method="kdtree", kdtree_method="order_mean", kdtree_n_neighbors_visiable=9, kdtree_inpainting=True),
+    }
+    r.register_query_field(field)
+    for name, kw in variants.items():
+        _, vis, m2d, col = r.infer(None, c2ws, intr, img, **common, **kw)
+        out[f"{name}.color_2d"] = col.numpy()
+        if name == "reproject":
+            out["mask_2d_visiable"] = np.packbits(vis.numpy())
+            out["mask_2d"] = np.packbits(m2d.numpy())
+    out["field.n_visible"] = np.array([c[0].shape[0] for c in field.calls])
+    out["field.query_sum"] = np.stack([c[2].double().sum(0).numpy() for c in field.calls])
+    # mv_to_pcd as the shipped path calls it (filt_gradient_points=False, pipeline.py:343-347)
+    mv0 = r.mv_to_pcd(c2ws, intr, (48, 48), image_attrs=img, perspective=False, filt_gradient_points=False)
+    out["mv.alpha_visiable"] = np.packbits(mv0["alpha_visiable"].numpy() > 0)
+
+    # function-level vectors (pure torch in the reference, no stand-ins involved)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(1, 3, 40, 56, generator=g)
+    m = torch.rand(1, 1, 40, 56, generator=g) > 0.6
+    out["fn.x"], out["fn.mask"] = x.numpy(), m.numpy()
+    out["fn.lens_blur"] = lens_blur_torch(x).numpy()                     # image/lens_blur.py:260-280
+    kd, km = pull_push(x * m, m)                                         # texture/stitching/mip.py:51-96
+    out["fn.pull_push"], out["fn.pull_push_mask"] = kd.numpy(), km.numpy()
+    mb = torch.rand(2, 24, 24, 1, generator=g) > 0.5
+    out["fn.bmask_in"] = mb.numpy()
+    out["fn.bmask"] = r.get_boundary_mask(mb, kernel_size=3).numpy()     # renderer_inverse.py:435-444
+    src, dst = torch.rand(300, 3, generator=g), torch.rand(40, 3, generator=g)
+    score, index = knn(src, dst, k=4)                                    # pcd/knn/__init__.py:104-114 (wrapper real, tree [ext])
+    out["fn.knn_src"], out["fn.knn_dst"], out["fn.knn_index"] = src.numpy(), dst.numpy(), index.numpy().astype(np.int32)
+    np.savez_compressed(os.path.join(HERE, "ref_bake.npz"), **{k: (a.astype(np.float32) if a.dtype == np.float64 and not k.startswith("field") else a)
+                                                               for k, a in out.items()})
+    return out
+
+
+class _Dist:
+    """DiagonalGaussianDistribution [ext]: sample = mean + std * randn_tensor(mean.shape, generator, dtype=mean.dtype)."""
+    def __init__(self, mean, logvar):
+        self.mean, self.logvar = mean, logvar
+
+    def sample(self, generator=None):
+        from diffusers.utils.torch_utils import randn_tensor
+        n = randn_tensor(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return ov.sample(self.mean, self.logvar, n)
+
+
+def flux_inputs():
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    yy, xx = np.mgrid[0:128, 0:128]
+    base = np.stack([127 + 100 * np.sin(xx / 9.0), 127 + 100 * np.cos(yy / 7.0), 127 + 90 * np.sin((xx + yy) / 11.0)], -1)
+    ctrl = np.clip(base + rng.normal(0, 6, base.shape), 0, 255).astype(np.uint8)
+    dual = np.clip(base[::2, ::2][:, ::-1] + rng.normal(0, 6, (64, 64, 3)), 0, 255).astype(np.uint8)
+    return Image.fromarray(ctrl), Image.fromarray(dual)
+
+
+FLUX_CFG = dict(num_layers=1, num_single_layers=1, num_attention_heads=2)     # text widths stay 4096 / 768: the reference hard-codes them (:538-543)
+FLUX_SEED, VAE_SEED, S_TXT, STEPS = 21, 5, 128, 3
+
+
+def flux_weights():
+    cfg = fd.FluxConfig(**FLUX_CFG)
+    P = {k: v.to(torch.bfloat16) for k, v in fd.init_params(cfg, FLUX_SEED, norm_weight_std=0.1).items()}
+    vcfg = ov.VaeConfig.tiny()
+    VP = {k: v.to(torch.bfloat16) for k, v in ov.init_params(vcfg, VAE_SEED).items()}
+    return cfg, P, vcfg, VP
+
+
+def flux():
+    """PBRFluxPipeline.__call__ (flux_piplines/{texturing,delight}/pipeline.py:404-700) -- the reference's class, its __init__,
+    prepare_latents_and_image_ids, pack / unpack / ids, calculate_shift, retrieve_timesteps and the condition-token loop --
+    around bf16 eager stand-ins for the diffusers modules (tiny FLUX: 1+1 blocks, 2 heads; tiny VAE)."""
+    from diffusers.schedulers.scheduling_flow_match_euler_discrete import FlowMatchEulerDiscreteScheduler
+    cfg, P, vcfg, VP = flux_weights()
+    ctrl, dual = flux_inputs()
+
+    class Vae:
+        config = rh._Cfg(latent_channels=vcfg.latent_channels, block_out_channels=vcfg.block_out_channels,
+                         scaling_factor=vcfg.scaling_factor, shift_factor=vcfg.shift_factor)
+        dtype, device = torch.bfloat16, torch.device("cpu")
+
+        def encode(self, image):
+            return types.SimpleNamespace(latent_dist=_Dist(*ov.encode_moments(VP, vcfg, image)))
+
+        def decode(self, z, return_dict=False):
+            return (ov.decode(VP, vcfg, z),)
+
+    class Transformer:
+        config = rh._Cfg(guidance_embeds=True)
+        calls = []
+
+        def __call__(self, hidden_states, timestep, guidance, pooled_projections, encoder_hidden_states, txt_ids, img_ids,
+                     joint_attention_kwargs=None, return_dict=False):
+            self.calls.append(dict(timestep=timestep.clone(), hidden=hidden_states.clone(), img_ids=img_ids.clone(), txt_ids=txt_ids.clone()))
+            return (fd.flux_forward(P, cfg, hidden_states, timestep, guidance, pooled_projections, encoder_hidden_states, txt_ids, img_ids),)
+
+    out = {"control_image": np.asarray(ctrl), "dual_image": np.asarray(dual)}
+    for task, use_dual in (("texturing", True), ("delight", False)):
+        mod = rh.flux(task)
+        tr = Transformer()
+        tr.calls = []
+        pipe = mod.PBRFluxPipeline(FlowMatchEulerDiscreteScheduler(), Vae(), None, None, None, None, tr)
+        kw = dict(prompt="[MVFLUX]", control_image=ctrl, dual_image=dual if use_dual else None, height=128, width=128, n_rows=1, n_cols=1,
+                  num_inference_steps=STEPS, guidance_scale=3.5, max_sequence_length=S_TXT)
+        lat = pipe(**kw, generator=torch.Generator().manual_seed(63), output_type="latent").images
+        n_tok = tr.calls[0]["hidden"].shape[1]
+        out[f"{task}.latents"] = lat.float().numpy()
+        out[f"{task}.timesteps"] = torch.stack([c["timestep"] for c in tr.calls[:STEPS]]).float().numpy()      # bf16(t)/1000 as fed (:643,:648)
+        out[f"{task}.img_ids"] = tr.calls[0]["img_ids"].float().numpy()
+        out[f"{task}.tokens_step0"] = tr.calls[0]["hidden"].float().numpy()                                       # [noise | control | dual] packed
+        out[f"{task}.sigmas"] = pipe.scheduler.sigmas.numpy()
+        assert lat.shape == (1, 64, 64) and n_tok == (64 + 64 + (16 if use_dual else 0))
+        img = pipe(**kw, generator=torch.Generator().manual_seed(63), output_type="pil").images[0]
+        out[f"{task}.image"] = np.asarray(img)
+        out[f"{task}.mu"] = np.float64(mod.calculate_shift(64, 256, 4096, 0.5, 1.15))
+    np.savez_compressed(os.path.join(HERE, "ref_flux_call.npz"), **out)
+    return out
+
+
+def attention():
+    """NativeFluxAttnProcessor2_0.__call__ (attention_processor.py:24-110) -- real -- on nn.Linear projections; RMSNorm and
+    apply_rotary_emb are diffusers [ext] and come from the oracle."""
+    import diffusers.models.embeddings as emb
+    emb.apply_rotary_emb = lambda x, freqs: fd.apply_rope(x, freqs[0], freqs[1])
+    ap = rh.flux_attention("texturing")
+    cfg = fd.FluxConfig(**FLUX_CFG)
+    P = fd.init_params(cfg, 33, norm_weight_std=0.1)
+    pre = "transformer_blocks.0.attn."
+
+    class Lin:
+        def __init__(self, n):
+            self.n = n
+
+        def __call__(self, x):
+            return torch.nn.functional.linear(x, P[pre + self.n + ".weight"], P[pre + self.n + ".bias"])
+
+    class Norm:
+        def __init__(self, n):
+            self.n = n
+
+        def __call__(self, x):
+            return fd.rms_norm(x, P[pre + self.n + ".weight"])
+
+    attn = types.SimpleNamespace(heads=2, to_q=Lin("to_q"), to_k=Lin("to_k"), to_v=Lin("to_v"), add_q_proj=Lin("add_q_proj"),
+                                 add_k_proj=Lin("add_k_proj"), add_v_proj=Lin("add_v_proj"), norm_q=Norm("norm_q"), norm_k=Norm("norm_k"),
+                                 norm_added_q=Norm("norm_added_q"), norm_added_k=Norm("norm_added_k"),
+                                 to_out=[Lin("to_out.0"), lambda x: x], to_add_out=Lin("to_add_out"))
+    g = torch.Generator().manual_seed(2)
+    x, ctx = torch.randn(1, 96, 256, generator=g), torch.randn(1, 32, 256, generator=g)
+    ids = torch.cat([torch.zeros(32, 3), torch.stack([torch.zeros(96), torch.arange(96) // 12, torch.arange(96) % 12], -1)])
+    cos, sin = fd.rope_table(ids, cfg)
+    hx, hc = ap.NativeFluxAttnProcessor2_0()(attn, x, encoder_hidden_states=ctx, image_rotary_emb=(cos, sin))
+    single = ap.NativeFluxAttnProcessor2_0()(attn, torch.cat([ctx, x], 1), image_rotary_emb=(cos, sin))
+    np.savez_compressed(os.path.join(HERE, "ref_attention.npz"), x=x.numpy(), ctx=ctx.numpy(), ids=ids.numpy(), out_x=hx.numpy(),
+                        out_ctx=hc.numpy(), out_single=single.numpy())
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    bake()
+    attention()
+    flux()
+    print(sorted(n for n in os.listdir(HERE) if n.startswith("ref_")))

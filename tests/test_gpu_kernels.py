@@ -238,11 +238,13 @@ def test_gemv_euler_lora(lib):
 
     lat = _bf(torch.randn(96, 64, device="cuda", generator=g))
     v = _bf(torch.randn(96, 64, device="cuda", generator=g))
-    want = lat.clone()
-    want[:64] = (lat[:64].float() + (-0.03125) * v[:64].float()).to(torch.bfloat16)
-    got = ops.euler_update_(lat.clone(), v, 64, -0.03125)
-    torch.cuda.synchronize()
-    assert torch.equal(got, want)                      # fp32 FMA then RN to bf16: bit-exact
+    for ds in (-0.03125, -0.0371094):
+        want = lat.clone()
+        dt = torch.tensor(ds, dtype=torch.float32, device="cuda")              # 0-dim fp32 sigma difference, as in diffusers' step
+        want[:64] = (lat[:64].float() + dt * v[:64]).to(torch.bfloat16)        # dt * v is formed in bf16 (torch promotion), then fp32 add
+        got = ops.euler_update_(lat.clone(), v, 64, ds)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)                  # mul -> bf16 RN -> fp32 add -> bf16 RN: bit-exact
 
     Wl = _bf(torch.randn(3 * 256, 320, device="cuda", generator=g) * 0.05)
     A = torch.randn(16, 320, device="cuda", generator=g) * 0.1

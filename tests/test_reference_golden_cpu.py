@@ -1,0 +1,126 @@
+"""CPU: the oracle against fixtures produced by the REFERENCE'S OWN Python (tests/golden/ref_*.npz, generated in the build
+container by tests/golden/make_reference_golden.py through ref_harness.py: the reference's renderer_inverse / PBRMesh / knn /
+pull_push / lens_blur / camera code and its PBRFluxPipeline.__call__ / attention processor, with the absent third-party
+packages supplied by the oracle's restatements).  Everything that is torch on both sides is compared bit for bit."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import bake as ob
+from oracle import flux_dit as fd
+from oracle import flux_sampler as fs
+from tests.bake_meshes import two_spheres
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _unpack(bits, shape):
+    return np.unpackbits(bits)[: int(np.prod(shape))].reshape(shape).astype(bool)
+
+
+def test_cameras_match_reference():
+    from unitex_b200.bake import c2w_to_w2c, generate_box_views_c2ws, generate_intrinsics, intr_to_proj
+    z = np.load(os.path.join(G, "ref_bake.npz"))
+    c2ws = generate_box_views_c2ws(2.8)
+    assert np.array_equal(c2ws.numpy(), z["c2ws_all"])                                   # camera/generator.py:153-185
+    intr = generate_intrinsics(1.0, 1.0, fov=False)
+    assert np.array_equal(intr.numpy(), z["intrinsics"])                                 # :93-114
+    assert np.array_equal(intr_to_proj(intr, perspective=False).numpy(), z["proj"])      # camera/conversion.py:8-28
+    assert np.array_equal(ob.intr_to_proj_ortho(intr).numpy(), z["proj"])
+    assert np.array_equal(c2w_to_w2c(c2ws[[0, 1, 4, 2, 3, 5]]).numpy(), z["w2c"])        # :50-57
+    assert np.array_equal(ob.c2w_to_w2c(c2ws[[0, 1, 4, 2, 3, 5]]).numpy(), z["w2c"])
+
+
+def test_mesh_normals_match_reference():
+    from unitex_b200.export import vertex_normals
+    z = np.load(os.path.join(G, "ref_bake.npz"))
+    v, f, _, _ = two_spheres(10, 20)
+    n = vertex_normals(torch.from_numpy(v), torch.from_numpy(f).long())                  # structure_v2.py:63-71
+    assert np.abs(n.numpy() - z["vertex_normals"]).max() < 1e-6
+
+
+def test_torch_tail_functions_bit_exact():
+    z = np.load(os.path.join(G, "ref_bake.npz"))
+    x, m = torch.from_numpy(z["fn.x"]), torch.from_numpy(z["fn.mask"])
+    assert np.array_equal(ob.lens_blur_torch(x).numpy(), z["fn.lens_blur"])              # image/lens_blur.py:260-280
+    kd, km = ob.pull_push(x * m, m)                                                      # texture/stitching/mip.py:51-96
+    assert np.array_equal(kd.numpy(), z["fn.pull_push"]) and np.array_equal(km.numpy(), z["fn.pull_push_mask"])
+    assert np.array_equal(ob.boundary_mask(torch.from_numpy(z["fn.bmask_in"]), 3).numpy(), z["fn.bmask"])     # renderer_inverse.py:435-444
+    _, idx = ob.nearest_k(torch.from_numpy(z["fn.knn_src"]), torch.from_numpy(z["fn.knn_dst"]), 4)
+    assert np.array_equal(idx.numpy().astype(np.int32), z["fn.knn_index"])
+
+
+def test_infer_every_variant_matches_reference():
+    """oracle/bake.py::infer against NVDiffRendererInverse.infer itself (renderer_inverse.py:635-726)."""
+    from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics
+    z, zi = np.load(os.path.join(G, "ref_bake.npz")), np.load(os.path.join(G, "bake_two_spheres.npz"))
+    v, f, uv, fuv = two_spheres(10, 20)
+    c2ws = generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]]
+    intr = generate_intrinsics(1.0, 1.0, fov=False)
+    img = torch.from_numpy(zi["image"])
+    calls = []
+
+    def field(pv, cv, pi):
+        calls.append((pv.shape[0], pi.double().sum(0).numpy()))
+        return 0.25 + 0.5 * torch.sigmoid(pi * 3.0)
+
+    variants = {
+        "reproject": dict(method="reproject"),
+        "kdtree_order_mean": dict(method="kdtree", kdtree_method="order_mean", k_vis=9, k_invis=32),
+        "kdtree_mean": dict(method="kdtree", kdtree_method="mean", k_all=32),
+        "reproject_inpaint": dict(method="reproject", query_field=field),
+        "kdtree_inpaint": dict(method="kdtree", kdtree_method="order_mean", k_vis=9, query_field=field),
+    }
+    for name, kw in variants.items():
+        out = ob.infer(v, f, uv, fuv, c2ws, intr, img, 48, 48, 64, 64, **kw)
+        assert np.array_equal(out["color_2d"].numpy(), z[f"{name}.color_2d"]), name
+        if name == "reproject":
+            assert np.array_equal(out["mask_2d_visiable"].numpy(), _unpack(z["mask_2d_visiable"], (6, 64, 64, 1)))
+            assert np.array_equal(out["mask_2d"].numpy(), _unpack(z["mask_2d"], (1, 64, 64, 1)))
+            assert np.array_equal(out["alpha_mv"].numpy() > 0, _unpack(z["mv.alpha_visiable"], (6, 48, 48, 1)))
+    assert [c[0] for c in calls] == z["field.n_visible"].tolist()
+    assert np.array_equal(np.stack([c[1] for c in calls]), z["field.query_sum"])
+
+
+def test_attention_processor_matches_reference():
+    """oracle joint_attention against NativeFluxAttnProcessor2_0.__call__ (attention_processor.py:24-110)."""
+    z = np.load(os.path.join(G, "ref_attention.npz"))
+    cfg = fd.FluxConfig(num_layers=1, num_single_layers=1, num_attention_heads=2)
+    P = fd.init_params(cfg, 33, norm_weight_std=0.1)
+    cos, sin = fd.rope_table(torch.from_numpy(z["ids"]), cfg)
+    x, ctx = torch.from_numpy(z["x"]), torch.from_numpy(z["ctx"])
+    ox, oc = fd.joint_attention(P, "transformer_blocks.0.attn.", cfg, x, ctx, cos, sin)
+    assert np.array_equal(ox.numpy(), z["out_x"]) and np.array_equal(oc.numpy(), z["out_ctx"])
+    Ps = {k.replace("transformer_blocks.0.", "single_transformer_blocks.0."): v for k, v in P.items() if k.startswith("transformer_blocks.0.attn.")}
+    o = fd.joint_attention(Ps, "single_transformer_blocks.0.attn.", cfg, torch.cat([ctx, x], 1), None, cos, sin)
+    assert np.array_equal(o.numpy(), z["out_single"])
+
+
+def _flux_setup():
+    from oracle import vae as ov
+    cfg = fd.FluxConfig(num_layers=1, num_single_layers=1, num_attention_heads=2)
+    P = {k: v.to(torch.bfloat16) for k, v in fd.init_params(cfg, 21, norm_weight_std=0.1).items()}
+    vcfg = ov.VaeConfig.tiny()
+    VP = {k: v.to(torch.bfloat16) for k, v in ov.init_params(vcfg, 5).items()}
+    return cfg, P, vcfg, VP
+
+
+def test_sampler_matches_reference_call():
+    """oracle/flux_sampler.py against PBRFluxPipeline.__call__ itself (flux_piplines/{texturing,delight}/pipeline.py:404-700):
+    schedule, bf16 timesteps, id offsets, token order, condition re-imposition, Euler update -- bit for bit in bf16."""
+    from PIL import Image
+    z = np.load(os.path.join(G, "ref_flux_call.npz"))
+    cfg, P, vcfg, VP = _flux_setup()
+    ctrl, dual = Image.fromarray(z["control_image"]), Image.fromarray(z["dual_image"])
+    for task, d in (("texturing", dual), ("delight", None)):
+        assert abs(fs.calculate_shift(64) - float(z[f"{task}.mu"])) < 1e-12
+        assert np.array_equal(fs.flow_match_sigmas(3, 64), z[f"{task}.sigmas"])
+        ids = fs.build_ids(16, 16, (16, 16), (8, 8) if d is not None else None)
+        assert np.array_equal(ids.numpy(), z[f"{task}.img_ids"])
+        t = torch.from_numpy(fs.flow_match_sigmas(3, 64)[:3] * np.float32(1000.0)).to(torch.bfloat16) / 1000
+        assert np.array_equal(t.float().numpy()[:, None], z[f"{task}.timesteps"])
+        lat = fs.pipeline_call(P, cfg, VP, vcfg, ctrl, d, 128, 128, 3, torch.Generator().manual_seed(63), S_txt=128)
+        assert np.array_equal(lat.float().numpy(), z[f"{task}.latents"]), task
+        img = fs.pipeline_call(P, cfg, VP, vcfg, ctrl, d, 128, 128, 3, torch.Generator().manual_seed(63), S_txt=128, output_type="pil")
+        assert np.array_equal(img[0], z[f"{task}.image"]), task

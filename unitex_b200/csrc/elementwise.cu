@@ -191,15 +191,20 @@ __global__ void rope_table_kernel(const float* __restrict__ ids, int S, float* _
 }
 
 // ----------------------------------------------------------------------------- Euler update (a6)
-// FlowMatchEulerDiscreteScheduler.step [ext]: x32 = x + (sigma' - sigma) v, stored back as bf16.
+// FlowMatchEulerDiscreteScheduler.step [ext]: `sample.float() + (sigma' - sigma) * model_output`, cast back to bf16.
+// The sigmas are 0-dim fp32 tensors there, so torch forms the product in model_output's dtype: the increment is rounded
+// to bf16 BEFORE the fp32 add.  Mirrored (pinned by tests/golden/ref_flux_call.npz, generated by the reference's own
+// __call__): torch casts BOTH operands of that product to bf16 (the 0-dim sigma difference included), multiplies in fp32
+// and rounds: bf16(dsigma) -> mul -> bf16 RN -> fp32 add -> bf16 RN, no fused multiply-add.
 __global__ void euler_kernel(bf16* __restrict__ lat, const bf16* __restrict__ v, long n8, float dsigma) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   float a[8], b[8];
   unpack8(reinterpret_cast<const uint4*>(lat)[i], a);
   unpack8(reinterpret_cast<const uint4*>(v)[i], b);
+  const float d = __bfloat162float(__float2bfloat16_rn(dsigma));
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = fmaf(dsigma, b[j], a[j]);
+  for (int j = 0; j < 8; ++j) a[j] = __fadd_rn(a[j], __bfloat162float(__float2bfloat16_rn(__fmul_rn(d, b[j]))));
   reinterpret_cast<uint4*>(lat)[i] = pack8(a);
 }
 

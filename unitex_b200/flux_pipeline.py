@@ -52,9 +52,8 @@ class FlowMatchEulerSchedule:
         self.timesteps = None
 
     def set_timesteps(self, sigmas, mu: float):
-        s = np.asarray(sigmas, dtype=np.float64)
-        s = math.exp(mu) / (math.exp(mu) + (1.0 / s - 1.0))
-        s = s.astype(np.float32)
+        s = np.array(sigmas).astype(np.float32)          # diffusers [ext] casts the grid to fp32 first, the shift runs in fp32
+        s = (math.exp(mu) / (math.exp(mu) + (1 / s - 1) ** 1.0)).astype(np.float32)
         self.timesteps = s * np.float32(self.config.num_train_timesteps)
         self.sigmas = np.concatenate([s, np.zeros(1, np.float32)])
         return self.timesteps
