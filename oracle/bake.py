@@ -343,3 +343,47 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
     return {"mask_2d": mask_2d, "mask_2d_visiable": vis, "raw_visible": raw_vis, "color_2d": color_2d, "tid_2d": tid_2d,
             "owner": owner, "seam": bnd, "nn_index": nn_index, "pre_blur": pre_blur, "rast_2d": torch.from_numpy(rast2),
             "alpha_mv": alpha_vis, "rays_tid": rt}
+
+
+# ------------------------------------------------------------------------------------------------ forward G-buffers (b1)
+@torch.no_grad()
+def export_condition(vert, tri, vertex_normals, geometry_scale=1.0, n_views=6, n_rows=2, n_cols=3, H=512, W=512, scale=1.0,
+                     background=128.0 / 255.0):
+    """VideoExporter.export_condition (video/export_nvdiffrast_video.py:900-999, orthographic box views) over
+    NVDiffRendererBase.simple_rendering(render_world_normal, render_world_position, enable_antialis=False)
+    (render/nvdiffrast/renderer_base.py:101-200) and Mesh.scale_to_bbox / apply_transform (mesh/structure.py:190-202,
+    :290-304).  -> uint8 grids alpha [n_rows H, n_cols W], ccm / normal [.., 3], c2ws, intrinsics.  Pinned against the
+    reference's own run by tests/golden/ref_glue.npz."""
+    from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics      # pinned themselves against camera/generator.py
+    v = torch.from_numpy(np.ascontiguousarray(vert, np.float32))
+    bbox = torch.stack([v.min(0).values, v.max(0).values])
+    ccc = bbox.mean(dim=0)
+    sss = ((bbox[1] - bbox[0]) / (2.0 * geometry_scale)).max()
+    T = torch.eye(4)
+    T[[0, 1, 2], [0, 1, 2]] = 1 / sss
+    T[:3, 3] = -ccc / sss
+    v = torch.matmul(torch.cat([v, torch.ones_like(v[:, :1])], -1), T.T)[:, :3].contiguous()
+    vn = F.normalize(torch.matmul(torch.from_numpy(np.ascontiguousarray(vertex_normals, np.float32)), T[:3, :3].T), dim=-1).contiguous()
+    sel = {1: [0], 2: [0, 2], 4: [0, 1, 2, 3], 6: [0, 1, 4, 2, 3, 5] if (n_rows, n_cols) == (2, 3) else list(range(6))}[n_views]
+    c2ws = generate_box_views_c2ws(radius=2.8)[sel]
+    intr = generate_intrinsics(scale, scale, fov=False, degree=False)
+    mvp = torch.matmul(intr_to_proj_ortho(intr), c2w_to_w2c(c2ws))
+    clip = torch.matmul(torch.cat([v, torch.ones_like(v[:, :1])], -1), mvp.permute(0, 2, 1))
+    tri = np.ascontiguousarray(tri, np.int32)
+    rast = rasterize(clip.numpy(), tri, H, W)
+    mask = torch.from_numpy(rast[..., 3:4] > 0)
+    alpha = mask.float()
+    nrm = F.normalize(torch.from_numpy(interpolate(vn.numpy(), rast, tri)), dim=-1)
+    nrm = torch.lerp(torch.full_like(nrm, -1.0), nrm, alpha)
+    pos = torch.from_numpy(interpolate(v.numpy(), rast, tri))
+    pos = torch.lerp(torch.full_like(pos, -1.0), pos, mask.float())
+    ccm, normal = pos.mul(0.5).add(0.5), nrm.mul(0.5).add(0.5)
+    if background is not None:
+        bg = torch.full((3,), float(background)).float()   # 'grey' = PIL #808080 = 128/255 (utils/parse_color.py:6)
+        ccm = ccm * alpha + bg * (1.0 - alpha)
+        normal = normal * alpha + bg * (1.0 - alpha)
+
+    def grid(t, c):
+        a = t.clamp(0.0, 1.0).mul(255.0).numpy().astype(np.uint8)
+        return a.reshape(n_rows, n_cols, H, W, c).transpose(0, 2, 1, 3, 4).reshape(n_rows * H, n_cols * W, c)
+    return {"alpha": grid(alpha, 1)[..., 0], "ccm": grid(ccm, 3), "normal": grid(normal, 3), "c2ws": c2ws, "intrinsics": intr}

@@ -124,7 +124,8 @@ class RGBTextureFullPipelineBase:
         self.inverse_renderer.update_from_file(input_mesh_path)
         _, reprojected_uv, visable_mask, completed_uv_map = self.inverse_renderer.infer(
             self.inverse_renderer.pbr_mesh, c2ws=cam["c2ws"].cpu(), intrinsics=cam["intrinsics"].cpu(), image_attrs=image_attrs,
-            perspective=cam["perspective"], H=HP, W=WP, H2D=2048, W2D=2048, method=method, reproject_inpainting=inpainting,
+            perspective=cam["perspective"], H=HP, W=WP, H2D=2048, W2D=2048, method=method, kdtree_inpainting=inpainting,
+            reproject_inpainting=inpainting, kdtree_n_neighbors=8, kdtree_n_neighbors_visiable=4,
             grad_norm_threhold=0.15, ray_normal_angle_threhold=100, filt_gradient_points=inpainting)
         V, F, UV, Ft = ub.load_obj(input_mesh_path)
         atlas = (completed_uv_map[0].clamp(0, 1) * 255.0).round().to(torch.uint8).cpu().numpy()

@@ -20,6 +20,7 @@ import ref_harness as rh                                      # noqa: E402
 from oracle import flux_dit as fd                             # noqa: E402
 from oracle import vae as ov                                  # noqa: E402
 from tests.bake_meshes import two_spheres                     # noqa: E402
+from tests.glue_fakes import FakeFlux, glue_inputs, sha as _sha   # noqa: E402
 
 
 def bake():
@@ -213,9 +214,79 @@ def attention():
                         out_ctx=hc.numpy(), out_single=single.numpy())
 
 
+def glue():
+    """export_condition (video/export_nvdiffrast_video.py:900-999 over renderer_base.simple_rendering :101-200 and
+    mesh/structure.py scale_to_bbox / apply_transform), and the top-level pipeline.py glue: infer_mv (:231-291, grid
+    re-ordering a9 + the two calls) and reproject_and_query_field (:312-360, view slicing + infer kwargs)."""
+    import tempfile
+    from PIL import Image
+    from unitex_b200.export import vertex_normals
+    v, f, uv, fuv = two_spheres(10, 20)
+    vn = vertex_normals(torch.from_numpy(v), torch.from_numpy(f).long()).numpy()
+    ve = rh.video_exporter(v, f, vn)
+    out = {}
+    for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2))):
+        r = ve.export_condition("mesh.obj", geometry_scale=0.95, H=64, W=64, fov_deg=49.1, scale=1.0, perspective=False, orbit=False,
+                                background="grey", return_info=False, return_image=True, return_mesh=False, return_camera=True, **kw)
+        for k in ("alpha", "ccm", "normal"):
+            out[f"cond.{name}.{k}"] = np.asarray(r[k])
+        out[f"cond.{name}.c2ws"], out[f"cond.{name}.intrinsics"] = r["c2ws"].numpy(), r["intrinsics"].numpy()
+        assert r["perspective"] is False
+
+    mod = rh.top_level_pipeline()
+    normal, ccm, ref = glue_inputs()
+    with tempfile.TemporaryDirectory() as d:
+        Image.fromarray(normal).save(os.path.join(d, "mv_normal.png"))
+        Image.fromarray(ccm).save(os.path.join(d, "mv_ccm.png"))
+        Image.fromarray(ref).save(os.path.join(d, "processed_image.png"))
+        fake = FakeFlux()
+        me = types.SimpleNamespace(pipeline=fake, pipeline_name="texture_plus", adapter_names=["texture", "delight"],
+                                   weights_for_texture=[1.0, 0.0], weights_for_delight=[0.0, 1.0], generator=None, super_resolutions=False)
+        mod.CustomRGBTextureFullPipeline.infer_mv(me, d, os.path.join(d, "processed_image.png"), os.path.join(d, "mv_normal.png"),
+                                                  os.path.join(d, "mv_ccm.png"))
+        out["mv.strip_sha"] = np.array(_sha(np.array(fake.calls[0]["control_image"])))
+        out["mv.strip_probe"] = np.array(fake.calls[0]["control_image"])[::64, ::64].copy()
+        out["mv.dual_sha"] = np.array(_sha(np.array(fake.calls[0]["dual_image"])))
+        out["mv.second_control_sha"] = np.array(_sha(np.array(fake.calls[1]["control_image"])))
+        out["mv.second_has_dual"] = np.array("dual_image" in fake.calls[1] and fake.calls[1]["dual_image"] is not None)
+        out["mv.kwargs"] = np.array(repr(sorted((k, v) for k, v in fake.calls[0].items() if k not in ("control_image", "dual_image"))))
+        out["mv.adapters"] = np.array(repr(fake.adapters))
+        out["mv.rgb_sha"] = np.array(_sha(np.array(Image.open(os.path.join(d, "mv_rgb.png")))))
+        out["mv.rgb_probe"] = np.array(Image.open(os.path.join(d, "mv_rgb.png")))[::64, ::64].copy()
+        out["mv.w_light_sha"] = np.array(_sha(np.array(Image.open(os.path.join(d, "mv_rgb_w_light.png")))))
+
+        # reproject_and_query_field: what the bake entry point is handed
+        rec = {}
+
+        class FakeInverse:
+            def update_from_file(self, path):
+                rec["mesh"] = os.path.basename(path)
+
+            def infer(self, blank, **kw):
+                rec.update(kw)
+                t = types.SimpleNamespace(export=lambda path: open(path, "wb").close())
+                n = kw["c2ws"].shape[0]
+                return t, torch.zeros(n, 8, 8, 1, dtype=torch.bool), torch.ones(1, 8, 8, 1, dtype=torch.bool), torch.full((1, 8, 8, 3), 0.25)
+
+            def clear(self):
+                rec["cleared"] = True
+        cam = {"c2ws": torch.from_numpy(out["cond.six.c2ws"]), "intrinsics": torch.from_numpy(out["cond.six.intrinsics"]), "perspective": False}
+        torch.save(cam, os.path.join(d, "camera_info.pth"))
+        me2 = types.SimpleNamespace(inverse_renderer=FakeInverse())
+        mod.CustomRGBTextureFullPipeline.reproject_and_query_field(me2, d, os.path.join(d, "processed_mesh.obj"), os.path.join(d, "mv_rgb.png"),
+                                                                   os.path.join(d, "camera_info.pth"), method="reproject", inpainting=False)
+        out["rq.image_attrs_sha"] = np.array(_sha(rec["image_attrs"].numpy()))
+        out["rq.image_attrs_probe"] = rec["image_attrs"].numpy()[:, ::64, ::64].copy()
+        out["rq.kwargs"] = np.array(repr(sorted((k, v) for k, v in rec.items() if k not in ("image_attrs", "c2ws", "intrinsics"))))
+        out["rq.files"] = np.array(repr(sorted(n for n in os.listdir(d) if n.endswith((".glb", "_mask.png", "_uv.png")))))
+    np.savez_compressed(os.path.join(HERE, "ref_glue.npz"), **out)
+    return out
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     bake()
     attention()
     flux()
+    glue()
     print(sorted(n for n in os.listdir(HERE) if n.startswith("ref_")))

@@ -34,7 +34,7 @@ import torch
 REF = "/root/reference"
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-ABSENT = ("nvdiffrast", "trimesh", "pymeshlab", "open3d", "gpytoolbox", "cupy", "imageio", "slangtorch", "torch_kdtree", "diffusers", "pyexr")
+ABSENT = ("nvdiffrast", "trimesh", "pymeshlab", "open3d", "gpytoolbox", "cupy", "imageio", "slangtorch", "torch_kdtree", "diffusers", "pyexr", "rembg", "fpsample", "xatlas", "peft", "lpips", "open_clip", "kornia", "pygltflib", "fast_simplification", "pyfqmr", "mcubes", "skimage", "timeout_decorator", "pymeshfix", "igl", "loguru", "omegaconf", "lightning", "pytorch_lightning", "safetensors_stub_never")
 
 
 class _StubMeta(type):
@@ -339,3 +339,71 @@ def flux_attention(task="texturing"):
     import importlib
     flux(task)
     return importlib.import_module(f"_ref_flux_piplines.{task}.attention_processor")
+
+
+# --------------------------------------------------------------------------------------------------------------------------
+# export_condition / top-level pipeline glue: needs 'cuda' -> 'cpu' (this container has no GPU) and a mesh without trimesh
+# --------------------------------------------------------------------------------------------------------------------------
+_cuda_remapped = False
+
+
+def remap_cuda_to_cpu():
+    """The reference hard-codes device='cuda' in places (`.to(device='cuda')`, `image_to_tensor(..., device='cuda')`); in
+    this CPU-only container those calls are redirected to 'cpu'.  Arithmetic is untouched."""
+    global _cuda_remapped
+    if _cuda_remapped:
+        return
+    _to, _as_tensor = torch.Tensor.to, torch.as_tensor
+
+    def fix(x):
+        return "cpu" if (isinstance(x, str) and x.startswith("cuda")) or (isinstance(x, torch.device) and x.type == "cuda") else x
+
+    def to(self, *a, **k):
+        return _to(self, *[fix(x) for x in a], **{n: fix(v) for n, v in k.items()})
+
+    def as_tensor(*a, **k):
+        return _as_tensor(*a, **{n: fix(v) for n, v in k.items()})
+    _load = torch.load
+
+    def load(*a, **k):
+        return _load(*a, **{n: fix(v) for n, v in k.items()})
+    torch.Tensor.to = to
+    torch.as_tensor = as_tensor
+    torch.load = load
+    torch.cuda.empty_cache = lambda: None
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    _cuda_remapped = True
+
+
+def video_exporter(vertices: np.ndarray, faces: np.ndarray, vertex_normals: np.ndarray):
+    """-> the reference's `VideoExporter` (video/export_nvdiffrast_video.py) whose mesh loader hands back the given arrays as
+    the reference's own `Mesh` (mesh/structure.py:306-).  trimesh [ext] would supply `vertex_normals`; they are an input here."""
+    install()
+    remap_cuda_to_cpu()
+    texturetools()
+    from texturetools.mesh import structure as ms
+    from texturetools.video import export_nvdiffrast_video as ev
+
+    def from_trimesh(_):
+        m = ms.Mesh(v_pos=torch.from_numpy(vertices).float(), t_pos_idx=torch.from_numpy(faces).long())
+        m._v_nrm = torch.from_numpy(vertex_normals).float()
+        return types.SimpleNamespace(mesh=m)
+    ev.load_whole_mesh = lambda path: None
+    ev.Texture = types.SimpleNamespace(from_trimesh=from_trimesh)
+    return ev.VideoExporter()
+
+
+def top_level_pipeline():
+    """-> the reference's top-level `pipeline.py` module (aliased `_ref_pipeline`)."""
+    install()
+    remap_cuda_to_cpu()
+    texturetools()
+    import importlib.util
+    if "_ref_pipeline" in sys.modules:
+        return sys.modules["_ref_pipeline"]
+    sys.path.insert(0, REF)        # `from TextureTools.texturetools...` / `from TSD_SR...` resolve against the reference root
+    spec = importlib.util.spec_from_file_location("_ref_pipeline", os.path.join(REF, "pipeline.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_ref_pipeline"] = mod
+    spec.loader.exec_module(mod)
+    return mod

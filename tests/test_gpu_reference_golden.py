@@ -92,3 +92,70 @@ def test_pipeline_call_matches_reference_call(lib):
         db_img = 10 * np.log10(255.0 ** 2 / max(np.mean((a - b) ** 2), 1e-12))
         assert db_img >= 30.0, f"{task}: image PSNR {db_img:.1f} dB"     # both sides are bf16 VAE chains + uint8 quantisation
         print(f"{task}: latent {db:.1f} dB, image {db_img:.1f} dB")
+
+
+def test_export_condition_matches_reference(lib):
+    """b1: this repo's VideoExporter.export_condition (CUDA rasteriser) against the reference's own export_condition run
+    (video/export_nvdiffrast_video.py:900-999): coverage exact, uint8 G-buffers within 1 LSB."""
+    from unitex_b200.export import VideoExporter
+    z = np.load(os.path.join(G, "ref_glue.npz"))
+    v, f, _, _ = two_spheres(10, 20)
+    for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2))):
+        out = VideoExporter().export_condition((v, f), geometry_scale=0.95, H=64, W=64, fov_deg=49.1, scale=1.0, perspective=False,
+                                               orbit=False, background="grey", return_image=True, return_camera=True, **kw)
+        assert np.array_equal(np.asarray(out["alpha"]), z[f"cond.{name}.alpha"]), name
+        for k in ("ccm", "normal"):
+            d = np.abs(np.asarray(out[k]).astype(np.int16) - z[f"cond.{name}.{k}"].astype(np.int16))
+            assert d.max() <= 1 and (d > 0).mean() < 0.01, (name, k, int(d.max()), float((d > 0).mean()))
+        assert np.array_equal(out["c2ws"].cpu().numpy(), z[f"cond.{name}.c2ws"])
+        assert np.array_equal(out["intrinsics"].cpu().numpy(), z[f"cond.{name}.intrinsics"])
+        assert out["perspective"] is False
+
+
+def test_reproject_glue_matches_reference(lib, tmp_path):
+    """b11: what `reproject_and_query_field` (pipeline.py:312-360) hands to the bake entry point -- view slicing of mv_rgb.png,
+    the infer kwargs, the files it leaves -- against the reference's own function driven with the same fake renderer."""
+    import ast
+    import types
+    from PIL import Image
+    import pipeline as drop_in
+    from tests.glue_fakes import FakeFlux, glue_inputs, sha
+    from unitex_b200 import export as ux
+    z = np.load(os.path.join(G, "ref_glue.npz"))
+    normal, ccm, ref = glue_inputs()
+    d = str(tmp_path)
+    for n, a in (("mv_normal.png", normal), ("mv_ccm.png", ccm), ("processed_image.png", ref)):
+        Image.fromarray(a).save(os.path.join(d, n))
+    me = types.SimpleNamespace(pipeline=FakeFlux(), pipeline_name="texture_plus", adapter_names=["texture", "delight"],
+                               weights_for_texture=[1.0, 0.0], weights_for_delight=[0.0, 1.0], generator=None, super_resolutions=False)
+    drop_in.CustomRGBTextureFullPipeline.infer_mv(me, d, os.path.join(d, "processed_image.png"), os.path.join(d, "mv_normal.png"),
+                                                  os.path.join(d, "mv_ccm.png"))                    # writes mv_rgb.png (hash-checked on CPU)
+    v, f, uv, fuv = two_spheres(6, 12)
+    ux.save_obj(os.path.join(d, "processed_mesh.obj"), v, f, uv * 0.5 + 0.5, fuv)
+    torch.save({"c2ws": torch.from_numpy(z["cond.six.c2ws"]), "intrinsics": torch.from_numpy(z["cond.six.intrinsics"]), "perspective": False},
+               os.path.join(d, "camera_info.pth"))
+    rec = {}
+
+    class FakeInverse:
+        pbr_mesh = None
+
+        def update_from_file(self, path):
+            rec["mesh"] = os.path.basename(path)
+
+        def infer(self, blank, **kw):
+            rec.update(kw)
+            n = kw["c2ws"].shape[0]
+            return None, torch.zeros(n, 8, 8, 1, dtype=torch.bool), torch.ones(1, 8, 8, 1, dtype=torch.bool), torch.full((1, 8, 8, 3), 0.25)
+
+        def clear(self):
+            rec["cleared"] = True
+    me2 = types.SimpleNamespace(inverse_renderer=FakeInverse())
+    drop_in.CustomRGBTextureFullPipeline.reproject_and_query_field(me2, d, os.path.join(d, "processed_mesh.obj"), os.path.join(d, "mv_rgb.png"),
+                                                                   os.path.join(d, "camera_info.pth"), method="reproject", inpainting=False)
+    assert sha(rec["image_attrs"].cpu().numpy()) == str(z["rq.image_attrs_sha"])
+    assert np.array_equal(rec["image_attrs"].cpu().numpy()[:, ::64, ::64], z["rq.image_attrs_probe"])
+    want = dict(ast.literal_eval(str(z["rq.kwargs"])))
+    got = {k: v for k, v in rec.items() if k not in ("image_attrs", "c2ws", "intrinsics")}
+    assert got == want, (got, want)
+    assert np.array_equal(rec["c2ws"].cpu().numpy(), z["cond.six.c2ws"])
+    assert sorted(n for n in os.listdir(d) if n.endswith((".glb", "_mask.png", "_uv.png"))) == ast.literal_eval(str(z["rq.files"]))

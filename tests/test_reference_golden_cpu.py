@@ -124,3 +124,45 @@ def test_sampler_matches_reference_call():
         assert np.array_equal(lat.float().numpy(), z[f"{task}.latents"]), task
         img = fs.pipeline_call(P, cfg, VP, vcfg, ctrl, d, 128, 128, 3, torch.Generator().manual_seed(63), S_txt=128, output_type="pil")
         assert np.array_equal(img[0], z[f"{task}.image"]), task
+
+
+def test_export_condition_matches_reference():
+    """oracle export_condition against VideoExporter.export_condition itself (video/export_nvdiffrast_video.py:900-999)."""
+    from unitex_b200.export import vertex_normals
+    z = np.load(os.path.join(G, "ref_glue.npz"))
+    v, f, _, _ = two_spheres(10, 20)
+    vn = vertex_normals(torch.from_numpy(v), torch.from_numpy(f).long()).numpy()
+    for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2))):
+        out = ob.export_condition(v, f, vn, geometry_scale=0.95, H=64, W=64, scale=1.0, **kw)
+        for k in ("alpha", "ccm", "normal"):
+            assert np.array_equal(out[k], z[f"cond.{name}.{k}"]), (name, k)
+        assert np.array_equal(out["c2ws"].numpy(), z[f"cond.{name}.c2ws"])
+        assert np.array_equal(out["intrinsics"].numpy(), z[f"cond.{name}.intrinsics"])
+
+
+def test_infer_mv_glue_matches_reference(tmp_path):
+    """This repo's drop-in `infer_mv` (pipeline.py) against the reference's own `infer_mv` (pipeline.py:231-291) driven with the
+    same fake FLUX object: control strip (blend + view permutation + flip), both calls' kwargs, adapter switching, mv_rgb grid."""
+    from PIL import Image
+    import types
+    import pipeline as drop_in
+    from tests.glue_fakes import FakeFlux, glue_inputs, sha
+    z = np.load(os.path.join(G, "ref_glue.npz"))
+    normal, ccm, ref = glue_inputs()
+    d = str(tmp_path)
+    Image.fromarray(normal).save(os.path.join(d, "mv_normal.png"))
+    Image.fromarray(ccm).save(os.path.join(d, "mv_ccm.png"))
+    Image.fromarray(ref).save(os.path.join(d, "processed_image.png"))
+    fake = FakeFlux()
+    me = types.SimpleNamespace(pipeline=fake, pipeline_name="texture_plus", adapter_names=["texture", "delight"],
+                               weights_for_texture=[1.0, 0.0], weights_for_delight=[0.0, 1.0], generator=None, super_resolutions=False)
+    drop_in.CustomRGBTextureFullPipeline.infer_mv(me, d, os.path.join(d, "processed_image.png"), os.path.join(d, "mv_normal.png"),
+                                                  os.path.join(d, "mv_ccm.png"))
+    assert sha(np.array(fake.calls[0]["control_image"])) == str(z["mv.strip_sha"])
+    assert sha(np.array(fake.calls[0]["dual_image"])) == str(z["mv.dual_sha"])
+    assert sha(np.array(fake.calls[1]["control_image"])) == str(z["mv.second_control_sha"])
+    assert fake.calls[1].get("dual_image") is None and not bool(z["mv.second_has_dual"])
+    assert repr(sorted((k, v) for k, v in fake.calls[0].items() if k not in ("control_image", "dual_image"))) == str(z["mv.kwargs"])
+    assert repr(fake.adapters) == str(z["mv.adapters"])
+    assert sha(np.array(Image.open(os.path.join(d, "mv_rgb.png")))) == str(z["mv.rgb_sha"])
+    assert sha(np.array(Image.open(os.path.join(d, "mv_rgb_w_light.png")))) == str(z["mv.w_light_sha"])

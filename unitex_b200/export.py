@@ -19,13 +19,21 @@ from . import bake as ub
 
 
 def parse_color(c):
+    """utils/parse_color.py:6-18: names resolve through PIL's colour table to 8-bit RGB / 255 ('grey' is #808080 = 128/255, not
+    0.5 -- pinned by tests/golden/ref_glue.npz); a float broadcasts; three floats are taken as given."""
     if c is None:
         return None
     if isinstance(c, str):
-        c = {"grey": 0.5, "gray": 0.5, "white": 1.0, "black": 0.0}[c.lower()]
-    if isinstance(c, (int, float)):
-        c = [float(c)] * 3
-    return torch.tensor(c, dtype=torch.float32)
+        from PIL.ImageColor import colormap
+        if c not in colormap:
+            raise NotImplementedError(f"unknown colour name {c!r}")
+        h = colormap[c]
+        return torch.tensor([int(h[1:3], 16), int(h[3:5], 16), int(h[5:7], 16)], dtype=torch.float32).div(255.0)
+    if isinstance(c, float):
+        return torch.tensor([c], dtype=torch.float32)
+    if isinstance(c, (tuple, list)) and len(c) == 3 and all(isinstance(x, float) for x in c):
+        return torch.tensor(c, dtype=torch.float32)
+    raise NotImplementedError(f"colour {c!r}")
 
 
 def vertex_normals(vertices: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
