@@ -69,18 +69,24 @@ class RGBTextureFullPipelineBase:
         self.super_resolutions = False
 
     # ------------------------------------------------------------------ step pieces
-    def preprocess_blank_mesh(self, save_dir, input_mesh_path):
-        """reference :170-179 rescales with open3d and unwraps when UVs are missing; here: UVs are required."""
+    def preprocess_blank_mesh(self, save_dir, input_mesh_path, min_faces=20_000, max_faces=200_000, scale=0.95):
+        """reference :170-179 -> geometry/uv/uv_atlas.py:131-194: the bounding box is centred and its longest side scaled to
+        2*scale (float64, like the open3d transform there) -- the bake's cameras assume that frame -- and the mesh is written as
+        processed_mesh.obj.  The UV unwrap of meshes without UVs (open3d compute_uvatlas [ext]) is out of scope: UVs are required."""
         V, F, UV, Ft = ub.load_obj(input_mesh_path)
         if len(UV) == 0:
             raise NotImplementedError("mesh without UVs: UV-atlas generation (open3d/xatlas) is out of scope")
+        V = np.asarray(V, dtype=np.float64)
+        aaa, bbb = V.min(0), V.max(0)
+        sss = (bbb - aaa).max() / (2.0 * scale)
+        V = V / sss - (aaa + bbb) / (2.0 * sss)
         ux.save_obj(os.path.join(save_dir, "processed_mesh.obj"), V, F, UV, Ft)
 
     def preprocess_reference_image(self, save_dir, input_image_path):
         """reference :182-196 (rembg + crop/pad): here resize onto a 1024^2 grey canvas, then 512^2."""
         img = Image.open(input_image_path).convert("RGB")
         img.save(os.path.join(save_dir, "rembg_image.png"))
-        canvas = Image.new("RGB", (1024, 1024), (127, 127, 127))
+        canvas = Image.new("RGB", (1024, 1024), "grey")        # PIL grey = (128, 128, 128), as image/process_image.py:68
         im = img.copy()
         im.thumbnail((1024, 1024))
         canvas.paste(im, ((1024 - im.width) // 2, (1024 - im.height) // 2))

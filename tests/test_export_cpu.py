@@ -46,3 +46,21 @@ def test_lens_blur_kernel_sums_to_one():
     from unitex_b200.bake import lens_blur_kernel_2d
     K = lens_blur_kernel_2d()
     assert K.shape == (7, 7) and abs(K.sum() - 1.0) < 1e-5 and np.allclose(K, K.T, atol=1e-7)
+
+
+def test_preprocess_blank_mesh_normalises_bbox(tmp_path):
+    """reference pipeline.py:170-179 -> uv_atlas.py:131-147: bbox centred, longest side = 2 * 0.95."""
+    import types
+    import pipeline as drop_in
+    from tests.bake_meshes import two_spheres
+    from unitex_b200 import bake as ub
+    from unitex_b200.export import save_obj
+    v, f, uv, fuv = two_spheres(6, 12)
+    src = str(tmp_path / "in.obj")
+    save_obj(src, v * 3.7 + np.array([5.0, -2.0, 1.0], np.float32), f, (uv + 1) / 2, fuv)
+    drop_in.CustomRGBTextureFullPipeline.preprocess_blank_mesh(types.SimpleNamespace(), str(tmp_path), src)
+    V, F, UV, Ft = ub.load_obj(str(tmp_path / "processed_mesh.obj"))
+    V = np.asarray(V)
+    lo, hi = V.min(0), V.max(0)
+    assert np.allclose((lo + hi) / 2, 0.0, atol=1e-6) and abs((hi - lo).max() - 1.9) < 1e-6
+    assert np.array_equal(np.asarray(F), f) and len(UV) == len(uv)

@@ -19,7 +19,7 @@ def test_custom_rgb_texture_full_pipeline(lib, tmp_path):
     from unitex_b200.flux import FluxConfig
     v, f, uv, fuv = two_spheres(24, 48)
     mesh_path, img_path = str(tmp_path / "mesh.obj"), str(tmp_path / "image.png")
-    save_obj(mesh_path, v, f, (uv + 1) / 2, fuv)
+    save_obj(mesh_path, v * 3.7 + np.array([5.0, -2.0, 1.0], np.float32), f, (uv + 1) / 2, fuv)   # arbitrary frame: preprocess_blank_mesh normalises it
     Image.fromarray(np.random.default_rng(0).integers(0, 255, (256, 256, 3), dtype=np.uint8)).save(img_path)
     cfg = FluxConfig(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=256, pooled_projection_dim=64)
     pipe = CustomRGBTextureFullPipeline(pretrain_models=cfg, super_resolutions=False, seed=63)
