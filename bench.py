@@ -180,6 +180,10 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    side = {}
+    if world == 1 and not args.no_bake:      # before the engine: metric 2 is measured on an idle, un-throttled GPU
+        side["uv_bake"] = bench_uv_bake(dev)
+        side["vae_decode"] = bench_vae_decode(dev)
     cfg = FluxConfig()
     eng = FluxTransformer(cfg, dev).random_init_(seed=0)
     # "LoRA merged": a random rank-64 texture_gen adapter folded into one block's q projection exercises the merge
@@ -283,9 +287,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(sum(launches.values())),
         "clocks": clocks,
     }
-    if world == 1 and not args.no_bake:
-        out["uv_bake"] = bench_uv_bake(dev)
-        out["vae_decode"] = bench_vae_decode(dev)
+    out.update(side)
     if world == 1 and not args.no_bake:
         out["delight"] = bench_delight(eng, dev, sig)
         out["pipeline_call"] = bench_pipeline_call(eng, dev)
@@ -417,6 +419,7 @@ def bench_uv_bake(dev, return_tensors=False):
     intr = ub.generate_intrinsics(1.0, 1.0, fov=False)
     mesh = ub.BakeMesh(v, f, uv, f.copy(), device=dev)
     r = ub.NVDiffRendererInverse(device=dev, pbr_mesh=mesh)
+    ub.RayTracing(mesh.vertices, mesh.faces, device=dev)   # untimed: first launch of the build kernels (lazy module load, cub temp)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     mesh.optix                                     # LBVH build (once per mesh)
@@ -428,9 +431,10 @@ def bench_uv_bake(dev, return_tensors=False):
     img = (0.5 + 0.4 * torch.sin(3.0 * pos + 0.3)) * (rast[..., 3:4] > 0)
     kw = dict(H=H, W=W, H2D=H2, W2D=W2, perspective=False, ray_normal_angle_threhold=100.0, method="reproject",
               filt_gradient_points=False)
-    r.infer(mesh, c2ws, intr, img, **kw)
+    for _ in range(3):
+        r.infer(mesh, c2ws, intr, img, **kw)
     torch.cuda.synchronize()
-    reps = 10
+    reps = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()

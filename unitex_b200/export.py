@@ -24,11 +24,10 @@ def parse_color(c):
     if c is None:
         return None
     if isinstance(c, str):
-        from PIL.ImageColor import colormap
-        if c not in colormap:
+        from PIL import ImageColor
+        if c not in ImageColor.colormap:
             raise NotImplementedError(f"unknown colour name {c!r}")
-        h = colormap[c]
-        return torch.tensor([int(h[1:3], 16), int(h[3:5], 16), int(h[5:7], 16)], dtype=torch.float32).div(255.0)
+        return torch.tensor(ImageColor.getrgb(c)[:3], dtype=torch.float32).div(255.0)   # (PIL caches tuples in `colormap`)
     if isinstance(c, float):
         return torch.tensor([c], dtype=torch.float32)
     if isinstance(c, (tuple, list)) and len(c) == 3 and all(isinstance(x, float) for x in c):
