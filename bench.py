@@ -290,6 +290,7 @@ def run_ours(args, rank, world, local_rank):
     out.update(side)
     if world == 1 and not args.no_bake:
         out["delight"] = bench_delight(eng, dev, sig)
+        out["six_view"] = bench_six_view(eng, dev, sig)
         out["pipeline_call"] = bench_pipeline_call(eng, dev)
     if world == 1 and not args.no_cpu_baseline:
         del eng
@@ -335,6 +336,39 @@ def bench_delight(eng, dev, sig):
     flops = 57 * 2 * 113246208 * S + 57 * 4 * 3072 * S * S
     return {"metric": METRIC, "workload": "delight 1024x1024 4-view: S=8704 = 512 txt + 4096 noise + 4096 control", "value": 1e3 / ms,
             "unit": UNIT, "ms_per_step": ms, "tflops": flops / (ms * 1e-3) / 1e12, "finite": bool(torch.isfinite(lat.float()).all())}
+
+
+def bench_six_view(eng, dev, sig):
+    """Side measurement at the shape UniTEX's own top-level pipeline runs (pipeline.py:246-259: 512 x 3072 strip of 6 views,
+    control strip + 512^2 reference image): S = 512 txt + 6144 noise + 6144 control + 1024 reference = 13824 tokens
+    (312.35 TFLOP per step).  Same engine and weights, CUDA events over 3 steps after 2 warm-up steps."""
+    import torch
+    s_noise, s_img = 6144, 6144 + 6144 + 1024
+
+    def grid(h, w, oy, ox):
+        t = torch.zeros(h, w, 3)
+        t[..., 1] = torch.arange(oy, oy + h)[:, None]
+        t[..., 2] = torch.arange(ox, ox + w)[None, :]
+        return t.reshape(-1, 3)
+    ids = torch.zeros(S_TXT + s_img, 3)
+    ids[S_TXT:] = torch.cat([grid(32, 192, 0, 0), grid(32, 192, 32, 0), grid(32, 32, 32, 192)])   # flux pipeline :303-393, HL=64 WL=384
+    eng.prepare(ids, None, None, s_txt=S_TXT)
+    lat = torch.randn(s_img, 64, device=dev, generator=torch.Generator(device=dev).manual_seed(6)).to(torch.bfloat16)
+    for i in range(2):
+        eng.denoise_(lat, s_noise, sig[i:i + 2], 3.5)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(3):
+        eng.denoise_(lat, s_noise, sig[i:i + 2], 3.5)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    S = S_TXT + s_img
+    flops = 57 * 2 * 113246208 * S + 57 * 4 * 3072 * S * S
+    return {"metric": METRIC, "workload": "texture_gen 512x3072 6-view strip (the reference's own call): S=13824 = 512 txt + 6144 noise + 6144 control + 1024 reference",
+            "value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "tflops": flops / (ms * 1e-3) / 1e12,
+            "finite": bool(torch.isfinite(lat.float()).all())}
 
 
 def bench_pipeline_call(eng, dev):

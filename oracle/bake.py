@@ -262,7 +262,8 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
     ndc_2d = torch.from_numpy(interpolate(ndc_v.numpy(), np.repeat(rast2, n, 0), tri))       # :288
     img = torch.cat([image_attrs, alpha_vis], -1)
     samp = F.grid_sample(img.permute(0, 3, 1, 2), ndc_2d, mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
-    col_2d, alpha_2d = samp[..., :3], samp[..., 3:4]
+    Cn = image_attrs.shape[-1]                                                               # 3 (RGB) or 9 (PBR, :711-719)
+    col_2d, alpha_2d = samp[..., :Cn], samp[..., Cn:Cn + 1]
     m = mask_2d[0, ..., 0]
     info, aabb, _ = lbvh_build(vert, tri)
     ro, rd = rays_o[:, m], rays_d[:, m]                                                      # [n,Nv,3]
@@ -286,7 +287,7 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
         mmv = rast_mv[..., 3] > 0
         clouds = [(attrs_mv[i][mmv[i]], image_attrs[i][mmv[i]]) for i in range(n)]
         P2 = pos_2d[0][m]                                                                    # point_cloud_2d.vertices
-        wc = torch.zeros(P2.shape[0], 3)
+        wc = torch.zeros(P2.shape[0], Cn)
         cur = torch.zeros(1, H2, W2, 1, dtype=torch.bool)
         if kdtree_method == "mean":                                                          # :385-389
             allp, allc = torch.cat([c[0] for c in clouds]), torch.cat([c[1] for c in clouds])
@@ -307,13 +308,13 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
                     kk = min(k_invis, int(vsel.sum()))
                     _, idx = nearest_k(P2[vsel], P2[~vsel], kk)
                     wc[~vsel] = wc[vsel][idx].mean(dim=-2)
-        color = torch.zeros(1, H2, W2, 3)
+        color = torch.zeros(1, H2, W2, Cn)
         color[0][m] = wc
         color_2d = pull_push(color.permute(0, 3, 1, 2), mask_2d.permute(0, 3, 1, 2))[0].permute(0, 2, 3, 1)
         return {"mask_2d": mask_2d, "mask_2d_visiable": vis, "color_2d": color_2d, "pre_pull_push": color,
                 "rast_2d": torch.from_numpy(rast2)}
     # bake_mv_to_uv_reproject_blur
-    color = torch.zeros(1, H2, W2, 3)
+    color = torch.zeros(1, H2, W2, Cn)
     cur = torch.zeros(1, H2, W2, 1, dtype=torch.bool)
     bnd = torch.zeros(1, H2, W2, 1, dtype=torch.bool)
     owner = torch.full((H2, W2), -1, dtype=torch.int64)

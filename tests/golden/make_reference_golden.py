@@ -67,6 +67,11 @@ def bake():
         if name == "reproject":
             out["mask_2d_visiable"] = np.packbits(vis.numpy())
             out["mask_2d"] = np.packbits(m2d.numpy())
+    img9 = torch.cat([img, 0.5 * img + 0.1 * (img.sum(-1, keepdim=True) > 0), (1.0 - img) * (img.sum(-1, keepdim=True) > 0)], dim=-1)
+    for name, kw in (("reproject", dict(method="reproject")), ("kdtree_order_mean", variants["kdtree_order_mean"])):
+        r.register_query_field(None)
+        _, _, _, col = r.infer(None, c2ws, intr, img9, **common, **kw)              # image_attrs.shape[-1] == 9 (:711-719)
+        out[f"{name}.pbr9.color_2d"] = col.numpy()
     out["field.n_visible"] = np.array([c[0].shape[0] for c in field.calls])
     out["field.query_sum"] = np.stack([c[2].double().sum(0).numpy() for c in field.calls])
     # mv_to_pcd as the shipped path calls it (filt_gradient_points=False, pipeline.py:343-347)

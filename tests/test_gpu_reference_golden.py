@@ -50,6 +50,14 @@ def test_bake_variants_match_reference_infer(lib):
         assert err < COLOR_ATOL, (name, err)
         assert np.array_equal(vis.cpu().numpy(), _unpack(z["mask_2d_visiable"], (6, 64, 64, 1))), name
         assert np.array_equal(m2.cpu().numpy(), _unpack(z["mask_2d"], (1, 64, 64, 1))), name
+    on = (img.sum(-1, keepdim=True) > 0)
+    img9 = torch.cat([img, 0.5 * img + 0.1 * on, (1.0 - img) * on], dim=-1)                 # PBR attributes, 9 channels (:711-719)
+    for name in ("reproject", "kdtree_order_mean"):
+        _, vis, m2, col = r.infer(r.pbr_mesh, c2ws, intr, img9, **common, **variants[name])
+        torch.cuda.synchronize()
+        assert col.shape == (1, 64, 64, 9)
+        err = np.abs(col.cpu().numpy() - z[f"{name}.pbr9.color_2d"]).max()
+        assert err < COLOR_ATOL, (name, "pbr9", err)
     assert [c[0] for c in calls] == z["field.n_visible"].tolist()          # the field sees the same visible / query sets
     assert np.array_equal(np.stack([c[1] for c in calls]), z["field.query_sum"])   # ... bit-identical query positions, same order
     mv = r.mv_to_pcd(c2ws, intr, (48, 48), image_attrs=img, perspective=False, filt_gradient_points=False)

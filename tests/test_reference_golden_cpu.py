@@ -81,6 +81,11 @@ def test_infer_every_variant_matches_reference():
             assert np.array_equal(out["alpha_mv"].numpy() > 0, _unpack(z["mv.alpha_visiable"], (6, 48, 48, 1)))
     assert [c[0] for c in calls] == z["field.n_visible"].tolist()
     assert np.array_equal(np.stack([c[1] for c in calls]), z["field.query_sum"])
+    on = (img.sum(-1, keepdim=True) > 0)
+    img9 = torch.cat([img, 0.5 * img + 0.1 * on, (1.0 - img) * on], dim=-1)                 # image_attrs.shape[-1] == 9 (:711-719)
+    for name in ("reproject", "kdtree_order_mean"):
+        out = ob.infer(v, f, uv, fuv, c2ws, intr, img9, 48, 48, 64, 64, **variants[name])
+        assert np.array_equal(out["color_2d"].numpy(), z[f"{name}.pbr9.color_2d"]), name
 
 
 def test_attention_processor_matches_reference():

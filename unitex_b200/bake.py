@@ -303,9 +303,23 @@ class NVDiffRendererInverse:
         uncovered texels through the registered query field (:387-389, :427-432, :609-614)."""
         assert method in ("kdtree", "reproject")
         assert image_attrs.shape[-1] in (3, 9)
-        if perspective or filt_gradient_points or image_attrs.shape[-1] != 3:
+        if perspective or filt_gradient_points:
             raise NotImplementedError("B200 bake implements what CustomRGBTextureFullPipeline passes: orthographic views, "
-                                      "RGB attributes, filt_gradient_points=False (pipeline.py:335-348)")
+                                      "filt_gradient_points=False (pipeline.py:335-348)")
+        if image_attrs.shape[-1] == 9:
+            # PBR attributes (albedo | metallic-roughness | bump, :711-719): visibility, ownership, seams and neighbour indices do
+            # not depend on the colours and every colour stage is per channel, so the 9-channel bake is three RGB bakes.
+            if kdtree_inpainting or reproject_inpainting:
+                raise NotImplementedError("9-channel attributes with a query field: the field would see 3-channel colours")
+            kw = dict(H=H, W=W, H2D=H2D, W2D=W2D, perspective=perspective, grad_norm_threhold=grad_norm_threhold,
+                      ray_normal_angle_threhold=ray_normal_angle_threhold, grid_interpolate_mode=grid_interpolate_mode, method=method,
+                      kdtree_n_neighbors=kdtree_n_neighbors, kdtree_n_neighbors_visiable=kdtree_n_neighbors_visiable,
+                      kdtree_n_neighbors_invisiable=kdtree_n_neighbors_invisiable, kdtree_method=kdtree_method,
+                      reproject_method=reproject_method, reproject_kernel_size_boundary=reproject_kernel_size_boundary,
+                      reproject_kernel_size_boundary_blur=reproject_kernel_size_boundary_blur,
+                      reproject_kernel_size_blur=reproject_kernel_size_blur, filt_gradient_points=filt_gradient_points)
+            parts = [self.infer(blank_mesh, c2ws, intrinsics, image_attrs[..., 3 * i:3 * i + 3], **kw) for i in range(3)]
+            return None, parts[0][1], parts[0][2], torch.cat([p[3] for p in parts], dim=-1)
         if method == "reproject" and (reproject_method != "lens" or (reproject_kernel_size_boundary, reproject_kernel_size_boundary_blur) != (3, 3)):
             raise NotImplementedError("reproject bake: only reproject_method='lens' with the 3x3 boundary kernels")
         if method == "kdtree" and kdtree_method not in ("order_mean", "mean"):
