@@ -168,12 +168,13 @@ int utx_knn1(const float* src, int n_src, const float* dst, long long M, long lo
 int utx_knn(const float* src, int n_src, const float* dst, long long M, int k, long long* index, float* score, void* nodes,
             void* workspace, size_t workspace_bytes, void* stream);
 /* uv_to_pcd + bake_mv_to_uv_reproject_blur (renderer_inverse.py:243-365,574-633) fused.  rast2d: UV raster [H2,W2,4];
- * view_mats/view_dirs/priority/grid_lo: HOST arrays ([n,16] P@W2C row-major, [n,3] = -c2w[:3,2], [n], [3]);
+ * view_mats/view_dirs/priority/grid_lo: HOST arrays ([n,16] P@W2C row-major, [n,3] = -c2w[:3,2] for orthographic views (perspective = 0) or the
+ * camera positions c2w[:3,3] (perspective = 1; renderer_inverse.py:279-284), [n], [3]);
  * images_rgba: device [n,H,W,4] = view colour + visible alpha; blur_k2d: device [49].  Outputs: mask2d u8 [H2*W2],
  * mask_vis u8 [n, H2*W2], color [H2*W2, 3] fp32, nn_index i32 [H2*W2] or NULL. */
 size_t utx_uv_bake_workspace_bytes(int H2, int W2);
 int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
-                int n_views, const float* view_mats, const float* view_dirs, const int32_t* priority,
+                int n_views, const float* view_mats, const float* view_dirs, int perspective, const int32_t* priority,
                 const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
                 const float* grid_lo, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color,
                 int32_t* nn_index, void* workspace, size_t workspace_bytes, void* stream);
@@ -195,7 +196,7 @@ int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void*
  * utx_uv_bake == visibility; fill(k = 1); finish(blur = 1). */
 int utx_uv_bake_layout(int H2, int W2, size_t* off_owner, size_t* off_pos, size_t* off_color, size_t* off_seam);
 int utx_uv_bake_visibility(const float* vert, int V, const int32_t* tri, int F, const void* nodes, const float* rast2d, int H2,
-                           int W2, int n_views, const float* view_mats, const float* view_dirs, const int32_t* priority,
+                           int W2, int n_views, const float* view_mats, const float* view_dirs, int perspective, const int32_t* priority,
                            const float* images_rgba, int H, int W, float cos_thresh, unsigned char* mask2d,
                            unsigned char* mask_vis, void* workspace, size_t workspace_bytes, void* stream);
 size_t utx_uv_bake_views_workspace_bytes(int n_views, int H, int W);

@@ -99,6 +99,18 @@ def intr_to_proj_ortho(intr: torch.Tensor, near=0.01, far=1000.0) -> torch.Tenso
     return p
 
 
+def intr_to_proj_persp(intr: torch.Tensor, near=0.01, far=1000.0) -> torch.Tensor:
+    """camera/conversion.py:11-18, perspective=True branch + the y-row negation."""
+    p = torch.zeros(4, 4)
+    p[0, 0], p[1, 1] = 2 * intr[0, 0], 2 * intr[1, 1]
+    p[2, 2] = -(far + near) / (far - near)
+    p[0, 2], p[1, 2] = 2 * intr[0, 2] - 1, 2 * intr[1, 2] - 1
+    p[3, 2] = -1.0
+    p[2, 3] = -2.0 * far * near / (far - near)
+    p[1, :] = -p[1, :]
+    return p
+
+
 def c2w_to_w2c(c2w: torch.Tensor) -> torch.Tensor:
     w2c = torch.zeros_like(c2w)
     w2c[..., :3, :3] = c2w[..., :3, :3].transpose(-1, -2)
@@ -229,7 +241,8 @@ def infer_reproject(*a, **kw):
 def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, image_attrs: torch.Tensor,
                     H: int, W: int, H2: int, W2: int, angle_deg: float = 100.0, index=(0, 3, 4, 1, 2, 5), method: str = "reproject",
                     kdtree_method: str = "order_mean", k_all: int = 32, k_vis: int = 1, k_invis: int = 32,
-                    query_field=None) -> Dict[str, torch.Tensor]:
+                    query_field=None, filt_gradient_points: bool = False, grad_norm_threhold: float = 0.20,
+                    perspective: bool = False) -> Dict[str, torch.Tensor]:
     """NVDiffRendererInverse.infer(perspective=False, filt_gradient_points=False) (:635-726) for method='reproject'
     (reproject_method='lens') and method='kdtree' (kdtree_method 'order_mean' | 'mean'); `query_field` set = the
     *_inpainting=True branches (:387-389, :427-432, :609-614)."""
@@ -238,12 +251,32 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
     tri_uv = np.ascontiguousarray(tri_uv, np.int32)
     n = c2ws.shape[0]
     V = torch.from_numpy(vert)
-    mats = torch.matmul(intr_to_proj_ortho(intrinsics), c2w_to_w2c(c2ws))                   # [n,4,4]
+    mats = torch.matmul(intr_to_proj_persp(intrinsics) if perspective else intr_to_proj_ortho(intrinsics), c2w_to_w2c(c2ws))   # [n,4,4]
     vh = torch.cat([V, torch.ones_like(V[:, :1])], -1)
     clip = torch.matmul(vh, mats.permute(0, 2, 1))                                           # :263  [n,V,4]
     # mv_to_pcd :183-214
     rast_mv = torch.from_numpy(rasterize(clip.numpy(), tri, H, W))
     alpha_vis = (rast_mv[..., 3:4] > 0).float()
+    if filt_gradient_points:                                                                 # mv_to_pcd :188-214
+        mask_mv = rast_mv[..., 3:4] > 0
+        Fl = torch.from_numpy(tri.astype(np.int64))
+        ar = torch.linalg.cross(V[Fl[:, 1]] - V[Fl[:, 0]], V[Fl[:, 2]] - V[Fl[:, 0]], dim=-1)
+        vn = torch.zeros(V.shape[0], 3, 3)
+        vn.scatter_add_(0, Fl.unsqueeze(-1).expand(-1, -1, 3), ar.unsqueeze(1).expand(-1, 3, -1))     # structure_v2.py:63-71
+        vn = F.normalize(vn.mean(dim=1), dim=-1)
+        attrs = torch.from_numpy(interpolate(torch.cat([V, vn], -1).numpy(), rast_mv.numpy(), tri))
+        a_dy, a_dx = torch.gradient(attrs, dim=(1, 2))
+        gnorm = (a_dx.square() + a_dy.square()).sum(dim=-1, keepdim=True).sqrt()
+        tid_mv = rast_mv[..., 3:4].to(torch.int64).sub(1)
+        fn_mv = F.normalize(ar, dim=-1).gather(0, torch.where(mask_mv, tid_mv, 0).reshape(-1, 1).repeat(1, 3)).reshape(n, H, W, 3)
+        rd = attrs[..., 0:3] - c2ws[:, :3, 3][:, None, None, :] if perspective else (-c2ws[:, :3, 2])[:, None, None, :]    # :191-196
+        rd = F.normalize(rd, dim=-1)
+        cos_mv = F.cosine_similarity(torch.broadcast_tensors(rd, fn_mv)[0], fn_mv, dim=-1).unsqueeze(-1)
+        ok_grad = gnorm < grad_norm_threhold
+        # nn.MaxPool2d(31, 1, 15) applied to the [n,H,W,1] tensor as it stands (:204-205): torch reads it as [N, C=H, H=W, W=1],
+        # so the erosion runs along the image x axis only -- kept
+        eroded = (1.0 - F.max_pool2d(1.0 - ok_grad.float(), kernel_size=31, stride=1, padding=15)).bool()
+        alpha_vis = (mask_mv & (cos_mv < math.cos(math.radians(angle_deg))) & eroded).float()
     # uv_to_pcd
     uvc = np.concatenate([uv, np.zeros_like(uv[:, :1]), np.ones_like(uv[:, :1])], -1)[None].astype(np.float32)
     rast2 = rasterize(uvc, tri_uv, H2, W2)
@@ -254,8 +287,12 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
     areas = torch.linalg.cross(V[Ft[:, 1]] - V[Ft[:, 0]], V[Ft[:, 2]] - V[Ft[:, 0]], dim=-1)
     normals = F.normalize(areas, dim=-1)
     fn_2d = normals[torch.where(mask_2d[..., 0], tid_2d, torch.zeros_like(tid_2d))]          # [1,H2,W2,3]
-    rays_d = (-c2ws[:, :3, 2])[:, None, None, :]
-    rays_o = pos_2d - (2.0 * math.sqrt(3.0)) * rays_d
+    if perspective:                                                                          # :279-284
+        rays_o = c2ws[:, :3, 3][:, None, None, :]
+        rays_d = pos_2d - rays_o
+    else:
+        rays_d = (-c2ws[:, :3, 2])[:, None, None, :]
+        rays_o = pos_2d - (2.0 * math.sqrt(3.0)) * rays_d
     rays_d = F.normalize(rays_d, dim=-1)
     rays_o, rays_d = torch.broadcast_tensors(rays_o, rays_d)
     ndc_v = clip[..., :2] / clip[..., 3:4]
@@ -349,7 +386,7 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
 # ------------------------------------------------------------------------------------------------ forward G-buffers (b1)
 @torch.no_grad()
 def export_condition(vert, tri, vertex_normals, geometry_scale=1.0, n_views=6, n_rows=2, n_cols=3, H=512, W=512, scale=1.0,
-                     background=128.0 / 255.0):
+                     background=128.0 / 255.0, perspective=False, fov_deg=49.1):
     """VideoExporter.export_condition (video/export_nvdiffrast_video.py:900-999, orthographic box views) over
     NVDiffRendererBase.simple_rendering(render_world_normal, render_world_position, enable_antialis=False)
     (render/nvdiffrast/renderer_base.py:101-200) and Mesh.scale_to_bbox / apply_transform (mesh/structure.py:190-202,
@@ -367,8 +404,8 @@ def export_condition(vert, tri, vertex_normals, geometry_scale=1.0, n_views=6, n
     vn = F.normalize(torch.matmul(torch.from_numpy(np.ascontiguousarray(vertex_normals, np.float32)), T[:3, :3].T), dim=-1).contiguous()
     sel = {1: [0], 2: [0, 2], 4: [0, 1, 2, 3], 6: [0, 1, 4, 2, 3, 5] if (n_rows, n_cols) == (2, 3) else list(range(6))}[n_views]
     c2ws = generate_box_views_c2ws(radius=2.8)[sel]
-    intr = generate_intrinsics(scale, scale, fov=False, degree=False)
-    mvp = torch.matmul(intr_to_proj_ortho(intr), c2w_to_w2c(c2ws))
+    intr = generate_intrinsics(fov_deg, fov_deg, fov=True, degree=True) if perspective else generate_intrinsics(scale, scale, fov=False, degree=False)
+    mvp = torch.matmul(intr_to_proj_persp(intr) if perspective else intr_to_proj_ortho(intr), c2w_to_w2c(c2ws))
     clip = torch.matmul(torch.cat([v, torch.ones_like(v[:, :1])], -1), mvp.permute(0, 2, 1))
     tri = np.ascontiguousarray(tri, np.int32)
     rast = rasterize(clip.numpy(), tri, H, W)

@@ -98,12 +98,13 @@ void ora_rasterize(const float* pos, int pos_batched, int V, const int32_t* tri,
         if (key == ~0ull) { o[0] = o[1] = o[2] = o[3] = 0.0f; continue; }
         int f = (int)(uint32_t)key;
         int32_t X[3], Y[3];
-        float zn[3];
+        float zn[3], cw[3];
         for (int k = 0; k < 3; ++k) {
           const float* p = P + (size_t)tri[f * 3 + k] * 4;
           X[k] = snap(p[0] / p[3], W);
           Y[k] = snap(p[1] / p[3], H);
           zn[k] = p[2] / p[3];
+          cw[k] = p[3];
         }
         int64_t area = edge_fn(X[0], Y[0], X[1], Y[1], X[2], Y[2]);
         int64_t sgn = area > 0 ? 1 : -1;
@@ -113,6 +114,11 @@ void ora_rasterize(const float* pos, int pos_batched, int V, const int32_t* tri,
         float v = (float)(edge_fn(X[2], Y[2], X[0], Y[0], px, py) * sgn) / fa;   /* weight of vertex 1 */
         float w2 = (float)(edge_fn(X[0], Y[0], X[1], Y[1], px, py) * sgn) / fa;
         o[0] = u; o[1] = v;
+        if (!(cw[0] == 1.0f && cw[1] == 1.0f && cw[2] == 1.0f)) {   /* perspective-correct weights (nvdiffrast [ext]); w == 1: unchanged */
+          float a0 = u / cw[0], a1 = v / cw[1], a2 = w2 / cw[2];
+          float sum = (a0 + a1) + a2;
+          o[0] = a0 / sum; o[1] = a1 / sum;
+        }
         o[2] = (u * zn[0] + v * zn[1]) + w2 * zn[2];
         o[3] = (float)(f + 1);
       }

@@ -74,6 +74,34 @@ def bake():
         out[f"{name}.pbr9.color_2d"] = col.numpy()
     out["field.n_visible"] = np.array([c[0].shape[0] for c in field.calls])
     out["field.query_sum"] = np.stack([c[2].double().sum(0).numpy() for c in field.calls])
+    # filt_gradient_points=True -- the DEFAULT of infer's signature (:657); needs views wide enough to survive the 31-pixel erosion
+    big = dict(common, H=128, W=128, filt_gradient_points=True, grad_norm_threhold=0.2)
+    from oracle import bake as ob
+    from tests.bake_meshes import analytic_color
+    mats = torch.matmul(intr_to_proj(intr, perspective=False), c2w_to_w2c(c2ws))
+    rast128 = ob.rasterize(torch.matmul(torch.cat([torch.from_numpy(v), torch.ones(len(v), 1)], -1), mats.permute(0, 2, 1)).numpy(), f, 128, 128)
+    img128 = torch.from_numpy(analytic_color(ob.interpolate(v, rast128, f)) * (rast128[..., 3:4] > 0)).float()
+    out["filt.image"] = img128.numpy().astype(np.float16)
+    img128 = torch.from_numpy(out["filt.image"].astype(np.float32))
+    mvf = r.mv_to_pcd(c2ws, intr, (128, 128), image_attrs=img128, perspective=False, grad_norm_threhold=0.2,
+                      ray_normal_angle_threhold=100.0, filt_gradient_points=True)
+    out["filt.alpha_visiable"] = np.packbits(mvf["alpha_visiable"].numpy() > 0)
+    r.register_query_field(None)
+    _, visf, _, colf = r.infer(None, c2ws, intr, img128, **big, method="reproject")
+    out["filt.reproject.color_2d"] = colf.numpy()
+    out["filt.mask_2d_visiable"] = np.packbits(visf.numpy())
+    # perspective=True -- the other DEFAULT of infer's signature (:639): pinhole views, rays from the camera position (:279-284)
+    intr_p = generate_intrinsics(49.1, 49.1, fov=True, degree=True)
+    out["persp.intrinsics"] = intr_p.numpy()
+    out["persp.proj"] = intr_to_proj(intr_p, perspective=True).numpy()
+    mats_p = torch.matmul(intr_to_proj(intr_p, perspective=True), c2w_to_w2c(c2ws))
+    rast_p = ob.rasterize(torch.matmul(torch.cat([torch.from_numpy(v), torch.ones(len(v), 1)], -1), mats_p.permute(0, 2, 1)).numpy(), f, 48, 48)
+    img_p = torch.from_numpy((analytic_color(ob.interpolate(v, rast_p, f)) * (rast_p[..., 3:4] > 0)).astype(np.float16).astype(np.float32))
+    out["persp.image"] = img_p.numpy().astype(np.float16)
+    for name in ("reproject", "kdtree_order_mean"):
+        _, visp, m2p, colp = r.infer(None, c2ws, intr_p, img_p, **dict(common, perspective=True), **variants[name])
+        out[f"persp.{name}.color_2d"] = colp.numpy()
+    out["persp.mask_2d_visiable"] = np.packbits(visp.numpy())
     # mv_to_pcd as the shipped path calls it (filt_gradient_points=False, pipeline.py:343-347)
     mv0 = r.mv_to_pcd(c2ws, intr, (48, 48), image_attrs=img, perspective=False, filt_gradient_points=False)
     out["mv.alpha_visiable"] = np.packbits(mv0["alpha_visiable"].numpy() > 0)
@@ -230,13 +258,15 @@ def glue():
     vn = vertex_normals(torch.from_numpy(v), torch.from_numpy(f).long()).numpy()
     ve = rh.video_exporter(v, f, vn)
     out = {}
-    for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2))):
-        r = ve.export_condition("mesh.obj", geometry_scale=0.95, H=64, W=64, fov_deg=49.1, scale=1.0, perspective=False, orbit=False,
+    for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2)),
+                     ("four_persp", dict(n_views=4, n_rows=2, n_cols=2, perspective=True))):
+        kw = dict(dict(perspective=False), **kw)
+        r = ve.export_condition("mesh.obj", geometry_scale=0.95, H=64, W=64, fov_deg=49.1, scale=1.0, orbit=False,
                                 background="grey", return_info=False, return_image=True, return_mesh=False, return_camera=True, **kw)
         for k in ("alpha", "ccm", "normal"):
             out[f"cond.{name}.{k}"] = np.asarray(r[k])
         out[f"cond.{name}.c2ws"], out[f"cond.{name}.intrinsics"] = r["c2ws"].numpy(), r["intrinsics"].numpy()
-        assert r["perspective"] is False
+        assert r["perspective"] is kw["perspective"]
 
     mod = rh.top_level_pipeline()
     normal, ccm, ref = glue_inputs()

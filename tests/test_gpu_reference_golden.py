@@ -108,8 +108,10 @@ def test_export_condition_matches_reference(lib):
     from unitex_b200.export import VideoExporter
     z = np.load(os.path.join(G, "ref_glue.npz"))
     v, f, _, _ = two_spheres(10, 20)
-    for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2))):
-        out = VideoExporter().export_condition((v, f), geometry_scale=0.95, H=64, W=64, fov_deg=49.1, scale=1.0, perspective=False,
+    for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2)),
+                     ("four_persp", dict(n_views=4, n_rows=2, n_cols=2, perspective=True))):
+        kw = dict(dict(perspective=False), **kw)
+        out = VideoExporter().export_condition((v, f), geometry_scale=0.95, H=64, W=64, fov_deg=49.1, scale=1.0,
                                                orbit=False, background="grey", return_image=True, return_camera=True, **kw)
         assert np.array_equal(np.asarray(out["alpha"]), z[f"cond.{name}.alpha"]), name
         for k in ("ccm", "normal"):
@@ -117,7 +119,7 @@ def test_export_condition_matches_reference(lib):
             assert d.max() <= 1 and (d > 0).mean() < 0.01, (name, k, int(d.max()), float((d > 0).mean()))
         assert np.array_equal(out["c2ws"].cpu().numpy(), z[f"cond.{name}.c2ws"])
         assert np.array_equal(out["intrinsics"].cpu().numpy(), z[f"cond.{name}.intrinsics"])
-        assert out["perspective"] is False
+        assert out["perspective"] is kw["perspective"]
 
 
 def test_reproject_glue_matches_reference(lib, tmp_path):
@@ -167,3 +169,41 @@ def test_reproject_glue_matches_reference(lib, tmp_path):
     assert got == want, (got, want)
     assert np.array_equal(rec["c2ws"].cpu().numpy(), z["cond.six.c2ws"])
     assert sorted(n for n in os.listdir(d) if n.endswith((".glb", "_mask.png", "_uv.png"))) == ast.literal_eval(str(z["rq.files"]))
+
+
+def test_infer_filt_gradient_points_matches_reference(lib):
+    """filt_gradient_points=True (the default of the reference's infer signature): gradient-filtered view masks, then the bake."""
+    from unitex_b200 import bake as ub
+    z = np.load(os.path.join(G, "ref_bake.npz"))
+    v, f, uv, fuv = two_spheres(10, 20)
+    c2ws, intr = ub.generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]], ub.generate_intrinsics(1.0, 1.0, fov=False)
+    img = torch.from_numpy(z["filt.image"].astype(np.float32))
+    r = ub.NVDiffRendererInverse(pbr_mesh=ub.BakeMesh(v, f, uv, fuv))
+    mv = r.mv_to_pcd(c2ws, intr, (128, 128), image_attrs=img, perspective=False, grad_norm_threhold=0.2,
+                     ray_normal_angle_threhold=100.0, filt_gradient_points=True)
+    want = _unpack(z["filt.alpha_visiable"], (6, 128, 128, 1))
+    got = mv["alpha_visiable"].cpu().numpy() > 0
+    assert (got != want).sum() == 0, int((got != want).sum())
+    _, vis, m2, col = r.infer(r.pbr_mesh, c2ws, intr, img, H=128, W=128, H2D=64, W2D=64, perspective=False, grad_norm_threhold=0.2,
+                              ray_normal_angle_threhold=100.0, method="reproject", filt_gradient_points=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(vis.cpu().numpy(), _unpack(z["filt.mask_2d_visiable"], (6, 64, 64, 1)))
+    assert np.abs(col.cpu().numpy() - z["filt.reproject.color_2d"]).max() < COLOR_ATOL
+
+
+def test_infer_perspective_matches_reference(lib):
+    """perspective=True (the other default of the reference's infer signature): pinhole views, rays leave the camera position."""
+    from unitex_b200 import bake as ub
+    z = np.load(os.path.join(G, "ref_bake.npz"))
+    v, f, uv, fuv = two_spheres(10, 20)
+    c2ws, intr = ub.generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]], ub.generate_intrinsics(49.1, 49.1, fov=True, degree=True)
+    img = torch.from_numpy(z["persp.image"].astype(np.float32))
+    r = ub.NVDiffRendererInverse(pbr_mesh=ub.BakeMesh(v, f, uv, fuv))
+    common = dict(H=48, W=48, H2D=64, W2D=64, perspective=True, ray_normal_angle_threhold=100.0, filt_gradient_points=False)
+    for name, kw in (("reproject", dict(method="reproject")),
+                     ("kdtree_order_mean", dict(method="kdtree", kdtree_method="order_mean", kdtree_n_neighbors_visiable=9, kdtree_n_neighbors_invisiable=32))):
+        _, vis, m2, col = r.infer(r.pbr_mesh, c2ws, intr, img, **common, **kw)
+        torch.cuda.synchronize()
+        assert np.array_equal(vis.cpu().numpy(), _unpack(z["persp.mask_2d_visiable"], (6, 64, 64, 1))), name
+        err = np.abs(col.cpu().numpy() - z[f"persp.{name}.color_2d"]).max()
+        assert err < COLOR_ATOL, (name, err)

@@ -137,7 +137,8 @@ def test_export_condition_matches_reference():
     z = np.load(os.path.join(G, "ref_glue.npz"))
     v, f, _, _ = two_spheres(10, 20)
     vn = vertex_normals(torch.from_numpy(v), torch.from_numpy(f).long()).numpy()
-    for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2))):
+    for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2)),
+                     ("four_persp", dict(n_views=4, n_rows=2, n_cols=2, perspective=True))):
         out = ob.export_condition(v, f, vn, geometry_scale=0.95, H=64, W=64, scale=1.0, **kw)
         for k in ("alpha", "ccm", "normal"):
             assert np.array_equal(out[k], z[f"cond.{name}.{k}"]), (name, k)
@@ -171,3 +172,37 @@ def test_infer_mv_glue_matches_reference(tmp_path):
     assert repr(fake.adapters) == str(z["mv.adapters"])
     assert sha(np.array(Image.open(os.path.join(d, "mv_rgb.png")))) == str(z["mv.rgb_sha"])
     assert sha(np.array(Image.open(os.path.join(d, "mv_rgb_w_light.png")))) == str(z["mv.w_light_sha"])
+
+
+def test_infer_filt_gradient_points_matches_reference():
+    """filt_gradient_points=True, the default of the reference's infer signature (renderer_inverse.py:657): mv_to_pcd's gradient
+    filter with its x-only 31-pixel erosion (:188-214), then the reproject bake."""
+    from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics
+    z = np.load(os.path.join(G, "ref_bake.npz"))
+    v, f, uv, fuv = two_spheres(10, 20)
+    c2ws = generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]]
+    intr = generate_intrinsics(1.0, 1.0, fov=False)
+    img = torch.from_numpy(z["filt.image"].astype(np.float32))
+    out = ob.infer(v, f, uv, fuv, c2ws, intr, img, 128, 128, 64, 64, method="reproject", filt_gradient_points=True, grad_norm_threhold=0.2)
+    assert np.array_equal(out["alpha_mv"].numpy() > 0, _unpack(z["filt.alpha_visiable"], (6, 128, 128, 1)))
+    assert np.array_equal(out["mask_2d_visiable"].numpy(), _unpack(z["filt.mask_2d_visiable"], (6, 64, 64, 1)))
+    assert np.array_equal(out["color_2d"].numpy(), z["filt.reproject.color_2d"])
+
+
+def test_infer_perspective_matches_reference():
+    """perspective=True, the other default of the reference's infer signature (renderer_inverse.py:639): pinhole projection
+    (camera/conversion.py:11-18), rays from the camera position (:279-284)."""
+    from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics, intr_to_proj
+    z = np.load(os.path.join(G, "ref_bake.npz"))
+    v, f, uv, fuv = two_spheres(10, 20)
+    c2ws = generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]]
+    intr = generate_intrinsics(49.1, 49.1, fov=True, degree=True)
+    assert np.array_equal(intr.numpy(), z["persp.intrinsics"])
+    assert np.array_equal(intr_to_proj(intr, perspective=True).numpy(), z["persp.proj"])
+    assert np.array_equal(ob.intr_to_proj_persp(intr).numpy(), z["persp.proj"])
+    img = torch.from_numpy(z["persp.image"].astype(np.float32))
+    for name, kw in (("reproject", dict(method="reproject")), ("kdtree_order_mean", dict(method="kdtree", kdtree_method="order_mean", k_vis=9, k_invis=32))):
+        out = ob.infer(v, f, uv, fuv, c2ws, intr, img, 48, 48, 64, 64, perspective=True, **kw)
+        assert np.array_equal(out["color_2d"].numpy(), z[f"persp.{name}.color_2d"]), name
+    assert np.array_equal(out["mask_2d_visiable"].numpy(), _unpack(z["persp.mask_2d_visiable"], (6, 64, 64, 1)))
+    assert out["mask_2d_visiable"].sum() > 1000

@@ -83,13 +83,13 @@ _SIGS = {
     "utx_knn": (i32, [vp, i32, vp, C.c_longlong, i32, vp, vp, vp, vp, C.c_size_t, vp]),
     "utx_uv_bake_workspace_bytes": (C.c_size_t, [i32, i32]),
     "utx_uv_bake_layout": (i32, [i32, i32] + [C.POINTER(C.c_size_t)] * 4),
-    "utx_uv_bake_visibility": (i32, [vp, i32, vp, i32, vp, vp, i32, i32, i32, fp, fp, C.POINTER(C.c_int32), vp, i32, i32, f32,
+    "utx_uv_bake_visibility": (i32, [vp, i32, vp, i32, vp, vp, i32, i32, i32, fp, fp, i32, C.POINTER(C.c_int32), vp, i32, i32, f32,
                                      vp, vp, vp, C.c_size_t, vp]),
     "utx_uv_bake_views_workspace_bytes": (C.c_size_t, [i32, i32, i32]),
     "utx_uv_bake_views_knn": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, C.c_size_t, vp, C.c_size_t, vp]),
     "utx_uv_bake_fill": (i32, [vp, i32, i32, i32, vp, vp, C.c_size_t, vp]),
     "utx_uv_bake_finish": (i32, [vp, i32, i32, i32, vp, f32, vp, vp, C.c_size_t, vp]),
-    "utx_uv_bake": (i32, [vp, i32, vp, i32, vp, vp, i32, i32, i32, fp, fp, C.POINTER(C.c_int32), vp, i32, i32, f32, vp, f32,
+    "utx_uv_bake": (i32, [vp, i32, vp, i32, vp, vp, i32, i32, i32, fp, fp, i32, C.POINTER(C.c_int32), vp, i32, i32, f32, vp, f32,
                           fp, f32, vp, vp, vp, vp, vp, C.c_size_t, vp]),
 }
 

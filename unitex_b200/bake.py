@@ -216,6 +216,33 @@ class BakeMesh:
         self.faces_2d = torch.as_tensor(faces_2d).to(device=self.device, dtype=torch.int32).contiguous()
         assert self.faces.shape == self.faces_2d.shape
         self._optix = None
+        self._normals = None
+        self._vertex_normals = None
+
+    @property
+    def areas(self) -> torch.Tensor:
+        """Face area vectors, mesh/structure_v2.py:49."""
+        f = self.faces.long()
+        v = self.vertices
+        return torch.linalg.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]], dim=-1)
+
+    @property
+    def normals(self) -> torch.Tensor:
+        """Face normals, :50."""
+        if self._normals is None:
+            self._normals = torch.nn.functional.normalize(self.areas, dim=-1)
+        return self._normals
+
+    @property
+    def vertex_normals(self) -> torch.Tensor:
+        """Area-weighted vertex normals, :63-71 (only the gradient filter of mv_to_pcd reads them)."""
+        if self._vertex_normals is None:
+            f, a = self.faces.long(), self.areas
+            vn = torch.zeros(self.vertices.shape[0], 3, 3, device=self.device)      # one slot per triangle corner, then their mean
+            for k in range(3):
+                vn[:, k].index_add_(0, f[:, k], a)
+            self._vertex_normals = torch.nn.functional.normalize(vn.mean(dim=1), dim=-1)
+        return self._vertex_normals
 
     @property
     def optix(self) -> RayTracing:
@@ -249,7 +276,9 @@ def load_obj(path: str):
 
 # ------------------------------------------------------------------------------------------------ NVDiffRendererInverse (b5-b7)
 class NVDiffRendererInverse:
-    """Drop-in for render/nvdiffrast/renderer_inverse.py::NVDiffRendererInverse, method='reproject' path."""
+    """Drop-in for render/nvdiffrast/renderer_inverse.py::NVDiffRendererInverse: `infer` with method 'reproject' (lens blur) and
+    'kdtree' ('order_mean' | 'mean'), orthographic or perspective views, RGB or 9-channel PBR attributes, the gradient filter of
+    mv_to_pcd, and the `*_inpainting` query-field hook."""
 
     def __init__(self, device="cuda", pbr_mesh: Optional[BakeMesh] = None):
         self.device = torch.device(device)
@@ -274,14 +303,39 @@ class NVDiffRendererInverse:
     def _view_mats(self, c2ws, intrinsics, perspective):
         return torch.matmul(intr_to_proj(intrinsics.float().cpu(), perspective=perspective), c2w_to_w2c(c2ws.float().cpu()))
 
-    def mv_to_pcd(self, c2ws, intrinsics, render_size, image_attrs=None, perspective=True, **_):
-        """:159-241 with filt_gradient_points=False (what pipeline.py:343-347 passes): the visible alpha is the raster mask."""
+    def mv_to_pcd(self, c2ws, intrinsics, render_size, image_attrs=None, perspective=True, grad_norm_threhold=0.20,
+                  ray_normal_angle_threhold=115.0, filt_gradient_points=False):
+        """:159-241, the raster masks of the views.  filt_gradient_points=False (what pipeline.py:343-347 passes): the visible
+        alpha is the coverage mask.  True (the default of the reference's `infer`): a pixel also has to face its ray and lie
+        in a stretch where the screen-space gradient of (position, vertex normal) stays below `grad_norm_threhold` (:188-214)."""
         H, W = (render_size, render_size) if isinstance(render_size, int) else render_size
+        m = self.pbr_mesh
+        n = c2ws.shape[0]
         mats = self._view_mats(c2ws, intrinsics, perspective).to(self.device)
-        clip = transform_points(self.pbr_mesh.vertices, mats)
-        rast = rasterize(clip, self.pbr_mesh.faces, (H, W))
+        clip = transform_points(m.vertices, mats)
+        rast = rasterize(clip, m.faces, (H, W))
         mask = rast[..., 3:4] > 0
-        return {"mask": mask, "alpha": mask.float(), "mask_visiable": mask, "alpha_visiable": mask.float(), "rast": rast}
+        mask_vis = mask
+        if filt_gradient_points:
+            F_ = torch.nn.functional
+            attrs = interpolate(torch.cat([m.vertices, m.vertex_normals], dim=-1).contiguous(), rast, m.faces)
+            a_dy, a_dx = torch.gradient(attrs, dim=(1, 2))
+            gnorm = (a_dx.square() + a_dy.square()).sum(dim=-1, keepdim=True).sqrt()
+            tid = rast[..., 3:4].to(torch.int64).sub(1)
+            fn = m.normals.gather(0, torch.where(mask, tid, 0).reshape(-1, 1).repeat(1, 3)).reshape(n, H, W, 3)
+            c2 = c2ws.to(self.device, torch.float32)
+            if perspective:
+                rays_d = attrs[..., 0:3] - c2[:, :3, 3].unsqueeze(1).unsqueeze(1)
+            else:
+                rays_d = c2[:, :3, 2].neg().unsqueeze(1).unsqueeze(1)
+            rays_d = torch.broadcast_tensors(F_.normalize(rays_d, dim=-1), fn)[0]
+            cos = F_.cosine_similarity(rays_d, fn, dim=-1).unsqueeze(-1)
+            ok = gnorm < grad_norm_threhold
+            # the reference hands the [n,H,W,1] tensor to nn.MaxPool2d(31, 1, 15) as it stands (:204-205), which pools over
+            # (W, 1): the erosion runs along the image x axis only.  Same call, same effect.
+            eroded = (1.0 - F_.max_pool2d(1.0 - ok.float(), kernel_size=31, stride=1, padding=15)).bool()
+            mask_vis = mask & (cos < math.cos(math.radians(ray_normal_angle_threhold))) & eroded
+        return {"mask": mask, "alpha": mask.float(), "mask_visiable": mask_vis, "alpha_visiable": mask_vis.float(), "rast": rast}
 
     def query_field(self, vertices_visiable, colors_visiable, vertices_invisiable):
         """:139-154."""
@@ -303,9 +357,6 @@ class NVDiffRendererInverse:
         uncovered texels through the registered query field (:387-389, :427-432, :609-614)."""
         assert method in ("kdtree", "reproject")
         assert image_attrs.shape[-1] in (3, 9)
-        if perspective or filt_gradient_points:
-            raise NotImplementedError("B200 bake implements what CustomRGBTextureFullPipeline passes: orthographic views, "
-                                      "filt_gradient_points=False (pipeline.py:335-348)")
         if image_attrs.shape[-1] == 9:
             # PBR attributes (albedo | metallic-roughness | bump, :711-719): visibility, ownership, seams and neighbour indices do
             # not depend on the colours and every colour stage is per channel, so the 9-channel bake is three RGB bakes.
@@ -332,12 +383,14 @@ class NVDiffRendererInverse:
         L = _lib.load()
         n = c2ws.shape[0]
         assert n == len(self.index), "the reference bake is hard-wired to 6 views (renderer_inverse.py:171,256,589)"
-        mv = self.mv_to_pcd(c2ws, intrinsics, (H, W), perspective=perspective)
+        mv = self.mv_to_pcd(c2ws, intrinsics, (H, W), perspective=perspective, grad_norm_threhold=grad_norm_threhold,
+                            ray_normal_angle_threhold=ray_normal_angle_threhold, filt_gradient_points=filt_gradient_points)
         rgba = torch.cat([_f32(image_attrs, self.device), mv["alpha_visiable"]], dim=-1).contiguous()
         uv_clip = torch.cat([m.uvs_2d, torch.zeros_like(m.uvs_2d[:, :1]), torch.ones_like(m.uvs_2d[:, :1])], dim=-1)[None]
         rast2d = rasterize(uv_clip, m.faces_2d, (H2D, W2D))
         mats = self._view_mats(c2ws, intrinsics, perspective).contiguous()
-        dirs = (-c2ws[:, :3, 2]).float().cpu().contiguous()
+        # orthographic: the common ray direction -c2w[:3, 2]; perspective: the camera position the rays leave from (:279-284)
+        dirs = (c2ws[:, :3, 3] if perspective else -c2ws[:, :3, 2]).float().cpu().contiguous()
         prio = (C.c_int32 * n)(*self.index)
         T = H2D * W2D
         mask2d = torch.empty(T, device=self.device, dtype=torch.uint8)
@@ -353,7 +406,7 @@ class NVDiffRendererInverse:
                     color.reshape(1, H2D, W2D, 3))
 
         vis_args = (_p(m.vertices), m.vertices.shape[0], _p(m.faces), m.faces.shape[0], _p(m.optix.nodes), _p(rast2d), H2D, W2D,
-                    n, mats.numpy().ctypes.data_as(_lib.fp), dirs.numpy().ctypes.data_as(_lib.fp), prio, _p(rgba), H, W, cos_t)
+                    n, mats.numpy().ctypes.data_as(_lib.fp), dirs.numpy().ctypes.data_as(_lib.fp), int(bool(perspective)), prio, _p(rgba), H, W, cos_t)
         if method == "reproject" and not reproject_inpainting:
             lo_arr = (C.c_float * 3)(0.0, 0.0, 0.0)
             _lib.check(L.utx_uv_bake(*vis_args, _p(self._k2d), 5.0, lo_arr, 1.0, _p(mask2d), _p(mask_vis), _p(color),

@@ -36,7 +36,7 @@ __device__ __forceinline__ int snap(float ndc, int size) {
 
 struct TriSetup {
   int X[3], Y[3];
-  float zn[3];
+  float zn[3], w[3];
   long long area;
   bool ok;
 };
@@ -51,6 +51,7 @@ __device__ __forceinline__ TriSetup setup_tri(const float* __restrict__ P, const
     t.X[k] = snap(p.x / p.w, W);
     t.Y[k] = snap(p.y / p.w, H);
     t.zn[k] = p.z / p.w;
+    t.w[k] = p.w;
   }
   t.area = edge_fn(t.X[0], t.Y[0], t.X[1], t.Y[1], t.X[2], t.Y[2]);
   if (t.area == 0) t.ok = false;
@@ -171,7 +172,16 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(const float* __rest
   const float u = static_cast<float>(edge_fn(t.X[1], t.Y[1], t.X[2], t.Y[2], px, py) * sgn) / fa;
   const float v = static_cast<float>(edge_fn(t.X[2], t.Y[2], t.X[0], t.Y[0], px, py) * sgn) / fa;
   const float w2 = static_cast<float>(edge_fn(t.X[0], t.Y[0], t.X[1], t.Y[1], px, py) * sgn) / fa;
-  out[i] = make_float4(u, v, (u * t.zn[0] + v * t.zn[1]) + w2 * t.zn[2], static_cast<float>(f + 1));
+  // (u, v) are perspective-correct like nvdiffrast's: screen-space weights divided by the clip w of their vertex and
+  // renormalised.  Skipped when all three w are exactly 1 (orthographic views, the UV-space raster): results there are unchanged.
+  float uu = u, vv = v;
+  if (!(t.w[0] == 1.0f && t.w[1] == 1.0f && t.w[2] == 1.0f)) {
+    const float a0 = u / t.w[0], a1 = v / t.w[1], a2 = w2 / t.w[2];
+    const float sum = (a0 + a1) + a2;
+    uu = a0 / sum;
+    vv = a1 / sum;
+  }
+  out[i] = make_float4(uu, vv, (u * t.zn[0] + v * t.zn[1]) + w2 * t.zn[2], static_cast<float>(f + 1));
 }
 
 __global__ void __launch_bounds__(256) interpolate_kernel(const float* __restrict__ attr, int attr_batched, int V, int C,

@@ -38,7 +38,8 @@ constexpr int MAXV = 8;
 struct Views {
   int n;
   float mat[MAXV][16];   // P @ W2C, row-major
-  float dir[MAXV][3];    // -c2w[:3, 2]
+  float dir[MAXV][3];    // orthographic: -c2w[:3, 2]; perspective: the camera position c2w[:3, 3]
+  int perspective;
   int priority[MAXV];
 };
 
@@ -126,7 +127,9 @@ __global__ void __launch_bounds__(128) texel_prep_kernel(const float4* __restric
       n[0] = n[0] / nl; n[1] = n[1] / nl; n[2] = n[2] / nl;
       const float nn = fmaxf(norm3(n[0], n[1], n[2]), 1e-8f);
       for (int i = 0; i < vw.n; ++i) {
-        const float* dr = vw.dir[i];
+        // ray direction (:279-285): the view direction (orthographic) or texel position - camera position (perspective)
+        const float dr[3] = {vw.perspective ? pos[0] - vw.dir[i][0] : vw.dir[i][0], vw.perspective ? pos[1] - vw.dir[i][1] : vw.dir[i][1],
+                             vw.perspective ? pos[2] - vw.dir[i][2] : vw.dir[i][2]};
         const float dl = fmaxf(norm3(dr[0], dr[1], dr[2]), 1e-12f);
         const float d[3] = {dr[0] / dl, dr[1] / dl, dr[2] / dl};
         const float dn = fmaxf(norm3(d[0], d[1], d[2]), 1e-8f);
@@ -177,8 +180,10 @@ __global__ void __launch_bounds__(128) ray_kernel(const int* __restrict__ lists,
   const int f = static_cast<int>(rast[t].w) - 1;
   const float pos[3] = {pos_in[static_cast<size_t>(t) * 3], pos_in[static_cast<size_t>(t) * 3 + 1], pos_in[static_cast<size_t>(t) * 3 + 2]};
   const float k2s3 = 3.4641016151377544f;   // float32(2 * sqrt(3)), renderer_inverse.py:284
-  const float* dr = vw.dir[view];
-  const float o[3] = {pos[0] - k2s3 * dr[0], pos[1] - k2s3 * dr[1], pos[2] - k2s3 * dr[2]};
+  const float* vd = vw.dir[view];
+  const float dr[3] = {vw.perspective ? pos[0] - vd[0] : vd[0], vw.perspective ? pos[1] - vd[1] : vd[1], vw.perspective ? pos[2] - vd[2] : vd[2]};
+  const float o[3] = {vw.perspective ? vd[0] : pos[0] - k2s3 * dr[0], vw.perspective ? vd[1] : pos[1] - k2s3 * dr[1],
+                      vw.perspective ? vd[2] : pos[2] - k2s3 * dr[2]};       // :279-284
   const float dl = fmaxf(norm3(dr[0], dr[1], dr[2]), 1e-12f);
   float d[3] = {dr[0] / dl, dr[1] / dl, dr[2] / dl};                    // F.normalize (:285)
   const float len = norm3(d[0], d[1], d[2]);                            // the tracer normalises again (intersect_test2.slang:283)
@@ -592,7 +597,7 @@ void uv_bake_layout(int H2, int W2, size_t* off_owner, size_t* off_pos, size_t* 
 // Leaves in the workspace: owner i8 [T] (winning view or -1), pos fp32 [T,3], colour fp32 [T,3] (the owner's reprojected
 // colour, 0 elsewhere), seam u8 [T].
 int uv_bake_visibility(const float* vert, int V, const int* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
-                       int n_views, const float* view_mats_host, const float* view_dirs_host, const int* priority_host,
+                       int n_views, const float* view_mats_host, const float* view_dirs_host, int perspective, const int* priority_host,
                        const float* images_rgba, int H, int W, float cos_thresh, unsigned char* mask2d,
                        unsigned char* mask_vis, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   (void)V;
@@ -601,6 +606,7 @@ int uv_bake_visibility(const float* vert, int V, const int* tri, int F, const vo
   const int T = H2 * W2;
   Views vw;
   vw.n = n_views;
+  vw.perspective = perspective != 0;
   for (int i = 0; i < n_views; ++i) {
     for (int k = 0; k < 16; ++k) vw.mat[i][k] = view_mats_host[i * 16 + k];
     for (int k = 0; k < 3; ++k) vw.dir[i][k] = view_dirs_host[i * 3 + k];
@@ -769,12 +775,12 @@ int uv_bake_finish(const unsigned char* mask2d, int H2, int W2, int blur, const 
 
 // The three stages back to back = NVDiffRendererInverse.infer(method='reproject', reproject_method='lens') (:635-726)
 int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
-            int n_views, const float* view_mats_host, const float* view_dirs_host, const int* priority_host,
+            int n_views, const float* view_mats_host, const float* view_dirs_host, int perspective, const int* priority_host,
             const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
             const float* grid_lo_host, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color_out,
             int* nn_index_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
   (void)grid_lo_host; (void)grid_extent;
-  UTX_TRY(uv_bake_visibility(vert, V, tri, F, nodes, rast2d, H2, W2, n_views, view_mats_host, view_dirs_host, priority_host,
+  UTX_TRY(uv_bake_visibility(vert, V, tri, F, nodes, rast2d, H2, W2, n_views, view_mats_host, view_dirs_host, perspective, priority_host,
                              images_rgba, H, W, cos_thresh, mask2d, mask_vis, workspace, ws_bytes, stream));
   UTX_TRY(uv_bake_fill(mask2d, H2, W2, 1, nn_index_out, workspace, ws_bytes, stream));
   return uv_bake_finish(mask2d, H2, W2, 1, blur_k2d, blur_gamma, color_out, workspace, ws_bytes, stream);

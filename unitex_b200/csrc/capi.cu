@@ -145,12 +145,12 @@ int utx_uv_bake_layout(int H2, int W2, size_t* off_owner, size_t* off_pos, size_
   return 0;
 }
 int utx_uv_bake_visibility(const float* vert, int V, const int32_t* tri, int F, const void* nodes, const float* rast2d, int H2,
-                           int W2, int n_views, const float* view_mats, const float* view_dirs, const int32_t* priority,
+                           int W2, int n_views, const float* view_mats, const float* view_dirs, int perspective, const int32_t* priority,
                            const float* images_rgba, int H, int W, float cos_thresh, unsigned char* mask2d,
                            unsigned char* mask_vis, void* workspace, size_t workspace_bytes, void* stream) {
   UTX_CHECK(vert && tri && nodes && rast2d && view_mats && view_dirs && priority && images_rgba && mask2d && mask_vis && workspace,
             "utx_uv_bake_visibility: null pointer");
-  return uv_bake_visibility(vert, V, tri, F, nodes, rast2d, H2, W2, n_views, view_mats, view_dirs, priority, images_rgba, H, W,
+  return uv_bake_visibility(vert, V, tri, F, nodes, rast2d, H2, W2, n_views, view_mats, view_dirs, perspective, priority, images_rgba, H, W,
                             cos_thresh, mask2d, mask_vis, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 int utx_uv_bake_fill(const unsigned char* mask2d, int H2, int W2, int k, int32_t* nn_index, void* workspace,
@@ -173,14 +173,14 @@ int utx_uv_bake_finish(const unsigned char* mask2d, int H2, int W2, int blur, co
                         static_cast<cudaStream_t>(stream));
 }
 int utx_uv_bake(const float* vert, int V, const int32_t* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
-                int n_views, const float* view_mats, const float* view_dirs, const int32_t* priority,
+                int n_views, const float* view_mats, const float* view_dirs, int perspective, const int32_t* priority,
                 const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
                 const float* grid_lo, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color,
                 int32_t* nn_index, void* workspace, size_t workspace_bytes, void* stream) {
   UTX_CHECK(vert && tri && nodes && rast2d && view_mats && view_dirs && priority && images_rgba && blur_k2d && grid_lo &&
                 mask2d && mask_vis && color && workspace,
             "utx_uv_bake: null pointer");
-  return uv_bake(vert, V, tri, F, nodes, rast2d, H2, W2, n_views, view_mats, view_dirs, priority, images_rgba, H, W,
+  return uv_bake(vert, V, tri, F, nodes, rast2d, H2, W2, n_views, view_mats, view_dirs, perspective, priority, images_rgba, H, W,
                  cos_thresh, blur_k2d, blur_gamma, grid_lo, grid_extent, mask2d, mask_vis, color, nn_index, workspace,
                  workspace_bytes, static_cast<cudaStream_t>(stream));
 }

@@ -111,7 +111,7 @@ size_t uv_bake_workspace_bytes(int H2, int W2);
 // staged form of uv_bake over one workspace (bake_uv.cu): visibility -> [views_knn] -> fill -> finish
 void uv_bake_layout(int H2, int W2, size_t* off_owner, size_t* off_pos, size_t* off_color, size_t* off_seam);
 int uv_bake_visibility(const float* vert, int V, const int* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
-                       int n_views, const float* view_mats_host, const float* view_dirs_host, const int* priority_host,
+                       int n_views, const float* view_mats_host, const float* view_dirs_host, int perspective, const int* priority_host,
                        const float* images_rgba, int H, int W, float cos_thresh, unsigned char* mask2d,
                        unsigned char* mask_vis, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int uv_bake_fill(const unsigned char* mask2d, int H2, int W2, int k, int* nn_index_out, void* workspace, size_t ws_bytes,
@@ -123,7 +123,7 @@ int uv_bake_views_knn(const float* pix_pos, const float* images_rgba, int n_view
 int uv_bake_finish(const unsigned char* mask2d, int H2, int W2, int blur, const float* blur_k2d, float blur_gamma,
                    float* color_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int uv_bake(const float* vert, int V, const int* tri, int F, const void* nodes, const float* rast2d, int H2, int W2,
-            int n_views, const float* view_mats_host, const float* view_dirs_host, const int* priority_host,
+            int n_views, const float* view_mats_host, const float* view_dirs_host, int perspective, const int* priority_host,
             const float* images_rgba, int H, int W, float cos_thresh, const float* blur_k2d, float blur_gamma,
             const float* grid_lo_host, float grid_extent, unsigned char* mask2d, unsigned char* mask_vis, float* color_out,
             int* nn_index_out, void* workspace, size_t ws_bytes, cudaStream_t stream);

@@ -65,8 +65,8 @@ class VideoExporter:
                          return_image=True, return_mesh=False, return_camera=False) -> Dict:
         from PIL import Image
         assert n_views == n_rows * n_cols, f"Value Error: (n_views, n_rows, n_cols)={(n_views, n_rows, n_cols)}"
-        if perspective or orbit:
-            raise NotImplementedError("B200 export_condition implements the orthographic box views UniTEX uses (pipeline.py:199-216)")
+        if orbit:
+            raise NotImplementedError("B200 export_condition implements the box views UniTEX uses (pipeline.py:199-216), not the orbit")
         if isinstance(mesh_path, str):
             V, F, _, _ = ub.load_obj(mesh_path)
         else:
@@ -77,8 +77,8 @@ class VideoExporter:
         c2ws = ub.generate_box_views_c2ws(radius=2.8)
         sel = {1: [0], 2: [0, 2], 4: [0, 1, 2, 3], 6: [0, 1, 4, 2, 3, 5] if (n_rows, n_cols) == (2, 3) else [0, 1, 2, 3, 4, 5]}[n_views]
         c2ws = c2ws[sel]
-        intr = ub.generate_intrinsics(scale, scale, fov=False)
-        mats = torch.matmul(ub.intr_to_proj(intr, perspective=False), ub.c2w_to_w2c(c2ws)).to(self.device)
+        intr = ub.generate_intrinsics(fov_deg, fov_deg, fov=True, degree=True) if perspective else ub.generate_intrinsics(scale, scale, fov=False)
+        mats = torch.matmul(ub.intr_to_proj(intr, perspective=bool(perspective)), ub.c2w_to_w2c(c2ws)).to(self.device)
         rast = ub.rasterize(ub.transform_points(v.contiguous(), mats), f, (H, W))
         alpha = (rast[..., 3:4] > 0).float()
         attrs = ub.interpolate(torch.cat([v, vn], -1).contiguous(), rast, f)
