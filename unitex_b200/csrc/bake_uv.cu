@@ -343,10 +343,8 @@ __global__ void __launch_bounds__(256) nn_compact_kernel(const signed char* __re
   pts[static_cast<size_t>(k) * 3 + 1] = pos[static_cast<size_t>(t) * 3 + 1];
   pts[static_cast<size_t>(k) * 3 + 2] = pos[static_cast<size_t>(t) * 3 + 2];
 }
-__global__ void __launch_bounds__(128) nn_query_kernel(const int* __restrict__ qlist, int n_q, const float* __restrict__ pos,
-                                                       const PointTree pt, const float* color_in, float* color_out,
-                                                       int* __restrict__ nn_index, int W2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void nn_query_run(const int* __restrict__ qlist, int n_q, const float* __restrict__ pos, const PointTree& pt,
+                                             const float* color_in, float* color_out, int* __restrict__ nn_index, int W2, int i) {
   if (i >= n_q) return;
   const int t = qlist[i];
   const float q[3] = {pos[static_cast<size_t>(t) * 3], pos[static_cast<size_t>(t) * 3 + 1], pos[static_cast<size_t>(t) * 3 + 2]};
@@ -366,6 +364,130 @@ __global__ void __launch_bounds__(128) nn_query_kernel(const int* __restrict__ q
     color_out[t * 3] = color_in[static_cast<size_t>(best) * 3];
     color_out[t * 3 + 1] = color_in[static_cast<size_t>(best) * 3 + 1];
     color_out[t * 3 + 2] = color_in[static_cast<size_t>(best) * 3 + 2];
+  }
+}
+// Per-lane refill ("persistent threads"): a lane whose walk has ended takes the next query of the list at once instead of idling
+// until the slowest lane of its warp is done.  The walks are long-tailed (points scored per query on the bench bake: median 112,
+// p90 448, p99 1456 -- scripts/nn_visits.py), so with one query per lane per warp-run 12.7 of 32 lanes were active on average.
+// Every loop iteration advances each active lane's walk by ONE entry (a 4-wide record or a leaf of 8 points); the walk itself is
+// point_tree_walk's (nearest entry first, bound re-checked at pop time), and the result -- exact nearest point, lowest id on
+// ties -- does not depend on the order in which queries or entries are taken.
+// MEASURED SLOWER (UTX_NN_IMPL=1, kept for the record): 2.9 ms against 2.5 ms for the run-per-warp kernel on the bench bake,
+// identical output.  Lanes then hold unrelated queries, every 16-byte record load touches its own line and the converged walks of
+// neighbouring queries are lost: the kernel is bound by memory latency (long-scoreboard 4.3 stalls per issue,
+// profiles/r01_nn_query_persist.ncu-rep), not by idle lanes.
+__global__ void __launch_bounds__(128) nn_query_refill_kernel(const int* __restrict__ qlist, int n_q, const float* __restrict__ pos,
+                                                              const PointTree pt, const float* color_in, float* color_out,
+                                                              int* __restrict__ nn_index, int* __restrict__ next_query) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int sn[64];
+  float sb[64];
+  bool active = false, exhausted = false, have = false;
+  int t = 0, count = 0, ref = 0, best_id = -1;
+  float q[3] = {0.f, 0.f, 0.f}, bound = 0.f, best = INFINITY;
+  for (;;) {
+    const unsigned need = __ballot_sync(FULL, !active && !exhausted);
+    if (need) {
+      const int leader = __ffs(need) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(next_query, __popc(need));
+      base = __shfl_sync(FULL, base, leader);
+      if (!active && !exhausted) {
+        const int i = base + __popc(need & ((1u << lane) - 1u));
+        if (i >= n_q) {
+          exhausted = true;
+        } else {
+          t = qlist[i];
+          q[0] = pos[static_cast<size_t>(t) * 3]; q[1] = pos[static_cast<size_t>(t) * 3 + 1]; q[2] = pos[static_cast<size_t>(t) * 3 + 2];
+          best = INFINITY; best_id = -1; count = 0;
+          have = true; ref = pt.n_c <= 1 ? ~0 : 0; bound = 0.f;      // a tree of one cluster is its only leaf
+          active = true;
+        }
+      }
+    }
+    if (__ballot_sync(FULL, active) == 0) break;                      // nobody holds a query and the list is exhausted
+    if (!active) continue;
+    if (!have) {
+      if (count == 0) {                                               // walk finished: publish, free the lane
+        if (nn_index) nn_index[t] = best_id;
+        if (best_id >= 0) {
+          color_out[t * 3] = color_in[static_cast<size_t>(best_id) * 3];
+          color_out[t * 3 + 1] = color_in[static_cast<size_t>(best_id) * 3 + 1];
+          color_out[t * 3 + 2] = color_in[static_cast<size_t>(best_id) * 3 + 2];
+        }
+        active = false;
+        continue;
+      }
+      --count;
+      ref = sn[count];
+      bound = sb[count];
+    }
+    have = false;
+    if (bound > best) continue;
+    if (ref < 0) {                                                    // leaf: score its points
+      const int c = ~ref;
+      const int j0 = c * PT_CLUSTER, j1 = min(j0 + PT_CLUSTER, pt.n);
+      for (int j = j0; j < j1; ++j) {
+        const float4 p = __ldg(pt.spts + j);
+        const float dx = p.x - q[0], dy = p.y - q[1], dz = p.z - q[2];
+        const float d2 = (dx * dx + dy * dy) + dz * dz;
+        const int id = __float_as_int(p.w);
+        if (d2 < best || (d2 == best && id < best_id) || best_id < 0) { best = d2; best_id = id; }
+      }
+      continue;
+    }
+    const WideRec r = wide_load(pt.wide, ref);
+    float bd[4];
+    int nearest = 0;
+    float nkey = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      bd[k] = r.ref[k] != WIDE_EMPTY ? box_dist2(r.bb + 6 * k, q) * 0.999999f : INFINITY;
+      if (bd[k] < nkey) { nkey = bd[k]; nearest = k; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (r.ref[k] == WIDE_EMPTY || !(bd[k] <= best)) continue;
+      if (k == nearest) { have = true; ref = r.ref[k]; bound = bd[k]; }
+      else if (count < 64) { sn[count] = r.ref[k]; sb[count] = bd[k]; ++count; }
+    }
+  }
+}
+
+#ifdef UTX_NN_DEBUG
+// diagnosis only (scripts/nn_visits.py): points scored per query instead of the neighbour index
+__global__ void __launch_bounds__(128) nn_count_kernel(const int* __restrict__ qlist, int n_q, const float* __restrict__ pos,
+                                                       const PointTree pt, int* __restrict__ count_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_q) return;
+  const int t = qlist[i];
+  const float q[3] = {pos[static_cast<size_t>(t) * 3], pos[static_cast<size_t>(t) * 3 + 1], pos[static_cast<size_t>(t) * 3 + 2]};
+  float best = INFINITY;
+  int best_id = -1, scored = 0;
+  point_tree_walk(pt, q, [&]() { return best; },
+                  [&](float d2, int id) {
+                    ++scored;
+                    if (d2 < best || (d2 == best && id < best_id) || best_id < 0) { best = d2; best_id = id; }
+                  });
+  count_out[t] = scored;
+}
+#endif
+// Persistent warps: every warp takes the next run of 32 consecutive list entries from a global counter until the list is
+// exhausted.  Walk lengths are very uneven (a query deep inside an occluded region scans the whole rim of its empty ball), and with
+// one fixed block of queries per CTA the kernel ran at 29 % of its resident warps (profiles/r01_bake_ray_nn.metrics.csv): a CTA's
+// slot was held until its slowest warp finished, and the last wave left most SMs idle.  (Measured: no change, 2.49 ms -- the
+// list is only 2.3 runs per resident warp, so the tail of one run remains; kept because it is never worse.)
+__global__ void __launch_bounds__(128) nn_query_kernel(const int* __restrict__ qlist, int n_q, const float* __restrict__ pos,
+                                                       const PointTree pt, const float* color_in, float* color_out,
+                                                       int* __restrict__ nn_index, int W2, int* __restrict__ next_run) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int run = 0;
+    if (lane == 0) run = atomicAdd(next_run, 1);
+    run = __shfl_sync(0xffffffffu, run, 0);
+    if (run * 32 >= n_q) return;
+    nn_query_run(qlist, n_q, pos, pt, color_in, color_out, nn_index, W2, run * 32 + lane);
   }
 }
 
@@ -657,9 +779,21 @@ int uv_bake_fill(const unsigned char* mask2d, int H2, int W2, int k, int* nn_ind
   const PointTree pt = point_tree_view(nn_nodes, n_pts);
   const unsigned gq = (n_q + 127) / 128;
   if (k == 1)
-    nn_query_kernel<<<gq, 128, 0, stream>>>(qlist, n_q, w.pos, pt, w.col_a, w.col_a, nn_index_out, W2);
+  {
+    int* next_run = w.counters + MAXV + 1;
+    UTX_CUDA(cudaMemsetAsync(next_run, 0, 4, stream));
+    const unsigned persistent = std::min<unsigned>(gq, static_cast<unsigned>(num_sms()) * 16u);   // 16 CTAs of 128 threads per SM
+    static const int impl = std::getenv("UTX_NN_IMPL") ? std::atoi(std::getenv("UTX_NN_IMPL")) : 0;   // 0 (default): runs of 32 neighbouring queries per warp; 1: per-lane refill
+    if (impl == 1)
+      nn_query_refill_kernel<<<persistent, 128, 0, stream>>>(qlist, n_q, w.pos, pt, w.col_a, w.col_a, nn_index_out, next_run);
+    else
+      nn_query_kernel<<<persistent, 128, 0, stream>>>(qlist, n_q, w.pos, pt, w.col_a, w.col_a, nn_index_out, W2, next_run);
+  }
   else
     knn_mean_kernel<<<gq, 128, 0, stream>>>(mask2d, w.owner, -1, w.pos, T, pt, k, w.col_a, w.col_a, nn_index_out, qlist, n_q);
+#ifdef UTX_NN_DEBUG
+  if (k == 1 && nn_index_out && std::getenv("UTX_NN_COUNT")) nn_count_kernel<<<gq, 128, 0, stream>>>(qlist, n_q, w.pos, pt, nn_index_out);
+#endif
   UTX_CUDA(cudaGetLastError());
   return 0;
 }
