@@ -154,6 +154,11 @@ def run_reference(args, rank, world):
     times = []
     cores = 1
     for i in range(args.warmup + args.steps):
+        if "uv_bake" in out:
+            try:
+                out["uv_bake"]["cpu_baseline"] = bench_uv_bake_cpu()
+            except Exception as e:      # the C oracle needs gcc on the box; the main line must not depend on it
+                out["uv_bake"]["cpu_baseline"] = {"unavailable": repr(e)[:200]}
         dt, cores = cpu_block_seconds(1)
         if i >= args.warmup:
             times.append(dt)
@@ -491,6 +496,29 @@ def bench_uv_bake(dev, return_tensors=False):
                          "frac": algo / (gpu_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": algo, "traffic": None,
                          "note": "compulsory bytes of SURVEY 8d; the bake is BVH-traversal (latency) bound, not streaming"},
             "mrays_per_s": 6 * covered / 1e6 / (gpu_ms * 1e-3)}
+
+
+def bench_uv_bake_cpu():
+    """CPU baseline of metric 2: the oracle's restatement of NVDiffRendererInverse.infer (C rasteriser / LBVH tracer of
+    oracle/bake_ref.c + the reference's torch tail) on the host cores, on a BOUNDED case: two-sphere mesh with 8 k faces, 6 views
+    128^2, atlas 256^2.  Reported as measured (no extrapolation: its exact nearest-neighbour fill is brute force, so the cost grows
+    faster than the texel count)."""
+    import numpy as np
+    import torch
+    from oracle import bake as ob
+    from tests.bake_meshes import analytic_color, two_spheres
+    from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics
+    v, f, uv, fuv = two_spheres(40, 80)
+    c2ws, intr = generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]], generate_intrinsics(1.0, 1.0, fov=False)
+    mats = torch.matmul(ob.intr_to_proj_ortho(intr), ob.c2w_to_w2c(c2ws))
+    H, H2 = 128, 256
+    rast = ob.rasterize(torch.matmul(torch.cat([torch.from_numpy(v), torch.ones(len(v), 1)], -1), mats.permute(0, 2, 1)).numpy(), f, H, H)
+    img = torch.from_numpy(analytic_color(ob.interpolate(v, rast, f)) * (rast[..., 3:4] > 0)).float()
+    t0 = time.perf_counter()
+    ob.infer(v, f, uv, fuv, c2ws, intr, img, H, H, H2, H2)
+    dt = time.perf_counter() - t0
+    return {"value": H2 * H2 / 1e6 / dt, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": "port", "seconds": dt,
+            "sample": "oracle infer(method='reproject') on a two-sphere mesh with 8000 faces, 6 views 128^2, atlas 256^2; measured, not extrapolated"}
 
 
 def main():

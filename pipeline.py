@@ -73,7 +73,7 @@ class RGBTextureFullPipelineBase:
         """reference :170-179 -> geometry/uv/uv_atlas.py:131-194: the bounding box is centred and its longest side scaled to
         2*scale (float64, like the open3d transform there) -- the bake's cameras assume that frame -- and the mesh is written as
         processed_mesh.obj.  The UV unwrap of meshes without UVs (open3d compute_uvatlas [ext]) is out of scope: UVs are required."""
-        V, F, UV, Ft = ub.load_obj(input_mesh_path)
+        V, F, UV, Ft = ub.load_mesh(input_mesh_path)           # .obj or .glb, like the reference's test cases
         if len(UV) == 0:
             raise NotImplementedError("mesh without UVs: UV-atlas generation (open3d/xatlas) is out of scope")
         V = np.asarray(V, dtype=np.float64)

@@ -4,8 +4,13 @@ import hashlib
 import json
 import sys
 sys.path.insert(0, ".")
+import os
 import torch
 import bench
+if os.environ.get("UTX_LIB"):      # A/B against an alternative build of the library
+    from pathlib import Path
+    from unitex_b200 import _lib
+    _lib._LIB_PATH = Path(os.environ["UTX_LIB"])
 
 dev = torch.device("cuda", 0)
 out = bench.bench_uv_bake(dev, return_tensors=True)

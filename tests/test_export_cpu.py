@@ -64,3 +64,51 @@ def test_preprocess_blank_mesh_normalises_bbox(tmp_path):
     lo, hi = V.min(0), V.max(0)
     assert np.allclose((lo + hi) / 2, 0.0, atol=1e-6) and abs((hi - lo).max() - 1.9) < 1e-6
     assert np.array_equal(np.asarray(F), f) and len(UV) == len(uv)
+
+
+def test_glb_reader_roundtrip_and_node_transform(tmp_path):
+    """load_glb inverts save_glb (positions, faces, UVs back in the OBJ convention) and applies node transforms."""
+    import struct as st
+    from unitex_b200 import bake as ub
+    from unitex_b200.export import save_glb
+    v, f, uv, fuv = two_spheres(6, 12)
+    uv01 = (uv + 1) / 2
+    p = str(tmp_path / "m.glb")
+    save_glb(p, v, f, uv01, fuv, np.zeros((8, 8, 3), np.uint8))
+    V, F, UV, Ft = ub.load_mesh(p)
+    assert F.shape == f.shape and np.array_equal(F, Ft)
+    assert np.allclose(V[F], v[f]) and np.allclose(UV[Ft], uv01[fuv], atol=1e-6)
+    # same file with a +90 degree rotation about x on the node (as the reference's gamda_style GLBs carry): y -> z, z -> -y
+    blob = open(p, "rb").read()
+    jl = st.unpack_from("<I", blob, 12)[0]
+    g = json.loads(blob[20:20 + jl])
+    g["nodes"][0]["rotation"] = [0.7071067811865476, 0.0, 0.0, 0.7071067811865476]
+    js = json.dumps(g, separators=(",", ":")).encode()
+    js += b" " * ((-len(js)) % 4)
+    rest = blob[20 + jl:]
+    with open(p, "wb") as fh:
+        fh.write(st.pack("<III", 0x46546C67, 2, 12 + 8 + len(js) + len(rest)) + st.pack("<II", len(js), 0x4E4F534A) + js + rest)
+    V2, F2, _, _ = ub.load_glb(p)
+    want = np.stack([v[:, 0], -v[:, 2], v[:, 1]], -1)
+    assert np.allclose(V2[F2], want[f], atol=1e-6)
+
+
+def test_obj_reader_bulk_and_fallback_paths(tmp_path):
+    from unitex_b200 import bake as ub
+    from unitex_b200.export import save_obj
+    v, f, uv, fuv = two_spheres(4, 8)
+    p = str(tmp_path / "tri.obj")
+    save_obj(p, v, f, (uv + 1) / 2, fuv)
+    V, F, UV, Ft = ub.load_obj(p)                                   # bulk path: all triangles, one corner format
+    Vs, UVs, Fs, Fts = ub._load_obj_slow(p)
+    assert np.array_equal(V, Vs) and np.array_equal(UV, UVs) and np.array_equal(F, Fs - 1) and np.array_equal(Ft, Fts - 1)
+    assert np.allclose(V, v, atol=1e-6) and np.array_equal(F, f) and np.array_equal(Ft, fuv)
+    q = str(tmp_path / "quad.obj")                                  # a quad, v/vt/vn corners, a negative index: line-by-line path
+    open(q, "w").write("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"
+                       "f 1/1/1 2/2/1 3/3/1 4/4/1\nf -4/1/1 -3/2/1 -2/3/1\n")
+    V, F, UV, Ft = ub.load_obj(q)
+    assert F.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 2]] and Ft.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 2]]
+    n = str(tmp_path / "nouv.obj")                                  # v//vn corners: no UVs
+    open(n, "w").write("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//1 3//1\n")
+    V, F, UV, Ft = ub.load_obj(n)
+    assert F.tolist() == [[0, 1, 2]] and len(UV) == 0

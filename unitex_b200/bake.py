@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Tuple, Union
 
 import numpy as np
@@ -251,8 +252,7 @@ class BakeMesh:
         return self._optix
 
 
-def load_obj(path: str):
-    """Minimal OBJ reader (v / vt / f with v/vt[/vn] corners, polygons fan-triangulated) -> (V[,3], F[,3], UV[,2], F_uv[,3])."""
+def _load_obj_slow(path: str):
     v, vt, f, ft = [], [], [], []
     with open(path) as fh:
         for line in fh:
@@ -267,11 +267,140 @@ def load_obj(path: str):
                 for k in range(1, len(vi) - 1):
                     f.append([vi[0], vi[k], vi[k + 1]])
                     ft.append([ti[0], ti[k], ti[k + 1]])
-    V, UV = np.asarray(v, np.float32), np.asarray(vt, np.float32)
-    Fv, Ft = np.asarray(f, np.int64), np.asarray(ft, np.int64)
+    return (np.asarray(v, np.float32).reshape(-1, 3), np.asarray(vt, np.float32).reshape(-1, 2),
+            np.asarray(f, np.int64).reshape(-1, 3), np.asarray(ft, np.int64).reshape(-1, 3))
+
+
+def load_obj(path: str):
+    """Minimal OBJ reader (v / vt / f with v[/vt[/vn]] corners, negative indices, polygons fan-triangulated)
+    -> (V[,3], F[,3], UV[,2], F_uv[,3]).  Files whose faces are all triangles of one corner format (what MeshLab / open3d /
+    trimesh write, e.g. the reference's 500 k-face teaser mesh) are parsed in bulk with numpy; anything else line by line."""
+    with open(path, "rb") as fh:
+        lines = fh.read().split(b"\n")
+    vl = [ln for ln in lines if ln[:2] == b"v "]
+    tl = [ln for ln in lines if ln[:3] == b"vt "]
+    fl = [ln for ln in lines if ln[:2] == b"f "]
+    V = UV = Fv = Ft = None
+    try:
+        if not vl or not fl:
+            raise ValueError
+        nv = len(vl[0].split()) - 1
+        V = np.array(b" ".join(ln[2:] for ln in vl).split(), dtype=np.float64).reshape(len(vl), nv)[:, :3].astype(np.float32)
+        if tl:
+            nt = len(tl[0].split()) - 1
+            UV = np.array(b" ".join(ln[3:] for ln in tl).split(), dtype=np.float64).reshape(len(tl), nt)[:, :2].astype(np.float32)
+        else:
+            UV = np.zeros((0, 2), np.float32)
+        first = fl[0].split()[1:]
+        per_corner = first[0].count(b"/") + 1
+        if len(first) != 3 or b"//" in fl[0]:
+            raise ValueError
+        tok = np.array(b" ".join(ln[2:] for ln in fl).replace(b"/", b" ").split(), dtype=np.int64)
+        if tok.size != len(fl) * 3 * per_corner:
+            raise ValueError                                   # mixed polygons / corner formats
+        tok = tok.reshape(len(fl), 3, per_corner)
+        Fv = tok[:, :, 0]
+        Ft = tok[:, :, 1] if per_corner > 1 else np.zeros_like(Fv)
+    except ValueError:
+        V, UV, Fv, Ft = _load_obj_slow(path)
     Fv = np.where(Fv < 0, Fv + len(V) + 1, Fv) - 1
     Ft = np.where(Ft < 0, Ft + len(UV) + 1, Ft) - 1
     return V, Fv.astype(np.int32), UV, Ft.astype(np.int32)
+
+
+def load_glb(path: str):
+    """Minimal binary glTF 2.0 reader for blank / textured input meshes (the reference's second test case ships `.glb`;
+    trimesh / open3d load them there: io/mesh_loader.py:22-30, geometry/uv/uv_atlas.py:181): every triangle primitive of every
+    mesh node of the default scene, node transforms (matrix or TRS, nested) applied, primitives concatenated.
+    -> (V[,3], F[,3], UV[,2], F_uv[,3]) with UV in the OBJ convention (v up: glTF's v axis points down, so v -> 1 - v);
+    UV is empty when a primitive has no TEXCOORD_0."""
+    import json
+    import struct
+    with open(path, "rb") as fh:
+        blob = fh.read()
+    magic, version, _ = struct.unpack_from("<III", blob, 0)
+    if magic != 0x46546C67 or version != 2:
+        raise ValueError(f"{path}: not a binary glTF 2.0 file")
+    off, gltf, binc = 12, None, b""
+    while off < len(blob):
+        clen, ctype = struct.unpack_from("<II", blob, off)
+        data = blob[off + 8: off + 8 + clen]
+        if ctype == 0x4E4F534A:
+            gltf = json.loads(data)
+        elif ctype == 0x004E4942:
+            binc = data
+        off += 8 + clen
+    comp = {5120: np.int8, 5121: np.uint8, 5122: np.int16, 5123: np.uint16, 5125: np.uint32, 5126: np.float32}
+    width = {"SCALAR": 1, "VEC2": 2, "VEC3": 3, "VEC4": 4, "MAT4": 16}
+
+    def accessor(i):
+        a = gltf["accessors"][i]
+        bv = gltf["bufferViews"][a["bufferView"]]
+        dt, w = np.dtype(comp[a["componentType"]]), width[a["type"]]
+        start = bv.get("byteOffset", 0) + a.get("byteOffset", 0)
+        stride = bv.get("byteStride", 0)
+        if stride and stride != dt.itemsize * w:
+            raw = np.frombuffer(binc, np.uint8, count=stride * (a["count"] - 1) + dt.itemsize * w, offset=start)
+            rows = np.lib.stride_tricks.as_strided(raw, (a["count"], dt.itemsize * w), (stride, 1))
+            return np.ascontiguousarray(rows).view(dt).reshape(a["count"], w)
+        return np.frombuffer(binc, dt, count=a["count"] * w, offset=start).reshape(a["count"], w)
+
+    def local_matrix(node):
+        if "matrix" in node:
+            return np.asarray(node["matrix"], np.float64).reshape(4, 4).T          # glTF stores column-major
+        m = np.eye(4)
+        x, y, z, w = node.get("rotation", [0.0, 0.0, 0.0, 1.0])
+        r = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        m[:3, :3] = r * np.asarray(node.get("scale", [1.0, 1.0, 1.0]))[None, :]
+        m[:3, 3] = node.get("translation", [0.0, 0.0, 0.0])
+        return m
+
+    Vs, Fs, UVs, have_uv, base = [], [], [], True, 0
+
+    def visit(ni, parent):
+        nonlocal base, have_uv
+        node = gltf["nodes"][ni]
+        world = parent @ local_matrix(node)
+        if "mesh" in node:
+            for prim in gltf["meshes"][node["mesh"]]["primitives"]:
+                if prim.get("mode", 4) != 4:
+                    continue
+                pos = accessor(prim["attributes"]["POSITION"]).astype(np.float64)
+                pos = pos @ world[:3, :3].T + world[:3, 3]
+                idx = accessor(prim["indices"]).reshape(-1) if "indices" in prim else np.arange(len(pos))
+                Vs.append(pos.astype(np.float32))
+                Fs.append(idx.astype(np.int64).reshape(-1, 3) + base)
+                if "TEXCOORD_0" in prim["attributes"]:
+                    uv = accessor(prim["attributes"]["TEXCOORD_0"]).astype(np.float32).copy()
+                    uv[:, 1] = 1.0 - uv[:, 1]
+                    UVs.append(uv)
+                else:
+                    have_uv = False
+                base += len(pos)
+        for c in node.get("children", []):
+            visit(c, world)
+
+    scene = gltf["scenes"][gltf.get("scene", 0)]
+    for ni in scene["nodes"]:
+        visit(ni, np.eye(4))
+    if not Vs:
+        raise ValueError(f"{path}: no triangle primitives")
+    V, F = np.concatenate(Vs), np.concatenate(Fs).astype(np.int32)
+    if have_uv:
+        return V, F, np.concatenate(UVs), F.copy()
+    return V, F, np.zeros((0, 2), np.float32), np.zeros((0, 3), np.int32)
+
+
+def load_mesh(path: str):
+    """OBJ or GLB by extension -> (V, F, UV, F_uv)."""
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".obj":
+        return load_obj(path)
+    if ext == ".glb":
+        return load_glb(path)
+    raise NotImplementedError(f"mesh format {ext!r}: .obj and .glb are read")
 
 
 # ------------------------------------------------------------------------------------------------ NVDiffRendererInverse (b5-b7)
@@ -293,7 +422,7 @@ class NVDiffRendererInverse:
         self.query_field_function = None
 
     def update_from_file(self, path: str):
-        V, F, UV, Ft = load_obj(path)
+        V, F, UV, Ft = load_mesh(path)
         self.pbr_mesh = BakeMesh(V, F, UV * 2.0 - 1.0, Ft, device=self.device)
         return self
 

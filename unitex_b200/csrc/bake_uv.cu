@@ -34,6 +34,9 @@ namespace utx {
 namespace {
 
 constexpr int MAXV = 8;
+#ifndef UTX_WALK_MIN_BLOCKS
+#define UTX_WALK_MIN_BLOCKS 1      // resident CTAs per SM the two tree-walk kernels are compiled for (register cap); A/B knob
+#endif
 
 struct Views {
   int n;
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(128) texel_prep_kernel(const float4* __restric
     }
   }
 }
-__global__ void __launch_bounds__(128) ray_kernel(const int* __restrict__ lists, const int* __restrict__ counts, int T,
+__global__ void __launch_bounds__(128, UTX_WALK_MIN_BLOCKS) ray_kernel(const int* __restrict__ lists, const int* __restrict__ counts, int T,
                                                   const float4* __restrict__ rast, const float* __restrict__ pos_in,
                                                   const float* __restrict__ vert, const int* __restrict__ tri,
                                                   const float4* __restrict__ wide, const Views vw, unsigned* raw_vis_words) {
@@ -478,7 +481,7 @@ __global__ void __launch_bounds__(128) nn_count_kernel(const int* __restrict__ q
 // one fixed block of queries per CTA the kernel ran at 29 % of its resident warps (profiles/r01_bake_ray_nn.metrics.csv): a CTA's
 // slot was held until its slowest warp finished, and the last wave left most SMs idle.  (Measured: no change, 2.49 ms -- the
 // list is only 2.3 runs per resident warp, so the tail of one run remains; kept because it is never worse.)
-__global__ void __launch_bounds__(128) nn_query_kernel(const int* __restrict__ qlist, int n_q, const float* __restrict__ pos,
+__global__ void __launch_bounds__(128, UTX_WALK_MIN_BLOCKS) nn_query_kernel(const int* __restrict__ qlist, int n_q, const float* __restrict__ pos,
                                                        const PointTree pt, const float* color_in, float* color_out,
                                                        int* __restrict__ nn_index, int W2, int* __restrict__ next_run) {
   const int lane = threadIdx.x & 31;

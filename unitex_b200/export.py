@@ -68,7 +68,7 @@ class VideoExporter:
         if orbit:
             raise NotImplementedError("B200 export_condition implements the box views UniTEX uses (pipeline.py:199-216), not the orbit")
         if isinstance(mesh_path, str):
-            V, F, _, _ = ub.load_obj(mesh_path)
+            V, F, _, _ = ub.load_mesh(mesh_path)
         else:
             V, F = mesh_path
         v = scale_to_bbox(torch.as_tensor(V, dtype=torch.float32, device=self.device), geometry_scale)
