@@ -133,7 +133,7 @@ class RGBTextureFullPipelineBase:
             perspective=cam["perspective"], H=HP, W=WP, H2D=2048, W2D=2048, method=method, kdtree_inpainting=inpainting,
             reproject_inpainting=inpainting, kdtree_n_neighbors=8, kdtree_n_neighbors_visiable=4,
             grad_norm_threhold=0.15, ray_normal_angle_threhold=100, filt_gradient_points=inpainting)
-        V, F, UV, Ft = ub.load_obj(input_mesh_path)
+        V, F, UV, Ft = ub.load_mesh(input_mesh_path)
         atlas = (completed_uv_map[0].clamp(0, 1) * 255.0).round().to(torch.uint8).cpu().numpy()
         ux.save_glb(os.path.join(save_dir, "textured_mesh.glb"), V, F, UV, Ft, atlas)
 

@@ -393,14 +393,26 @@ def load_glb(path: str):
     return V, F, np.zeros((0, 2), np.float32), np.zeros((0, 3), np.int32)
 
 
+_MESH_CACHE: dict = {}
+
+
 def load_mesh(path: str):
-    """OBJ or GLB by extension -> (V, F, UV, F_uv)."""
+    """OBJ or GLB by extension -> (V, F, UV, F_uv).  The last few files are kept parsed, keyed by (path, mtime, size): the
+    pipeline stages hand each other file paths (reference pipeline.py:568-575), so the same mesh is opened four times per asset."""
     ext = os.path.splitext(path)[1].lower()
-    if ext == ".obj":
-        return load_obj(path)
-    if ext == ".glb":
-        return load_glb(path)
-    raise NotImplementedError(f"mesh format {ext!r}: .obj and .glb are read")
+    if ext not in (".obj", ".glb"):
+        raise NotImplementedError(f"mesh format {ext!r}: .obj and .glb are read")
+    st = os.stat(path)
+    key = (os.path.abspath(path), st.st_mtime_ns, st.st_size)
+    hit = _MESH_CACHE.get(key)
+    if hit is None:
+        hit = load_obj(path) if ext == ".obj" else load_glb(path)
+        for a in hit:
+            a.setflags(write=False)
+        if len(_MESH_CACHE) >= 4:
+            _MESH_CACHE.pop(next(iter(_MESH_CACHE)))
+        _MESH_CACHE[key] = hit
+    return hit
 
 
 # ------------------------------------------------------------------------------------------------ NVDiffRendererInverse (b5-b7)

@@ -122,18 +122,21 @@ def strip_to_view_grid(strip: np.ndarray) -> np.ndarray:
 
 # ------------------------------------------------------------------------------------------------ OBJ / GLB
 def save_obj(path: str, V, F, UV=None, F_uv=None):
+    """Wavefront OBJ (v / vt / f a/b corners, 1-based), written in bulk: the 500 k-face reference mesh takes ~1 s."""
+    V = np.asarray(V, np.float64).reshape(-1, 3)
+    F = np.asarray(F, np.int64).reshape(-1, 3) + 1
     with open(path, "w") as fh:
-        for p in V:
-            fh.write(f"v {p[0]:.8f} {p[1]:.8f} {p[2]:.8f}\n")
+        fh.write("\n".join("v %.8f %.8f %.8f" % (a, b, c) for a, b, c in V.tolist()))
+        fh.write("\n")
         if UV is not None:
-            for t in UV:
-                fh.write(f"vt {t[0]:.8f} {t[1]:.8f}\n")
-        for i, tri in enumerate(F):
-            if UV is not None:
-                u = F_uv[i]
-                fh.write(f"f {tri[0]+1}/{u[0]+1} {tri[1]+1}/{u[1]+1} {tri[2]+1}/{u[2]+1}\n")
-            else:
-                fh.write(f"f {tri[0]+1} {tri[1]+1} {tri[2]+1}\n")
+            UV = np.asarray(UV, np.float64).reshape(-1, 2)
+            Fu = np.asarray(F_uv, np.int64).reshape(-1, 3) + 1
+            fh.write("\n".join("vt %.8f %.8f" % (a, b) for a, b in UV.tolist()))
+            fh.write("\n")
+            fh.write("\n".join("f %d/%d %d/%d %d/%d" % (r[0], r[3], r[1], r[4], r[2], r[5]) for r in np.concatenate([F, Fu], 1).tolist()))
+        else:
+            fh.write("\n".join("f %d %d %d" % (a, b, c) for a, b, c in F.tolist()))
+        fh.write("\n")
 
 
 def save_glb(path: str, V, F, UV, F_uv, texture_rgb: np.ndarray):
