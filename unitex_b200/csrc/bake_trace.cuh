@@ -183,7 +183,10 @@ __device__ __forceinline__ RayHit bvh_trace(const float4* __restrict__ W, const 
 //   spts   [n] float4, Morton order
 // Results do not depend on the tree: fp32 squared distance ((dx^2+dy^2)+dz^2), ties by lowest id; a box is pruned only when
 // its slightly deflated distance bound exceeds the current worst kept distance, so rounding can never drop a true neighbour.
-constexpr int PT_CLUSTER = 8;
+#ifndef UTX_PT_CLUSTER
+#define UTX_PT_CLUSTER 8      // measured on the bench bake / the reference's teaser mesh: 8 -> 8.6 / 11.0 ms, 16 -> 9.4 / 11.4, 32 -> 10.6 / 12.5
+#endif
+constexpr int PT_CLUSTER = UTX_PT_CLUSTER;
 struct PointTree {
   const float4* wide;   // traversal records of the cluster tree (layout as above; leaf reference = ~cluster), unused when n_c == 1
   const float4* spts;

@@ -35,7 +35,9 @@ namespace {
 
 constexpr int MAXV = 8;
 #ifndef UTX_WALK_MIN_BLOCKS
-#define UTX_WALK_MIN_BLOCKS 1      // resident CTAs per SM the two tree-walk kernels are compiled for (register cap); A/B knob
+#define UTX_WALK_MIN_BLOCKS 1      // resident CTAs per SM the two tree-walk kernels are compiled for (register cap).  Measured on
+                                   // the bench bake: 1 (46-47 registers, 10 CTAs) 8.54 ms, 12 (40 registers, spills) 9.05, 16 (32) 10.25:
+                                   // more resident warps thrash the L1 the walks live in
 #endif
 
 struct Views {
