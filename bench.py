@@ -216,6 +216,8 @@ def run_ours(args, rank, world, local_rank):
     mu = 1.15                                                          # calculate_shift(4096)
     sig = np.concatenate([np.exp(mu) / (np.exp(mu) + (1 / s - 1)), [0.0]]).astype(np.float32)
 
+    decoded_tile = torch.zeros(3, 1024, 1024, dtype=torch.uint8, device=dev)   # stands for this rank's VAE-decoded grid in the gather
+
     def step(i):
         j = i % n_sched
         eng.denoise_(lat, S_NOISE, sig[j:j + 2], 3.5)
@@ -236,9 +238,9 @@ def run_ours(args, rank, world, local_rank):
     e0.record()
     for i in range(args.steps):
         step(i)
-    if world > 1:   # the path's one collective: gather every rank's finished tile (north_star)
-        tiles = [torch.empty_like(lat[:S_NOISE]) for _ in range(world)]
-        dist.all_gather(tiles, lat[:S_NOISE].contiguous())
+    if world > 1:   # the path's one collective: every rank receives every rank's finished (decoded) tile before UV projection
+        from unitex_b200.parallel import all_gather_tiles          # (north_star; SURVEY 8e: uint8 [3,1024,1024] = 3 MB per rank)
+        tiles = all_gather_tiles(decoded_tile)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
