@@ -120,6 +120,16 @@ def bake():
     src, dst = torch.rand(300, 3, generator=g), torch.rand(40, 3, generator=g)
     score, index = knn(src, dst, k=4)                                    # pcd/knn/__init__.py:104-114 (wrapper real, tree [ext])
     out["fn.knn_src"], out["fn.knn_dst"], out["fn.knn_index"] = src.numpy(), dst.numpy(), index.numpy().astype(np.int32)
+    # the ray-tracer plug-in as the reference exposes it: RayTracing dispatcher -> APRMISRayTracing wrapper (raytracing/__init__.py:12-80,
+    # rt_aprmis/__init__.py:10-86; the Slang launch inside is the oracle's restatement), batch-shaped rays, misses included
+    from texturetools.raytracing import RayTracing
+    rt = RayTracing(torch.from_numpy(v), torch.from_numpy(f).long())
+    ro = torch.rand(3, 50, 3, generator=g) * 2.4 - 1.2
+    rdir = torch.nn.functional.normalize(torch.rand(3, 50, 3, generator=g) - 0.5 - 0.4 * ro, dim=-1)
+    hit, front, tri_idx, loc, ruv = rt.intersects_closest(ro, rdir)
+    assert front is None and hit.dtype == torch.bool and tri_idx.dtype == torch.int64
+    out["rt.rays_o"], out["rt.rays_d"] = ro.numpy(), rdir.numpy()
+    out["rt.hit"], out["rt.tri_idx"], out["rt.loc"], out["rt.uv"] = hit.numpy(), tri_idx.numpy().astype(np.int32), loc.numpy(), ruv.numpy()
     np.savez_compressed(os.path.join(HERE, "ref_bake.npz"), **{k: (a.astype(np.float32) if a.dtype == np.float64 and not k.startswith("field") else a)
                                                                for k, a in out.items()})
     return out

@@ -207,3 +207,18 @@ def test_infer_perspective_matches_reference(lib):
         assert np.array_equal(vis.cpu().numpy(), _unpack(z["persp.mask_2d_visiable"], (6, 64, 64, 1))), name
         err = np.abs(col.cpu().numpy() - z[f"persp.{name}.color_2d"]).max()
         assert err < COLOR_ATOL, (name, err)
+
+
+def test_raytracing_plugin_matches_reference_wrapper(lib):
+    """RayTracing(vertices, faces).intersects_closest(rays_o, rays_d) against the reference's dispatcher + APRMIS wrapper run
+    (raytracing/__init__.py:12-80, rt_aprmis/__init__.py:10-86): shapes, dtypes, -1 for misses, ids / positions / uv bit for bit."""
+    from unitex_b200.bake import RayTracing
+    z = np.load(os.path.join(G, "ref_bake.npz"))
+    v, f, _, _ = two_spheres(10, 20)
+    rt = RayTracing(torch.from_numpy(v), torch.from_numpy(f).long())
+    hit, front, tri_idx, loc, uv = rt.intersects_closest(torch.from_numpy(z["rt.rays_o"]), torch.from_numpy(z["rt.rays_d"]))
+    assert front is None and hit.dtype == torch.bool and tri_idx.dtype == torch.int64
+    assert hit.shape == (3, 50) and tri_idx.shape == (3, 50) and loc.shape == (3, 50, 3) and uv.shape == (3, 50, 2)
+    assert np.array_equal(hit.cpu().numpy(), z["rt.hit"]) and 5 < int(z["rt.hit"].sum()) < 145
+    assert np.array_equal(tri_idx.cpu().numpy().astype(np.int32), z["rt.tri_idx"])
+    assert np.array_equal(loc.cpu().numpy(), z["rt.loc"]) and np.array_equal(uv.cpu().numpy(), z["rt.uv"])
