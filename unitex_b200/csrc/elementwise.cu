@@ -25,8 +25,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ----------------------------------------------------------------------------- LayerNorm + modulate
 // AdaLayerNormZero / ZeroSingle / Continuous [ext diffusers]: LN(eps 1e-6, no affine) * (1 + scale) + shift.
 // One warp per row; the row (NV x 256 elements) lives in registers between the statistics and the output pass.
+// Register cap: left alone, ptxas hoists the modulation-vector loads of the whole output pass and the D = 3072 instance needs 179
+// registers -- ONE resident block of 8 rows per SM (37.9 us per launch = 3.2 TB/s, profiles/r01_launches_final.csv).  Capped at
+// 128 (two resident blocks, 16 rows = 96 KB in flight per SM; 85 for three blocks spills the row).
 template <int NV>
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict__ x, long ldx, bf16* __restrict__ y,
+__global__ void __launch_bounds__(256, (NV <= 6 ? 3 : NV <= 12 ? 2 : 1)) ln_modulate_kernel(const bf16* __restrict__ x, long ldx, bf16* __restrict__ y,
                                                           long ldy, int rows, int D, int rows0,
                                                           const float* __restrict__ shift0,
                                                           const float* __restrict__ scale0,
