@@ -319,9 +319,10 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
         vis = vis | (conv >= ((k - 1) ** 2 - 1) * ((k - 2) ** 2))
     vis = vis & mask_2d & (alpha_2d > 0.999)
     if method == "kdtree":
+        assert kdtree_method in ("mean", "mvpaint", "order_mean")
         # mv_to_pcd point clouds (:188, :227-231): positions interpolated at the pixels, one cloud per view
         attrs_mv = torch.from_numpy(interpolate(vert, rast_mv.numpy(), tri))                 # [n,H,W,3]
-        mmv = rast_mv[..., 3] > 0
+        mmv = alpha_vis[..., 0] > 0                                                          # mask_visiable (:233-239): the raster mask unless filtered
         clouds = [(attrs_mv[i][mmv[i]], image_attrs[i][mmv[i]]) for i in range(n)]
         P2 = pos_2d[0][m]                                                                    # point_cloud_2d.vertices
         wc = torch.zeros(P2.shape[0], Cn)
@@ -329,6 +330,16 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
         if kdtree_method == "mean":                                                          # :385-389
             allp, allc = torch.cat([c[0] for c in clouds]), torch.cat([c[1] for c in clouds])
             wc = query_field(allp, allc, P2) if query_field is not None else allc[nearest_k(allp, P2, k_all)[1]].mean(dim=-2)
+        elif kdtree_method == "mvpaint":                                                     # :390-399 (MVPaint, arXiv 2411.02336 sec. 3.2)
+            allp, allc = torch.cat([c[0] for c in clouds]), torch.cat([c[1] for c in clouds])
+            tid_mv = rast_mv[..., 3].to(torch.int64) - 1
+            alln = torch.cat([normals[tid_mv[i][mmv[i]]] for i in range(n)])                  # point_cloud_visiable.normals: face normals (:236)
+            score, idx = nearest_k(allp, P2, k_all)
+            weight = F.normalize(score.reciprocal().nan_to_num(nan=0.0), p=1, dim=-1) * \
+                F.cosine_similarity(alln[idx], fn_2d[0][m].unsqueeze(-2), dim=-1)
+            weight = weight.unsqueeze(-1)
+            wc = (allc[idx] * weight).sum(dim=-2) / weight.sum(dim=-2)
+            wc = torch.nan_to_num(wc, nan=0.0, posinf=0.0, neginf=0.0)
         else:                                                                                # order_mean :406-432
             for i in index:
                 extra = (~cur) & vis[i:i + 1]

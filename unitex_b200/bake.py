@@ -514,8 +514,8 @@ class NVDiffRendererInverse:
             return None, parts[0][1], parts[0][2], torch.cat([p[3] for p in parts], dim=-1)
         if method == "reproject" and (reproject_method != "lens" or (reproject_kernel_size_boundary, reproject_kernel_size_boundary_blur) != (3, 3)):
             raise NotImplementedError("reproject bake: only reproject_method='lens' with the 3x3 boundary kernels")
-        if method == "kdtree" and kdtree_method not in ("order_mean", "mean"):
-            raise NotImplementedError("kdtree bake: kdtree_method 'order_mean' or 'mean' ('mvpaint' needs per-point normals)")
+        if method == "kdtree":
+            assert kdtree_method in ("mean", "mvpaint", "order_mean")
         if isinstance(blank_mesh, str):
             self.update_from_file(blank_mesh)
         elif isinstance(blank_mesh, BakeMesh):
@@ -560,7 +560,9 @@ class NVDiffRendererInverse:
         self.last_nn_index = None
         skip_fill = False
         if method == "kdtree":
-            if kdtree_method == "mean" and kdtree_inpainting:
+            if kdtree_method == "mvpaint":
+                self._mvpaint_fill(ws, mask2d, rgba, mv["rast"], rast2d, H2D, W2D, kdtree_n_neighbors)
+            elif kdtree_method == "mean" and kdtree_inpainting:
                 self._field_fill(ws, mask2d, rgba, mv["rast"], H2D, W2D, union_cloud=True)
             else:
                 merge = int(kdtree_method == "mean")
@@ -569,7 +571,7 @@ class NVDiffRendererInverse:
                 scratch = torch.empty(L.utx_uv_bake_views_workspace_bytes(n, H, W), device=self.device, dtype=torch.uint8)
                 _lib.check(L.utx_uv_bake_views_knn(_p(pix_pos), _p(rgba), n, H, W, k, merge, _p(mask2d), H2D, W2D, _p(ws),
                                                    ws.numel(), _p(scratch), scratch.numel(), _stream()), "utx_uv_bake_views_knn")
-            skip_fill = kdtree_method == "mean"
+            skip_fill = kdtree_method in ("mean", "mvpaint")
             inpaint, k_fill, blur = kdtree_inpainting, kdtree_n_neighbors_invisiable, 0
         else:
             inpaint, k_fill, blur = True, 1, 1
@@ -583,6 +585,32 @@ class NVDiffRendererInverse:
         _lib.check(L.utx_uv_bake_finish(_p(mask2d), H2D, W2D, blur, _p(self._k2d), 5.0, _p(color), _p(ws), ws.numel(), _stream()),
                    "utx_uv_bake_finish")
         return out()
+
+    def _mvpaint_fill(self, ws, mask2d, rgba, rast_mv, rast2d, H2D, W2D, k: int):
+        """kdtree_method='mvpaint' (:390-399; MVPaint, arXiv 2411.02336 sec. 3.2): every covered texel takes its k nearest points of
+        the union pixel cloud, weighted by normalised inverse distance x cosine between the face normals of point and texel.  The
+        neighbour search is `utx_knn`; the weighting of the [M, k] table is torch plumbing, written into the staged bake's colour
+        plane.  (`score` is the Euclidean distance here, the reference's scipy convention -- see INTEGRATION.md on torch_kdtree.)"""
+        L = _lib.load()
+        F_ = torch.nn.functional
+        off = [C.c_size_t() for _ in range(4)]
+        _lib.check(L.utx_uv_bake_layout(H2D, W2D, *[C.byref(o) for o in off]), "utx_uv_bake_layout")
+        T = H2D * W2D
+        pos = ws[off[1].value:off[1].value + T * 12].view(torch.float32).reshape(T, 3)
+        col = ws[off[2].value:off[2].value + T * 12].view(torch.float32).reshape(T, 3)
+        m = self.pbr_mesh
+        covered = mask2d.bool()
+        sel = rgba[..., 3] > 0.5
+        cloud_p = interpolate(m.vertices, rast_mv, m.faces)[sel]
+        cloud_c = rgba[..., :3][sel]
+        cloud_n = m.normals[(rast_mv[..., 3].to(torch.int64) - 1)[sel]]
+        tex_n = m.normals[(rast2d[0, ..., 3].to(torch.int64) - 1).reshape(-1)[covered]]
+        score, index = knn(cloud_p, pos[covered], k=k, device=self.device)
+        weight = F_.normalize(score.reciprocal().nan_to_num(nan=0.0), p=1, dim=-1) * \
+            F_.cosine_similarity(cloud_n[index], tex_n.unsqueeze(-2), dim=-1)
+        weight = weight.unsqueeze(-1)
+        out = (cloud_c[index] * weight).sum(dim=-2) / weight.sum(dim=-2)
+        col[covered] = torch.nan_to_num(out, nan=0.0, posinf=0.0, neginf=0.0)
 
     def _field_fill(self, ws, mask2d, rgba, rast_mv, H2D, W2D, union_cloud: bool):
         """The `*_inpainting=True` branches: the registered query field colours the texels the views do not own
