@@ -205,6 +205,7 @@ int utx_uv_bake_views_knn(const float* pix_pos, const float* images_rgba, int n_
                           size_t scratch_bytes, void* stream);
 int utx_uv_bake_fill(const unsigned char* mask2d, int H2, int W2, int k, int32_t* nn_index, void* workspace,
                      size_t workspace_bytes, void* stream);
+/* blur: 0 none, 1 the 7x7 kernel with a zero border (lens blur, gamma 5), 2 with a mirrored border (gaussian, gamma 1) */
 int utx_uv_bake_finish(const unsigned char* mask2d, int H2, int W2, int blur, const float* blur_k2d, float blur_gamma,
                        float* color, void* workspace, size_t workspace_bytes, void* stream);
 

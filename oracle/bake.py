@@ -242,7 +242,7 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
                     H: int, W: int, H2: int, W2: int, angle_deg: float = 100.0, index=(0, 3, 4, 1, 2, 5), method: str = "reproject",
                     kdtree_method: str = "order_mean", k_all: int = 32, k_vis: int = 1, k_invis: int = 32,
                     query_field=None, filt_gradient_points: bool = False, grad_norm_threhold: float = 0.20,
-                    perspective: bool = False) -> Dict[str, torch.Tensor]:
+                    perspective: bool = False, reproject_method: str = "lens", kernel_size_blur: int = 5) -> Dict[str, torch.Tensor]:
     """NVDiffRendererInverse.infer(perspective=False, filt_gradient_points=False) (:635-726) for method='reproject'
     (reproject_method='lens') and method='kdtree' (kdtree_method 'order_mean' | 'mean'); `query_field` set = the
     *_inpainting=True branches (:387-389, :427-432, :609-614)."""
@@ -386,7 +386,11 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
             color[0][inv_m] = color[0][vis_m][idx]
             nn_index[inv_m.reshape(-1)] = src_idx[idx]
     pre_blur = color.clone()
-    blur = lens_blur_torch(color.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    if reproject_method == "gaussian":                                                       # :619-620 -> torchvision gaussian_blur [ext, present]
+        from torchvision.transforms.functional import gaussian_blur
+        blur = gaussian_blur(color.permute(0, 3, 1, 2), kernel_size=(kernel_size_blur, kernel_size_blur), sigma=None).permute(0, 2, 3, 1)
+    else:
+        blur = lens_blur_torch(color.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
     color = torch.where(bnd, blur, color)
     color_2d = pull_push(color.permute(0, 3, 1, 2), mask_2d.permute(0, 3, 1, 2))[0].permute(0, 2, 3, 1)
     return {"mask_2d": mask_2d, "mask_2d_visiable": vis, "raw_visible": raw_vis, "color_2d": color_2d, "tid_2d": tid_2d,

@@ -58,6 +58,7 @@ def bake():
         "kdtree_order_mean": dict(method="kdtree", kdtree_method="order_mean", kdtree_n_neighbors_visiable=9, kdtree_n_neighbors_invisiable=32),
         "kdtree_mean": dict(method="kdtree", kdtree_method="mean", kdtree_n_neighbors=32),
         "kdtree_mvpaint": dict(method="kdtree", kdtree_method="mvpaint", kdtree_n_neighbors=8),
+        "reproject_gaussian": dict(method="reproject", reproject_method="gaussian"),
         "reproject_inpaint": dict(method="reproject", reproject_inpainting=True),
         "kdtree_inpaint": dict(method="kdtree", kdtree_method="order_mean", kdtree_n_neighbors_visiable=9, kdtree_inpainting=True),
     }

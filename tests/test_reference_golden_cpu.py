@@ -70,6 +70,7 @@ def test_infer_every_variant_matches_reference():
         "kdtree_order_mean": dict(method="kdtree", kdtree_method="order_mean", k_vis=9, k_invis=32),
         "kdtree_mean": dict(method="kdtree", kdtree_method="mean", k_all=32),
         "kdtree_mvpaint": dict(method="kdtree", kdtree_method="mvpaint", k_all=8),
+        "reproject_gaussian": dict(method="reproject", reproject_method="gaussian"),
         "reproject_inpaint": dict(method="reproject", query_field=field),
         "kdtree_inpaint": dict(method="kdtree", kdtree_method="order_mean", k_vis=9, query_field=field),
     }

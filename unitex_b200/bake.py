@@ -204,6 +204,21 @@ def lens_blur_kernel_2d(radius: float = 3.0, scale: float = 1.2) -> np.ndarray:
     return K.astype(np.float32)
 
 
+def gaussian_kernel_2d(kernel_size: int = 5) -> torch.Tensor:
+    """The kernel of image/gaussian_blur.py:42-44 -> torchvision gaussian_blur [ext, present in this image] with its default
+    sigma = 0.3 ((k - 1) / 2 - 1) + 0.8, embedded in the 7x7 frame the seam-blur kernel reads (fp32 like torchvision's)."""
+    sigma = 0.3 * ((kernel_size - 1) * 0.5 - 1) + 0.8
+    half = (kernel_size - 1) * 0.5
+    x = torch.linspace(-half, half, steps=kernel_size, dtype=torch.float32)
+    pdf = torch.exp(-0.5 * (x / sigma).pow(2))
+    k1 = pdf / pdf.sum()
+    k2 = torch.mm(k1[:, None], k1[None, :])
+    out = torch.zeros(7, 7, dtype=torch.float32)
+    o = (7 - kernel_size) // 2
+    out[o:o + kernel_size, o:o + kernel_size] = k2
+    return out.contiguous()
+
+
 # ------------------------------------------------------------------------------------------------ mesh container (b3)
 class BakeMesh:
     """The fields of PBRMesh the bake reads (mesh/structure_v2.py:25-77): vertices [V,3], faces [F,3], uvs_2d [V2,2] in
@@ -407,12 +422,10 @@ def load_mesh(path: str):
     hit = _MESH_CACHE.get(key)
     if hit is None:
         hit = load_obj(path) if ext == ".obj" else load_glb(path)
-        for a in hit:
-            a.setflags(write=False)
         if len(_MESH_CACHE) >= 4:
             _MESH_CACHE.pop(next(iter(_MESH_CACHE)))
         _MESH_CACHE[key] = hit
-    return hit
+    return tuple(a.copy() for a in hit)       # callers own their arrays (a few MB; the parse is what costs seconds)
 
 
 # ------------------------------------------------------------------------------------------------ NVDiffRendererInverse (b5-b7)
@@ -512,8 +525,12 @@ class NVDiffRendererInverse:
                       reproject_kernel_size_blur=reproject_kernel_size_blur, filt_gradient_points=filt_gradient_points)
             parts = [self.infer(blank_mesh, c2ws, intrinsics, image_attrs[..., 3 * i:3 * i + 3], **kw) for i in range(3)]
             return None, parts[0][1], parts[0][2], torch.cat([p[3] for p in parts], dim=-1)
-        if method == "reproject" and (reproject_method != "lens" or (reproject_kernel_size_boundary, reproject_kernel_size_boundary_blur) != (3, 3)):
-            raise NotImplementedError("reproject bake: only reproject_method='lens' with the 3x3 boundary kernels")
+        if method == "reproject":
+            assert reproject_method in ("gaussian", "lens")
+            if (reproject_kernel_size_boundary, reproject_kernel_size_boundary_blur) != (3, 3):
+                raise NotImplementedError("reproject bake: the seam mask is built for the 3x3 boundary kernels (the defaults, :649-650)")
+            if reproject_method == "gaussian" and reproject_kernel_size_blur not in (3, 5, 7):
+                raise NotImplementedError("reproject bake: gaussian kernel sizes 3, 5, 7")
         if method == "kdtree":
             assert kdtree_method in ("mean", "mvpaint", "order_mean")
         if isinstance(blank_mesh, str):
@@ -548,7 +565,7 @@ class NVDiffRendererInverse:
 
         vis_args = (_p(m.vertices), m.vertices.shape[0], _p(m.faces), m.faces.shape[0], _p(m.optix.nodes), _p(rast2d), H2D, W2D,
                     n, mats.numpy().ctypes.data_as(_lib.fp), dirs.numpy().ctypes.data_as(_lib.fp), int(bool(perspective)), prio, _p(rgba), H, W, cos_t)
-        if method == "reproject" and not reproject_inpainting:
+        if method == "reproject" and reproject_method == "lens" and not reproject_inpainting:
             lo_arr = (C.c_float * 3)(0.0, 0.0, 0.0)
             _lib.check(L.utx_uv_bake(*vis_args, _p(self._k2d), 5.0, lo_arr, 1.0, _p(mask2d), _p(mask_vis), _p(color),
                                      _p(nn_index), _p(ws), ws.numel(), _stream()), "utx_uv_bake")
@@ -574,7 +591,8 @@ class NVDiffRendererInverse:
             skip_fill = kdtree_method in ("mean", "mvpaint")
             inpaint, k_fill, blur = kdtree_inpainting, kdtree_n_neighbors_invisiable, 0
         else:
-            inpaint, k_fill, blur = True, 1, 1
+            inpaint, k_fill, blur = reproject_inpainting, 1, (1 if reproject_method == "lens" else 2)
+        k2d, gamma = (self._k2d, 5.0) if blur != 2 else (gaussian_kernel_2d(reproject_kernel_size_blur).to(self.device), 1.0)
         if not skip_fill:
             if inpaint:
                 self._field_fill(ws, mask2d, rgba, mv["rast"], H2D, W2D, union_cloud=False)
@@ -582,7 +600,7 @@ class NVDiffRendererInverse:
                 _lib.check(L.utx_uv_bake_fill(_p(mask2d), H2D, W2D, k_fill, _p(nn_index), _p(ws), ws.numel(), _stream()),
                            "utx_uv_bake_fill")
                 self.last_nn_index = nn_index
-        _lib.check(L.utx_uv_bake_finish(_p(mask2d), H2D, W2D, blur, _p(self._k2d), 5.0, _p(color), _p(ws), ws.numel(), _stream()),
+        _lib.check(L.utx_uv_bake_finish(_p(mask2d), H2D, W2D, blur, _p(k2d), gamma, _p(color), _p(ws), ws.numel(), _stream()),
                    "utx_uv_bake_finish")
         return out()
 

@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(128, UTX_WALK_MIN_BLOCKS) nn_query_kernel(cons
 // ------------------------------------------------------------------------------------------------ lens blur on seams
 __global__ void __launch_bounds__(256) lens_blur_kernel(const float* __restrict__ color_in, const unsigned char* __restrict__ seam,
                                                         const float* __restrict__ k2d /*[49]*/, float gamma, int H, int W,
-                                                        float* __restrict__ color_out) {
+                                                        float* __restrict__ color_out, int reflect) {
   __shared__ float ks[49];
   if (threadIdx.x < 49) ks[threadIdx.x] = k2d[threadIdx.x];
   __syncthreads();
@@ -509,20 +509,24 @@ __global__ void __launch_bounds__(256) lens_blur_kernel(const float* __restrict_
   if (seam[t]) {
     const int y = t / W, x = t % W;
     float acc[3] = {0.f, 0.f, 0.f};
+    // border: zeros (the lens blur's conv2d padding) or mirrored without the edge texel (torchvision gaussian_blur pads 'reflect')
     for (int dy = -3; dy <= 3; ++dy) {
-      const int yy = y + dy;
+      int yy = y + dy;
+      if (reflect) yy = yy < 0 ? -yy : (yy >= H ? 2 * H - 2 - yy : yy);
       if (yy < 0 || yy >= H) continue;
       for (int dx = -3; dx <= 3; ++dx) {
-        const int xx = x + dx;
+        int xx = x + dx;
+        if (reflect) xx = xx < 0 ? -xx : (xx >= W ? 2 * W - 2 - xx : xx);
         if (xx < 0 || xx >= W) continue;
         const float kw = ks[(dy + 3) * 7 + (dx + 3)];
         const float* p = color_in + (static_cast<size_t>(yy) * W + xx) * 3;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) acc[a] = acc[a] + kw * powf(p[a], gamma);
+        for (int a = 0; a < 3; ++a) acc[a] = acc[a] + kw * (gamma == 1.0f ? p[a] : powf(p[a], gamma));
       }
     }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) c[a] = fminf(fmaxf(powf(fmaxf(acc[a], 0.f), 1.0f / gamma), 0.f), 1.f);
+    for (int a = 0; a < 3; ++a)
+      c[a] = gamma == 1.0f ? acc[a] : fminf(fmaxf(powf(fmaxf(acc[a], 0.f), 1.0f / gamma), 0.f), 1.f);
   }
   color_out[t * 3] = c[0]; color_out[t * 3 + 1] = c[1]; color_out[t * 3 + 2] = c[2];
 }
@@ -879,7 +883,7 @@ int uv_bake_finish(const unsigned char* mask2d, int H2, int W2, int blur, const 
   const unsigned g256 = (T + 255) / 256;
   const float* src = w.col_a;
   if (blur) {
-    lens_blur_kernel<<<g256, 256, 0, stream>>>(w.col_a, w.seam, blur_k2d, blur_gamma, H2, W2, w.col_b);
+    lens_blur_kernel<<<g256, 256, 0, stream>>>(w.col_a, w.seam, blur_k2d, blur_gamma, H2, W2, w.col_b, blur == 2);
     src = w.col_b;
   }
   int levels = 0;
