@@ -401,13 +401,13 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
 # ------------------------------------------------------------------------------------------------ forward G-buffers (b1)
 @torch.no_grad()
 def export_condition(vert, tri, vertex_normals, geometry_scale=1.0, n_views=6, n_rows=2, n_cols=3, H=512, W=512, scale=1.0,
-                     background=128.0 / 255.0, perspective=False, fov_deg=49.1):
+                     background=128.0 / 255.0, perspective=False, fov_deg=49.1, orbit=False):
     """VideoExporter.export_condition (video/export_nvdiffrast_video.py:900-999, orthographic box views) over
     NVDiffRendererBase.simple_rendering(render_world_normal, render_world_position, enable_antialis=False)
     (render/nvdiffrast/renderer_base.py:101-200) and Mesh.scale_to_bbox / apply_transform (mesh/structure.py:190-202,
     :290-304).  -> uint8 grids alpha [n_rows H, n_cols W], ccm / normal [.., 3], c2ws, intrinsics.  Pinned against the
     reference's own run by tests/golden/ref_glue.npz."""
-    from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics      # pinned themselves against camera/generator.py
+    from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics, generate_orbit_views_c2ws   # pinned themselves against camera/generator.py
     v = torch.from_numpy(np.ascontiguousarray(vert, np.float32))
     bbox = torch.stack([v.min(0).values, v.max(0).values])
     ccc = bbox.mean(dim=0)
@@ -417,8 +417,8 @@ def export_condition(vert, tri, vertex_normals, geometry_scale=1.0, n_views=6, n
     T[:3, 3] = -ccc / sss
     v = torch.matmul(torch.cat([v, torch.ones_like(v[:, :1])], -1), T.T)[:, :3].contiguous()
     vn = F.normalize(torch.matmul(torch.from_numpy(np.ascontiguousarray(vertex_normals, np.float32)), T[:3, :3].T), dim=-1).contiguous()
-    sel = {1: [0], 2: [0, 2], 4: [0, 1, 2, 3], 6: [0, 1, 4, 2, 3, 5] if (n_rows, n_cols) == (2, 3) else list(range(6))}[n_views]
-    c2ws = generate_box_views_c2ws(radius=2.8)[sel]
+    sel = {1: [0], 2: [0, 2], 4: [0, 1, 2, 3], 6: [0, 1, 4, 2, 3, 5] if (n_rows, n_cols) == (2, 3) else list(range(6))}.get(n_views)
+    c2ws = generate_orbit_views_c2ws(n_views + 1, radius=2.8, height=0.0, theta_0=0.0, degree=True)[:n_views] if orbit else generate_box_views_c2ws(radius=2.8)[sel]
     intr = generate_intrinsics(fov_deg, fov_deg, fov=True, degree=True) if perspective else generate_intrinsics(scale, scale, fov=False, degree=False)
     mvp = torch.matmul(intr_to_proj_persp(intr) if perspective else intr_to_proj_ortho(intr), c2w_to_w2c(c2ws))
     clip = torch.matmul(torch.cat([v, torch.ones_like(v[:, :1])], -1), mvp.permute(0, 2, 1))

@@ -271,9 +271,10 @@ def glue():
     ve = rh.video_exporter(v, f, vn)
     out = {}
     for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2)),
-                     ("four_persp", dict(n_views=4, n_rows=2, n_cols=2, perspective=True))):
-        kw = dict(dict(perspective=False), **kw)
-        r = ve.export_condition("mesh.obj", geometry_scale=0.95, H=64, W=64, fov_deg=49.1, scale=1.0, orbit=False,
+                     ("four_persp", dict(n_views=4, n_rows=2, n_cols=2, perspective=True)),
+                     ("orbit8", dict(n_views=8, n_rows=2, n_cols=4, orbit=True))):
+        kw = dict(dict(perspective=False, orbit=False), **kw)
+        r = ve.export_condition("mesh.obj", geometry_scale=0.95, H=64, W=64, fov_deg=49.1, scale=1.0,
                                 background="grey", return_info=False, return_image=True, return_mesh=False, return_camera=True, **kw)
         for k in ("alpha", "ccm", "normal"):
             out[f"cond.{name}.{k}"] = np.asarray(r[k])

@@ -111,10 +111,11 @@ def test_export_condition_matches_reference(lib):
     z = np.load(os.path.join(G, "ref_glue.npz"))
     v, f, _, _ = two_spheres(10, 20)
     for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2)),
-                     ("four_persp", dict(n_views=4, n_rows=2, n_cols=2, perspective=True))):
-        kw = dict(dict(perspective=False), **kw)
+                     ("four_persp", dict(n_views=4, n_rows=2, n_cols=2, perspective=True)),
+                     ("orbit8", dict(n_views=8, n_rows=2, n_cols=4, orbit=True))):
+        kw = dict(dict(perspective=False, orbit=False), **kw)
         out = VideoExporter().export_condition((v, f), geometry_scale=0.95, H=64, W=64, fov_deg=49.1, scale=1.0,
-                                               orbit=False, background="grey", return_image=True, return_camera=True, **kw)
+                                               background="grey", return_image=True, return_camera=True, **kw)
         assert np.array_equal(np.asarray(out["alpha"]), z[f"cond.{name}.alpha"]), name
         for k in ("ccm", "normal"):
             d = np.abs(np.asarray(out[k]).astype(np.int16) - z[f"cond.{name}.{k}"].astype(np.int16))

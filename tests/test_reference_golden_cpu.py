@@ -140,7 +140,8 @@ def test_export_condition_matches_reference():
     v, f, _, _ = two_spheres(10, 20)
     vn = vertex_normals(torch.from_numpy(v), torch.from_numpy(f).long()).numpy()
     for name, kw in (("six", dict(n_views=6, n_rows=2, n_cols=3)), ("four", dict(n_views=4, n_rows=2, n_cols=2)),
-                     ("four_persp", dict(n_views=4, n_rows=2, n_cols=2, perspective=True))):
+                     ("four_persp", dict(n_views=4, n_rows=2, n_cols=2, perspective=True)),
+                     ("orbit8", dict(n_views=8, n_rows=2, n_cols=4, orbit=True))):
         out = ob.export_condition(v, f, vn, geometry_scale=0.95, H=64, W=64, scale=1.0, **kw)
         for k in ("alpha", "ccm", "normal"):
             assert np.array_equal(out[k], z[f"cond.{name}.{k}"]), (name, k)

@@ -73,6 +73,27 @@ def generate_box_views_c2ws(radius=2.8) -> torch.Tensor:
     ], dtype=torch.float32)
 
 
+def generate_orbit_views_c2ws(num_views: int, radius: float = 1.0, height: float = 0.0, theta_0: float = 0.0, degree=False) -> torch.Tensor:
+    """camera/generator.py:115-125 over lookat_to_matrix :8-41: cameras on a horizontal circle (world x forward, y right, z up, then
+    re-labelled to the renderer's z forward, x right, y up), each looking at the origin; the angle grid includes both end points."""
+    if degree:
+        theta_0 = math.radians(theta_0)
+    pr = math.sqrt(radius ** 2 - height ** 2)
+    theta = torch.linspace(theta_0, 2.0 * math.pi + theta_0, num_views, dtype=torch.float32)
+    eye = torch.stack([pr * torch.cos(theta), pr * torch.sin(theta), torch.full((num_views,), height, dtype=torch.float32)], dim=-1)
+    z_axis = torch.nn.functional.normalize(eye, dim=-1)
+    up = torch.tensor([0.0, 0.0, 1.0]).expand_as(z_axis)
+    x_axis = torch.linalg.cross(up, z_axis, dim=-1)
+    degenerate = (x_axis == 0).all(dim=-1, keepdim=True)                    # looking straight down / up: the reference hard-codes +y
+    x_axis = torch.where(degenerate, torch.tensor([0.0, 1.0, 0.0]), x_axis)
+    y_axis = torch.linalg.cross(z_axis, x_axis, dim=-1)
+    c2w = torch.zeros(num_views, 4, 4)
+    c2w[:, :3, 0], c2w[:, :3, 1], c2w[:, :3, 2], c2w[:, :3, 3] = x_axis, y_axis, z_axis, eye
+    c2w[:, 3, 3] = 1.0
+    relabel = torch.tensor([[0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0], [1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 1.0]])
+    return torch.matmul(relabel, c2w)
+
+
 # ------------------------------------------------------------------------------------------------ raster wrappers
 def _f32(t, device):
     return t.to(device=device, dtype=torch.float32).contiguous()

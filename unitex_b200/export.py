@@ -54,7 +54,7 @@ def scale_to_bbox(vertices: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
 
 
 class VideoExporter:
-    """export_condition only (the orbit video / CAD exporters are out of scope)."""
+    """export_condition (box or orbit views, orthographic or perspective); the orbit VIDEO / CAD exporters are out of scope."""
 
     def __init__(self, device="cuda"):
         self.device = torch.device(device)
@@ -65,8 +65,6 @@ class VideoExporter:
                          return_image=True, return_mesh=False, return_camera=False) -> Dict:
         from PIL import Image
         assert n_views == n_rows * n_cols, f"Value Error: (n_views, n_rows, n_cols)={(n_views, n_rows, n_cols)}"
-        if orbit:
-            raise NotImplementedError("B200 export_condition implements the box views UniTEX uses (pipeline.py:199-216), not the orbit")
         if isinstance(mesh_path, str):
             V, F, _, _ = ub.load_mesh(mesh_path)
         else:
@@ -74,9 +72,12 @@ class VideoExporter:
         v = scale_to_bbox(torch.as_tensor(V, dtype=torch.float32, device=self.device), geometry_scale)
         f = torch.as_tensor(F, device=self.device).to(torch.int32).contiguous()
         vn = vertex_normals(v, f)
-        c2ws = ub.generate_box_views_c2ws(radius=2.8)
-        sel = {1: [0], 2: [0, 2], 4: [0, 1, 2, 3], 6: [0, 1, 4, 2, 3, 5] if (n_rows, n_cols) == (2, 3) else [0, 1, 2, 3, 4, 5]}[n_views]
-        c2ws = c2ws[sel]
+        if orbit:                                                              # :922-923
+            c2ws = ub.generate_orbit_views_c2ws(n_views + 1, radius=2.8, height=0.0, theta_0=0.0, degree=True)[:n_views]
+        else:
+            assert n_views in (1, 2, 4, 6), f"Value Error: n_views={n_views}"
+            sel = {1: [0], 2: [0, 2], 4: [0, 1, 2, 3], 6: [0, 1, 4, 2, 3, 5] if (n_rows, n_cols) == (2, 3) else [0, 1, 2, 3, 4, 5]}[n_views]
+            c2ws = ub.generate_box_views_c2ws(radius=2.8)[sel]
         intr = ub.generate_intrinsics(fov_deg, fov_deg, fov=True, degree=True) if perspective else ub.generate_intrinsics(scale, scale, fov=False)
         mats = torch.matmul(ub.intr_to_proj(intr, perspective=bool(perspective)), ub.c2w_to_w2c(c2ws)).to(self.device)
         rast = ub.rasterize(ub.transform_points(v.contiguous(), mats), f, (H, W))
