@@ -271,7 +271,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "model": "FLUX.1-dev MM-DiT 19+38 blocks, random-init, rank-64 LoRA merged",
+        "config": {"workload": WORKLOAD, "weights": "random-init, FLUX.1-dev-shaped (19 double + 38 single blocks), rank-64 LoRA merged",
                    "tokens": S_TOT, "per_gpu_batch": 1, "parallelism": f"dp{world} (one independent grid per rank)",
                    "l2": "inputs larger than L2: 23.8 GB of weights stream through every step",
                    "timing": "CUDA events on the launching stream, max over ranks"},
