@@ -209,3 +209,20 @@ def test_infer_perspective_matches_reference():
         assert np.array_equal(out["color_2d"].numpy(), z[f"persp.{name}.color_2d"]), name
     assert np.array_equal(out["mask_2d_visiable"].numpy(), _unpack(z["persp.mask_2d_visiable"], (6, 64, 64, 1)))
     assert out["mask_2d_visiable"].sum() > 1000
+
+
+def test_lora_target_list_matches_reference_source():
+    """Only where the reference tree is present (the build container): the LoRA target modules the oracle and the product merge
+    are the ones the reference trains (flux_piplines/texturing/trainer.py:282-304)."""
+    import ast
+    import re
+    import pytest
+    path = "/root/reference/flux_piplines/texturing/trainer.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree absent")
+    src = open(path).read()
+    targets = ast.literal_eval(re.search(r"target_modules = (\[\s*#[^\n]*\n.*?\])", src, re.S).group(1))
+    saved = ast.literal_eval(re.search(r"modules_to_save = (\[.*?\])", src, re.S).group(1))
+    assert set(targets) == set(fs.LORA_TARGETS_DOUBLE)
+    assert set(fs.LORA_TARGETS_SINGLE) <= set(targets)                  # single blocks only own attn.to_q/k/v of that list
+    assert saved[0] == "x_embedder"                                      # the one modules_to_save entry that has parameters
