@@ -52,6 +52,27 @@ def build_pipeline(pretrain_models=None, pipeline_name="texture_plus", model="rg
     return pipeline, weights_for_texture, weights_for_delight, adapter_names
 
 
+def reference_image_on_canvas(rgb: Image.Image, alpha: Image.Image, H=2048, W=2048, scale=0.8, color="white") -> Image.Image:
+    """image/process_image.py:31-81 (`preprocess` with a given alpha): bounding box of the matte, uniform scale so that it spans
+    `scale` of the canvas, object pasted centred on a `color` canvas through the matte; the matte itself becomes the alpha channel."""
+    m = np.asarray(alpha)
+    rows, cols = np.where(m.sum(-1) > 0)[0], np.where(m.sum(-2) > 0)[0]
+    x1, y1, x2, y2 = cols.min(), rows.min(), cols.max(), rows.max()
+    dy, dx = y2 - y1, x2 - x1
+    s = min(H * scale / dy, W * scale / dx)
+    Ht, Wt = int(dy * s), int(dx * s)
+    ox, oy = int((W - Wt) / 2), int((H - Ht) / 2)
+    box_src, box_dst = (int(x1), int(y1), int(x2), int(y2)), (ox, oy, ox + Wt, oy + Ht)
+    rgbc = rgb.crop(box_src).resize((Wt, Ht))
+    alphac = alpha.crop(box_src).resize((Wt, Ht))
+    alphat = Image.new("L", (W, H))
+    alphat.paste(alphac, box_dst)
+    out = Image.new("RGBA", (W, H), color)
+    out.paste(rgbc, box_dst, alphac)
+    out.putalpha(alphat)
+    return out
+
+
 class RGBTextureFullPipelineBase:
     step_seq = []
 
@@ -82,15 +103,24 @@ class RGBTextureFullPipelineBase:
         V = V / sss - (aaa + bbb) / (2.0 * sss)
         ux.save_obj(os.path.join(save_dir, "processed_mesh.obj"), V, F, UV, Ft)
 
-    def preprocess_reference_image(self, save_dir, input_image_path):
-        """reference :182-196 (rembg + crop/pad): here resize onto a 1024^2 grey canvas, then 512^2."""
-        img = Image.open(input_image_path).convert("RGB")
-        img.save(os.path.join(save_dir, "rembg_image.png"))
-        canvas = Image.new("RGB", (1024, 1024), "grey")        # PIL grey = (128, 128, 128), as image/process_image.py:68
-        im = img.copy()
-        im.thumbnail((1024, 1024))
-        canvas.paste(im, ((1024 - im.width) // 2, (1024 - im.height) // 2))
-        canvas.resize((512, 512), Image.BILINEAR).save(os.path.join(save_dir, "processed_image.png"))
+    def preprocess_reference_image(self, save_dir, input_image_path, scale=0.95, color="grey"):
+        """reference :182-196 -> image/process_image.py:31-81.  There the matte always comes from a background-removal network
+        (RMBG-2.0 / rembg [ext], out of scope).  Here: an input image that carries its own alpha channel is cropped to the matte's
+        bounding box, scaled so the object spans `scale` of the 1024^2 canvas and pasted on the `color` canvas through the matte --
+        `preprocess` restated, pinned against the reference's own function (tests/golden/ref_glue.npz).  An image without alpha
+        is centred on the canvas as it is."""
+        src = Image.open(input_image_path)
+        if src.mode == "RGBA" and (np.asarray(src.getchannel("A")) > 0).sum() < src.size[0] * src.size[1] - 8:
+            src = src.resize((1024, 1024))                                   # :183 resizes before the matte is used
+            out = reference_image_on_canvas(src.convert("RGB"), src.getchannel("A"), 1024, 1024, scale, color)
+        else:
+            img = src.convert("RGB")
+            out = Image.new("RGB", (1024, 1024), color)                      # PIL grey = (128, 128, 128), as image/process_image.py:68
+            im = img.copy()
+            im.thumbnail((1024, 1024))
+            out.paste(im, ((1024 - im.width) // 2, (1024 - im.height) // 2))
+        out.save(os.path.join(save_dir, "rembg_image.png"))
+        out.convert("RGB").resize((512, 512)).save(os.path.join(save_dir, "processed_image.png"))
 
     def render_geometry_images(self, save_dir, input_mesh_path, geometry_scale=0.95, scale=1.0, color="grey"):
         """reference :199-228."""

@@ -33,3 +33,12 @@ class FakeFlux:
         self.calls.append({k: v for k, v in kw.items() if k not in ("generator",)})
         out = 255 - c if len(self.calls) == 1 else np.roll(c, 7, axis=1)
         return types.SimpleNamespace(images=[Image.fromarray(out)])
+
+
+def reference_rgba():
+    """A 1024^2 RGBA reference image with an off-centre elliptical matte (soft edge) over a colour pattern."""
+    yy, xx = np.mgrid[0:1024, 0:1024].astype(np.float32)
+    rgb = np.stack([127 + 100 * np.sin(xx / 37.0), 127 + 100 * np.cos(yy / 29.0), 127 + 90 * np.sin((xx + yy) / 53.0)], -1)
+    d = np.sqrt(((xx - 430.0) / 260.0) ** 2 + ((yy - 560.0) / 330.0) ** 2)
+    alpha = np.clip((1.0 - d) * 12.0, 0.0, 1.0) * 255.0
+    return np.concatenate([np.clip(rgb, 0, 255), alpha[..., None]], -1).astype(np.uint8)

@@ -20,7 +20,7 @@ import ref_harness as rh                                      # noqa: E402
 from oracle import flux_dit as fd                             # noqa: E402
 from oracle import vae as ov                                  # noqa: E402
 from tests.bake_meshes import two_spheres                     # noqa: E402
-from tests.glue_fakes import FakeFlux, glue_inputs, sha as _sha   # noqa: E402
+from tests.glue_fakes import FakeFlux, glue_inputs, reference_rgba, sha as _sha   # noqa: E402
 
 
 def bake():
@@ -302,6 +302,16 @@ def glue():
         out["mv.rgb_sha"] = np.array(_sha(np.array(Image.open(os.path.join(d, "mv_rgb.png")))))
         out["mv.rgb_probe"] = np.array(Image.open(os.path.join(d, "mv_rgb.png")))[::64, ::64].copy()
         out["mv.w_light_sha"] = np.array(_sha(np.array(Image.open(os.path.join(d, "mv_rgb_w_light.png")))))
+
+        # preprocess_reference_image (:182-196) over image/process_image.py::preprocess (:31-81), the matte supplied by a stand-in for
+        # the background-removal network [ext]: it hands back the test image's own alpha
+        rgba = Image.fromarray(reference_rgba(), mode="RGBA")
+        rgba.save(os.path.join(d, "ref_rgba.png"))
+        me3 = types.SimpleNamespace(rembg_session=lambda image: rgba)
+        mod.CustomRGBTextureFullPipeline.preprocess_reference_image(me3, d, os.path.join(d, "ref_rgba.png"))
+        a_full, a_small = np.array(Image.open(os.path.join(d, "rembg_image.png"))), np.array(Image.open(os.path.join(d, "processed_image.png")))
+        out["pre.rembg_sha"], out["pre.rembg_shape"], out["pre.rembg_probe"] = np.array(_sha(a_full)), np.array(a_full.shape), a_full[::64, ::64].copy()
+        out["pre.processed_sha"], out["pre.processed_shape"], out["pre.processed_probe"] = np.array(_sha(a_small)), np.array(a_small.shape), a_small[::32, ::32].copy()
 
         # reproject_and_query_field: what the bake entry point is handed
         rec = {}

@@ -226,3 +226,20 @@ def test_lora_target_list_matches_reference_source():
     assert set(targets) == set(fs.LORA_TARGETS_DOUBLE)
     assert set(fs.LORA_TARGETS_SINGLE) <= set(targets)                  # single blocks only own attn.to_q/k/v of that list
     assert saved[0] == "x_embedder"                                      # the one modules_to_save entry that has parameters
+
+
+def test_preprocess_reference_image_matches_reference(tmp_path):
+    """The matte-driven crop / scale / paste of the reference image (pipeline.py:182-196, image/process_image.py:31-81) against the
+    reference's own functions run with a stand-in matte source."""
+    import types
+    from PIL import Image
+    import pipeline as drop_in
+    from tests.glue_fakes import reference_rgba, sha
+    z = np.load(os.path.join(G, "ref_glue.npz"))
+    src = str(tmp_path / "ref_rgba.png")
+    Image.fromarray(reference_rgba(), mode="RGBA").save(src)
+    drop_in.CustomRGBTextureFullPipeline.preprocess_reference_image(types.SimpleNamespace(), str(tmp_path), src)
+    a_full, a_small = np.array(Image.open(tmp_path / "rembg_image.png")), np.array(Image.open(tmp_path / "processed_image.png"))
+    assert a_full.shape == tuple(z["pre.rembg_shape"]) and a_small.shape == tuple(z["pre.processed_shape"])
+    assert np.array_equal(a_full[::64, ::64], z["pre.rembg_probe"]) and np.array_equal(a_small[::32, ::32], z["pre.processed_probe"])
+    assert sha(a_full) == str(z["pre.rembg_sha"]) and sha(a_small) == str(z["pre.processed_sha"])
