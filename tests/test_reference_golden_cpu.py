@@ -38,6 +38,8 @@ def test_mesh_normals_match_reference():
     v, f, _, _ = two_spheres(10, 20)
     n = vertex_normals(torch.from_numpy(v), torch.from_numpy(f).long())                  # structure_v2.py:63-71
     assert np.abs(n.numpy() - z["vertex_normals"]).max() < 1e-6
+    from unitex_b200.bake import area_weighted_vertex_normals                             # the bake's own copy: slot-wise like the reference
+    assert np.array_equal(area_weighted_vertex_normals(torch.from_numpy(v), torch.from_numpy(f)).numpy(), z["vertex_normals"])
 
 
 def test_torch_tail_functions_bit_exact():

@@ -240,6 +240,16 @@ def gaussian_kernel_2d(kernel_size: int = 5) -> torch.Tensor:
     return out.contiguous()
 
 
+def area_weighted_vertex_normals(vertices: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
+    """PBRMesh.vertex_normals (mesh/structure_v2.py:49,63-71): each face's area vector is scattered into one slot per triangle
+    corner, the three slots are averaged, the result normalised."""
+    f = faces.long()
+    areas = torch.linalg.cross(vertices[f[:, 1]] - vertices[f[:, 0]], vertices[f[:, 2]] - vertices[f[:, 0]], dim=-1)
+    vn = torch.zeros(vertices.shape[0], 3, 3, dtype=vertices.dtype, device=vertices.device)
+    vn.scatter_add_(0, f.unsqueeze(-1).expand(-1, -1, 3), areas.unsqueeze(1).expand(-1, 3, -1))
+    return torch.nn.functional.normalize(vn.mean(dim=1), dim=-1)
+
+
 # ------------------------------------------------------------------------------------------------ mesh container (b3)
 class BakeMesh:
     """The fields of PBRMesh the bake reads (mesh/structure_v2.py:25-77): vertices [V,3], faces [F,3], uvs_2d [V2,2] in
@@ -274,11 +284,9 @@ class BakeMesh:
     def vertex_normals(self) -> torch.Tensor:
         """Area-weighted vertex normals, :63-71 (only the gradient filter of mv_to_pcd reads them)."""
         if self._vertex_normals is None:
-            f, a = self.faces.long(), self.areas
-            vn = torch.zeros(self.vertices.shape[0], 3, 3, device=self.device)      # one slot per triangle corner, then their mean
-            for k in range(3):
-                vn[:, k].index_add_(0, f[:, k], a)
-            self._vertex_normals = torch.nn.functional.normalize(vn.mean(dim=1), dim=-1)
+            # once per mesh, on the host: a sequential scatter is reproducible run to run (atomics on the device are not), and the
+            # gradient filter thresholds quantities derived from these normals
+            self._vertex_normals = area_weighted_vertex_normals(self.vertices.cpu(), self.faces.cpu()).to(self.device)
         return self._vertex_normals
 
     @property
