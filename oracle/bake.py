@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Dict
+from typing import Dict, Optional
 
 import numpy as np
 import torch
@@ -242,10 +242,14 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
                     H: int, W: int, H2: int, W2: int, angle_deg: float = 100.0, index=(0, 3, 4, 1, 2, 5), method: str = "reproject",
                     kdtree_method: str = "order_mean", k_all: int = 32, k_vis: int = 1, k_invis: int = 32,
                     query_field=None, filt_gradient_points: bool = False, grad_norm_threhold: float = 0.20,
-                    perspective: bool = False, reproject_method: str = "lens", kernel_size_blur: int = 5) -> Dict[str, torch.Tensor]:
+                    perspective: bool = False, reproject_method: str = "lens", kernel_size_blur: int = 5,
+                    nn_index_given: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """NVDiffRendererInverse.infer(perspective=False, filt_gradient_points=False) (:635-726) for method='reproject'
     (reproject_method='lens') and method='kdtree' (kdtree_method 'order_mean' | 'mean'); `query_field` set = the
-    *_inpainting=True branches (:387-389, :427-432, :609-614)."""
+    *_inpainting=True branches (:387-389, :427-432, :609-614).
+    `nn_index_given` [H2*W2] int64 (flat texel index of the source, -1 elsewhere): at atlas sizes where the brute-force 1-NN of
+    the fill is out of reach (2048^2: 0.7 M x 2.1 M pairs) the caller supplies the neighbour table -- after checking a sample of
+    it against `nearest_index` -- and everything else (visibility, composite, seams, blur, pull-push) is still computed here."""
     vert = np.ascontiguousarray(vert, np.float32)
     tri = np.ascontiguousarray(tri, np.int32)
     tri_uv = np.ascontiguousarray(tri_uv, np.int32)
@@ -380,6 +384,9 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
     if inv_m.any() and vis_m.any():
         if query_field is not None:                                                          # inpainting=True (:612-613)
             color[0][inv_m] = query_field(pos_2d[0][vis_m], color[0][vis_m], pos_2d[0][inv_m])
+        elif nn_index_given is not None:
+            nn_index = nn_index_given.reshape(-1).to(torch.int64).clone()
+            color[0][inv_m] = color[0].reshape(-1, Cn)[nn_index[inv_m.reshape(-1)]]
         else:
             src_idx = torch.nonzero(vis_m.reshape(-1))[:, 0]
             idx = nearest_index(pos_2d[0][vis_m], pos_2d[0][inv_m])
@@ -395,7 +402,7 @@ def infer(vert, tri, uv, tri_uv, c2ws: torch.Tensor, intrinsics: torch.Tensor, i
     color_2d = pull_push(color.permute(0, 3, 1, 2), mask_2d.permute(0, 3, 1, 2))[0].permute(0, 2, 3, 1)
     return {"mask_2d": mask_2d, "mask_2d_visiable": vis, "raw_visible": raw_vis, "color_2d": color_2d, "tid_2d": tid_2d,
             "owner": owner, "seam": bnd, "nn_index": nn_index, "pre_blur": pre_blur, "rast_2d": torch.from_numpy(rast2),
-            "alpha_mv": alpha_vis, "rays_tid": rt}
+            "alpha_mv": alpha_vis, "rays_tid": rt, "pos_2d": pos_2d, "rast_mv": rast_mv}
 
 
 # ------------------------------------------------------------------------------------------------ forward G-buffers (b1)

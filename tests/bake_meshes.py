@@ -33,3 +33,34 @@ def two_spheres(rows=20, cols=40):
 def analytic_color(p):
     """Smooth colour field of world position, in [0.1, 0.9]."""
     return 0.5 + 0.4 * np.stack([np.sin(3.1 * p[..., 0] + 0.3), np.cos(2.7 * p[..., 1] - 0.2), np.sin(2.3 * p[..., 2] + 1.1)], -1)
+
+
+_TEASER = None
+
+
+def teaser_robot_raw():
+    """The reference's own test mesh (test_cases/teaser_robot/inputmesh.obj, BASELINE.json config 4) as parsed from the OBJ:
+    (V [269026,3] f32, F [499981,3] i32, UV [268818,2] f32 in [0,1], F_uv [499981,3] i32).  Stored losslessly in
+    tests/golden/teaser_robot.npz.xz (tests/golden/make_teaser_fixture.py)."""
+    global _TEASER
+    if _TEASER is None:
+        import io
+        import lzma
+        from pathlib import Path
+        z = np.load(io.BytesIO(lzma.decompress((Path(__file__).resolve().parent / "golden" / "teaser_robot.npz.xz").read_bytes())))
+        F = np.cumsum(z["F_delta"].astype(np.int64)).reshape(-1, 3)
+        Ft = F + z["Ft_minus_F"]
+        _TEASER = (z["V"].view(np.float32), F.astype(np.int32), z["UV"].view(np.float32), Ft.astype(np.int32))
+    return tuple(a.copy() for a in _TEASER)
+
+
+def teaser_robot(scale=0.95):
+    """teaser_robot in the frame the bake's cameras assume: bounding box centred, longest side = 2*scale (float64 like
+    `preprocess_blank_mesh`, reference pipeline.py:170-179 -> geometry/uv/uv_atlas.py:131-194), uvs_2d = uv*2-1
+    (mesh/structure_v2.py:287).  -> (V f32, F i32, uvs_2d f32, F_uv i32)."""
+    V, F, UV, Ft = teaser_robot_raw()
+    V = V.astype(np.float64)
+    lo, hi = V.min(0), V.max(0)
+    s = (hi - lo).max() / (2.0 * scale)
+    V = (V / s - (lo + hi) / (2.0 * s)).astype(np.float32)
+    return V, F, (UV * 2.0 - 1.0).astype(np.float32), Ft

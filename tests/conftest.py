@@ -29,3 +29,19 @@ def lib():
     if not _lib.lib_path().exists():
         build.build()
     return _lib.load()
+
+
+_PARITY_LINES = []
+
+
+@pytest.fixture
+def parity_log():
+    """Tests hand measured parity figures (dB, counts) to the terminal summary, so they show in the run's tail."""
+    return _PARITY_LINES.append
+
+
+def pytest_terminal_summary(terminalreporter):
+    if _PARITY_LINES:
+        terminalreporter.write_sep("-", "parity figures")
+        for ln in _PARITY_LINES:
+            terminalreporter.write_line("parity: " + ln)
