@@ -29,6 +29,17 @@ S_IMG = S_NOISE + S_CTRL + S_DUAL
 S_TOT = S_TXT + S_IMG
 WORKLOAD = "texture_gen 1024x1024 4-view (2x2 of 512^2): S=9728 = 512 txt + 4096 noise + 4096 control + 1024 reference"
 METRIC, UNIT = "multi-view denoise steps/s", "steps/s"
+LORA_RANK = 64
+
+
+def bench_config(world: int) -> dict:
+    """The workload description, IDENTICAL for the B200 arm and the reference arm (the driver compares the two dicts)."""
+    return {"workload": WORKLOAD,
+            "weights": f"random-init, FLUX.1-dev-shaped (19 double + 38 single blocks), rank-{LORA_RANK} texture_gen LoRA merged into "
+                       "every target Linear (trainer.py:283-305: 12 per double block, q/k/v per single block) + x_embedder replacement",
+            "tokens": S_TOT, "per_gpu_batch": 1, "parallelism": f"dp{world} (one independent grid per rank)",
+            "schedule": "flow-match Euler, 28-step sigma grid, guidance 3.5",
+            "l2": "inputs larger than L2: 23.8 GB of weights stream through every step"}
 
 
 def _flops():
@@ -148,25 +159,34 @@ def cpu_block_seconds(repeats: int = 1, device="cpu", frac: int = CPU_FRAC):
     return best * frac, torch.get_num_threads()
 
 
+REF_SAMPLE = ("per step: ONE whole single-stream block (of 57 equal-cost blocks: every block touches the same 113 246 208 "
+              "parameters per token and runs the same 24-head attention over all 9728 keys, SURVEY 8d) at the full S=9728 on the "
+              "host cores -- all rows through LN/QKV/MLP/proj_out, all heads through RMSNorm+RoPE+SDPA -- eager oracle port of the "
+              "diffusers CPU path, bf16 weights like the reference")
+
+
 def run_reference(args, rank, world):
+    """The reference's own implementation of the path (diffusers eager, CPU) cannot be installed here, so this arm
+    times the oracle port of it.  One whole step is ~10 minutes of host time, so each timed step is a BOUNDED SAMPLE: one
+    whole block, measured; the step time reported is that x 57 and the line says so in `extrapolated`."""
     if rank != 0:
         return
     times = []
     cores = 1
     for i in range(args.warmup + args.steps):
-        dt, cores = cpu_block_seconds(1)
+        dt, cores = cpu_block_seconds(1, frac=1)
         if i >= args.warmup:
             times.append(dt)
-    step_s = 57.0 * sum(times) / len(times)
+    block_s = sum(times) / len(times)
+    step_s = 57.0 * block_s
     val = 1.0 / step_s
-    sample = ("per step: a 1/4 sample of 1 single-stream block (of 57 equal-cost blocks) at the full S=9728 on the host "
-              "cores -- a quarter of the token rows through LN/MLP/proj_out, a quarter of the heads through "
-              "qkv+RMSNorm+RoPE+SDPA over all keys -- eager oracle port of the diffusers CPU path, bf16 weights; "
-              "step time = 57 x 4 x sample time")
     out = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-           "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD, "timing": "host wall clock"},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "data": "synthetic", "impl": "reference", "config": bench_config(world), "timing": "host wall clock",
+           "extrapolated": {"factor": 57, "measured_unit": "one whole single-stream block at S=9728", "measured_ms": block_s * 1e3,
+                            "note": "value = 1 / (57 x measured block time); the timed region of this run covers "
+                                    f"{args.steps} blocks, not {args.steps} steps"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": REF_SAMPLE},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -182,16 +202,36 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     side = {}
     if world == 1 and not args.no_bake:      # before the engine: metric 2 is measured on an idle, un-throttled GPU
-        side["uv_bake"] = bench_uv_bake(dev)
+        side["uv_bake"] = bench_uv_bake(dev, return_tensors=True)
+        bake_nn = side["uv_bake"].pop("tensors")[3].cpu().long()       # the GPU run's 1-NN table, handed to the CPU baseline of the same workload
+        side["uv_bake_synthetic"] = bench_uv_bake(dev, mesh_name="two_spheres", reps=10)
         side["vae_decode"] = bench_vae_decode(dev)
     cfg = FluxConfig()
     eng = FluxTransformer(cfg, dev).random_init_(seed=0)
-    # "LoRA merged": a random rank-64 texture_gen adapter folded into one block's q projection exercises the merge
-    # kernel; merging adds no work to the step (W' = W + s B A is done once, before the loop).
-    g = torch.Generator(device=dev).manual_seed(63 + rank)           # rank r = independent grid r (run.py:5 seed 63)
-    A = torch.randn(64, 3072, device=dev, generator=g) * 0.02
-    B = torch.randn(3072, 64, device=dev, generator=g) * 0.02
-    eng.merge_lora_({"transformer_blocks.0.attn.to_q.lora_A.weight": A, "transformer_blocks.0.attn.to_q.lora_B.weight": B}, 1.0)
+    # "LoRA merged" (BASELINE config 2): a random rank-64 texture_gen adapter over the reference's whole target list
+    # (flux_piplines/texturing/trainer.py:283-305: the 12 Linears of every double block, to_q/k/v of every single block) plus
+    # the x_embedder replacement, folded into the resident weights once before the loop: W' = W + s B A.  Merging adds no
+    # work to the step, which is the point of merging.
+    g = torch.Generator(device=dev).manual_seed(1)
+    dbl_t = ("attn.to_q", "attn.to_k", "attn.to_v", "attn.to_out.0", "attn.add_q_proj", "attn.add_k_proj", "attn.add_v_proj",
+             "attn.to_add_out", "ff.net.0.proj", "ff.net.2", "ff_context.net.0.proj", "ff_context.net.2")
+    names = [f"transformer_blocks.{i}.{t}" for i in range(cfg.num_layers) for t in dbl_t]
+    names += [f"single_transformer_blocks.{i}.attn.{t}" for i in range(cfg.num_single_layers) for t in ("to_q", "to_k", "to_v")]
+    adapter = {}
+    for n in names:
+        k, r0, r1 = eng.where[n]
+        o, i_f = r1 - r0, eng.T["w_" + k].shape[1]
+        adapter[n + ".lora_A.weight"] = torch.randn(LORA_RANK, i_f, device=dev, generator=g) * 0.02
+        adapter[n + ".lora_B.weight"] = torch.randn(o, LORA_RANK, device=dev, generator=g) * 0.02
+    adapter["x_embedder.weight"] = torch.randn(3072, 64, device=dev, generator=g) * 0.02
+    adapter["x_embedder.bias"] = torch.randn(3072, device=dev, generator=g) * 0.02
+    eng.merge_lora_(adapter, 1.0)
+    n_lora_targets = len(names)
+    del adapter
+    torch.cuda.empty_cache()
+    from unitex_b200.vae import AutoencoderKLB200
+    from unitex_b200 import parallel as par
+    vae = AutoencoderKLB200.from_random(seed=1, device=dev)
 
     ids = torch.zeros(S_TOT, 3)
     def grid(h, w, oy, ox):
@@ -211,11 +251,18 @@ def run_ours(args, rank, world, local_rank):
     mu = 1.15                                                          # calculate_shift(4096)
     sig = np.concatenate([np.exp(mu) / (np.exp(mu) + (1 / s - 1)), [0.0]]).astype(np.float32)
 
-    decoded_tile = torch.zeros(3, 1024, 1024, dtype=torch.uint8, device=dev)   # stands for this rank's VAE-decoded grid in the gather
-
     def step(i):
         j = i % n_sched
         eng.denoise_(lat, S_NOISE, sig[j:j + 2], 3.5)
+
+    def finish_asset():
+        """What follows the loop for every asset (pipeline.py:688-692 + north_star): unpack the noise rows, VAE-decode them to
+        the uint8 view tile [3,1024,1024] and -- the path's ONE collective -- all-gather the ranks' tiles so every rank holds
+        every asset's tile before UV projection.  Real data: this rank's own latents through the real decode."""
+        z = lat[:S_NOISE].view(1, 64, 64, 16, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(1, 16, 128, 128)
+        img = vae.decode(z / vae.scaling_factor + vae.shift_factor)
+        tile = ((img[0].float() / 2 + 0.5).clamp(0, 1) * 255.0 + 0.5).to(torch.uint8)
+        return par.all_gather_grid_tiles([tile], world, (3, 1024, 1024), torch.uint8, dev)
 
     def barrier():
         if world > 1:
@@ -224,26 +271,31 @@ def run_ours(args, rank, world, local_rank):
 
     for i in range(args.warmup):
         step(i)
+    tiles = finish_asset()                                             # untimed first pass (NCCL communicator set-up, VAE first launches)
     barrier()
     eng.profile(True)
     eng.profile_read(reset=True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     barrier()
     e0.record()
     for i in range(args.steps):
         step(i)
-    if world > 1:   # the path's one collective: every rank receives every rank's finished (decoded) tile before UV projection
-        from unitex_b200.parallel import all_gather_tiles          # (north_star; SURVEY 8e: uint8 [3,1024,1024] = 3 MB per rank)
-        tiles = all_gather_tiles(decoded_tile)
     e1.record()
+    tiles = finish_asset()                                             # inside the timed region at every N (at N = 1: decode only)
+    e2.record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = e0.elapsed_time(e2)
+    ms_steps = e0.elapsed_time(e1)
+    ms_finish = e1.elapsed_time(e2)
+    assert len(tiles) == world and all(t.shape == (3, 1024, 1024) for t in tiles)
+    tile_checks = [int(t.sum().item()) for t in tiles]                 # every rank's tile arrived (non-trivial data)
     clocks = sampler.stop() if sampler else None
     launches, cat_ms = eng.profile_read(reset=True)
     eng.profile(False)
 
     # end to end through the public call with HOST buffers: pinned H2D of the latents, one step, D2H of the result
+    tile_host = torch.empty(world, 3, 1024, 1024, dtype=torch.uint8).pin_memory()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
@@ -251,14 +303,17 @@ def run_ours(args, rank, world, local_rank):
         lat.copy_(lat_host, non_blocking=True)
         step(i)
         out_host.copy_(lat[:S_NOISE], non_blocking=True)
+    tiles = finish_asset()
+    for r_, t_ in enumerate(tiles):
+        tile_host[r_].copy_(t_, non_blocking=True)                     # the gathered tiles reach the host
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, ms_steps, ms_finish], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_steps, ms_finish = t.tolist()
     if rank != 0:
         return
     total, f_gemm, f_attn = _flops()
@@ -271,10 +326,11 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": world * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "weights": "random-init, FLUX.1-dev-shaped (19 double + 38 single blocks), rank-64 LoRA merged",
-                   "tokens": S_TOT, "per_gpu_batch": 1, "parallelism": f"dp{world} (one independent grid per rank)",
-                   "l2": "inputs larger than L2: 23.8 GB of weights stream through every step",
-                   "timing": "CUDA events on the launching stream, max over ranks"},
+        "config": bench_config(world), "timing": "CUDA events on the launching stream, max over ranks",
+        "timed_region": {"what": f"{args.steps} denoise steps, then this rank's VAE decode to the uint8 view tile and the all-gather of "
+                                 f"the {world} ranks' tiles (once per asset; the reference does it once per 28 steps, pipeline.py:688-692)",
+                         "denoise_only_ms_per_step": ms_steps / args.steps, "decode_and_gather_ms": ms_finish,
+                         "gathered_tile_checksums": tile_checks, "lora_targets_merged": n_lora_targets},
         "roofline": {"bound": "tensor", "kernel": "gemm2_bf16_tn_kernel (tcgen05 cta_group::2; 1-CTA gemm_bf16_tn_kernel for narrow N)",
                      "achieved": gemm_tf, "peak": peak_sus, "unit": "TFLOP/s", "frac": gemm_tf / peak_sus,
                      "traffic": 5.20e8, "traffic_note": "dram read+write of ONE qkv-shaped launch (M 9728, N 9216, K 3072), warm L2 as inside the step (ncu --cache-control none, profiles/r01_gemm_groupm_sweep.txt: 335 MB read + 185 MB written); 1046 MB with ncu's cache flush (profiles/r01_gemm2_bf16_tn_final.ncu-rep); algorithmic 296 MB",
@@ -283,9 +339,12 @@ def run_ours(args, rank, world, local_rank):
                      "attention": {"kernel": "attention2_kernel (tcgen05, P in TMEM)", "achieved": attn_tf, "frac": attn_tf / peak_sus,
                                    "flops_per_step": f_attn, "ms_per_step": cat_ms["attn"] / args.steps},
                      "elementwise_ms_per_step": cat_ms["elem"] / args.steps,
-                     "whole_step": {"achieved": total / (step_ms * 1e-3) / 1e12, "frac": total / (step_ms * 1e-3) / 1e12 / peak_sus}},
+                     "whole_step": {"achieved": total / (ms_steps / args.steps * 1e-3) / 1e12,
+                                    "frac": total / (ms_steps / args.steps * 1e-3) / 1e12 / peak_sus,
+                                    "note": "DiT FLOPs of one step / denoise-only time per step (the decode + gather tail excluded)"}},
         "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": S_IMG * 64 * 2,
-                "d2h_bytes_per_step": S_NOISE * 64 * 2},
+                "d2h_bytes_per_step": S_NOISE * 64 * 2, "d2h_bytes_once": world * 3 * 1024 * 1024,
+                "note": "per step: latents from pinned host memory in, noise rows back out; after the loop: decode, gather, tiles to the host"},
         "gpu_launches": int(sum(launches.values())),
         "clocks": clocks,
     }
@@ -305,14 +364,12 @@ def run_ours(args, rank, world, local_rank):
                                                "stand-in for 'the reference on B200' (SURVEY 8d); reported, not a target"}
         if "uv_bake" in out:
             try:
-                out["uv_bake"]["cpu_baseline"] = bench_uv_bake_cpu()
+                out["uv_bake"]["cpu_baseline"] = bench_uv_bake_cpu(bake_nn)
             except Exception as e:      # the C oracle needs its prebuilt .so (or gcc) on the box; the main line must not depend on it
                 out["uv_bake"]["cpu_baseline"] = {"unavailable": repr(e)[:200]}
-        dt, cores = cpu_block_seconds(1)
+        dt, cores = cpu_block_seconds(1, frac=1)
         out["cpu_baseline"] = {"value": 1.0 / (57.0 * dt), "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": "1/4 of one single-stream block (of 57 equal-cost blocks) at S=9728 (quarter of the "
-                                         "rows for LN/MLP/proj_out, quarter of the heads for attention over all keys), "
-                                         "eager oracle port of the diffusers CPU path, bf16 weights; step = 57 x 4 x sample"}
+                               "sample": REF_SAMPLE + "; step = 57 x the measured block", "measured_block_ms": dt * 1e3}
     print(json.dumps(out), flush=True)
 
 
@@ -429,14 +486,14 @@ def bench_vae_decode(dev):
             "note": "implicit-GEMM 3x3 convolutions (TMA boxes shifted by the tap) on the tcgen05 GEMM, NHWC bf16, deterministic GroupNorm+SiLU"}
 
 
-def bench_uv_bake(dev, return_tensors=False):
-    """Second metric of BASELINE.json: UV-bake Mpix/s = atlas texels / time of NVDiffRendererInverse.infer(method=
-    'reproject') with the mesh resident on the GPU (SURVEY 8d metric 2), on a synthetic teaser-robot-sized mesh
-    (two UV-mapped spheres, ~500k faces; the reference fixture is not available on the GPU box), 6 box views of 512^2
-    with an analytic colour field, 2048^2 atlas."""
+# dram__bytes_read.sum + dram__bytes_write.sum summed over every kernel of ONE bake of the teaser_robot workload, from the ncu pass
+# committed as profiles/r02_bake_teaser_dram.csv (scripts/profile_bake_teaser.py under `ncu --metrics dram__bytes_read.sum,
+# dram__bytes_write.sum,gpu__time_duration.sum`); None until that capture exists
+BAKE_TRAFFIC_BYTES = None
+
+
+def _two_sphere_mesh():
     import numpy as np
-    import torch
-    from unitex_b200 import bake as ub
 
     def sphere(rows, cols, radius, center, rect):
         th = np.linspace(0.02, np.pi - 0.02, rows + 1)
@@ -452,13 +509,32 @@ def bench_uv_bake(dev, return_tensors=False):
 
     v1, f1, uv1 = sphere(316, 632, 0.55, (0, 0, 0), (0.01, 0.01, 0.48, 0.98))
     v2, f2, uv2 = sphere(158, 316, 0.25, (0.62, 0.1, 0.05), (0.51, 0.01, 0.48, 0.98))
-    v, f, uv = np.concatenate([v1, v2]), np.concatenate([f1, f2 + len(v1)]), np.concatenate([uv1, uv2]) * 2 - 1
+    f = np.concatenate([f1, f2 + len(v1)])
+    return np.concatenate([v1, v2]), f, np.concatenate([uv1, uv2]) * 2 - 1, f.copy()
+
+
+def bench_uv_bake(dev, return_tensors=False, mesh_name="teaser_robot", reps=20):
+    """Second metric of BASELINE.json: UV-bake Mpix/s = atlas texels / time of NVDiffRendererInverse.infer(method='reproject')
+    with the mesh resident on the GPU (SURVEY 8d metric 2).  Workload = BASELINE config 4's geometry: the reference's own
+    test mesh test_cases/teaser_robot (V 269 026, F 499 981; lossless fixture tests/golden/teaser_robot.npz.xz), the 6 box views
+    the reference bake is hard-wired to (renderer_inverse.py:171,256) at 512^2 with an analytic colour field, 2048^2 atlas.
+    mesh_name='two_spheres': the synthetic mesh of round 1 (side key `uv_bake_synthetic`)."""
+    import numpy as np
+    import torch
+    from unitex_b200 import bake as ub
+    if mesh_name == "teaser_robot":
+        from tests.bake_meshes import teaser_robot
+        v, f, uv, fuv = teaser_robot()
+        label = "teaser_robot (reference test_cases/teaser_robot/inputmesh.obj)"
+    else:
+        v, f, uv, fuv = _two_sphere_mesh()
+        label = "synthetic 2-sphere mesh"
     V, F = len(v), len(f)
     H = W = 512
     H2 = W2 = 2048
     c2ws = ub.generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]]
     intr = ub.generate_intrinsics(1.0, 1.0, fov=False)
-    mesh = ub.BakeMesh(v, f, uv, f.copy(), device=dev)
+    mesh = ub.BakeMesh(v, f, uv, fuv, device=dev)
     r = ub.NVDiffRendererInverse(device=dev, pbr_mesh=mesh)
     ub.RayTracing(mesh.vertices, mesh.faces, device=dev)   # untimed: first launch of the build kernels (lazy module load, cub temp)
     torch.cuda.synchronize()
@@ -475,7 +551,6 @@ def bench_uv_bake(dev, return_tensors=False):
     for _ in range(3):
         r.infer(mesh, c2ws, intr, img, **kw)
     torch.cuda.synchronize()
-    reps = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
@@ -489,38 +564,50 @@ def bench_uv_bake(dev, return_tensors=False):
     algo = V * 24 + len(uv) * 8 + F * 24 + (2 * F - 1) * 36 + 6 * H * W * 16 + T * 12 + T + 6 * T
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6589.6) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     covered = int(m2.sum())
-    extra = {"tensors": (vis, m2, col, r.last_nn_index)} if return_tensors else {}
+    nn = r.last_nn_index
+    extra = {"tensors": (vis, m2, col, nn)} if return_tensors else {}
+    traffic = BAKE_TRAFFIC_BYTES if mesh_name == "teaser_robot" else None
     return {**extra, "metric": "UV-bake Mpix/s", "value": T / 1e6 / (wall_ms * 1e-3), "unit": "Mpix/s", "ms_per_bake": wall_ms,
             "gpu_ms_per_bake": gpu_ms, "bvh_build_ms": build_ms,
-            "config": {"workload": f"synthetic 2-sphere mesh V={V} F={F}, 6 box views 512^2, atlas 2048^2, method=reproject",
-                       "covered_texels": covered, "rays": 6 * covered, "visible_texels": int(vis.any(dim=0).sum())},
+            "config": {"workload": f"{label}: V={V} F={F}, 6 box views 512^2, atlas 2048^2, method=reproject",
+                       "covered_texels": covered, "rays": 6 * covered, "visible_texels": int(vis.any(dim=0).sum()),
+                       "nn_queries": int((nn >= 0).sum())},
             "roofline": {"bound": "hbm", "achieved": algo / (gpu_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": algo / (gpu_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": algo, "traffic": None,
+                         "frac": algo / (gpu_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": algo, "traffic": traffic,
+                         "traffic_source": "profiles/r02_bake_teaser_dram.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum over every kernel of one bake)" if traffic else None,
                          "note": "compulsory bytes of SURVEY 8d; the bake is BVH-traversal (latency) bound, not streaming"},
             "mrays_per_s": 6 * covered / 1e6 / (gpu_ms * 1e-3)}
 
 
-def bench_uv_bake_cpu():
+def bench_uv_bake_cpu(nn_index=None):
     """CPU baseline of metric 2: the oracle's restatement of NVDiffRendererInverse.infer (C rasteriser / LBVH tracer of
-    oracle/bake_ref.c + the reference's torch tail) on the host cores, on a BOUNDED case: two-sphere mesh with 8 k faces, 6 views
-    128^2, atlas 256^2.  Reported as measured (no extrapolation: its exact nearest-neighbour fill is brute force, so the cost grows
-    faster than the texel count)."""
+    oracle/bake_ref.c + the reference's torch tail) on the host cores.
+    With `nn_index` (the 1-NN table of the GPU run, int tensor [2048^2]): the SAME workload as the GPU figure -- teaser_robot,
+    6 views 512^2, atlas 2048^2 -- with the nearest-neighbour table supplied instead of searched (the oracle's exact search is
+    brute force, 0.7 M x 1.4 M pairs; the reference uses a kd-tree there), so the CPU figure is optimistic by that stage.
+    Without: a bounded small case (two-sphere mesh with 8 k faces, 6 views 128^2, atlas 256^2), everything computed."""
     import numpy as np
     import torch
     from oracle import bake as ob
-    from tests.bake_meshes import analytic_color, two_spheres
+    from tests.bake_meshes import analytic_color, teaser_robot, two_spheres
     from unitex_b200.bake import generate_box_views_c2ws, generate_intrinsics
-    v, f, uv, fuv = two_spheres(40, 80)
     c2ws, intr = generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]], generate_intrinsics(1.0, 1.0, fov=False)
     mats = torch.matmul(ob.intr_to_proj_ortho(intr), ob.c2w_to_w2c(c2ws))
-    H, H2 = 128, 256
+    if nn_index is not None:
+        v, f, uv, fuv = teaser_robot()
+        H, H2 = 512, 2048
+        sample = ("oracle infer(method='reproject') on the same workload: teaser_robot, 6 views 512^2, atlas 2048^2; the 1-NN table of "
+                  "the fill is supplied (not searched), everything else computed; measured, not extrapolated")
+    else:
+        v, f, uv, fuv = two_spheres(40, 80)
+        H, H2 = 128, 256
+        sample = "oracle infer(method='reproject') on a two-sphere mesh with 8000 faces, 6 views 128^2, atlas 256^2; measured, not extrapolated"
     rast = ob.rasterize(torch.matmul(torch.cat([torch.from_numpy(v), torch.ones(len(v), 1)], -1), mats.permute(0, 2, 1)).numpy(), f, H, H)
     img = torch.from_numpy(analytic_color(ob.interpolate(v, rast, f)) * (rast[..., 3:4] > 0)).float()
     t0 = time.perf_counter()
-    ob.infer(v, f, uv, fuv, c2ws, intr, img, H, H, H2, H2)
+    ob.infer(v, f, uv, fuv, c2ws, intr, img, H, H, H2, H2, nn_index_given=nn_index)
     dt = time.perf_counter() - t0
-    return {"value": H2 * H2 / 1e6 / dt, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": "port", "seconds": dt,
-            "sample": "oracle infer(method='reproject') on a two-sphere mesh with 8000 faces, 6 views 128^2, atlas 256^2; measured, not extrapolated"}
+    return {"value": H2 * H2 / 1e6 / dt, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": "port", "seconds": dt, "sample": sample}
 
 
 def main():

@@ -234,6 +234,92 @@ int utx_gemm_bf16_f32out(const void* A, long lda, const void* W, long ldw, const
 int utx_softmax_rows(const float* S, long lds, void* P, long ldp, int M, int N, void* stream);
 int utx_transpose_bf16(const void* x, long ldx, void* y, long ldy, int R, int C, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * FLUX VAE, whole passes.  Replaces `self.vae.encode(image).latent_dist` and `self.vae.decode(latents)` of the reference
+ * sampler (flux_piplines/texturing/pipeline.py:226-238 and :688-692; diffusers AutoencoderKL [ext]).  Tensors at the boundary
+ * are NCHW like the reference's; activations inside are NHWC bf16.  Weight layout (packed once by the caller):
+ *   3x3 conv    bf16 [ceil8(Cout)][ceil64(9*Cin)], K ordered (ky, kx, cin), zero padded; bias bf16 [ceil8(Cout)]
+ *   1x1 conv / Linear   bf16 [Cout][Cin], bias bf16 [Cout]
+ *   GroupNorm   fp32 weight / bias [C]
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct utx_vae utx_vae;
+
+typedef struct utx_vae_config {
+  int in_channels;             /* 3 */
+  int latent_channels;         /* 16 */
+  int num_blocks;              /* 4 */
+  int block_out_channels[8];   /* 128, 256, 512, 512 */
+  int layers_per_block;        /* 2 (the decoder runs layers_per_block + 1 resnets per up block) */
+  int norm_num_groups;         /* 32 */
+} utx_vae_config;
+
+typedef struct utx_vae_resnet {   /* ResnetBlock2D */
+  const float *gn1_w, *gn1_b;
+  const void *conv1_w, *conv1_b;
+  const float *gn2_w, *gn2_b;
+  const void *conv2_w, *conv2_b;
+  const void *short_w, *short_b;   /* conv_shortcut (1x1) or NULL when cin == cout */
+  int cin, cout;
+} utx_vae_resnet;
+
+typedef struct utx_vae_attn {     /* mid_block.attentions.0: one head of C channels */
+  const float *gn_w, *gn_b;
+  const void *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo;
+} utx_vae_attn;
+
+typedef struct utx_vae_mid {
+  utx_vae_resnet res0;
+  utx_vae_attn attn;
+  utx_vae_resnet res1;
+} utx_vae_mid;
+
+typedef struct utx_vae_weights {
+  const void *enc_conv_in_w, *enc_conv_in_b;
+  const utx_vae_resnet* enc_res;            /* host array [num_blocks * layers_per_block], block-major            */
+  const void* const* enc_down_w;            /* host arrays [num_blocks - 1]: down_blocks.i.downsamplers.0.conv    */
+  const void* const* enc_down_b;
+  utx_vae_mid enc_mid;
+  const float *enc_norm_w, *enc_norm_b;     /* conv_norm_out */
+  const void *enc_conv_out_w, *enc_conv_out_b;
+  const void *dec_conv_in_w, *dec_conv_in_b;
+  utx_vae_mid dec_mid;
+  const utx_vae_resnet* dec_res;            /* host array [num_blocks * (layers_per_block + 1)]                   */
+  const void* const* dec_up_w;              /* host arrays [num_blocks - 1]: up_blocks.i.upsamplers.0.conv        */
+  const void* const* dec_up_b;
+  const float *dec_norm_w, *dec_norm_b;
+  const void *dec_conv_out_w, *dec_conv_out_b;
+} utx_vae_weights;
+
+int utx_vae_create(const utx_vae_config* cfg, utx_vae** out);
+void utx_vae_destroy(utx_vae* h);
+/* copies the pointer tables; the device memory stays owned by the caller */
+int utx_vae_set_weights(utx_vae* h, const utx_vae_weights* w);
+/* decode != 0: (H, W) is the latent size; else the image size.  256B-aligned workspace of this many bytes. */
+size_t utx_vae_workspace_bytes(utx_vae* h, int N, int H, int W, int decode);
+/* z [N, latent_channels, h, w] bf16 (already latents / scaling_factor + shift_factor, :689) -> img [N, in_channels, 8h, 8w] bf16 */
+int utx_vae_decode(utx_vae* h, const void* z, int N, int H, int W, void* img, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* img [N, in_channels, H, W] bf16 in [-1, 1] -> moments [N, 2 * latent_channels, H/8, W/8] fp32 = mean | logvar, logvar clamped
+ * to [-30, 20] (DiagonalGaussianDistribution [ext]); the caller draws the sample (:234) */
+int utx_vae_encode(utx_vae* h, const void* img, int N, int H, int W, float* moments, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* launcher calls issued by the engine since the last reset (bench instrumentation) */
+long utx_vae_launches(utx_vae* h, int reset);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The path's one collective (north_star): after the denoise loop and the VAE decode every rank contributes its
+ * finished view tile(s) and receives every rank's, before UV projection.  The reference has no counterpart (it runs the
+ * assets one after another on one GPU: run.py:5-10, pipeline.py:231-291).  One ncclAllGather over NVLink / NVSwitch.
+ * Bootstrap like NCCL's own: rank 0 makes a 128-byte id, the host shares it out of band, every rank joins; the communicator
+ * is bound to the device that is current at utx_comm_init.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct utx_comm utx_comm;
+int utx_comm_unique_id(void* id128 /* host, 128 bytes out */);
+int utx_comm_init(utx_comm** out, const void* id128 /* host */, int nranks, int rank);
+void utx_comm_destroy(utx_comm* c);
+/* out [nranks * bytes_per_rank] (rank-major) <- every rank's tile [bytes_per_rank]; uneven shards are padded by the caller */
+int utx_allgather_tiles(utx_comm* c, const void* tile, void* out, size_t bytes_per_rank, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

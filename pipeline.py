@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import os
 import shutil
+import warnings
 from typing import Optional, Tuple
 
 import numpy as np
@@ -77,7 +78,16 @@ class RGBTextureFullPipelineBase:
     step_seq = []
 
     def __init__(self, pretrain_models=None, pipeline_name="texture_plus", super_resolutions=False, seed=0, speedup_mode=None,
-                 add_lora_path=None, add_lora_weights=None, enable_rembg=False):
+                 add_lora_path=None, add_lora_weights=None, enable_rembg=False, rembg_session=None):
+        """`rembg_session`: the matte source the reference builds itself (reference pipeline.py:146-149: rembg when
+        `enable_rembg`, else RMBG-2.0 -- both background-removal NETWORKS, out of scope here): any callable
+        `image -> RGBA PIL image` (what `preprocess` calls, image/process_image.py:52).  Without one, `enable_rembg=True`
+        cannot be honoured and raises; with `enable_rembg=False` an input image that has no alpha channel of its own is
+        used un-matted, with a warning (see `preprocess_reference_image`)."""
+        if enable_rembg and rembg_session is None:
+            raise NotImplementedError("enable_rembg=True needs a matte source: pass rembg_session=<callable image -> RGBA image> "
+                                      "(the rembg / RMBG-2.0 networks are out of scope of the B200 hot path)")
+        self.rembg_session = rembg_session
         if super_resolutions:
             raise NotImplementedError("TSD_SR super-resolution is out of scope (reference run.py:4 leaves it off)")
         (self.pipeline, self.weights_for_texture, self.weights_for_delight, self.adapter_names) = build_pipeline(
@@ -86,6 +96,7 @@ class RGBTextureFullPipelineBase:
         self.pipeline_name = pipeline_name
         self.video_exporter = ux.VideoExporter()
         self.inverse_renderer = ub.NVDiffRendererInverse(device="cuda")
+        self.seed = seed
         self.generator = torch.Generator().manual_seed(seed)
         self.super_resolutions = False
 
@@ -104,16 +115,25 @@ class RGBTextureFullPipelineBase:
         ux.save_obj(os.path.join(save_dir, "processed_mesh.obj"), V, F, UV, Ft)
 
     def preprocess_reference_image(self, save_dir, input_image_path, scale=0.95, color="grey"):
-        """reference :182-196 -> image/process_image.py:31-81.  There the matte always comes from a background-removal network
-        (RMBG-2.0 / rembg [ext], out of scope).  Here: an input image that carries its own alpha channel is cropped to the matte's
-        bounding box, scaled so the object spans `scale` of the 1024^2 canvas and pasted on the `color` canvas through the matte --
-        `preprocess` restated, pinned against the reference's own function (tests/golden/ref_glue.npz).  An image without alpha
-        is centred on the canvas as it is."""
+        """reference :182-196 -> image/process_image.py:31-81 (`preprocess`, restated in `reference_image_on_canvas` and pinned
+        against the reference's own function, tests/golden/ref_glue.npz): the matte's bounding box is cropped, scaled so the
+        object spans `scale` of the 1024^2 canvas and pasted on the `color` canvas through the matte.  Matte source, in the
+        reference's order (:48-54): the image's own alpha channel if it has a real one; else `self.rembg_session(image)`
+        (the constructor's hook for the background-removal network the reference runs there).  With neither, the image
+        is centred on the canvas un-matted and a warning says so: the conditioning then differs from the reference's."""
         src = Image.open(input_image_path)
-        if src.mode == "RGBA" and (np.asarray(src.getchannel("A")) > 0).sum() < src.size[0] * src.size[1] - 8:
+        has_alpha = src.mode == "RGBA" and (np.asarray(src.getchannel("A")) > 0).sum() < src.size[0] * src.size[1] - 8
+        if has_alpha:
             src = src.resize((1024, 1024))                                   # :183 resizes before the matte is used
             out = reference_image_on_canvas(src.convert("RGB"), src.getchannel("A"), 1024, 1024, scale, color)
+        elif self.rembg_session is not None:
+            rgb = src.convert("RGB").resize((1024, 1024))                    # :183
+            alpha = self.rembg_session(rgb).getchannel("A")                  # image/process_image.py:52-53
+            out = reference_image_on_canvas(rgb, alpha, 1024, 1024, scale, color)
         else:
+            warnings.warn("preprocess_reference_image: the input image has no alpha channel and no rembg_session was given -- "
+                          "the reference would matte it with RMBG-2.0 / rembg, crop and rescale; here it is used un-matted, so "
+                          "rembg_image.png / processed_image.png differ from the reference's", stacklevel=2)
             img = src.convert("RGB")
             out = Image.new("RGB", (1024, 1024), color)                      # PIL grey = (128, 128, 128), as image/process_image.py:68
             im = img.copy()
@@ -146,7 +166,9 @@ class RGBTextureFullPipelineBase:
         out_image.save(os.path.join(save_dir, "mv_rgb_w_light.png"))
         self.pipeline.set_adapters(adapter_names=self.adapter_names, adapter_weights=self.weights_for_delight)
         out_delighted = self.pipeline(control_image=out_image, **kw).images[0]
-        Image.fromarray(ux.strip_to_view_grid(np.array(out_delighted))).save(os.path.join(save_dir, "mv_rgb.png"))
+        grid = ux.strip_to_view_grid(np.array(out_delighted))
+        Image.fromarray(grid).save(os.path.join(save_dir, "mv_rgb.png"))
+        return grid                                                          # uint8 [1024, 1536, 3]: the asset's finished view tile
 
     def reproject_and_query_field(self, save_dir, input_mesh_path, input_mv_image_path, camera_info_path, method="reproject",
                                   inpainting=False):
@@ -164,11 +186,13 @@ class RGBTextureFullPipelineBase:
             reproject_inpainting=inpainting, kdtree_n_neighbors=8, kdtree_n_neighbors_visiable=4,
             grad_norm_threhold=0.15, ray_normal_angle_threhold=100, filt_gradient_points=inpainting)
         V, F, UV, Ft = ub.load_mesh(input_mesh_path)
-        atlas = (completed_uv_map[0].clamp(0, 1) * 255.0).round().to(torch.uint8).cpu().numpy()
+        # the GLB base colour goes through the reference's `tensor_to_image` (renderer_utils.py:64: clamp * 255 -> uint8, i.e.
+        # truncation); the three PNGs below through torchvision's save_image (round half up)
+        atlas = (completed_uv_map[0].clamp(0, 1) * 255.0).to(torch.uint8).cpu().numpy()
         ux.save_glb(os.path.join(save_dir, "textured_mesh.glb"), V, F, UV, Ft, atlas)
 
         def save(t, name):
-            a = (t.float().clamp(0, 1) * 255.0).round().to(torch.uint8).cpu().numpy()
+            a = (t.float() * 255.0).add(0.5).clamp(0, 255).to(torch.uint8).cpu().numpy()     # torchvision save_image's quantiser
             Image.fromarray(a[..., 0] if a.shape[-1] == 1 else a).save(os.path.join(save_dir, name))
         save(reprojected_uv.any(dim=0), "visable_uv_mask.png")
         save(visable_mask[0], "valid_uv_mask.png")
@@ -181,8 +205,8 @@ class RGBTextureFullPipelineBase:
         self.preprocess_blank_mesh(cache, input_mesh_path)
         self.preprocess_reference_image(cache, input_image_path)
         self.render_geometry_images(cache, os.path.join(cache, "processed_mesh.obj"))
-        self.infer_mv(cache, os.path.join(cache, "processed_image.png"), os.path.join(cache, "mv_normal.png"),
-                      os.path.join(cache, "mv_ccm.png"))
+        return self.infer_mv(cache, os.path.join(cache, "processed_image.png"), os.path.join(cache, "mv_normal.png"),
+                             os.path.join(cache, "mv_ccm.png"))
 
     def step_2_ablition(self, save_dir, input_image_path, input_mesh_path):
         cache = os.path.join(save_dir, "cache")
@@ -202,6 +226,52 @@ class RGBTextureFullPipelineBase:
         if clear_cache:
             shutil.rmtree(cache)
         return os.path.join(save_dir, "rembg_image.png"), os.path.join(save_dir, "textured_mesh.glb")
+
+
+    # ------------------------------------------------------------------ multi-asset, multi-GPU (north_star)
+    def run_batch(self, assets, clear_cache=False, base_seed: Optional[int] = None):
+        """A batch of assets over the ranks of one box.  `assets`: list of (save_dir, input_image_path, input_mesh_path), the
+        arguments of `__call__` -- the reference runs them one after another on one GPU (run.py:5-10).
+
+        The path shards by INDEPENDENT assets: rank r runs the two FLUX calls + VAE decode of assets r, r + world, ...
+        (`parallel.shard_grids`) with no data-path collective during the 28 steps (all views of one asset share one attention
+        sequence, flux_piplines/texturing/pipeline.py:630-656, so views are never split).  Then the path's ONE exchange: a
+        single all-gather of the finished uint8 view tiles (mv_rgb, [1024,1536,3] = 4.7 MB per asset) so that every rank
+        holds every asset's tile before UV projection; each rank then bakes its own assets FROM THE GATHERED tile.
+        Asset g draws from a generator seeded `base_seed + g` (run.py:5 uses 63 for its one asset), so the result of an
+        asset does not depend on the world size or on which rank ran it -- the 2-GPU test compares against 1 GPU.
+        Returns [(rembg_image.png, textured_mesh.glb)] for ALL assets, and leaves the gathered tiles in `self.last_tiles`.
+        Works without torch.distributed (world = 1)."""
+        import torch.distributed as dist
+        from unitex_b200 import parallel as par
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        base = self.seed if base_seed is None else base_seed
+        mine = par.shard_grids(len(assets), rank, world)
+        dev = self.inverse_renderer.device
+        local = []
+        for g in mine:
+            save_dir, image_path, mesh_path = assets[g]
+            os.makedirs(os.path.join(save_dir, "cache"), exist_ok=True)
+            self.generator.manual_seed(par.grid_seed(base, g))
+            grid = self.step_1_1(save_dir, image_path, mesh_path)
+            local.append(torch.from_numpy(np.ascontiguousarray(grid)).to(dev))
+        shape = tuple(local[0].shape) if local else (1024, 1536, 3)
+        tiles = par.all_gather_grid_tiles(local, len(assets), shape, torch.uint8, dev)
+        self.last_tiles = tiles
+        for g in mine:
+            save_dir, image_path, mesh_path = assets[g]
+            cache = os.path.join(save_dir, "cache")
+            Image.fromarray(tiles[g].cpu().numpy()).save(os.path.join(cache, "mv_rgb.png"))      # the gathered tile is what gets baked
+            self.step_2_ablition(save_dir, image_path, mesh_path)
+            shutil.copy(os.path.join(cache, "rembg_image.png"), os.path.join(save_dir, "rembg_image.png"))
+            shutil.copy(os.path.join(cache, "mv_rgb.png"), os.path.join(save_dir, "mv_rgb.png"))
+            shutil.copy(os.path.join(cache, "wo_LTM", "textured_mesh.glb"), os.path.join(save_dir, "textured_mesh.glb"))
+            if clear_cache:
+                shutil.rmtree(cache)
+        if world > 1:
+            dist.barrier()
+        return [(os.path.join(a[0], "rembg_image.png"), os.path.join(a[0], "textured_mesh.glb")) for a in assets]
 
 
 class CustomRGBTextureFullPipeline(RGBTextureFullPipelineBase):

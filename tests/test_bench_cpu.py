@@ -14,6 +14,9 @@ def test_reference_arm_prints_contract_line(monkeypatch, capsys):
     assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"] == bench.bench_config(1)      # the identical workload dict the B200 arm prints
+    ex = line["extrapolated"]                           # a whole block is measured, the step figure says it is 57 x that
+    assert ex["factor"] == 57 and abs(line["ms_per_step"] - 57 * ex["measured_ms"]) < 1e-6 * line["ms_per_step"]
     bench.run_reference(args, 1, 2)                    # other ranks: no work, no output
     assert capsys.readouterr().out == ""
 

@@ -15,6 +15,10 @@ def _worker(rank, world, port, q):
     tile = torch.full((4, 8), float(rank), dtype=torch.bfloat16)
     tiles = par.all_gather_tiles(tile)
     t = par.max_over_ranks([10.0 + rank, 3.0 - rank], "cpu")
+    # uneven shards (3 + 2 grids): one padded gather per batch, every rank ends with all five tiles in grid order
+    local = [torch.full((2, 3), float(g), dtype=torch.uint8) for g in mine]
+    allt = par.all_gather_grid_tiles(local, 5, (2, 3), torch.uint8, "cpu")
+    assert [int(x[0, 0]) for x in allt] == [0, 1, 2, 3, 4] and all(x.shape == (2, 3) for x in allt)
     q.put((rank, mine, seeds, [float(x[0, 0]) for x in tiles], t))
     dist.barrier()
     dist.destroy_process_group()
@@ -42,3 +46,5 @@ def test_single_process_is_identity():
     t = torch.ones(2, 2)
     assert par.all_gather_tiles(t)[0] is t and par.shard_grids(3, 0, 1) == [0, 1, 2]
     assert par.max_over_ranks([1.5], "cpu") == [1.5]
+    tiles = par.all_gather_grid_tiles([torch.full((2,), 7, dtype=torch.uint8)] * 3, 3, (2,), torch.uint8, "cpu")
+    assert len(tiles) == 3 and all(int(x[0]) == 7 for x in tiles)

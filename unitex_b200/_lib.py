@@ -40,6 +40,35 @@ class FluxWeightsC(C.Structure):
                    ("w_proj_out", vp), ("b_proj_out", vp)])
 
 
+class VaeConfigC(C.Structure):
+    _fields_ = [("in_channels", i32), ("latent_channels", i32), ("num_blocks", i32), ("block_out_channels", i32 * 8),
+                ("layers_per_block", i32), ("norm_num_groups", i32)]
+
+
+_VRES = ("gn1_w", "gn1_b", "conv1_w", "conv1_b", "gn2_w", "gn2_b", "conv2_w", "conv2_b", "short_w", "short_b")
+_VATT = ("gn_w", "gn_b", "wq", "bq", "wk", "bk", "wv", "bv", "wo", "bo")
+
+
+class VaeResnetC(C.Structure):
+    _fields_ = [(n, vp) for n in _VRES] + [("cin", i32), ("cout", i32)]
+
+
+class VaeAttnC(C.Structure):
+    _fields_ = [(n, vp) for n in _VATT]
+
+
+class VaeMidC(C.Structure):
+    _fields_ = [("res0", VaeResnetC), ("attn", VaeAttnC), ("res1", VaeResnetC)]
+
+
+class VaeWeightsC(C.Structure):
+    _fields_ = [("enc_conv_in_w", vp), ("enc_conv_in_b", vp), ("enc_res", C.POINTER(VaeResnetC)), ("enc_down_w", C.POINTER(vp)),
+                ("enc_down_b", C.POINTER(vp)), ("enc_mid", VaeMidC), ("enc_norm_w", vp), ("enc_norm_b", vp),
+                ("enc_conv_out_w", vp), ("enc_conv_out_b", vp), ("dec_conv_in_w", vp), ("dec_conv_in_b", vp), ("dec_mid", VaeMidC),
+                ("dec_res", C.POINTER(VaeResnetC)), ("dec_up_w", C.POINTER(vp)), ("dec_up_b", C.POINTER(vp)),
+                ("dec_norm_w", vp), ("dec_norm_b", vp), ("dec_conv_out_w", vp), ("dec_conv_out_b", vp)]
+
+
 _SIGS = {
     "utx_last_error": (C.c_char_p, []),
     "utx_version": (i32, []),
@@ -79,6 +108,17 @@ _SIGS = {
     "utx_gemm_bf16_f32out": (i32, [vp, lng, vp, lng, vp, vp, lng, i32, i32, i32, f32, vp]),
     "utx_softmax_rows": (i32, [vp, lng, vp, lng, i32, i32, vp]),
     "utx_transpose_bf16": (i32, [vp, lng, vp, lng, i32, i32, vp]),
+    "utx_vae_create": (i32, [C.POINTER(VaeConfigC), C.POINTER(vp)]),
+    "utx_vae_destroy": (None, [vp]),
+    "utx_vae_set_weights": (i32, [vp, C.POINTER(VaeWeightsC)]),
+    "utx_vae_workspace_bytes": (C.c_size_t, [vp, i32, i32, i32, i32]),
+    "utx_vae_decode": (i32, [vp, vp, i32, i32, i32, vp, vp, C.c_size_t, vp]),
+    "utx_vae_encode": (i32, [vp, vp, i32, i32, i32, vp, vp, C.c_size_t, vp]),
+    "utx_vae_launches": (C.c_long, [vp, i32]),
+    "utx_comm_unique_id": (i32, [vp]),
+    "utx_comm_init": (i32, [C.POINTER(vp), vp, i32, i32]),
+    "utx_comm_destroy": (None, [vp]),
+    "utx_allgather_tiles": (i32, [vp, vp, vp, C.c_size_t, vp]),
     "utx_knn1": (i32, [vp, i32, vp, C.c_longlong, vp, vp, vp, vp, C.c_size_t, vp]),
     "utx_knn": (i32, [vp, i32, vp, C.c_longlong, i32, vp, vp, vp, vp, C.c_size_t, vp]),
     "utx_uv_bake_workspace_bytes": (C.c_size_t, [i32, i32]),

@@ -330,6 +330,9 @@ int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S,
     const char* e = std::getenv("UTX_ATTN_POLY");   // tuning knob; default measured best at S = 9728
     poly = e ? std::atoi(e) : 2;
     if (poly < 0 || poly > 3) poly = 2;
+  }
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     UTX_CUDA(cudaFuncSetAttribute(attention2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     UTX_CUDA(cudaFuncSetAttribute(attention2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     UTX_CUDA(cudaFuncSetAttribute(attention2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
@@ -345,6 +348,13 @@ int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S,
   }
   UTX_CUDA(cudaGetLastError());
   return 0;
+}
+
+// The engine's attention entry point (kernels.h).  Round 1 kept two more kernels behind UTX_ATTN_IMPL (v1: one query tile per
+// CTA with P through shared memory; v3: S and P double-buffered in TMEM); both lost to this one in situ and were removed
+// from the product library (git history: attn_sm100.cu, attn3_sm100.cu; measurements in profiles/r01_summary.md).
+int attention_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream) {
+  return attention2_bf16(qkv, ld_qkv, out, ld_out, S, H, stream);
 }
 
 }  // namespace utx

@@ -1,0 +1,112 @@
+// The path's one exchange as a C-ABI call: every rank contributes its finished uint8 view tile and receives all of them
+// (north_star: "a single NCCL all-gather of decoded tiles before UV projection").  Thin on purpose: the data plane
+// is one ncclAllGather over NVLink / NVSwitch of a few MB per asset batch -- latency-bound, nothing to fuse it with (the VAE
+// decode before it and the bake after it are per-asset local).
+//
+// NCCL is resolved at run time (dlopen of libnccl.so.2: the copy torch already mapped when the caller is a torch process, the
+// system one otherwise), so the library links and loads on a box without NCCL and only these entry points fail there.
+// Bootstrap follows NCCL's own model: one rank makes a 128-byte unique id, the host side shares it out of band
+// (torch.distributed broadcast, MPI, a file), every rank joins with (id, nranks, rank).
+#include <dlfcn.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "../../include/unitex_b200.h"
+#include "common.h"
+
+using namespace utx;
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclInt8 = 0 };   // ncclChar / ncclInt8 == 0 (nccl.h: ncclDataType_t)
+
+struct Nccl {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+Nccl& nccl() {
+  static Nccl n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_LAZY | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_LAZY | RTLD_GLOBAL);
+    if (!h) return;
+    n.GetUniqueId = reinterpret_cast<decltype(n.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    n.CommInitRank = reinterpret_cast<decltype(n.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    n.AllGather = reinterpret_cast<decltype(n.AllGather)>(dlsym(h, "ncclAllGather"));
+    n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather && n.GetErrorString;
+  });
+  return n;
+}
+
+#define UTX_NCCL(expr)                                                                                        \
+  do {                                                                                                        \
+    ncclResult_t _r = (expr);                                                                                 \
+    if (_r != 0) {                                                                                            \
+      set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": NCCL: " + nccl().GetErrorString(_r)); \
+      return 3;                                                                                               \
+    }                                                                                                         \
+  } while (0)
+
+}  // namespace
+
+struct utx_comm {
+  ncclComm_t comm = nullptr;
+  int nranks = 0, rank = 0;
+};
+
+extern "C" {
+
+int utx_comm_unique_id(void* id128) {
+  UTX_CHECK(id128, "utx_comm_unique_id: null pointer");
+  UTX_CHECK(nccl().ok, "utx_comm: libnccl.so.2 not found");
+  ncclUniqueId id;
+  UTX_NCCL(nccl().GetUniqueId(&id));
+  std::memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int utx_comm_init(utx_comm** out, const void* id128, int nranks, int rank) {
+  UTX_CHECK(out && id128 && nranks > 0 && rank >= 0 && rank < nranks, "utx_comm_init: bad argument");
+  UTX_CHECK(nccl().ok, "utx_comm: libnccl.so.2 not found");
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  utx_comm* c = new utx_comm();
+  c->nranks = nranks;
+  c->rank = rank;
+  ncclResult_t r = nccl().CommInitRank(&c->comm, nranks, id, rank);   // uses the CURRENT device, like every other utx_ call
+  if (r != 0) {
+    set_error(std::string("utx_comm_init: NCCL: ") + nccl().GetErrorString(r));
+    delete c;
+    return 3;
+  }
+  *out = c;
+  return 0;
+}
+
+void utx_comm_destroy(utx_comm* c) {
+  if (!c) return;
+  if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+  delete c;
+}
+
+int utx_allgather_tiles(utx_comm* c, const void* tile, void* out, size_t bytes_per_rank, void* stream) {
+  UTX_CHECK(c && c->comm, "utx_allgather_tiles: communicator not initialised");
+  UTX_CHECK(tile && out, "utx_allgather_tiles: null pointer");
+  if (bytes_per_rank == 0) return 0;
+  UTX_NCCL(nccl().AllGather(tile, out, bytes_per_rank, ncclInt8, c->comm, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+}  // extern "C"

@@ -64,14 +64,15 @@ int make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, uint64_t N, uint64_t
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = n[dev & 63];
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
   }
-  return n;
+  return v;
 }
 
 }  // namespace utx

@@ -48,6 +48,20 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t box_w,
                         uint32_t box_h);
 
-int num_sms();
+int num_sms();   // of the CURRENT device
+
+// Opt-in kernel attributes (dynamic shared memory size) are per device: `static PerDeviceOnce once; if (once.first()) {...}`
+// runs the block once for every device a process drives, not once per process.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
 
 }  // namespace utx

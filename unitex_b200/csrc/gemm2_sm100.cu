@@ -33,6 +33,7 @@ constexpr int SMEM_TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
 
 struct DevParams {
   int K, tiles_n, nprob, total_tiles, group_m;
+  int conv_cblk, conv_w, conv_hw;   // implicit 3x3 convolution (see gemm_sm100.cu): channel blocks per tap (0 = plain GEMM), width, pixels per image
   EpiParams e;
   EpiProblem prob[2];
 };
@@ -97,11 +98,27 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
       const CUtensorMap* tb = tc.pi ? &tmB1 : &tmB0;
       const int row_a = tc.m_blk * (2 * BM) + static_cast<int>(rank) * BM;
       const int row_b = tc.n_blk * BN + static_cast<int>(rank) * (BN / 2);
+      // implicit convolution: this CTA's 128 output pixels start at (img, y0, x0); tap (ky, kx) reads the same activation box
+      // shifted by (ky - 1, kx - 1), TMA's out-of-bounds zero fill is the padding ring (and the tail past the last image)
+      int img = 0, y0 = 0, x0 = 0;
+      if (p.conv_cblk > 0) {
+        img = row_a / p.conv_hw;
+        const int rem = row_a - img * p.conv_hw;
+        y0 = rem / p.conv_w;
+        x0 = rem - y0 * p.conv_w;
+      }
+      int tap = 0, cb = 0;
       for (int kb = 0; kb < nk; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
         if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * STAGE_BYTES);   // bytes of BOTH CTAs land on the leader's barrier
         uint8_t* st = smem + s * STAGE_BYTES;
-        tma_load_2d_2sm(st, ta, &full[s], kb * BK, row_a);
+        if (p.conv_cblk > 0) {
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          tma_load_4d_2sm(st, ta, &full[s], cb * BK, x0 + kx - 1, y0 + ky - 1, img);
+          if (++cb == p.conv_cblk) { cb = 0; ++tap; }
+        } else {
+          tma_load_2d_2sm(st, ta, &full[s], kb * BK, row_a);
+        }
         tma_load_2d_2sm(st + A_BYTES, tb, &full[s], kb * BK, row_b);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
@@ -183,6 +200,9 @@ int gemm2_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
     if (group_m < 1) group_m = GROUP_M_DEFAULT;
   }
   p.group_m = group_m;
+  p.conv_cblk = a.conv_c / BK;
+  p.conv_w = a.conv_w;
+  p.conv_hw = a.conv_h * a.conv_w;
   p.e = EpiParams{a.N, a.epi, a.gelu_col_start, a.out_scale, a.qk_cols, a.cos_t, a.sin_t};
   CUtensorMap tm[4];
   int total = 0;
@@ -192,16 +212,20 @@ int gemm2_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
     d = EpiProblem{g.M, (g.M + 2 * BM - 1) / (2 * BM), g.C, g.ldc, g.bias, g.gate, g.res, g.ldres, g.split_col, g.C2, g.ldc2,
                    g.wq, g.wk, g.row_offset};
     total += d.tiles_m * p.tiles_n;
-    UTX_TRY(make_tmap_2d_bf16(&tm[2 * i], g.A, g.M, a.K, g.lda, BM, BK));
+    if (a.conv_c > 0) {
+      const int bw = a.conv_w < BM ? a.conv_w : BM;
+      UTX_TRY(make_tmap_nhwc_bf16(&tm[2 * i], g.A, a.conv_n, a.conv_h, a.conv_w, a.conv_c, bw, BM / bw));
+    } else {
+      UTX_TRY(make_tmap_2d_bf16(&tm[2 * i], g.A, g.M, a.K, g.lda, BM, BK));
+    }
     UTX_TRY(make_tmap_2d_bf16(&tm[2 * i + 1], g.W, a.N, a.K, g.ldw, BN / 2, BK));
   }
   if (a.nprob == 1) { tm[2] = tm[0]; tm[3] = tm[1]; }
   p.total_tiles = total;
   if (total == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     UTX_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    attr_set = true;
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = total < max_pairs ? total : max_pairs;

@@ -249,10 +249,9 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
   p.total_tiles = total;
   if (total == 0) return 0;
   auto kern = gemm_bf16_tn_kernel<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     UTX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
   }
   const int grid = total < num_sms() ? total : num_sms();
   kern<<<grid, kThreads, L::TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
@@ -285,7 +284,7 @@ int gemm_bf16_tn(const GemmArgs& a_in, cudaStream_t stream) {
   // Default: cta_group::2 kernel (256x256 tiles per CTA pair, gemm2_sm100.cu) whenever N % 256 == 0 -- 2-3 % faster at the
   // DiT shapes (profiles/r01_microbench_gemm.json).  UTX_GEMM_IMPL=1 forces the 1-CTA kernel of this file.
   const char* impl = getenv("UTX_GEMM_IMPL");
-  if ((impl == nullptr || impl[0] != '1') && a.N % 256 == 0 && a.conv_c == 0) {
+  if ((impl == nullptr || impl[0] != '1') && a.N % 256 == 0) {   // plain and implicit-convolution (Cout 256 / 512) problems alike
     const int r = gemm2_bf16_tn(a, stream);
     if (r >= 0) return r;
   }

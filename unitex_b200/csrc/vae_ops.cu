@@ -200,7 +200,70 @@ __global__ void __launch_bounds__(256) transpose_kernel(const bf16* __restrict__
     if (bx + j < Cc && by + tx < R) y[static_cast<long long>(bx + j) * ldy + by + tx] = tile[tx][j];
 }
 
+__global__ void __launch_bounds__(256) fill_f32_kernel(float* __restrict__ p, float v, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// layout changes at the two ends of the VAE (the reference's tensors are NCHW; the kernels in between run NHWC).  Small
+// tensors (a 3-channel image, a 16-channel latent): one thread per element, reads or writes coalesced along W.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const bf16* __restrict__ x, int C, int HW, bf16* __restrict__ y,
+                                                           long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // index into y: ((n*HW + p)*C + c)
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const long long np = i / C;
+  const long long p = np % HW, n = np / HW;
+  y[i] = x[(n * C + c) * HW + p];
+}
+template <typename OutT>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const bf16* __restrict__ x, long ldx, int C, int HW, int clamp_from,
+                                                           float lo, float hi, OutT* __restrict__ y, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // index into y: ((n*C + c)*HW + p)
+  if (i >= total) return;
+  const long long p = i % HW;
+  const long long nc = i / HW;
+  const int c = static_cast<int>(nc % C);
+  const long long n = nc / C;
+  float v = __bfloat162float(x[(n * HW + p) * ldx + c]);
+  if (c >= clamp_from) v = fminf(fmaxf(v, lo), hi);
+  if constexpr (sizeof(OutT) == 2) y[i] = __float2bfloat16(v);
+  else y[i] = v;
+}
+
 }  // namespace
+
+int fill_f32(float* p, float v, long long n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  fill_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(p, v, n);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+// x [N, C, H, W] -> y [N*H*W, C]
+int nchw_to_nhwc_bf16(const bf16* x, int N, int C, int H, int W, bf16* y, cudaStream_t stream) {
+  const long long total = static_cast<long long>(N) * C * H * W;
+  if (total == 0) return 0;
+  nchw_to_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, C, H * W, y, total);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+// x [N*H*W, ldx] (first C columns) -> y [N, C, H, W]
+int nhwc_to_nchw_bf16(const bf16* x, long ldx, int N, int C, int H, int W, bf16* y, cudaStream_t stream) {
+  const long long total = static_cast<long long>(N) * C * H * W;
+  if (total == 0) return 0;
+  nhwc_to_nchw_kernel<bf16><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, ldx, C, H * W, C, 0.f, 0.f, y, total);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+// encoder head: x [N*H*W, ldx] (first C2 = 2*latent columns: mean | logvar) -> y [N, C2, H, W] fp32, logvar clamped to [lo, hi]
+// (DiagonalGaussianDistribution [ext]: torch.clamp(logvar, -30, 20))
+int moments_to_nchw_f32(const bf16* x, long ldx, int N, int C2, int H, int W, float lo, float hi, float* y, cudaStream_t stream) {
+  const long long total = static_cast<long long>(N) * C2 * H * W;
+  if (total == 0) return 0;
+  nhwc_to_nchw_kernel<float><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(x, ldx, C2, H * W, C2 / 2, lo, hi, y, total);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int im2col3x3(const bf16* x, int N, int Hin, int Win, int C, int up, int stride, int pad, int Ho, int Wo, int Kpad, bf16* out,
               cudaStream_t stream) {

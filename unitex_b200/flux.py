@@ -170,20 +170,46 @@ class FluxTransformer:
         o._commit()
         return o
 
-    def merge_lora_(self, lora: Dict[str, torch.Tensor], scale: float):
-        """W += scale * B @ A for every `<linear>.lora_A.weight / lora_B.weight` pair (peft naming without the
-        `transformer.` prefix); plain `<linear>.weight/.bias` entries are modules_to_save replacements
-        (trainer.py:297-304: x_embedder).  scale = adapter_weight * lora_alpha / r (pipeline.py:245,263)."""
+    def merge_lora_(self, lora: Dict[str, torch.Tensor], scale: float, replace_modules: bool = True):
+        """W += scale * (alpha / r) * B @ A for every `<linear>.lora_A.weight / lora_B.weight` pair (peft naming without the
+        `transformer.` prefix).  `scale` = adapter_weight * lora_alpha / r as resolved by the caller (pipeline.py:245,263); a
+        per-module `<linear>.alpha` entry (kohya-style files) overrides the file-level ratio for that module:
+        scale_module = scale * alpha / r.
+        Plain `<module>.weight / .bias` entries are peft `modules_to_save` replacements (trainer.py:297-304: x_embedder): they
+        REPLACE the base tensor and, unlike LoRA deltas, do not blend -- peft routes the forward through the active adapter's
+        copy.  `replace_modules=False` skips them (adapters merged with weight 0, or all but the last active adapter:
+        `PBRFluxPipeline.set_adapters` lets the LAST adapter with a non-zero weight win, which is peft's behaviour for the
+        reference's two calls, where exactly one of texture / delight is active).
+        Any other key suffix, or a module this model does not have, raises: silently dropping or mis-broadcasting a tensor
+        would corrupt the weights."""
         names = sorted(k[: -len(".lora_A.weight")] for k in lora if k.endswith(".lora_A.weight"))
+        handled = set()
         for n in names:
+            if n not in self.where:
+                raise KeyError(f"merge_lora_: LoRA target '{n}' is not a Linear of this transformer")
+            if n + ".lora_B.weight" not in lora:
+                raise KeyError(f"merge_lora_: '{n}.lora_A.weight' without its lora_B")
             k, r0, r1 = self.where[n]
-            ops.lora_merge_(self.T["w_" + k][r0:r1], lora[n + ".lora_A.weight"], lora[n + ".lora_B.weight"], scale)
+            A, B = lora[n + ".lora_A.weight"], lora[n + ".lora_B.weight"]
+            s = float(scale)
+            if n + ".alpha" in lora:
+                s = s * float(lora[n + ".alpha"]) / A.shape[0]
+                handled.add(n + ".alpha")
+            ops.lora_merge_(self.T["w_" + k][r0:r1], A, B, s)
+            handled.update((n + ".lora_A.weight", n + ".lora_B.weight"))
         for key, v in lora.items():
-            if ".lora_" in key:
+            if key in handled:
                 continue
-            n, kind = key.rsplit(".", 1)
+            n, _, kind = key.rpartition(".")
+            if ".lora_" in key or kind not in ("weight", "bias") or n not in self.where:
+                raise KeyError(f"merge_lora_: unsupported adapter entry '{key}'")
+            if not replace_modules:
+                continue
             k, r0, r1 = self.where[n]
-            self.T[("w_" if kind == "weight" else "b_") + k][r0:r1].copy_(v.to(torch.bfloat16))
+            dst = self.T[("w_" if kind == "weight" else "b_") + k][r0:r1]
+            if tuple(v.shape) != tuple(dst.shape):
+                raise ValueError(f"merge_lora_: '{key}' has shape {tuple(v.shape)}, the module expects {tuple(dst.shape)}")
+            dst.copy_(v.to(torch.bfloat16))
         return self
 
     def _commit(self):

@@ -164,8 +164,10 @@ class PBRFluxPipeline:
             return self.transformer
         if self._active not in self._merged:
             eng = self.transformer.clone()
-            for name, w in self._active:
-                eng.merge_lora_(self._adapters[name], w * self._adapter_scale[name])
+            for i, (name, w) in enumerate(self._active):
+                # LoRA deltas blend by weight; `modules_to_save` replacements (x_embedder) do not -- the last active adapter's
+                # copy is the one in effect (see FluxTransformer.merge_lora_)
+                eng.merge_lora_(self._adapters[name], w * self._adapter_scale[name], replace_modules=(i == len(self._active) - 1))
             self._merged[self._active] = eng
         return self._merged[self._active]
 

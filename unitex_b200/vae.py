@@ -1,13 +1,15 @@
-"""FLUX AutoencoderKL on B200: host orchestration over libunitex_b200.so (im2col + tcgen05 GEMM convolutions, GroupNorm+SiLU,
-single-head mid-block attention as two GEMMs around an fp32 row softmax).  Replaces `self.vae.encode / self.vae.decode`
-of the reference sampler (flux_piplines/texturing/pipeline.py:226-238, :688-692; diffusers AutoencoderKL [ext], FLUX config:
-latent 16, blocks (128,256,512,512), 2 layers/block, GN32, scaling 0.3611, shift 0.1159, no quant convs).
+"""FLUX AutoencoderKL on B200: weight packing + two calls into libunitex_b200.so (`utx_vae_encode` / `utx_vae_decode`, the C++
+host loop of csrc/vae_engine.cu over implicit-GEMM tcgen05 convolutions, GroupNorm+SiLU and the chunked single-head mid-block
+attention).  Replaces `self.vae.encode / self.vae.decode` of the reference sampler (flux_piplines/texturing/pipeline.py:226-238,
+:688-692; diffusers AutoencoderKL [ext], FLUX config: latent 16, blocks (128,256,512,512), 2 layers/block, GN32, scaling
+0.3611, shift 0.1159, no quant convs).
 
-Layout: activations NHWC bf16 ([N*H*W, C] matrices), conv weights re-arranged once to [Cout, ky, kx, Cin] (K padded to a
-multiple of 64, Cout to a multiple of 8).  torch is used for allocation and the final NCHW views only.
+Conv weights are re-arranged once to [Cout, ky, kx, Cin] (K padded to a multiple of 64, Cout to a multiple of 8); torch is
+used for allocation only.
 """
 from __future__ import annotations
 
+import ctypes as C
 import json
 import os
 from typing import Dict, Optional
@@ -33,7 +35,6 @@ class AutoencoderKLB200:
         self.scaling_factor, self.shift_factor = scaling_factor, shift_factor
         self.dtype = torch.bfloat16
         self.lib = _lib.load()
-        self.implicit_conv = os.environ.get("UTX_VAE_IM2COL", "0") != "1"   # debug knob: force the im2col path
         self.W: Dict[str, torch.Tensor] = {}
         for k, v in state_dict.items():
             if not k.endswith(".weight"):
@@ -52,8 +53,8 @@ class AutoencoderKLB200:
                 self.W[n + ".w"], self.W[n + ".b"] = v.to(self.device, torch.bfloat16).contiguous(), b.to(self.device, torch.bfloat16)
             else:                                              # GroupNorm affine (kept fp32)
                 self.W[n + ".w"], self.W[n + ".b"] = v.to(self.device, torch.float32), b.to(self.device, torch.float32)
-        self._ones: Dict[int, torch.Tensor] = {}
-        self._stats = torch.zeros(64 * 2 * 8, device=self.device, dtype=torch.float64)
+        self._ws = None
+        self._bind()
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -112,135 +113,104 @@ class AutoencoderKLB200:
         gn("decoder.conv_norm_out", rb[-1]); conv("decoder.conv_out", 3, rb[-1])
         return cls(sd, boc, device=device)
 
-    # ------------------------------------------------------------------ building blocks
-    def _conv3(self, name, x, N, H, W, C, up=1, stride=1, pad=1, res=None):
-        """x [N*H*W, C] NHWC bf16 -> (y [N*Ho*Wo, Cout_pad], Ho, Wo).  `res`: fused residual add in the GEMM epilogue."""
-        w, b = self.W[name + ".w"], self.W[name + ".b"]
-        Hs, Ws = H * up, W * up
-        if stride == 1:
-            Ho, Wo = Hs, Ws
-        else:                                                   # Downsample2D: pad (0,1,0,1), stride 2
-            Ho, Wo = (Hs + 1 - 3) // 2 + 1, (Ws + 1 - 3) // 2 + 1
-        Kp = w.shape[1]
-        if (self.implicit_conv and up == 2 and stride == 1 and pad == 1 and C % 64 == 0 and Kp == 9 * C and
-                (Ws % 128 == 0 or (128 % Ws == 0 and Hs % (128 // Ws) == 0))):
-            # Upsample2D: materialise the nearest-neighbour upsampling (4x the input, not the 36x of an im2col buffer)
-            xu = torch.empty(N * Hs * Ws, C, device=self.device, dtype=torch.bfloat16)
-            _lib.check(self.lib.utx_upsample2x_nhwc(_p(x), N, H, W, C, _p(xu), _stream()), "utx_upsample2x_nhwc")
-            x, H, W, up = xu, Hs, Ws, 1
-        if (self.implicit_conv and up == 1 and stride == 1 and pad == 1 and C % 64 == 0 and Kp == 9 * C and
-                (W % 128 == 0 or (128 % W == 0 and H % (128 // W) == 0))):
-            # implicit GEMM: TMA boxes of the activation shifted by the tap are the A tiles, no im2col buffer
-            Co = w.shape[0]
-            y = res if res is not None else torch.empty(N * H * W, Co, device=self.device, dtype=torch.bfloat16)
-            _lib.check(self.lib.utx_conv3x3_nhwc(_p(x), N, H, W, C, _p(w), _p(b), Co, _p(y), y.stride(0),
-                                                 _p(self._one(Co)) if res is not None else None, _p(res), 0 if res is None else res.stride(0),
-                                                 _stream()), "utx_conv3x3_nhwc")
-            return y, H, W
-        col = torch.empty(N * Ho * Wo, Kp, device=self.device, dtype=torch.bfloat16)
-        _lib.check(self.lib.utx_im2col3x3(_p(x), N, H, W, C, up, stride, pad, Ho, Wo, Kp, _p(col), _stream()), "utx_im2col3x3")
-        if res is None:
-            y = ops.gemm(col, w, b)
-        else:
-            y = res                                             # callers pass a buffer they own: updated in place
-            ops.gemm(col, w, b, epi=ops.EPI_GATE_RES, gate=self._one(w.shape[0]), res=y, out=y)
-        return y, Ho, Wo
+    # ------------------------------------------------------------------ the C engine (csrc/vae_engine.cu)
+    def _bind(self):
+        """Hands the packed weights to `utx_vae_*` (include/unitex_b200.h): pointer tables only, the tensors stay owned here."""
+        W, L = self.W, self.lib
+        nb = len(self.boc)
+        cfg = _lib.VaeConfigC(self.in_channels, self.latent_channels, nb, (C.c_int * 8)(*self.boc, *([0] * (8 - nb))), self.layers,
+                              self.groups)
+        self._handle = _lib.vp()
+        _lib.check(L.utx_vae_create(C.byref(cfg), C.byref(self._handle)), "utx_vae_create")
+        p = lambda k: W[k].data_ptr() if k in W else None
 
-    def _lin(self, name, x, res=None):
-        w, b = self.W[name + ".w"], self.W[name + ".b"]
-        if res is None:
-            return ops.gemm(x, w, b)
-        ops.gemm(x, w, b, epi=ops.EPI_GATE_RES, gate=self._one(w.shape[0]), res=res, out=res)
-        return res
+        def resnet(prefix, cin, cout):
+            r = _lib.VaeResnetC()
+            for f, k in (("gn1_w", "norm1.w"), ("gn1_b", "norm1.b"), ("conv1_w", "conv1.w"), ("conv1_b", "conv1.b"),
+                         ("gn2_w", "norm2.w"), ("gn2_b", "norm2.b"), ("conv2_w", "conv2.w"), ("conv2_b", "conv2.b"),
+                         ("short_w", "conv_shortcut.w"), ("short_b", "conv_shortcut.b")):
+                setattr(r, f, p(prefix + k))
+            r.cin, r.cout = cin, cout
+            assert (cin != cout) == ((prefix + "conv_shortcut.w") in W), prefix
+            return r
 
-    def _one(self, n):
-        if n not in self._ones:
-            self._ones[n] = torch.ones(n, device=self.device, dtype=torch.float32)
-        return self._ones[n]
+        def mid(prefix, c):
+            m = _lib.VaeMidC()
+            m.res0, m.res1 = resnet(prefix + "resnets.0.", c, c), resnet(prefix + "resnets.1.", c, c)
+            a = prefix + "attentions.0."
+            for f, k in (("gn_w", "group_norm.w"), ("gn_b", "group_norm.b"), ("wq", "to_q.w"), ("bq", "to_q.b"), ("wk", "to_k.w"),
+                         ("bk", "to_k.b"), ("wv", "to_v.w"), ("bv", "to_v.b"), ("wo", "to_out.0.w"), ("bo", "to_out.0.b")):
+                setattr(m.attn, f, p(a + k))
+            return m
 
-    def _gn(self, name, x, N, HW, C, silu=True):
-        y = torch.empty_like(x)
-        need = (self.lib.utx_groupnorm_workspace_bytes(N, HW, C, self.groups) + 7) // 8     # in doubles
-        if self._stats.numel() < need:
-            self._stats = torch.zeros(need, device=self.device, dtype=torch.float64)
-        _lib.check(self.lib.utx_groupnorm_nhwc(_p(x), _p(y), N, HW, C, self.groups, _p(self.W[name + ".w"]), _p(self.W[name + ".b"]),
-                                               int(silu), _p(self._stats), _stream()), "utx_groupnorm_nhwc")
-        return y
+        w = _lib.VaeWeightsC()
+        enc, cin = [], self.boc[0]
+        for i, c in enumerate(self.boc):
+            for j in range(self.layers):
+                enc.append(resnet(f"encoder.down_blocks.{i}.resnets.{j}.", cin, c))
+                cin = c
+        rb = self.boc[::-1]
+        dec, cin = [], rb[0]
+        for i, c in enumerate(rb):
+            for j in range(self.layers + 1):
+                dec.append(resnet(f"decoder.up_blocks.{i}.resnets.{j}.", cin, c))
+                cin = c
+        enc_arr, dec_arr = (_lib.VaeResnetC * len(enc))(*enc), (_lib.VaeResnetC * len(dec))(*dec)
+        n1 = max(nb - 1, 1)
+        tabs = [(_lib.vp * n1)(*[p(f"encoder.down_blocks.{i}.downsamplers.0.conv.{s}") for i in range(nb - 1)]) for s in ("w", "b")]
+        tabs += [(_lib.vp * n1)(*[p(f"decoder.up_blocks.{i}.upsamplers.0.conv.{s}") for i in range(nb - 1)]) for s in ("w", "b")]
+        w.enc_conv_in_w, w.enc_conv_in_b = p("encoder.conv_in.w"), p("encoder.conv_in.b")
+        w.enc_res, w.enc_down_w, w.enc_down_b = enc_arr, tabs[0], tabs[1]
+        w.enc_mid = mid("encoder.mid_block.", self.boc[-1])
+        w.enc_norm_w, w.enc_norm_b = p("encoder.conv_norm_out.w"), p("encoder.conv_norm_out.b")
+        w.enc_conv_out_w, w.enc_conv_out_b = p("encoder.conv_out.w"), p("encoder.conv_out.b")
+        w.dec_conv_in_w, w.dec_conv_in_b = p("decoder.conv_in.w"), p("decoder.conv_in.b")
+        w.dec_mid = mid("decoder.mid_block.", rb[0])
+        w.dec_res, w.dec_up_w, w.dec_up_b = dec_arr, tabs[2], tabs[3]
+        w.dec_norm_w, w.dec_norm_b = p("decoder.conv_norm_out.w"), p("decoder.conv_norm_out.b")
+        w.dec_conv_out_w, w.dec_conv_out_b = p("decoder.conv_out.w"), p("decoder.conv_out.b")
+        self._keep = (enc_arr, dec_arr, tabs, w)
+        _lib.check(L.utx_vae_set_weights(self._handle, C.byref(w)), "utx_vae_set_weights")
 
-    def _resnet(self, p, x, N, H, W, Cin):
-        Cout = self.W[p + "conv1.w"].shape[0]
-        h = self._gn(p + "norm1", x, N, H * W, Cin)
-        h, _, _ = self._conv3(p + "conv1", h, N, H, W, Cin)
-        h = self._gn(p + "norm2", h, N, H * W, Cout)
-        if (p + "conv_shortcut.w") in self.W:                   # 1x1 conv == Linear over channels
-            sc = ops.gemm(x, self.W[p + "conv_shortcut.w"], self.W[p + "conv_shortcut.b"])
-        else:
-            sc = x.clone()
-        y, _, _ = self._conv3(p + "conv2", h, N, H, W, Cout, res=sc)
-        return y, Cout
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self.lib.utx_vae_destroy(self._handle)
+        except Exception:
+            pass
 
-    def _attn(self, p, x, N, HW, C):
-        outs = []
-        for n in range(N):
-            xs = x[n * HW:(n + 1) * HW]
-            h = self._gn(p + "group_norm", xs, 1, HW, C, silu=False)
-            q, k, v = (self._lin(p + t, h) for t in ("to_q", "to_k", "to_v"))
-            S = torch.empty(HW, HW, device=self.device, dtype=torch.float32)
-            _lib.check(self.lib.utx_gemm_bf16_f32out(_p(q), C, _p(k), C, None, _p(S), HW, HW, HW, C, float(C) ** -0.5, _stream()),
-                       "utx_gemm_bf16_f32out")
-            P = torch.empty(HW, HW, device=self.device, dtype=torch.bfloat16)
-            _lib.check(self.lib.utx_softmax_rows(_p(S), HW, _p(P), HW, HW, HW, _stream()), "utx_softmax_rows")
-            vt = torch.empty(C, HW, device=self.device, dtype=torch.bfloat16)
-            _lib.check(self.lib.utx_transpose_bf16(_p(v), C, _p(vt), HW, HW, C, _stream()), "utx_transpose_bf16")
-            o = ops.gemm(P, vt, None)
-            outs.append(self._lin(p + "to_out.0", o, res=xs.clone()))
-        return torch.cat(outs, 0) if N > 1 else outs[0]
-
-    def _mid(self, p, x, N, H, W, C):
-        x, _ = self._resnet(p + "resnets.0.", x, N, H, W, C)
-        x = self._attn(p + "attentions.0.", x, N, H * W, C)
-        x, _ = self._resnet(p + "resnets.1.", x, N, H, W, C)
-        return x
+    def _workspace(self, N, H, W, decode):
+        n = self.lib.utx_vae_workspace_bytes(self._handle, N, H, W, int(decode))
+        if n == 0:
+            raise _lib.UtxError(f"utx_vae_workspace_bytes: {self.lib.utx_last_error().decode()}")
+        if self._ws is None or self._ws.numel() < n:
+            self._ws = None
+            self._ws = torch.empty(n, device=self.device, dtype=torch.uint8)
+        return self._ws
 
     # ------------------------------------------------------------------ public
     @torch.no_grad()
     def decode(self, z: torch.Tensor) -> torch.Tensor:
-        """z [N,16,h,w] (already / scaling + shift, :689) -> image [N,3,8h,8w] bf16."""
+        """z [N,16,h,w] (already / scaling + shift, :689) -> image [N,3,8h,8w] bf16: ONE call into the C ABI."""
         N, Cz, H, W = z.shape
-        assert H * W % 8 == 0, "latent area must be a multiple of 8"
-        x = z.to(self.device, torch.bfloat16).permute(0, 2, 3, 1).reshape(N * H * W, Cz).contiguous()
-        x, _, _ = self._conv3("decoder.conv_in", x, N, H, W, Cz)
-        C = self.boc[-1]
-        x = self._mid("decoder.mid_block.", x, N, H, W, C)
-        nb = len(self.boc)
-        for i in range(nb):
-            for j in range(self.layers + 1):
-                x, C = self._resnet(f"decoder.up_blocks.{i}.resnets.{j}.", x, N, H, W, C)
-            if i < nb - 1:
-                x, H, W = self._conv3(f"decoder.up_blocks.{i}.upsamplers.0.conv", x, N, H, W, C, up=2)
-        x = self._gn("decoder.conv_norm_out", x, N, H * W, C)
-        y, _, _ = self._conv3("decoder.conv_out", x, N, H, W, C)
-        return y[:, :self.in_channels].reshape(N, H, W, self.in_channels).permute(0, 3, 1, 2).contiguous()
+        z = z.to(self.device, torch.bfloat16).contiguous()
+        f = 2 ** (len(self.boc) - 1)
+        img = torch.empty(N, self.in_channels, H * f, W * f, device=self.device, dtype=torch.bfloat16)
+        ws = self._workspace(N, H, W, True)
+        _lib.check(self.lib.utx_vae_decode(self._handle, _p(z), N, H, W, _p(img), _p(ws), ws.numel(), _stream()), "utx_vae_decode")
+        return img
 
     @torch.no_grad()
     def encode_moments(self, img: torch.Tensor):
-        """img [N,3,H,W] in [-1,1] -> (mean, logvar) [N,16,H/8,W/8] fp32."""
+        """img [N,3,H,W] in [-1,1] -> (mean, logvar) [N,16,H/8,W/8] fp32 (logvar clamped to [-30, 20]): ONE call into the C ABI."""
         N, Ci, H, W = img.shape
-        x = img.to(self.device, torch.bfloat16).permute(0, 2, 3, 1).reshape(N * H * W, Ci).contiguous()
-        x, _, _ = self._conv3("encoder.conv_in", x, N, H, W, Ci)
-        C = self.boc[0]
-        nb = len(self.boc)
-        for i in range(nb):
-            for j in range(self.layers):
-                x, C = self._resnet(f"encoder.down_blocks.{i}.resnets.{j}.", x, N, H, W, C)
-            if i < nb - 1:
-                x, H, W = self._conv3(f"encoder.down_blocks.{i}.downsamplers.0.conv", x, N, H, W, C, stride=2, pad=0)
-        x = self._mid("encoder.mid_block.", x, N, H, W, C)
-        x = self._gn("encoder.conv_norm_out", x, N, H * W, C)
-        m, _, _ = self._conv3("encoder.conv_out", x, N, H, W, C)
-        m = m[:, :2 * self.latent_channels].float().reshape(N, H, W, 2 * self.latent_channels).permute(0, 3, 1, 2)
-        mean, logvar = m.chunk(2, dim=1)
-        return mean.contiguous(), logvar.clamp(-30.0, 20.0).contiguous()
+        img = img.to(self.device, torch.bfloat16).contiguous()
+        f = 2 ** (len(self.boc) - 1)
+        mom = torch.empty(N, 2 * self.latent_channels, H // f, W // f, device=self.device, dtype=torch.float32)
+        ws = self._workspace(N, H, W, False)
+        _lib.check(self.lib.utx_vae_encode(self._handle, _p(img), N, H, W, _p(mom), _p(ws), ws.numel(), _stream()), "utx_vae_encode")
+        mean, logvar = mom.chunk(2, dim=1)
+        return mean.contiguous(), logvar.contiguous()
 
     @torch.no_grad()
     def encode_sample(self, img: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
