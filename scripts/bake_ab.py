@@ -13,7 +13,7 @@ if os.environ.get("UTX_LIB"):      # A/B against an alternative build of the lib
     _lib._LIB_PATH = Path(os.environ["UTX_LIB"])
 
 dev = torch.device("cuda", 0)
-out = bench.bench_uv_bake(dev, return_tensors=True)
+out = bench.bench_uv_bake(dev, return_tensors=True, mesh_name=sys.argv[1] if len(sys.argv) > 1 else "teaser_robot")
 vis, m2, col, nn = out.pop("tensors")
 h = hashlib.sha256()
 for t in (vis, m2, col, nn):

@@ -371,93 +371,79 @@ __device__ __forceinline__ void nn_query_run(const int* __restrict__ qlist, int 
     color_out[t * 3 + 2] = color_in[static_cast<size_t>(best) * 3 + 2];
   }
 }
-// Per-lane refill ("persistent threads"): a lane whose walk has ended takes the next query of the list at once instead of idling
-// until the slowest lane of its warp is done.  The walks are long-tailed (points scored per query on the bench bake: median 112,
-// p90 448, p99 1456 -- scripts/nn_visits.py), so with one query per lane per warp-run 12.7 of 32 lanes were active on average.
-// Every loop iteration advances each active lane's walk by ONE entry (a 4-wide record or a leaf of 8 points); the walk itself is
-// point_tree_walk's (nearest entry first, bound re-checked at pop time), and the result -- exact nearest point, lowest id on
-// ties -- does not depend on the order in which queries or entries are taken.
-// MEASURED SLOWER (UTX_NN_IMPL=1, kept for the record): 2.9 ms against 2.5 ms for the run-per-warp kernel on the bench bake,
-// identical output.  Lanes then hold unrelated queries, every 16-byte record load touches its own line and the converged walks of
-// neighbouring queries are lost: the kernel is bound by memory latency (long-scoreboard 4.3 stalls per issue,
-// profiles/r01_nn_query_persist.ncu-rep), not by idle lanes.
-__global__ void __launch_bounds__(128) nn_query_refill_kernel(const int* __restrict__ qlist, int n_q, const float* __restrict__ pos,
-                                                              const PointTree pt, const float* color_in, float* color_out,
-                                                              int* __restrict__ nn_index, int* __restrict__ next_query) {
+// Warp-cooperative walk: the 32 lanes of a warp hold 32 NEIGHBOURING queries (one 8x4 texel patch of the query list) and
+// descend the point tree TOGETHER -- one warp-uniform stack, every record / leaf load a broadcast, every lane scoring every
+// visited leaf against its own query.
+// Why this is exact: nearest-neighbour search has no order dependence -- scoring a point a lane "did not need" can only
+// confirm its current best, so a lane may visit any superset of the nodes its own pruned walk would visit.  The only pruning
+// left is warp-wide: an entry is skipped when EVERY lane's (deflated) box bound exceeds that lane's current best -- at push
+// time lane by lane (ballot), at pop time through the conservative scalars  min over lanes of the bound  vs  max over lanes
+// of the best.  Ties go to the lowest id as in nn_trace.
+// Why it is fast: the per-lane walks of r01 (nn_query_run below, kept for warps whose queries are NOT neighbours) ran at
+// 12.7 of 32 lanes with every 16-byte record load touching its own line and 4.3 long-scoreboard stalls per issue
+// (profiles/r01_bake_ray_nn.metrics.csv, r01_nn_query_persist.ncu-rep): neighbouring queries need almost the same nodes, but
+// lanes that prune differently fall out of step and never re-converge.  Here the union of the needed nodes is walked once with
+// all lanes busy.  (A per-lane refill variant -- a lane takes a new query as soon as its walk ends -- was measured SLOWER in
+// r01, 2.9 vs 2.5 ms: lanes then hold unrelated queries; it is in the history of this file.)
+__device__ __forceinline__ void nn_query_run_coop(const float q[3], const PointTree& pt, int* s_ref, float* s_bound,
+                                                  float& best_out, int& best_id_out) {
   constexpr unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  int sn[64];
-  float sb[64];
-  bool active = false, exhausted = false, have = false;
-  int t = 0, count = 0, ref = 0, best_id = -1;
-  float q[3] = {0.f, 0.f, 0.f}, bound = 0.f, best = INFINITY;
+  float best = INFINITY;
+  int best_id = -1;
+  float wbest = INFINITY;          // max over lanes of `best` (warp-uniform)
+  int count = 0;
+  bool have = true;
+  int ref = pt.n_c <= 1 ? ~0 : 0;  // a tree of one cluster is its only leaf
+  float bound = 0.f;
   for (;;) {
-    const unsigned need = __ballot_sync(FULL, !active && !exhausted);
-    if (need) {
-      const int leader = __ffs(need) - 1;
-      int base = 0;
-      if (lane == leader) base = atomicAdd(next_query, __popc(need));
-      base = __shfl_sync(FULL, base, leader);
-      if (!active && !exhausted) {
-        const int i = base + __popc(need & ((1u << lane) - 1u));
-        if (i >= n_q) {
-          exhausted = true;
-        } else {
-          t = qlist[i];
-          q[0] = pos[static_cast<size_t>(t) * 3]; q[1] = pos[static_cast<size_t>(t) * 3 + 1]; q[2] = pos[static_cast<size_t>(t) * 3 + 2];
-          best = INFINITY; best_id = -1; count = 0;
-          have = true; ref = pt.n_c <= 1 ? ~0 : 0; bound = 0.f;      // a tree of one cluster is its only leaf
-          active = true;
-        }
-      }
-    }
-    if (__ballot_sync(FULL, active) == 0) break;                      // nobody holds a query and the list is exhausted
-    if (!active) continue;
     if (!have) {
-      if (count == 0) {                                               // walk finished: publish, free the lane
-        if (nn_index) nn_index[t] = best_id;
-        if (best_id >= 0) {
-          color_out[t * 3] = color_in[static_cast<size_t>(best_id) * 3];
-          color_out[t * 3 + 1] = color_in[static_cast<size_t>(best_id) * 3 + 1];
-          color_out[t * 3 + 2] = color_in[static_cast<size_t>(best_id) * 3 + 2];
-        }
-        active = false;
-        continue;
-      }
+      if (count == 0) break;
       --count;
-      ref = sn[count];
-      bound = sb[count];
+      ref = s_ref[count];
+      bound = s_bound[count];
     }
     have = false;
-    if (bound > best) continue;
-    if (ref < 0) {                                                    // leaf: score its points
+    if (bound > wbest) continue;                                        // min bound over lanes > max best over lanes: nobody needs it
+    if (ref < 0) {
       const int c = ~ref;
       const int j0 = c * PT_CLUSTER, j1 = min(j0 + PT_CLUSTER, pt.n);
       for (int j = j0; j < j1; ++j) {
-        const float4 p = __ldg(pt.spts + j);
+        const float4 p = __ldg(pt.spts + j);                             // broadcast load
         const float dx = p.x - q[0], dy = p.y - q[1], dz = p.z - q[2];
         const float d2 = (dx * dx + dy * dy) + dz * dz;
         const int id = __float_as_int(p.w);
         if (d2 < best || (d2 == best && id < best_id) || best_id < 0) { best = d2; best_id = id; }
       }
+      wbest = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(best)));   // non-negative floats order like their bits
       continue;
     }
-    const WideRec r = wide_load(pt.wide, ref);
-    float bd[4];
-    int nearest = 0;
-    float nkey = INFINITY;
+    const WideRec r = wide_load(pt.wide, ref);                           // broadcast load
+    int e_ref[4];
+    float e_b[4];
+    int n_e = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      bd[k] = r.ref[k] != WIDE_EMPTY ? box_dist2(r.bb + 6 * k, q) * 0.999999f : INFINITY;
-      if (bd[k] < nkey) { nkey = bd[k]; nearest = k; }
+      if (r.ref[k] == WIDE_EMPTY) continue;                              // warp-uniform
+      const float bd = box_dist2(r.bb + 6 * k, q) * 0.999999f;
+      const bool need = bd <= best;
+      if (__ballot_sync(FULL, need) == 0u) continue;
+      const float mb = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(bd)));
+      // insertion into e_* kept DESCENDING by bound, so the nearest entry ends up last (visited next) and the others are
+      // pushed farthest first (popped nearest first)
+      int j = n_e++;
+      while (j > 0 && e_b[j - 1] < mb) { e_b[j] = e_b[j - 1]; e_ref[j] = e_ref[j - 1]; --j; }
+      e_b[j] = mb;
+      e_ref[j] = r.ref[k];
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (r.ref[k] == WIDE_EMPTY || !(bd[k] <= best)) continue;
-      if (k == nearest) { have = true; ref = r.ref[k]; bound = bd[k]; }
-      else if (count < 64) { sn[count] = r.ref[k]; sb[count] = bd[k]; ++count; }
-    }
+    if (n_e == 0) continue;
+    for (int j = 0; j + 1 < n_e; ++j)
+      if (count < 64) { s_ref[count] = e_ref[j]; s_bound[count] = e_b[j]; ++count; }
+    have = true;
+    ref = e_ref[n_e - 1];
+    bound = e_b[n_e - 1];
   }
+  best_out = best;
+  best_id_out = best_id;
 }
 
 #ifdef UTX_NN_DEBUG
@@ -483,16 +469,49 @@ __global__ void __launch_bounds__(128) nn_count_kernel(const int* __restrict__ q
 // one fixed block of queries per CTA the kernel ran at 29 % of its resident warps (profiles/r01_bake_ray_nn.metrics.csv): a CTA's
 // slot was held until its slowest warp finished, and the last wave left most SMs idle.  (Measured: no change, 2.49 ms -- the
 // list is only 2.3 runs per resident warp, so the tail of one run remains; kept because it is never worse.)
+template <bool kCoop>
 __global__ void __launch_bounds__(128, UTX_WALK_MIN_BLOCKS) nn_query_kernel(const int* __restrict__ qlist, int n_q, const float* __restrict__ pos,
                                                        const PointTree pt, const float* color_in, float* color_out,
-                                                       int* __restrict__ nn_index, int W2, int* __restrict__ next_run) {
-  const int lane = threadIdx.x & 31;
+                                                       int* __restrict__ nn_index, int W2, int* __restrict__ next_run, int always_coop) {
+  __shared__ int s_ref[4][64];
+  __shared__ float s_bound[4][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (;;) {
     int run = 0;
     if (lane == 0) run = atomicAdd(next_run, 1);
     run = __shfl_sync(0xffffffffu, run, 0);
     if (run * 32 >= n_q) return;
-    nn_query_run(qlist, n_q, pos, pt, color_in, color_out, nn_index, W2, run * 32 + lane);
+    if (!kCoop) {
+      nn_query_run(qlist, n_q, pos, pt, color_in, color_out, nn_index, W2, run * 32 + lane);
+      continue;
+    }
+    // `always_coop` (default): every run walks cooperatively -- a run that straddles charts holds a few groups of neighbours and
+    // pays the union of their walks, still far less than 32 divergent ones.  Otherwise (A/B) only runs whose texels lie within
+    // 16 rows / columns of the first one do, the rest fall back to the per-lane walks
+    const int i = run * 32 + lane;
+    const bool valid = i < n_q;
+    const int t = qlist[valid ? i : run * 32];                          // tail lanes duplicate the first query (harmless)
+    const int tl = __shfl_sync(0xffffffffu, t, 0);
+    const int dy = t / W2 - tl / W2, dx = t % W2 - tl % W2;
+    const bool common = __all_sync(0xffffffffu, dy > -16 && dy < 16 && dx > -16 && dx < 16) || always_coop;
+    if (!common) {
+      if (valid) nn_query_run(qlist, n_q, pos, pt, color_in, color_out, nn_index, W2, i);
+      __syncwarp();
+      continue;
+    }
+    const float q[3] = {pos[static_cast<size_t>(t) * 3], pos[static_cast<size_t>(t) * 3 + 1], pos[static_cast<size_t>(t) * 3 + 2]};
+    float best;
+    int best_id;
+    nn_query_run_coop(q, pt, s_ref[warp], s_bound[warp], best, best_id);
+    __syncwarp();
+    if (valid) {
+      if (nn_index) nn_index[t] = best_id;
+      if (best_id >= 0) {
+        color_out[t * 3] = color_in[static_cast<size_t>(best_id) * 3];
+        color_out[t * 3 + 1] = color_in[static_cast<size_t>(best_id) * 3 + 1];
+        color_out[t * 3 + 2] = color_in[static_cast<size_t>(best_id) * 3 + 2];
+      }
+    }
   }
 }
 
@@ -792,11 +811,15 @@ int uv_bake_fill(const unsigned char* mask2d, int H2, int W2, int k, int* nn_ind
     int* next_run = w.counters + MAXV + 1;
     UTX_CUDA(cudaMemsetAsync(next_run, 0, 4, stream));
     const unsigned persistent = std::min<unsigned>(gq, static_cast<unsigned>(num_sms()) * 16u);   // 16 CTAs of 128 threads per SM
-    static const int impl = std::getenv("UTX_NN_IMPL") ? std::atoi(std::getenv("UTX_NN_IMPL")) : 0;   // 0 (default): runs of 32 neighbouring queries per warp; 1: per-lane refill
-    if (impl == 1)
-      nn_query_refill_kernel<<<persistent, 128, 0, stream>>>(qlist, n_q, w.pos, pt, w.col_a, w.col_a, nn_index_out, next_run);
+    // UTX_NN_IMPL (A/B knob; identical output): 0 (default) every run of 32 queries walks cooperatively; 1 cooperative only for
+    // runs inside one 16-texel neighbourhood, per-lane walks otherwise; 2 the per-lane walks of r01.  teaser_robot, ncu
+    // (profiles/r02_nn_variants.md): 2 -> 4.30 ms, 12.1 of 32 lanes, 1.81 G warp instructions, 539 M L1 wavefronts;
+    // 1 -> 3.66 ms, 23.7 lanes; 0 -> 3.03 ms, 32.0 lanes, 1.41 G instructions, 317 M wavefronts.
+    static const int impl = std::getenv("UTX_NN_IMPL") ? std::atoi(std::getenv("UTX_NN_IMPL")) : 0;
+    if (impl == 2)
+      nn_query_kernel<false><<<persistent, 128, 0, stream>>>(qlist, n_q, w.pos, pt, w.col_a, w.col_a, nn_index_out, W2, next_run, 0);
     else
-      nn_query_kernel<<<persistent, 128, 0, stream>>>(qlist, n_q, w.pos, pt, w.col_a, w.col_a, nn_index_out, W2, next_run);
+      nn_query_kernel<true><<<persistent, 128, 0, stream>>>(qlist, n_q, w.pos, pt, w.col_a, w.col_a, nn_index_out, W2, next_run, impl != 1);
   }
   else
     knn_mean_kernel<<<gq, 128, 0, stream>>>(mask2d, w.owner, -1, w.pos, T, pt, k, w.col_a, w.col_a, nn_index_out, qlist, n_q);
