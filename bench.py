@@ -273,11 +273,10 @@ def run_ours(args, rank, world, local_rank):
         step(i)
     tiles = finish_asset()                                             # untimed first pass (NCCL communicator set-up, VAE first launches)
     barrier()
-    eng.profile(True)
-    eng.profile_read(reset=True)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     barrier()
+    replays0 = eng.graph_replays()
     e0.record()
     for i in range(args.steps):
         step(i)
@@ -288,9 +287,24 @@ def run_ours(args, rank, world, local_rank):
     ms = e0.elapsed_time(e2)
     ms_steps = e0.elapsed_time(e1)
     ms_finish = e1.elapsed_time(e2)
+    graph_steps = eng.graph_replays() - replays0
     assert len(tiles) == world and all(t.shape == (3, 1024, 1024) for t in tiles)
     tile_checks = [int(t.sum().item()) for t in tiles]                 # every rank's tile arrived (non-trivial data)
     clocks = sampler.stop() if sampler else None
+
+    # per-kernel breakdown for the roofline: the SAME K steps once more with the engine's per-launch CUDA events switched on
+    # (eager launches: a step that runs as one graph launch cannot be bracketed kernel by kernel; the events themselves
+    # cost a few microseconds per launch, which is why they are kept out of the region that produces `value`)
+    eng.profile(True)
+    eng.profile_read(reset=True)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for i in range(args.steps):
+        step(i)
+    p1.record()
+    barrier()
+    ms_profiled = p0.elapsed_time(p1)
     launches, cat_ms = eng.profile_read(reset=True)
     eng.profile(False)
 
@@ -330,7 +344,11 @@ def run_ours(args, rank, world, local_rank):
         "timed_region": {"what": f"{args.steps} denoise steps, then this rank's VAE decode to the uint8 view tile and the all-gather of "
                                  f"the {world} ranks' tiles (once per asset; the reference does it once per 28 steps, pipeline.py:688-692)",
                          "denoise_only_ms_per_step": ms_steps / args.steps, "decode_and_gather_ms": ms_finish,
-                         "gathered_tile_checksums": tile_checks, "lora_targets_merged": n_lora_targets},
+                         "gathered_tile_checksums": tile_checks, "lora_targets_merged": n_lora_targets,
+                         "steps_as_cuda_graph_launches": graph_steps,
+                         "profiled_pass_ms_per_step": ms_profiled / args.steps,
+                         "profiled_pass_note": "the roofline's per-kernel times come from a second pass over the same K steps with per-launch "
+                                               "CUDA events on the launching stream (eager launches); `value` comes from the un-instrumented pass"},
         "roofline": {"bound": "tensor", "kernel": "gemm2_bf16_tn_kernel (tcgen05 cta_group::2; 1-CTA gemm_bf16_tn_kernel for narrow N)",
                      "achieved": gemm_tf, "peak": peak_sus, "unit": "TFLOP/s", "frac": gemm_tf / peak_sus,
                      "traffic": 5.20e8, "traffic_note": "dram read+write of ONE qkv-shaped launch (M 9728, N 9216, K 3072), warm L2 as inside the step (ncu --cache-control none, profiles/r01_gemm_groupm_sweep.txt: 335 MB read + 185 MB written); 1046 MB with ncu's cache flush (profiles/r01_gemm2_bf16_tn_final.ncu-rep); algorithmic 296 MB",

@@ -93,6 +93,11 @@ int utx_flux_forward(utx_flux* h, const void* latents, float timestep, float gui
  * (:644-645) amounts to.  sigmas: HOST fp32 [n_steps + 1]. */
 int utx_flux_denoise(utx_flux* h, void* latents, int s_noise, const float* sigmas, int n_steps, float guidance,
                      void* stream);
+/* utx_flux_denoise runs a step (forward + Euler update) as ONE CUDA-graph launch from the second step on a given
+ * (latents, s_noise) onwards: the ~240 kernel launches of a step are captured once, the step's scalars (timestep, guidance,
+ * sigma difference) live in device memory and are rewritten before every launch.  Bit-identical to the eager path
+ * (UTX_FLUX_GRAPH=0 disables it; profiling mode runs eagerly).  Number of steps that ran as graph launches so far: */
+long utx_flux_graph_replays(const utx_flux* h);
 
 /* Instrumentation for bench.py: kernel launches issued by the engine per category, and (after
  * utx_flux_profile(h, 1)) the CUDA-event time of each category on the launching stream.  launches/ms: [4]

@@ -69,6 +69,36 @@ def test_denoise_matches_oracle_and_keeps_condition(lib):
     assert db >= PSNR_MIN_DB, f"denoise PSNR {db:.1f} dB"
 
 
+def test_graph_replay_is_bit_identical_to_eager(lib, monkeypatch):
+    """utx_flux_denoise replays a captured CUDA graph of the step from the second step on; the per-step scalars come from
+    device memory.  Same bits as the eager launches, step by step and as one call."""
+    fd, fs, ocfg, P, eng, img_ids, noise, cond, s_txt, s_noise = _setup(layers=(2, 2), HL=32, WL=16, ctrl=(32, 16), dual=(16, 16))
+    ids = torch.cat([torch.zeros(s_txt, 3), img_ids])
+    sig = fs.flow_match_sigmas(6, s_noise)
+    lat0 = torch.cat([noise, cond], 1)[0].cuda().contiguous()
+
+    def run(e, one_call):
+        e.prepare(ids, None, None, s_txt=s_txt)
+        lat = lat0.clone()
+        if one_call:
+            e.denoise_(lat, s_noise, sig, 3.5)
+        else:
+            for i in range(6):
+                e.denoise_(lat, s_noise, sig[i:i + 2], 3.5)
+        torch.cuda.synchronize()
+        return lat
+
+    a = run(eng, False)
+    assert eng.graph_replays() >= 4                          # steps 2..6 of the same (latents, s_noise) ran as graph launches
+    b = run(eng, True)
+    monkeypatch.setenv("UTX_FLUX_GRAPH", "0")
+    from unitex_b200.flux import FluxConfig, FluxTransformer
+    eager = FluxTransformer(eng.cfg).load_state_dict(P)      # a fresh handle reads the knob
+    c = run(eager, False)
+    assert eager.graph_replays() == 0
+    assert torch.equal(a, c) and torch.equal(b, c)
+
+
 def test_product_path_does_not_import_oracle():
     import subprocess, sys
     code = ("import sys; import unitex_b200.flux, unitex_b200.ops; "

@@ -79,6 +79,7 @@ _SIGS = {
     "utx_flux_prepare": (i32, [vp, vp, C.c_size_t, vp, vp, vp, i32, i32, vp]),
     "utx_flux_forward": (i32, [vp, vp, f32, f32, vp, vp]),
     "utx_flux_denoise": (i32, [vp, vp, i32, fp, i32, f32, vp]),
+    "utx_flux_graph_replays": (C.c_long, [vp]),
     "utx_flux_profile": (i32, [vp, i32]),
     "utx_flux_profile_read": (i32, [vp, C.POINTER(C.c_long), fp, i32]),
     "utx_lora_merge": (i32, [vp, lng, vp, vp, i32, i32, i32, f32, vp]),

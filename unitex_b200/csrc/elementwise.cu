@@ -174,6 +174,23 @@ __global__ void time_sinusoid_kernel(float t, float g, float* __restrict__ out) 
   out[384 + i] = sinf(g * freq);
 }
 
+// the same with the two scalars read from device memory (CUDA-graph replay of the denoise step: the graph is captured once,
+// the per-step scalars are written by set_step_scalars just before every launch)
+__global__ void time_sinusoid_dev_kernel(const float* __restrict__ tg, float* __restrict__ out) {
+  const int i = threadIdx.x;   // 0..127
+  const float t = tg[0], g = tg[1];
+  const float freq = expf(-9.210340371976184f * static_cast<float>(i) / 128.0f);
+  out[i] = cosf(t * freq);
+  out[128 + i] = sinf(t * freq);
+  out[256 + i] = cosf(g * freq);
+  out[384 + i] = sinf(g * freq);
+}
+__global__ void set_step_scalars_kernel(float* __restrict__ p, float t, float g, float dsigma) {
+  p[0] = t;
+  p[1] = g;
+  p[2] = dsigma;
+}
+
 // ----------------------------------------------------------------------------- RoPE table (FluxPosEmbed [ext])
 __global__ void rope_table_kernel(const float* __restrict__ ids, int S, float* __restrict__ cos_t,
                                   float* __restrict__ sin_t) {
@@ -199,9 +216,11 @@ __global__ void rope_table_kernel(const float* __restrict__ ids, int S, float* _
 // to bf16 BEFORE the fp32 add.  Mirrored (pinned by tests/golden/ref_flux_call.npz, generated by the reference's own
 // __call__): torch casts BOTH operands of that product to bf16 (the 0-dim sigma difference included), multiplies in fp32
 // and rounds: bf16(dsigma) -> mul -> bf16 RN -> fp32 add -> bf16 RN, no fused multiply-add.
-__global__ void euler_kernel(bf16* __restrict__ lat, const bf16* __restrict__ v, long n8, float dsigma) {
+__global__ void euler_kernel(bf16* __restrict__ lat, const bf16* __restrict__ v, long n8, float dsigma,
+                             const float* __restrict__ dsigma_dev) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
+  if (dsigma_dev) dsigma = *dsigma_dev;     // graph replay: the step's sigma difference lives in device memory
   float a[8], b[8];
   unpack8(reinterpret_cast<const uint4*>(lat)[i], a);
   unpack8(reinterpret_cast<const uint4*>(v)[i], b);
@@ -300,6 +319,16 @@ int time_sinusoid(float t_scaled, float g_scaled, float* out512, cudaStream_t st
   UTX_CUDA(cudaGetLastError());
   return 0;
 }
+int time_sinusoid_dev(const float* tg_dev, float* out512, cudaStream_t stream) {
+  time_sinusoid_dev_kernel<<<1, 128, 0, stream>>>(tg_dev, out512);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+int set_step_scalars(float* dev3, float t_scaled, float g_scaled, float dsigma, cudaStream_t stream) {
+  set_step_scalars_kernel<<<1, 1, 0, stream>>>(dev3, t_scaled, g_scaled, dsigma);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int rope_table(const float* ids, int S, float* cos_t, float* sin_t, cudaStream_t stream) {
   if (S == 0) return 0;
@@ -308,12 +337,12 @@ int rope_table(const float* ids, int S, float* cos_t, float* sin_t, cudaStream_t
   return 0;
 }
 
-int euler_update(bf16* latents, const bf16* v, int rows, int cols, float dsigma, cudaStream_t stream) {
+int euler_update(bf16* latents, const bf16* v, int rows, int cols, float dsigma, cudaStream_t stream, const float* dsigma_dev) {
   const long n = static_cast<long>(rows) * cols;
   UTX_CHECK(n % 8 == 0, "euler_update: element count must be a multiple of 8");
   if (n == 0) return 0;
   const long n8 = n / 8;
-  euler_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(latents, v, n8, dsigma);
+  euler_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(latents, v, n8, dsigma, dsigma_dev);
   UTX_CUDA(cudaGetLastError());
   return 0;
 }

@@ -4,6 +4,7 @@
 // blocks address the two streams as row ranges of one buffer (grouped GEMM launches) and the torch.cat before the
 // single-stream blocks costs nothing.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -32,6 +33,22 @@ struct utx_flux {
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<int, int>> ev_used;   // (category, index of start event); stop = start + 1
   size_t ev_next = 0;
+  // CUDA graph of one denoise step (forward + Euler update), captured once per (latents, s_noise) and replayed every step:
+  // the step's scalars (t, guidance, sigma difference) live in device memory (step_params) and are written by a one-thread
+  // kernel just before each launch, so ONE graph serves all 28 steps.  Capture runs on a stream the engine owns (the legacy
+  // default stream cannot capture); the instantiated graph is launched on the caller's stream.
+  struct StepGraph {
+    void* latents = nullptr;
+    int s_noise = 0;
+    int seen = 0;                 // eager calls seen with this key (the graph is built on the second one)
+    cudaGraphExec_t exec = nullptr;
+    long launches[UTX_PROF_NCAT] = {0, 0, 0, 0};
+  };
+  std::vector<StepGraph> graphs;
+  cudaStream_t capture_stream = nullptr;
+  float* step_params = nullptr;   // device [4]: t_eff, g_eff, dsigma
+  int use_graph = -1;             // -1 = not read yet (UTX_FLUX_GRAPH, default on)
+  long graph_replays = 0;
 };
 
 namespace {
@@ -77,7 +94,7 @@ inline float bf16_round(float f) {
 }
 
 struct WsLayout {
-  size_t x, xn, qkv, cat, ctx0, v_tmp, cos_t, sin_t, mod, temb, sincos, hvec, pooled, total;
+  size_t x, xn, qkv, cat, ctx0, v_tmp, cos_t, sin_t, mod, temb, sincos, hvec, pooled, step_params, total;
 };
 WsLayout ws_layout(const utx_flux_config& c, int s_txt, int s_img) {
   const size_t S = static_cast<size_t>(s_txt) + s_img, D = D_of(c);
@@ -101,6 +118,7 @@ WsLayout ws_layout(const utx_flux_config& c, int s_txt, int s_img) {
   L.sincos = take(512 * 4);
   L.hvec = take(D * 4);
   L.pooled = take(static_cast<size_t>(c.pooled_projection_dim) * 4);
+  L.step_params = take(16);
   L.total = off;
   return L;
 }
@@ -135,6 +153,14 @@ int gemm_streams(const utx_flux* h, const bf16* A, long lda, const void* W_txt, 
   return gemm_bf16_tn(a, st);
 }
 
+void drop_graphs(utx_flux* h) {
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
+int forward_impl(utx_flux* h, const void* latents, float t_eff, float g_eff, const float* tg_dev, void* v_out, cudaStream_t st);
+
 }  // namespace
 
 extern "C" {
@@ -154,6 +180,8 @@ int utx_flux_create(const utx_flux_config* cfg, utx_flux** out) {
 
 void utx_flux_destroy(utx_flux* h) {
   if (!h) return;
+  drop_graphs(h);
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
@@ -166,6 +194,7 @@ int utx_flux_set_weights(utx_flux* h, const utx_flux_weights* w) {
   h->w.double_blocks = h->dbl.data();
   h->w.single_blocks = h->sgl.data();
   h->has_weights = true;
+  drop_graphs(h);                 // captured launches hold the old weight pointers
   return 0;
 }
 
@@ -192,6 +221,8 @@ int utx_flux_prepare(utx_flux* h, void* workspace, size_t workspace_bytes, const
   h->mod = reinterpret_cast<float*>(b + L.mod); h->temb = reinterpret_cast<float*>(b + L.temb);
   h->sincos = reinterpret_cast<float*>(b + L.sincos); h->hvec = reinterpret_cast<float*>(b + L.hvec);
   h->pooled = reinterpret_cast<float*>(b + L.pooled);
+  h->step_params = reinterpret_cast<float*>(b + L.step_params);
+  drop_graphs(h);                 // buffers, sequence lengths or RoPE table may have changed
   const int D = D_of(h->cfg);
   UTX_TRY(rope_table(ids, s_txt + s_img, h->cos_t, h->sin_t, st));
   if (s_txt > 0)
@@ -204,20 +235,28 @@ int utx_flux_prepare(utx_flux* h, void* workspace, size_t workspace_bytes, const
   return 0;
 }
 
+// timestep.to(bf16) * 1000 and guidance.to(bf16) * 1000, each product rounded to bf16 [ext transformer forward]
+static inline float scaled_bf16(float v) { return bf16_round(bf16_round(v) * 1000.0f); }
+
 int utx_flux_forward(utx_flux* h, const void* latents, float timestep, float guidance, void* v_out, void* stream) {
   UTX_CHECK(h && h->prepared, "utx_flux_forward: call utx_flux_prepare first");
   UTX_CHECK(latents && v_out, "utx_flux_forward: null argument");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return forward_impl(h, latents, scaled_bf16(timestep), scaled_bf16(guidance), nullptr, v_out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+namespace {
+// tg_dev != nullptr: the sinusoid reads (t_eff, g_eff) from device memory (graph capture / replay), else from the arguments
+int forward_impl(utx_flux* h, const void* latents, float t_eff, float g_eff, const float* tg_dev, void* v_out, cudaStream_t st) {
   const utx_flux_config& c = h->cfg;
   const utx_flux_weights& w = h->w;
   const int D = D_of(c), M4 = 4 * D, H = c.num_heads;
   const int s_txt = h->s_txt, s_img = h->s_img, S = s_txt + s_img;
   const long ldc5 = 5L * D;
 
-  // timestep.to(bf16) * 1000 and guidance.to(bf16) * 1000, each product rounded to bf16 [ext transformer forward]
-  const float t_eff = bf16_round(bf16_round(timestep) * 1000.0f);
-  const float g_eff = bf16_round(bf16_round(guidance) * 1000.0f);
-  CAT_ELEM(time_sinusoid(t_eff, g_eff, h->sincos, st));
+  if (tg_dev) CAT_ELEM(time_sinusoid_dev(tg_dev, h->sincos, st));
+  else CAT_ELEM(time_sinusoid(t_eff, g_eff, h->sincos, st));
   auto B = [](const void* p) { return static_cast<const bf16*>(p); };
   // temb = MLP_t(sin) + MLP_g(sin) + MLP_p(pooled)
   CAT_ELEM(gemv_bf16(B(w.w_t1), B(w.b_t1), h->sincos, h->hvec, D, 256, 0, 0, st));
@@ -279,6 +318,68 @@ int utx_flux_forward(utx_flux* h, const void* latents, float timestep, float gui
   return 0;
 }
 
+// One denoise step through a captured graph.  Returns 0 and sets *done when the step ran as a graph launch; leaves *done false
+// when the caller should run the step eagerly (graphs disabled, profiling on, first call with this key, capture failed).
+int step_via_graph(utx_flux* h, void* latents, int s_noise, float t_eff, float g_eff, float dsigma, cudaStream_t st, bool* done) {
+  *done = false;
+  if (h->use_graph < 0) {
+    const char* e = std::getenv("UTX_FLUX_GRAPH");
+    h->use_graph = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!h->use_graph || h->profile) return 0;
+  utx_flux::StepGraph* g = nullptr;
+  for (auto& c : h->graphs)
+    if (c.latents == latents && c.s_noise == s_noise) g = &c;
+  if (!g) {
+    if (h->graphs.size() >= 8) drop_graphs(h);
+    h->graphs.emplace_back();
+    g = &h->graphs.back();
+    g->latents = latents;
+    g->s_noise = s_noise;
+  }
+  if (!g->exec) {
+    if (g->seen++ == 0) return 0;          // first step with this key runs eagerly (lazy kernel attributes, module load)
+    if (g->seen > 2) return 0;             // a capture already failed for this key: stay eager
+    if (!h->capture_stream) UTX_CUDA(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+    long before[UTX_PROF_NCAT];
+    for (int i = 0; i < UTX_PROF_NCAT; ++i) before[i] = h->launches[i];
+    cudaStream_t cs = h->capture_stream;
+    UTX_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int r = forward_impl(h, latents, 0.f, 0.f, h->step_params, h->v_tmp, cs);
+    if (r == 0) r = run_cat(h, UTX_PROF_ELEM, cs, [&] {
+      return euler_update(static_cast<bf16*>(latents), h->v_tmp, s_noise, h->cfg.in_channels, 0.f, cs, h->step_params + 2);
+    });
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    for (int i = 0; i < UTX_PROF_NCAT; ++i) {
+      g->launches[i] = h->launches[i] - before[i];
+      h->launches[i] = before[i];          // nothing ran yet
+    }
+    if (r != 0 || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return 0;                            // eager fallback; g->seen > 2 from now on
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      g->exec = nullptr;
+      cudaGetLastError();
+      return 0;
+    }
+  }
+  UTX_TRY(set_step_scalars(h->step_params, t_eff, g_eff, dsigma, st));
+  UTX_CUDA(cudaGraphLaunch(g->exec, st));
+  for (int i = 0; i < UTX_PROF_NCAT; ++i) h->launches[i] += g->launches[i];
+  h->launches[UTX_PROF_OTHER] += 1;        // set_step_scalars
+  h->graph_replays++;
+  *done = true;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
 int utx_flux_denoise(utx_flux* h, void* latents, int s_noise, const float* sigmas, int n_steps, float guidance,
                      void* stream) {
   UTX_CHECK(h && h->prepared, "utx_flux_denoise: call utx_flux_prepare first");
@@ -288,12 +389,17 @@ int utx_flux_denoise(utx_flux* h, void* latents, int s_noise, const float* sigma
   for (int i = 0; i < n_steps; ++i) {
     // t = 1000 sigma (fp32) -> .to(bf16) (:643) -> / 1000 in bf16 (:648)
     const float t_in = bf16_round(bf16_round(sigmas[i] * 1000.0f) / 1000.0f);
+    bool done = false;
+    UTX_TRY(step_via_graph(h, latents, s_noise, scaled_bf16(t_in), scaled_bf16(guidance), sigmas[i + 1] - sigmas[i], st, &done));
+    if (done) continue;
     UTX_TRY(utx_flux_forward(h, latents, t_in, guidance, h->v_tmp, stream));
     CAT_ELEM(euler_update(static_cast<bf16*>(latents), h->v_tmp, s_noise, h->cfg.in_channels, sigmas[i + 1] - sigmas[i],
                           st));
   }
   return 0;
 }
+
+long utx_flux_graph_replays(const utx_flux* h) { return h ? h->graph_replays : 0; }
 
 int utx_flux_profile(utx_flux* h, int enable) {
   UTX_CHECK(h, "utx_flux_profile: null handle");

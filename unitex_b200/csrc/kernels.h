@@ -74,10 +74,15 @@ int gemv_bf16(const bf16* W, const bf16* b, const float* x, float* y, int N, int
               cudaStream_t stream);
 // out[0:256] = sinusoid(1000 * t) ; out[256:512] = sinusoid(1000 * g)   (flip_sin_to_cos, fp32)
 int time_sinusoid(float t_scaled, float g_scaled, float* out512, cudaStream_t stream);
+// the same with (t, g) read from device memory tg_dev[0..1]; set_step_scalars writes (t, g, dsigma) to dev3[0..2] on `stream`
+int time_sinusoid_dev(const float* tg_dev, float* out512, cudaStream_t stream);
+int set_step_scalars(float* dev3, float t_scaled, float g_scaled, float dsigma, cudaStream_t stream);
 // cos/sin table [S,128] fp32 from ids [S,3] fp32 with axes (16,56,56), theta 1e4, angles in fp64
 int rope_table(const float* ids, int S, float* cos_t, float* sin_t, cudaStream_t stream);
 // latents[r,c] = bf16( float(latents[r,c]) + dsigma * float(v[r,c]) ) for r < rows
-int euler_update(bf16* latents, const bf16* v, int rows, int cols, float dsigma, cudaStream_t stream);
+// dsigma_dev != nullptr: the sigma difference is read from device memory instead (CUDA-graph replay)
+int euler_update(bf16* latents, const bf16* v, int rows, int cols, float dsigma, cudaStream_t stream,
+                 const float* dsigma_dev = nullptr);
 // W[o,i] += scale * sum_r B[o,r] * A[r,i]   (fp32 math, bf16 storage; LoRA merge)
 int lora_merge(bf16* W, long ldw, const float* A, const float* B, int out_f, int in_f, int rank, float scale,
                cudaStream_t stream);

@@ -275,6 +275,10 @@ class FluxTransformer:
                    "utx_flux_denoise")
         return latents
 
+    def graph_replays(self) -> int:
+        """Denoise steps that ran as one CUDA-graph launch (include/unitex_b200.h: utx_flux_graph_replays)."""
+        return int(self.lib.utx_flux_graph_replays(self._handle))
+
     def profile(self, enable: bool = True):
         _lib.check(self.lib.utx_flux_profile(self._handle, int(enable)), "utx_flux_profile")
 
