@@ -324,6 +324,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
+    sp = bench_single_grid_sp(eng, dev, ids, sig, world, rank, args.steps) if world > 1 else None
     t = torch.tensor([ms, ms_e2e, ms_steps, ms_finish], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -367,6 +368,8 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
     }
     out.update(side)
+    if sp is not None:
+        out["single_grid_sequence_parallel"] = sp
     if world == 1 and not args.no_bake:
         out["delight"] = bench_delight(eng, dev, sig)
         out["six_view"] = bench_six_view(eng, dev, sig)
@@ -389,6 +392,44 @@ def run_ours(args, rank, world, local_rank):
         out["cpu_baseline"] = {"value": 1.0 / (57.0 * dt), "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": REF_SAMPLE + "; step = 57 x the measured block", "measured_block_ms": dt * 1e3}
     print(json.dumps(out), flush=True)
+
+
+def bench_single_grid_sp(eng, dev, ids, sig, world, rank, steps):
+    """N > 1 side measurement: ONE texture_gen grid (the same S = 9728 workload) whose token sequence is split over all N ranks
+    (sequence-parallel / Ulysses mode of the engine: include/unitex_b200.h utx_flux_set_sequence_parallel) -- the latency of a
+    single asset's denoise step when the other GPUs would otherwise idle.  Same weights on every rank, rank 0's latents
+    broadcast; CUDA events, max over ranks.  The headline `value` stays the batch-sharded throughput."""
+    import torch
+    import torch.distributed as dist
+    from unitex_b200 import parallel as par
+    if 24 % world or S_TOT % world:
+        return {"unavailable": f"world size {world} does not divide 24 heads / {S_TOT} tokens"}
+    eng.set_sequence_parallel(par.tile_comm(dev))
+    eng.prepare(ids, None, None, s_txt=S_TXT)
+    lat = torch.randn(S_IMG, 64, generator=torch.Generator().manual_seed(63)).to(torch.bfloat16).to(dev)
+    dist.broadcast(lat, 0)
+    for i in range(2):
+        eng.denoise_(lat, S_NOISE, sig[i:i + 2], 3.5)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        eng.denoise_(lat, S_NOISE, sig[i:i + 2], 3.5)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    chk = lat[:S_NOISE].float().sum().reshape(1)
+    allc = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    eng.set_sequence_parallel(None)
+    ms = t.item() / steps
+    return {"metric": "single-grid denoise steps/s (one asset over all GPUs)", "value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms,
+            "n_gpus": world, "workload": WORKLOAD, "rows_per_rank": S_TOT // world, "heads_per_rank": 24 // world,
+            "collectives_per_step": "2 all-to-all per block (57 blocks) + 1 all-gather of v, NCCL over NVLink",
+            "ranks_agree": bool(all(torch.equal(c, allc[0]) for c in allc)), "finite": bool(torch.isfinite(chk).all())}
 
 
 def bench_delight(eng, dev, sig):

@@ -99,6 +99,17 @@ int utx_flux_denoise(utx_flux* h, void* latents, int s_noise, const float* sigma
  * (UTX_FLUX_GRAPH=0 disables it; profiling mode runs eagerly).  Number of steps that ran as graph launches so far: */
 long utx_flux_graph_replays(const utx_flux* h);
 
+/* Sequence-parallel ("Ulysses") mode: ONE grid's token sequence split over the ranks of `comm` (SURVEY 8e "if one grid must
+ * span GPUs"; the reference has no counterpart, it runs one grid on one GPU).  Every rank keeps the full merged weights and owns
+ * S / nranks consecutive rows of the [txt | img] sequence for every Linear / LayerNorm; around each joint attention
+ * (attention_processor.py:81-91) an all-to-all turns "my rows, all heads" into "all rows, my heads" and back:
+ * the QKV GEMM's epilogue writes q | k | v straight into the per-peer send layout, the attention runs over the whole sequence
+ * for num_heads / nranks heads.  Every rank passes the SAME ids / enc / latents to utx_flux_prepare / forward / denoise and ends
+ * with the SAME v / latents (v is all-gathered), bit-identical to the single-GPU result.  Requires nranks | num_heads and
+ * nranks | (s_txt + s_img).  comm = NULL switches back; call utx_flux_prepare again after changing the mode. */
+typedef struct utx_comm utx_comm;
+int utx_flux_set_sequence_parallel(utx_flux* h, utx_comm* comm);
+
 /* Instrumentation for bench.py: kernel launches issued by the engine per category, and (after
  * utx_flux_profile(h, 1)) the CUDA-event time of each category on the launching stream.  launches/ms: [4]
  * indexed by UTX_PROF_*; reading synchronises on the recorded events. */
@@ -318,10 +329,11 @@ long utx_vae_launches(utx_vae* h, int reset);
  * Bootstrap like NCCL's own: rank 0 makes a 128-byte id, the host shares it out of band, every rank joins; the communicator
  * is bound to the device that is current at utx_comm_init.
  * ------------------------------------------------------------------------------------------------------------------ */
-typedef struct utx_comm utx_comm;
 int utx_comm_unique_id(void* id128 /* host, 128 bytes out */);
 int utx_comm_init(utx_comm** out, const void* id128 /* host */, int nranks, int rank);
 void utx_comm_destroy(utx_comm* c);
+/* send[p * bytes_per_peer ..] goes to rank p, recv[p * bytes_per_peer ..] comes from rank p (grouped ncclSend / ncclRecv) */
+int utx_comm_alltoall(utx_comm* c, const void* send, void* recv, size_t bytes_per_peer, void* stream);
 /* out [nranks * bytes_per_rank] (rank-major) <- every rank's tile [bytes_per_rank]; uneven shards are padded by the caller */
 int utx_allgather_tiles(utx_comm* c, const void* tile, void* out, size_t bytes_per_rank, void* stream);
 

@@ -1,0 +1,85 @@
+"""GPU, 2 ranks (NCCL): ONE grid's token sequence split over the GPUs (SURVEY 8e "if one grid must span GPUs": Ulysses).
+Every Linear / LayerNorm runs on S / P rows per rank, the joint attention (attention_processor.py:81-91) on all rows for
+H / P heads per rank, with an all-to-all before and after; the QKV GEMM's epilogue writes straight into the send layout.
+The result must be BIT-IDENTICAL to the single-GPU engine: rows and heads are independent in every kernel.
+Skipped with fewer than 2 GPUs (run under `gpurun --gpus 2`)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(s_txt):
+    from oracle import flux_dit as fd
+    from oracle import flux_sampler as fs
+    ocfg = fd.FluxConfig.tiny(2, 2, heads=4)
+    P = {k: v.to(torch.bfloat16).float() for k, v in fd.init_params(ocfg, 0, norm_weight_std=0.1).items()}
+    img_ids = fs.build_ids(32, 32, (32, 32), (16, 16))                    # 256 + 256 + 64 image tokens
+    g = torch.Generator().manual_seed(63)
+    s_noise = 256
+    lat = torch.randn(img_ids.shape[0], 64, generator=g).to(torch.bfloat16)
+    ids = torch.cat([torch.zeros(s_txt, 3), img_ids])
+    enc = (torch.randn(s_txt, ocfg.joint_attention_dim, generator=g) * 0.5).to(torch.bfloat16)
+    return ocfg, P, ids, enc, lat, s_noise, fs.flow_match_sigmas(3, s_noise)
+
+
+def _engine(ocfg, P):
+    from unitex_b200.flux import FluxConfig, FluxTransformer
+    cfg = FluxConfig(num_layers=ocfg.num_layers, num_single_layers=ocfg.num_single_layers, num_attention_heads=ocfg.num_attention_heads,
+                     joint_attention_dim=ocfg.joint_attention_dim, pooled_projection_dim=ocfg.pooled_projection_dim)
+    return FluxTransformer(cfg).load_state_dict(P)
+
+
+def _worker(rank, world, port, s_txt, ref_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from unitex_b200 import parallel as par
+        ocfg, P, ids, enc, lat, s_noise, sig = _problem(s_txt)
+        eng = _engine(ocfg, P).set_sequence_parallel(par.tile_comm(torch.device("cuda", rank)))
+        eng.prepare(ids, enc, None, s_txt=s_txt)
+        x = lat.cuda().contiguous()
+        v = eng.forward(x, 0.62, 3.5)
+        eng.denoise_(x, s_noise, sig, 3.5)
+        torch.cuda.synchronize()
+        ref = torch.load(ref_path)
+        assert torch.equal(v.cpu(), ref["v"]), f"rank {rank}: forward differs from the single-GPU engine"
+        assert torch.equal(x.cpu(), ref["x"]), f"rank {rank}: denoised latents differ from the single-GPU engine"
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run under gpurun --gpus 2)")
+@pytest.mark.parametrize("s_txt", [128, 64])      # 704 / 640 tokens: rank 0 holds the text rows + part of the image rows
+def test_two_rank_sequence_parallel_is_bit_identical(lib, tmp_path, s_txt):
+    import torch.multiprocessing as mp
+    ocfg, P, ids, enc, lat, s_noise, sig = _problem(s_txt)
+    eng = _engine(ocfg, P)
+    eng.prepare(ids, enc, None, s_txt=s_txt)
+    x = lat.cuda().contiguous()
+    v = eng.forward(x, 0.62, 3.5)
+    eng.denoise_(x, s_noise, sig, 3.5)
+    torch.cuda.synchronize()
+    ref_path = str(tmp_path / "ref.pt")
+    torch.save({"v": v.cpu(), "x": x.cpu()}, ref_path)
+    del eng
+    mp.spawn(_worker, args=(2, 29500 + os.getpid() % 2000, s_txt, ref_path), nprocs=2, join=True)
+
+
+def test_sequence_parallel_off_is_the_default(lib):
+    """set_sequence_parallel(None) is the plain engine (and the mode needs a fresh prepare)."""
+    ocfg, P, ids, enc, lat, s_noise, sig = _problem(128)
+    eng = _engine(ocfg, P)
+    eng.prepare(ids, enc, None, s_txt=128)
+    x = lat.cuda().contiguous()
+    a = eng.forward(x, 0.62, 3.5).clone()
+    eng.set_sequence_parallel(None)
+    with pytest.raises(Exception):
+        eng.forward(x, 0.62, 3.5)                                      # not prepared for the (re)set mode
+    eng.prepare(ids, enc, None, s_txt=128)
+    assert torch.equal(eng.forward(x, 0.62, 3.5), a)

@@ -80,6 +80,7 @@ _SIGS = {
     "utx_flux_forward": (i32, [vp, vp, f32, f32, vp, vp]),
     "utx_flux_denoise": (i32, [vp, vp, i32, fp, i32, f32, vp]),
     "utx_flux_graph_replays": (C.c_long, [vp]),
+    "utx_flux_set_sequence_parallel": (i32, [vp, vp]),
     "utx_flux_profile": (i32, [vp, i32]),
     "utx_flux_profile_read": (i32, [vp, C.POINTER(C.c_long), fp, i32]),
     "utx_lora_merge": (i32, [vp, lng, vp, vp, i32, i32, i32, f32, vp]),
@@ -120,6 +121,7 @@ _SIGS = {
     "utx_comm_init": (i32, [C.POINTER(vp), vp, i32, i32]),
     "utx_comm_destroy": (None, [vp]),
     "utx_allgather_tiles": (i32, [vp, vp, vp, C.c_size_t, vp]),
+    "utx_comm_alltoall": (i32, [vp, vp, vp, C.c_size_t, vp]),
     "utx_knn1": (i32, [vp, i32, vp, C.c_longlong, vp, vp, vp, vp, C.c_size_t, vp]),
     "utx_knn": (i32, [vp, i32, vp, C.c_longlong, i32, vp, vp, vp, vp, C.c_size_t, vp]),
     "utx_uv_bake_workspace_bytes": (C.c_size_t, [i32, i32]),

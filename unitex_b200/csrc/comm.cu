@@ -29,6 +29,10 @@ struct Nccl {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -45,7 +49,12 @@ Nccl& nccl() {
     n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     n.AllGather = reinterpret_cast<decltype(n.AllGather)>(dlsym(h, "ncclAllGather"));
     n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather && n.GetErrorString;
+    n.Send = reinterpret_cast<decltype(n.Send)>(dlsym(h, "ncclSend"));
+    n.Recv = reinterpret_cast<decltype(n.Recv)>(dlsym(h, "ncclRecv"));
+    n.GroupStart = reinterpret_cast<decltype(n.GroupStart)>(dlsym(h, "ncclGroupStart"));
+    n.GroupEnd = reinterpret_cast<decltype(n.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather && n.GetErrorString && n.Send && n.Recv && n.GroupStart &&
+           n.GroupEnd;
   });
   return n;
 }
@@ -65,6 +74,30 @@ struct utx_comm {
   ncclComm_t comm = nullptr;
   int nranks = 0, rank = 0;
 };
+
+namespace utx {
+// used by the FLUX engine's sequence-parallel mode (flux_engine.cu)
+int comm_nranks(const utx_comm* c) { return c ? c->nranks : 1; }
+int comm_rank(const utx_comm* c) { return c ? c->rank : 0; }
+// send[p * bytes .. ] goes to rank p, recv[p * bytes ..] comes from rank p (grouped ncclSend / ncclRecv: an all-to-all)
+int comm_alltoall(utx_comm* c, const void* send, void* recv, size_t bytes_per_peer, cudaStream_t stream) {
+  UTX_CHECK(c && c->comm, "comm_alltoall: communicator not initialised");
+  if (bytes_per_peer == 0) return 0;
+  UTX_NCCL(nccl().GroupStart());
+  for (int p = 0; p < c->nranks; ++p) {
+    UTX_NCCL(nccl().Send(static_cast<const char*>(send) + static_cast<size_t>(p) * bytes_per_peer, bytes_per_peer, ncclInt8, p, c->comm, stream));
+    UTX_NCCL(nccl().Recv(static_cast<char*>(recv) + static_cast<size_t>(p) * bytes_per_peer, bytes_per_peer, ncclInt8, p, c->comm, stream));
+  }
+  UTX_NCCL(nccl().GroupEnd());
+  return 0;
+}
+int comm_allgather(utx_comm* c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream) {
+  UTX_CHECK(c && c->comm, "comm_allgather: communicator not initialised");
+  if (bytes_per_rank == 0) return 0;
+  UTX_NCCL(nccl().AllGather(send, recv, bytes_per_rank, ncclInt8, c->comm, stream));
+  return 0;
+}
+}  // namespace utx
 
 extern "C" {
 
@@ -99,6 +132,11 @@ void utx_comm_destroy(utx_comm* c) {
   if (!c) return;
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   delete c;
+}
+
+int utx_comm_alltoall(utx_comm* c, const void* send, void* recv, size_t bytes_per_peer, void* stream) {
+  UTX_CHECK(send && recv, "utx_comm_alltoall: null pointer");
+  return comm_alltoall(c, send, recv, bytes_per_peer, static_cast<cudaStream_t>(stream));
 }
 
 int utx_allgather_tiles(utx_comm* c, const void* tile, void* out, size_t bytes_per_rank, void* stream) {

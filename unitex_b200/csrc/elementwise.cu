@@ -314,6 +314,28 @@ int gemv_bf16(const bf16* W, const bf16* b, const float* x, float* y, int N, int
   return 0;
 }
 
+// sequence-parallel attention tail: recv [P][rows][w] (peer p's heads for this rank's rows) -> cat[row, p * w + j]
+__global__ void __launch_bounds__(256) sp_unpack_kernel(const uint4* __restrict__ recv, bf16* __restrict__ cat, long ld_cat, int rows,
+                                                        int w8, long total) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % w8);
+    const long pr = i / w8;
+    const int row = static_cast<int>(pr % rows), p = static_cast<int>(pr / rows);
+    *reinterpret_cast<uint4*>(cat + row * ld_cat + (static_cast<long>(p) * w8 + j) * 8) = recv[i];
+  }
+}
+int sp_unpack_heads(const bf16* recv, bf16* cat, long ld_cat, int rows, int w, int npeers, cudaStream_t stream) {
+  UTX_CHECK(w % 8 == 0 && ld_cat % 8 == 0, "sp_unpack_heads: widths must be multiples of 8");
+  const long total = static_cast<long>(npeers) * rows * (w / 8);
+  if (total == 0) return 0;
+  long blocks = (total + 255) / 256;
+  const long cap = static_cast<long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  sp_unpack_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(reinterpret_cast<const uint4*>(recv), cat, ld_cat, rows, w / 8, total);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int time_sinusoid(float t_scaled, float g_scaled, float* out512, cudaStream_t stream) {
   time_sinusoid_kernel<<<1, 128, 0, stream>>>(t_scaled, g_scaled, out512);
   UTX_CUDA(cudaGetLastError());

@@ -3,6 +3,7 @@
 // loop :634-681.  Token layout in the residual buffer: [txt rows | img rows] from the start, so the double-stream
 // blocks address the two streams as row ranges of one buffer (grouped GEMM launches) and the torch.cat before the
 // single-stream blocks costs nothing.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -14,13 +15,29 @@
 
 using namespace utx;
 
+namespace utx {   // comm.cu
+int comm_nranks(const utx_comm* c);
+int comm_rank(const utx_comm* c);
+int comm_alltoall(utx_comm* c, const void* send, void* recv, size_t bytes_per_peer, cudaStream_t stream);
+int comm_allgather(utx_comm* c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream);
+// elementwise.cu: cat[row, p * w + j] = recv[p][row][j]  (the received attention heads of peer p into their columns)
+int sp_unpack_heads(const bf16* recv, bf16* cat, long ld_cat, int rows, int w, int npeers, cudaStream_t stream);
+}  // namespace utx
+
 struct utx_flux {
   utx_flux_config cfg;
   utx_flux_weights w;
   std::vector<utx_double_block> dbl;
   std::vector<utx_single_block> sgl;
   bool has_weights = false;
-  // per-call state (set by prepare)
+  // sequence-parallel ("Ulysses") mode: ONE grid's tokens split over the ranks of sp_comm (nullptr: off, everything local)
+  utx_comm* sp_comm = nullptr;
+  int sp_n = 1, sp_rank = 0;
+  // per-call state (set by prepare).  Rows this rank owns: global rows [r0, r0 + S_loc) of the [txt | img] sequence, of which
+  // the first st_loc are text rows and the other si_loc image rows (image tokens img0 ...); without sequence parallelism
+  // r0 = 0, S_loc = s_txt + s_img, st_loc = s_txt, si_loc = s_img.
+  int r0 = 0, S_loc = 0, st_loc = 0, si_loc = 0, img0 = 0;
+  bf16 *qkv_all = nullptr, *attn_all = nullptr, *attn_recv = nullptr, *v_loc = nullptr, *v_all = nullptr;
   int s_txt = 0, s_img = 0;
   bf16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *cat = nullptr, *ctx0 = nullptr, *v_tmp = nullptr;
   float *cos_t = nullptr, *sin_t = nullptr, *mod = nullptr, *temb = nullptr, *sincos = nullptr, *hvec = nullptr,
@@ -76,6 +93,7 @@ int run_cat(utx_flux* h, int cat, cudaStream_t st, F&& f) {
 #define CAT_GEMM(expr) UTX_TRY(run_cat(h, UTX_PROF_GEMM, st, [&] { return (expr); }))
 #define CAT_ATTN(expr) UTX_TRY(run_cat(h, UTX_PROF_ATTN, st, [&] { return (expr); }))
 #define CAT_ELEM(expr) UTX_TRY(run_cat(h, UTX_PROF_ELEM, st, [&] { return (expr); }))
+#define CAT_OTHER(expr) UTX_TRY(run_cat(h, UTX_PROF_OTHER, st, [&] { return (expr); }))
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 inline int D_of(const utx_flux_config& c) { return c.num_heads * c.head_dim; }
@@ -94,10 +112,14 @@ inline float bf16_round(float f) {
 }
 
 struct WsLayout {
-  size_t x, xn, qkv, cat, ctx0, v_tmp, cos_t, sin_t, mod, temb, sincos, hvec, pooled, step_params, total;
+  size_t x, xn, qkv, cat, ctx0, v_tmp, cos_t, sin_t, mod, temb, sincos, hvec, pooled, step_params;
+  size_t qkv_all, attn_all, attn_recv, v_loc, v_all;   // sequence-parallel mode only
+  size_t total;
 };
-WsLayout ws_layout(const utx_flux_config& c, int s_txt, int s_img) {
+// rows per rank: S / P (P = 1 without sequence parallelism)
+WsLayout ws_layout(const utx_flux_config& c, int s_txt, int s_img, int P) {
   const size_t S = static_cast<size_t>(s_txt) + s_img, D = D_of(c);
+  const size_t Sl = S / P;
   WsLayout L{};
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -105,11 +127,11 @@ WsLayout ws_layout(const utx_flux_config& c, int s_txt, int s_img) {
     off += align_up(bytes);
     return o;
   };
-  L.x = take(S * D * 2);
-  L.xn = take(S * D * 2);
-  L.qkv = take(S * 3 * D * 2);
-  L.cat = take(S * (1 + c.mlp_ratio) * D * 2);
-  L.ctx0 = take(static_cast<size_t>(s_txt) * D * 2);
+  L.x = take(Sl * D * 2);
+  L.xn = take(Sl * D * 2);
+  L.qkv = take(Sl * 3 * D * 2);
+  L.cat = take(Sl * (1 + c.mlp_ratio) * D * 2);
+  L.ctx0 = take(std::min<size_t>(s_txt, Sl) * D * 2);
   L.v_tmp = take(static_cast<size_t>(s_img) * c.in_channels * 2);
   L.cos_t = take(S * 128 * 4);
   L.sin_t = take(S * 128 * 4);
@@ -119,6 +141,13 @@ WsLayout ws_layout(const utx_flux_config& c, int s_txt, int s_img) {
   L.hvec = take(D * 4);
   L.pooled = take(static_cast<size_t>(c.pooled_projection_dim) * 4);
   L.step_params = take(16);
+  if (P > 1) {
+    L.qkv_all = take(Sl * 3 * D * 2);       // [S, 3 * (H/P) * 128]: every token, this rank's heads
+    L.attn_all = take(Sl * D * 2);          // [S, (H/P) * 128]
+    L.attn_recv = take(Sl * D * 2);         // [P][S_loc][(H/P) * 128]
+    L.v_loc = take(Sl * c.in_channels * 2);
+    L.v_all = take(S * c.in_channels * 2);
+  }
   L.total = off;
   return L;
 }
@@ -126,31 +155,56 @@ WsLayout ws_layout(const utx_flux_config& c, int s_txt, int s_img) {
 int gemm1(const bf16* A, long lda, const bf16* W, long ldw, const bf16* bias, bf16* C, long ldc, int M, int N, int K,
           int epi, const float* gate, const bf16* res, long ldres, cudaStream_t st, int gelu_start = 0,
           int split_col = 0, bf16* C2 = nullptr, long ldc2 = 0, int qk_cols = 0, const bf16* wq = nullptr,
-          const bf16* wk = nullptr, const float* cos_t = nullptr, const float* sin_t = nullptr) {
+          const bf16* wk = nullptr, const float* cos_t = nullptr, const float* sin_t = nullptr, int row_offset = 0,
+          int sc_hl = 0, int sc_rows = 0, int sc_D = 0) {
   GemmArgs a{};
   a.N = N; a.K = K; a.epi = epi; a.gelu_col_start = gelu_start; a.nprob = 1;
   a.qk_cols = qk_cols; a.cos_t = cos_t; a.sin_t = sin_t;
-  a.prob[0] = GemmProblem{A, lda, W, ldw, M, C, ldc, bias, gate, res, ldres, split_col, C2, ldc2, wq, wk, 0};
+  a.prob[0] = GemmProblem{A, lda, W, ldw, M, C, ldc, bias, gate, res, ldres, split_col, C2, ldc2, wq, wk, row_offset,
+                          sc_hl, sc_rows, 0, sc_D};
   return gemm_bf16_tn(a, st);
 }
 
-// txt rows [0, s_txt) with the *_txt weights and img rows [s_txt, S) with the *_img weights, one launch
+// this rank's txt rows [0, st_loc) with the *_txt weights and img rows [st_loc, S_loc) with the *_img weights, one launch.
+// scatter: the q | k | v columns go to the all-to-all send layout (sequence-parallel mode), C is then the send buffer.
 int gemm_streams(const utx_flux* h, const bf16* A, long lda, const void* W_txt, const void* b_txt, const void* W_img,
                  const void* b_img, long ldw, bf16* C, long ldc, int N, int K, int epi, const float* gate_txt,
                  const float* gate_img, const bf16* res, long ldres, cudaStream_t st, int qk_cols = 0,
                  const void* wq_txt = nullptr, const void* wk_txt = nullptr, const void* wq_img = nullptr,
-                 const void* wk_img = nullptr) {
+                 const void* wk_img = nullptr, bool scatter = false) {
   GemmArgs a{};
   a.N = N; a.K = K; a.epi = epi; a.gelu_col_start = 0; a.nprob = 2;
   a.qk_cols = qk_cols; a.cos_t = h->cos_t; a.sin_t = h->sin_t;
-  const long st_rows = h->s_txt;
-  a.prob[0] = GemmProblem{A, lda, static_cast<const bf16*>(W_txt), ldw, h->s_txt, C, ldc,
+  const long st_rows = h->st_loc;
+  const int hl = scatter ? h->cfg.num_heads / h->sp_n : 0, D = D_of(h->cfg);
+  a.prob[0] = GemmProblem{A, lda, static_cast<const bf16*>(W_txt), ldw, h->st_loc, C, ldc,
                           static_cast<const bf16*>(b_txt), gate_txt, res, ldres, 0, nullptr, 0,
-                          static_cast<const bf16*>(wq_txt), static_cast<const bf16*>(wk_txt), 0};
-  a.prob[1] = GemmProblem{A + st_rows * lda, lda, static_cast<const bf16*>(W_img), ldw, h->s_img, C + st_rows * ldc, ldc,
+                          static_cast<const bf16*>(wq_txt), static_cast<const bf16*>(wk_txt), h->r0, hl, h->S_loc, 0, D};
+  a.prob[1] = GemmProblem{A + st_rows * lda, lda, static_cast<const bf16*>(W_img), ldw, h->si_loc,
+                          scatter ? C : C + st_rows * ldc, ldc,
                           static_cast<const bf16*>(b_img), gate_img, res ? res + st_rows * ldres : nullptr, ldres, 0,
-                          nullptr, 0, static_cast<const bf16*>(wq_img), static_cast<const bf16*>(wk_img), h->s_txt};
+                          nullptr, 0, static_cast<const bf16*>(wq_img), static_cast<const bf16*>(wk_img), h->r0 + h->st_loc,
+                          hl, h->S_loc, h->st_loc, D};
   return gemm_bf16_tn(a, st);
+}
+
+// joint attention of one block.  Local: qkv [S, 3D] -> cat[:, :D].  Sequence-parallel: the QKV GEMM left every peer's heads in
+// the send layout; all-to-all -> this rank holds ALL tokens of ITS heads -> attention -> all-to-all back -> the heads of all
+// peers for THIS rank's tokens, unpacked into cat[:, :D].
+int attention_block(utx_flux* h, cudaStream_t st) {
+  const int D = D_of(h->cfg), H = h->cfg.num_heads;
+  const long ldc5 = 5L * D;
+  if (h->sp_n == 1) {
+    CAT_ATTN(attention_bf16(h->qkv, 3L * D, h->cat, ldc5, h->S_loc, H, st));
+    return 0;
+  }
+  const int P = h->sp_n, Hl = H / P, S = h->S_loc * P;
+  const size_t w = static_cast<size_t>(Hl) * 128;
+  CAT_OTHER(comm_alltoall(h->sp_comm, h->qkv, h->qkv_all, static_cast<size_t>(h->S_loc) * 3 * w * 2, st));
+  CAT_ATTN(attention_bf16(h->qkv_all, 3L * w, h->attn_all, static_cast<long>(w), S, Hl, st));
+  CAT_OTHER(comm_alltoall(h->sp_comm, h->attn_all, h->attn_recv, static_cast<size_t>(h->S_loc) * w * 2, st));
+  CAT_ELEM(sp_unpack_heads(h->attn_recv, h->cat, ldc5, h->S_loc, static_cast<int>(w), P, st));
+  return 0;
 }
 
 void drop_graphs(utx_flux* h) {
@@ -200,7 +254,8 @@ int utx_flux_set_weights(utx_flux* h, const utx_flux_weights* w) {
 
 size_t utx_flux_workspace_bytes(const utx_flux* h, int s_txt, int s_img) {
   if (!h) return 0;
-  return ws_layout(h->cfg, s_txt, s_img).total;
+  if ((s_txt + s_img) % h->sp_n != 0) return 0;
+  return ws_layout(h->cfg, s_txt, s_img, h->sp_n).total;
 }
 
 int utx_flux_prepare(utx_flux* h, void* workspace, size_t workspace_bytes, const float* ids, const void* enc,
@@ -209,11 +264,18 @@ int utx_flux_prepare(utx_flux* h, void* workspace, size_t workspace_bytes, const
   UTX_CHECK(workspace && ids && enc && pooled, "utx_flux_prepare: null argument");
   UTX_CHECK(s_txt >= 0 && s_img > 0, "utx_flux_prepare: bad sequence lengths");
   UTX_CHECK((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "utx_flux_prepare: workspace must be 256B aligned");
-  const WsLayout L = ws_layout(h->cfg, s_txt, s_img);
+  const int P = h->sp_n;
+  UTX_CHECK((s_txt + s_img) % P == 0, "utx_flux_prepare: the sequence length must be a multiple of the sequence-parallel world size");
+  const WsLayout L = ws_layout(h->cfg, s_txt, s_img, P);
   UTX_CHECK(workspace_bytes >= L.total, "utx_flux_prepare: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* b = static_cast<uint8_t*>(workspace);
   h->s_txt = s_txt; h->s_img = s_img;
+  h->S_loc = (s_txt + s_img) / P;
+  h->r0 = h->sp_rank * h->S_loc;
+  h->st_loc = std::min(std::max(s_txt - h->r0, 0), h->S_loc);
+  h->si_loc = h->S_loc - h->st_loc;
+  h->img0 = std::max(h->r0 - s_txt, 0);
   h->x = reinterpret_cast<bf16*>(b + L.x); h->xn = reinterpret_cast<bf16*>(b + L.xn);
   h->qkv = reinterpret_cast<bf16*>(b + L.qkv); h->cat = reinterpret_cast<bf16*>(b + L.cat);
   h->ctx0 = reinterpret_cast<bf16*>(b + L.ctx0); h->v_tmp = reinterpret_cast<bf16*>(b + L.v_tmp);
@@ -222,13 +284,19 @@ int utx_flux_prepare(utx_flux* h, void* workspace, size_t workspace_bytes, const
   h->sincos = reinterpret_cast<float*>(b + L.sincos); h->hvec = reinterpret_cast<float*>(b + L.hvec);
   h->pooled = reinterpret_cast<float*>(b + L.pooled);
   h->step_params = reinterpret_cast<float*>(b + L.step_params);
+  if (P > 1) {
+    h->qkv_all = reinterpret_cast<bf16*>(b + L.qkv_all); h->attn_all = reinterpret_cast<bf16*>(b + L.attn_all);
+    h->attn_recv = reinterpret_cast<bf16*>(b + L.attn_recv); h->v_loc = reinterpret_cast<bf16*>(b + L.v_loc);
+    h->v_all = reinterpret_cast<bf16*>(b + L.v_all);
+  }
   drop_graphs(h);                 // buffers, sequence lengths or RoPE table may have changed
   const int D = D_of(h->cfg);
-  UTX_TRY(rope_table(ids, s_txt + s_img, h->cos_t, h->sin_t, st));
-  if (s_txt > 0)
-    UTX_TRY(gemm1(static_cast<const bf16*>(enc), h->cfg.joint_attention_dim, static_cast<const bf16*>(h->w.w_ctx_embed),
-                  h->cfg.joint_attention_dim, static_cast<const bf16*>(h->w.b_ctx_embed), h->ctx0, D, s_txt, D,
-                  h->cfg.joint_attention_dim, EPI_BIAS, nullptr, nullptr, 0, st));
+  UTX_TRY(rope_table(ids, s_txt + s_img, h->cos_t, h->sin_t, st));     // every rank keeps the whole table: rows are global tokens
+  if (h->st_loc > 0)
+    UTX_TRY(gemm1(static_cast<const bf16*>(enc) + static_cast<long>(h->r0) * h->cfg.joint_attention_dim, h->cfg.joint_attention_dim,
+                  static_cast<const bf16*>(h->w.w_ctx_embed), h->cfg.joint_attention_dim,
+                  static_cast<const bf16*>(h->w.b_ctx_embed), h->ctx0, D, h->st_loc, D, h->cfg.joint_attention_dim, EPI_BIAS,
+                  nullptr, nullptr, 0, st));
   UTX_CUDA(cudaMemcpyAsync(h->pooled, pooled, sizeof(float) * h->cfg.pooled_projection_dim, cudaMemcpyDeviceToDevice,
                            st));
   h->prepared = true;
@@ -251,8 +319,11 @@ namespace {
 int forward_impl(utx_flux* h, const void* latents, float t_eff, float g_eff, const float* tg_dev, void* v_out, cudaStream_t st) {
   const utx_flux_config& c = h->cfg;
   const utx_flux_weights& w = h->w;
-  const int D = D_of(c), M4 = 4 * D, H = c.num_heads;
-  const int s_txt = h->s_txt, s_img = h->s_img, S = s_txt + s_img;
+  const int D = D_of(c), M4 = 4 * D;
+  // rows of THIS rank (everything when not sequence-parallel): st text rows, then si image rows = image tokens img0 ...
+  const int st_n = h->st_loc, si_n = h->si_loc, S = h->S_loc;
+  const bool sp = h->sp_n > 1;
+  const int sc_hl = sp ? c.num_heads / h->sp_n : 0;
   const long ldc5 = 5L * D;
 
   if (tg_dev) CAT_ELEM(time_sinusoid_dev(tg_dev, h->sincos, st));
@@ -270,26 +341,27 @@ int forward_impl(utx_flux* h, const void* latents, float t_eff, float g_eff, con
   // every adaLN modulation vector of the step in one HBM-bound pass
   CAT_ELEM(gemv_bf16(B(w.w_mod), B(w.b_mod), h->temb, h->mod, static_cast<int>(n_mod_rows(c)), D, 1, 0, st));
 
-  // embedders: x = [ctx0 | x_embedder(latents)]
-  if (s_txt > 0)
-    UTX_CUDA(cudaMemcpyAsync(h->x, h->ctx0, static_cast<size_t>(s_txt) * D * 2, cudaMemcpyDeviceToDevice, st));
-  CAT_GEMM(gemm1(B(latents), c.in_channels, B(w.w_x_embed), c.in_channels, B(w.b_x_embed), h->x + static_cast<long>(s_txt) * D,
-                D, s_img, D, c.in_channels, EPI_BIAS, nullptr, nullptr, 0, st));
+  // embedders: x = [ctx0 | x_embedder(latents)] (this rank's rows of it)
+  if (st_n > 0)
+    UTX_CUDA(cudaMemcpyAsync(h->x, h->ctx0, static_cast<size_t>(st_n) * D * 2, cudaMemcpyDeviceToDevice, st));
+  if (si_n > 0)
+    CAT_GEMM(gemm1(B(latents) + static_cast<long>(h->img0) * c.in_channels, c.in_channels, B(w.w_x_embed), c.in_channels,
+                  B(w.b_x_embed), h->x + static_cast<long>(st_n) * D, D, si_n, D, c.in_channels, EPI_BIAS, nullptr, nullptr, 0, st));
 
   const float* mod = h->mod;
   for (int i = 0; i < c.num_layers; ++i) {
     const utx_double_block& b = h->dbl[i];
     const float* mi = mod + static_cast<long>(i) * 12 * D;   // img: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
     const float* mt = mi + 6L * D;                           // txt: same order
-    CAT_ELEM(ln_modulate(h->x, D, h->xn, D, S, D, s_txt, mt, mt + D, mi, mi + D, st));
+    CAT_ELEM(ln_modulate(h->x, D, h->xn, D, S, D, st_n, mt, mt + D, mi, mi + D, st));
     // q|k|v projection of both streams; per-head RMSNorm + RoPE of q and k fused into the epilogue
     CAT_GEMM(gemm_streams(h, h->xn, D, b.w_qkv_txt, b.b_qkv_txt, b.w_qkv_img, b.b_qkv_img, D, h->qkv, 3L * D, 3 * D, D,
                          EPI_BIAS, nullptr, nullptr, nullptr, 0, st, 2 * D, b.rms_q_txt, b.rms_k_txt, b.rms_q_img,
-                         b.rms_k_img));
-    CAT_ATTN(attention_bf16(h->qkv, 3L * D, h->cat, ldc5, S, H, st));
+                         b.rms_k_img, sp));
+    UTX_TRY(attention_block(h, st));
     CAT_GEMM(gemm_streams(h, h->cat, ldc5, b.w_out_txt, b.b_out_txt, b.w_out_img, b.b_out_img, D, h->x, D, D, D,
                          EPI_GATE_RES, mt + 2L * D, mi + 2L * D, h->x, D, st));
-    CAT_ELEM(ln_modulate(h->x, D, h->xn, D, S, D, s_txt, mt + 3L * D, mt + 4L * D, mi + 3L * D, mi + 4L * D, st));
+    CAT_ELEM(ln_modulate(h->x, D, h->xn, D, S, D, st_n, mt + 3L * D, mt + 4L * D, mi + 3L * D, mi + 4L * D, st));
     CAT_GEMM(gemm_streams(h, h->xn, D, b.w_ff1_txt, b.b_ff1_txt, b.w_ff1_img, b.b_ff1_img, D, h->cat + D, ldc5, M4, D,
                          EPI_BIAS_GELU, nullptr, nullptr, nullptr, 0, st));
     CAT_GEMM(gemm_streams(h, h->cat + D, ldc5, b.w_ff2_txt, b.b_ff2_txt, b.w_ff2_img, b.b_ff2_img, M4, h->x, D, D, M4,
@@ -300,21 +372,33 @@ int forward_impl(utx_flux* h, const void* latents, float t_eff, float g_eff, con
     const utx_single_block& b = h->sgl[i];
     const float* ms = mod_s + static_cast<long>(i) * 3 * D;   // shift, scale, gate
     CAT_ELEM(ln_modulate(h->x, D, h->xn, D, S, D, 0, ms, ms + D, ms, ms + D, st));
-    // one GEMM for to_q|to_k|to_v|proj_mlp: q,k,v -> qkv buffer, GELU(mlp) -> cat[:, D:]
+    // one GEMM for to_q|to_k|to_v|proj_mlp: q,k,v -> qkv buffer (or the all-to-all send layout), GELU(mlp) -> cat[:, D:]
     // (RMSNorm + RoPE of q and k fused into the same epilogue)
     CAT_GEMM(gemm1(h->xn, D, B(b.w_qkvmlp), D, B(b.b_qkvmlp), h->qkv, 3L * D, S, 7 * D, D, EPI_BIAS_GELU, nullptr,
-                  nullptr, 0, st, 3 * D, 3 * D, h->cat + D, ldc5, 2 * D, B(b.rms_q), B(b.rms_k), h->cos_t, h->sin_t));
-    CAT_ATTN(attention_bf16(h->qkv, 3L * D, h->cat, ldc5, S, H, st));
+                  nullptr, 0, st, 3 * D, 3 * D, h->cat + D, ldc5, 2 * D, B(b.rms_q), B(b.rms_k), h->cos_t, h->sin_t, h->r0,
+                  sc_hl, S, D));
+    UTX_TRY(attention_block(h, st));
     CAT_GEMM(gemm1(h->cat, ldc5, B(b.w_out), ldc5, B(b.b_out), h->x, D, S, D, 5 * D, EPI_GATE_RES, ms + 2L * D, h->x, D,
                   st));
   }
   // AdaLayerNormContinuous (chunk order: scale, shift) + proj_out on the img rows
   const float* mf = mod_s + static_cast<long>(c.num_single_layers) * 3 * D;
-  bf16* ximg = h->x + static_cast<long>(s_txt) * D;
-  bf16* xnimg = h->xn + static_cast<long>(s_txt) * D;
-  CAT_ELEM(ln_modulate(ximg, D, xnimg, D, s_img, D, 0, mf + D, mf, mf + D, mf, st));
-  CAT_GEMM(gemm1(xnimg, D, B(w.w_proj_out), D, B(w.b_proj_out), static_cast<bf16*>(v_out), c.in_channels, s_img,
-                c.in_channels, D, EPI_BIAS, nullptr, nullptr, 0, st));
+  bf16* ximg = h->x + static_cast<long>(st_n) * D;
+  bf16* xnimg = h->xn + static_cast<long>(st_n) * D;
+  if (si_n > 0) CAT_ELEM(ln_modulate(ximg, D, xnimg, D, si_n, D, 0, mf + D, mf, mf + D, mf, st));
+  if (!sp) {
+    CAT_GEMM(gemm1(xnimg, D, B(w.w_proj_out), D, B(w.b_proj_out), static_cast<bf16*>(v_out), c.in_channels, si_n,
+                  c.in_channels, D, EPI_BIAS, nullptr, nullptr, 0, st));
+    return 0;
+  }
+  // sequence-parallel: v for this rank's image rows, all-gathered (rows in global token order) so that EVERY rank ends the
+  // forward with the whole v and applies the same Euler update to its copy of the latents
+  if (si_n > 0)
+    CAT_GEMM(gemm1(xnimg, D, B(w.w_proj_out), D, B(w.b_proj_out), h->v_loc + static_cast<long>(st_n) * c.in_channels, c.in_channels,
+                  si_n, c.in_channels, D, EPI_BIAS, nullptr, nullptr, 0, st));
+  CAT_OTHER(comm_allgather(h->sp_comm, h->v_loc, h->v_all, static_cast<size_t>(S) * c.in_channels * 2, st));
+  UTX_CUDA(cudaMemcpyAsync(v_out, h->v_all + static_cast<long>(h->s_txt) * c.in_channels,
+                           static_cast<size_t>(h->s_img) * c.in_channels * 2, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -326,7 +410,7 @@ int step_via_graph(utx_flux* h, void* latents, int s_noise, float t_eff, float g
     const char* e = std::getenv("UTX_FLUX_GRAPH");
     h->use_graph = (e && e[0] == '0') ? 0 : 1;
   }
-  if (!h->use_graph || h->profile) return 0;
+  if (!h->use_graph || h->profile || h->sp_n > 1) return 0;   // (collectives stay outside graphs)
   utx_flux::StepGraph* g = nullptr;
   for (auto& c : h->graphs)
     if (c.latents == latents && c.s_noise == s_noise) g = &c;
@@ -396,6 +480,18 @@ int utx_flux_denoise(utx_flux* h, void* latents, int s_noise, const float* sigma
     CAT_ELEM(euler_update(static_cast<bf16*>(latents), h->v_tmp, s_noise, h->cfg.in_channels, sigmas[i + 1] - sigmas[i],
                           st));
   }
+  return 0;
+}
+
+int utx_flux_set_sequence_parallel(utx_flux* h, utx_comm* comm) {
+  UTX_CHECK(h, "utx_flux_set_sequence_parallel: null handle");
+  const int n = comm ? comm_nranks(comm) : 1;
+  UTX_CHECK(n >= 1 && h->cfg.num_heads % n == 0, "utx_flux_set_sequence_parallel: the world size must divide the number of heads");
+  h->sp_comm = n > 1 ? comm : nullptr;
+  h->sp_n = n;
+  h->sp_rank = n > 1 ? comm_rank(comm) : 0;
+  h->prepared = false;            // the workspace layout depends on the mode: prepare again
+  drop_graphs(h);
   return 0;
 }
 

@@ -20,16 +20,21 @@ namespace utx {
 namespace {
 
 constexpr int BM = 128;        // rows per CTA (256 per pair)
-constexpr int BN = 256;        // tile columns; each CTA stages BN/2 rows of W
 constexpr int BK = 64;
-constexpr int STAGES = 6;
 constexpr int GROUP_M_DEFAULT = 8;   // bands of 8 pair-row-blocks (2048 rows); UTX_GEMM_GROUP_M overrides (tuning knob)
 constexpr int kThreads = 256;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = (BN / 2) * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-constexpr int SMEM_TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+// BN = tile columns (each CTA stages BN/2 rows of W): 256 for every DiT Linear; 128 for the Cout = 128 convolutions of the VAE's
+// 1024^2 stage, where the 1-CTA 128 x 128 tile needs 128 B/clk of shared-memory fill per MMA clock (its whole port) and the
+// pair tile 96 B/clk
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = BN == 256 ? 6 : 8;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
 
 struct DevParams {
   int K, tiles_n, nprob, total_tiles, group_m;
@@ -56,9 +61,11 @@ __device__ __forceinline__ TileCoord decode_tile(const DevParams& p, int t) {
   return tc;
 }
 
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                      const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const DevParams p) {
+  constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, BAR_OFF = Cfg<BN>::BAR_OFF;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
@@ -184,11 +191,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
   }
 }
 
-}  // namespace
-
-// returns -1 when the shape does not fit this kernel (caller falls back to the 1-CTA kernel)
-int gemm2_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
-  if (a.N % BN != 0) return -1;
+template <int BN>
+int launch2(const GemmArgs& a, cudaStream_t stream) {
   DevParams p{};
   p.K = a.K;
   p.tiles_n = a.N / BN;
@@ -210,7 +214,7 @@ int gemm2_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
     const GemmProblem& g = a.prob[i];
     EpiProblem& d = p.prob[i];
     d = EpiProblem{g.M, (g.M + 2 * BM - 1) / (2 * BM), g.C, g.ldc, g.bias, g.gate, g.res, g.ldres, g.split_col, g.C2, g.ldc2,
-                   g.wq, g.wk, g.row_offset};
+                   g.wq, g.wk, g.row_offset, g.sc_hl, g.sc_rows, g.sc_row_base, g.sc_D};
     total += d.tiles_m * p.tiles_n;
     if (a.conv_c > 0) {
       const int bw = a.conv_w < BM ? a.conv_w : BM;
@@ -225,13 +229,28 @@ int gemm2_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
   if (total == 0) return 0;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
-    UTX_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    UTX_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_TOTAL));
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = total < max_pairs ? total : max_pairs;
-  gemm2_bf16_tn_kernel<<<2 * pairs, kThreads, SMEM_TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+  gemm2_bf16_tn_kernel<BN><<<2 * pairs, kThreads, Cfg<BN>::SMEM_TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
   UTX_CUDA(cudaGetLastError());
   return 0;
+}
+
+}  // namespace
+
+// returns -1 when the shape does not fit this kernel (caller falls back to the 1-CTA kernel)
+int gemm2_bf16_tn(const GemmArgs& a, cudaStream_t stream) {
+  if (a.N % 256 == 0) {
+    // few, long tiles (a [4096, 512] x K = 16384 product has 32 tiles of 256 x 256 for 74 CTA pairs): halve the tile width
+    long tiles = 0;
+    for (int i = 0; i < a.nprob; ++i) tiles += static_cast<long>((a.prob[i].M + 2 * BM - 1) / (2 * BM)) * (a.N / 256);
+    if (tiles < num_sms() / 2 && a.qk_cols == 0 && a.prob[0].split_col == 0) return launch2<128>(a, stream);
+    return launch2<256>(a, stream);
+  }
+  if (a.N % 128 == 0 && a.qk_cols == 0) return launch2<128>(a, stream);
+  return -1;
 }
 
 }  // namespace utx

@@ -25,6 +25,11 @@ struct EpiProblem {
   const bf16* wq;      // [128] RMSNorm weights of this problem's q / k heads (qk_cols > 0)
   const bf16* wk;
   int row_offset;      // token index of row 0 (img stream of a grouped launch starts at s_txt)
+  // Sequence-parallel head scatter (sc_hl = 0: off).  Columns [0, 3*sc_D) are q | k | v with sc_D = heads * 128; head h belongs
+  // to peer p = h / sc_hl and the element lands in the all-to-all SEND layout [peer][sc_rows][3][sc_hl * 128]:
+  //   C[((p * sc_rows + sc_row_base + row) * 3 + third) * (sc_hl * 128) + (h % sc_hl) * 128 + c]
+  // so that every peer's share is one contiguous chunk and, once received, reads as a [S, 3 * sc_hl * 128] qkv matrix.
+  int sc_hl, sc_rows, sc_row_base, sc_D;
 };
 struct EpiParams {
   int N, epi, gelu_col_start;
@@ -33,6 +38,15 @@ struct EpiParams {
   const float* cos_t;  // [S, 128] fp32
   const float* sin_t;
 };
+
+__device__ __forceinline__ bf16* epi_dst(const EpiProblem& pr, bf16* crow, int col_shift, int row, int col) {
+  if (pr.sc_hl == 0 || col >= 3 * pr.sc_D) return crow + (col - col_shift);
+  const int third = col / pr.sc_D, within = col - third * pr.sc_D;
+  const int h = within >> 7, c = within & 127;
+  const int peer = h / pr.sc_hl, hl = h - peer * pr.sc_hl;
+  const long w = static_cast<long>(pr.sc_hl) * 128;
+  return pr.C + ((static_cast<long>(peer) * pr.sc_rows + pr.sc_row_base + row) * 3 + third) * w + hl * 128 + c;
+}
 
 __device__ __forceinline__ void epi_store8(const EpiParams& p, const EpiProblem& pr, float (&f)[8], int row, int col,
                                            bf16* crow, int col_shift, const bf16* rrow) {
@@ -55,7 +69,7 @@ __device__ __forceinline__ void epi_store8(const EpiParams& p, const EpiProblem&
     *reinterpret_cast<float4*>(c32 + 4) = make_float4(f[4] * p.out_scale, f[5] * p.out_scale, f[6] * p.out_scale, f[7] * p.out_scale);
     return;
   }
-  *reinterpret_cast<uint4*>(crow + (col - col_shift)) =
+  *reinterpret_cast<uint4*>(epi_dst(pr, crow, col_shift, row, col)) =
       make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
@@ -130,7 +144,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const EpiProbl
             o[j] = x[j] * cv[j] - x[j + 1] * sv[j];
             o[j + 1] = x[j + 1] * cv[j + 1] + x[j] * sv[j + 1];
           }
-          *reinterpret_cast<uint4*>(crow + (col0 + e - col_shift)) =
+          *reinterpret_cast<uint4*>(epi_dst(pr, crow, col_shift, row, col0 + e)) =
               make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
         }
     }

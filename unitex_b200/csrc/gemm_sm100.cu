@@ -232,7 +232,7 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
     const GemmProblem& g = a.prob[i];
     EpiProblem& d = p.prob[i];
     d = EpiProblem{g.M, (g.M + BM - 1) / BM, g.C, g.ldc, g.bias, g.gate, g.res, g.ldres, g.split_col, g.C2, g.ldc2, g.wq, g.wk,
-                   g.row_offset};
+                   g.row_offset, g.sc_hl, g.sc_rows, g.sc_row_base, g.sc_D};
     total += d.tiles_m * p.tiles_n;
     if (a.conv_c > 0) {
       const int bw = a.conv_w < BM ? a.conv_w : BM;
@@ -284,7 +284,7 @@ int gemm_bf16_tn(const GemmArgs& a_in, cudaStream_t stream) {
   // Default: cta_group::2 kernel (256x256 tiles per CTA pair, gemm2_sm100.cu) whenever N % 256 == 0 -- 2-3 % faster at the
   // DiT shapes (profiles/r01_microbench_gemm.json).  UTX_GEMM_IMPL=1 forces the 1-CTA kernel of this file.
   const char* impl = getenv("UTX_GEMM_IMPL");
-  if ((impl == nullptr || impl[0] != '1') && a.N % 256 == 0) {   // plain and implicit-convolution (Cout 256 / 512) problems alike
+  if ((impl == nullptr || impl[0] != '1') && a.N % 128 == 0) {   // plain and implicit-convolution problems alike; N % 256 != 0 -> 256 x 128 pair tiles
     const int r = gemm2_bf16_tn(a, stream);
     if (r >= 0) return r;
   }

@@ -39,6 +39,8 @@ struct GemmProblem {
   const bf16* wq;
   const bf16* wk;
   int row_offset;
+  // sequence-parallel head scatter of the q | k | v columns into the all-to-all send layout (gemm_epilogue.cuh); sc_hl = 0: off
+  int sc_hl, sc_rows, sc_row_base, sc_D;
 };
 struct GemmArgs {
   int N, K;

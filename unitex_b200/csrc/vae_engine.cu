@@ -9,9 +9,12 @@
 // (only conv_in and the encoder's stride-2 convolutions use it), the attention scratch and the GroupNorm statistics.  Sizes
 // come from a dry run of the same traversal (`Run::dry`), so the layout can never disagree with the execution.
 //
-// Mid attention (HW x HW scores, one 512-wide head): scores are produced, normalised and consumed in ROW CHUNKS sized to
-// stay L2-resident (fp32 scores + bf16 probabilities of a chunk <= 48 MB) instead of materialising the 16 384^2 fp32 matrix
-// (1.07 GB at 1024^2; 2.4 GB at the reference's 512 x 3072 strip) as round 1 did.
+// Mid attention (HW x HW scores, one 512-wide head): scores are produced, normalised and consumed in ROW CHUNKS that bound the
+// scratch at 384 MB (fp32 scores + bf16 probabilities of 4096 rows at 1024^2) instead of materialising the whole 16 384^2
+// fp32 matrix (1.07 GB + 0.5 GB at 1024^2; 2.4 + 1.2 GB at the reference's 512 x 3072 strip) as round 1 did.  Chunks are kept
+// LARGE on purpose: the P @ V product of a chunk is an [R, 512] x K = HW GEMM with only R/256 x 4 output tiles, and with
+// L2-sized chunks of 512 rows it ran on 4 of the 74 CTA pairs (82 us per chunk, 5.2 ms per decode for 0.55 TFLOP:
+// profiles/r02_vae_launches.csv); the extra HBM traffic of a chunk that does not fit L2 is ~0.5 ms per decode.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -43,7 +46,7 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 inline int ceil_to(int v, int m) { return (v + m - 1) / m * m; }
-constexpr size_t kAttnChunkBytes = 48u << 20;   // fp32 scores + bf16 probabilities of one row chunk
+constexpr size_t kAttnChunkBytes = 384u << 20;   // fp32 scores + bf16 probabilities of one row chunk
 
 struct Layout {
   size_t act = 0;       // bytes of one activation slot

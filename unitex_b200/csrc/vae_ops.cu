@@ -69,12 +69,21 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; ss[j] = 0.f; }
-  for (long long v = static_cast<long long>(r0) * nv + threadIdx.x; v < static_cast<long long>(r1) * nv; v += blockDim.x) {
-    const uint4 raw = xv[v];
+  // four independent 16-byte loads in flight per thread (with one, the kernel ran at ~1.2 TB/s: profiles/r02_vae_launches.csv,
+  // 187 us per launch against 93 us for the apply pass that moves twice the bytes); blockDim is a multiple of nv, so all of a
+  // thread's vectors hold the same 8 channels
+  const long long vend = static_cast<long long>(r1) * nv, bd = blockDim.x;
+  long long v = static_cast<long long>(r0) * nv + threadIdx.x;
+  auto acc = [&](const uint4 raw) {
     const float f[8] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y), bf16lo(raw.z), bf16hi(raw.z), bf16lo(raw.w), bf16hi(raw.w)};
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+  };
+  for (; v + 3 * bd < vend; v += 4 * bd) {
+    const uint4 q0 = xv[v], q1 = xv[v + bd], q2 = xv[v + 2 * bd], q3 = xv[v + 3 * bd];
+    acc(q0); acc(q1); acc(q2); acc(q3);
   }
+  for (; v < vend; v += bd) acc(xv[v]);
   float* part = sm + threadIdx.x * 16;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { part[j] = s[j]; part[8 + j] = ss[j]; }
@@ -97,26 +106,37 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
   (void)cv;
 }
 
-// per (image, channel) affine of the normalisation: y = x * a + b with a = rstd * gamma, b = beta - mean * rstd * gamma
+// per (image, channel) affine of the normalisation: y = x * a + b with a = rstd * gamma, b = beta - mean * rstd * gamma.
+// One WARP per (image, group): lanes take the chunks k = lane, lane + 32, ... in order, then a fixed shuffle tree -- the same
+// summation order on every run (deterministic), and 32-way parallel (one thread per channel walking all chunks serially took
+// 38 us per launch at 1024^2, 1.1 ms per decode).
 __global__ void __launch_bounds__(256) gn_coef_kernel(const double* __restrict__ partial, int nchunks, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, int HW, int C, int G, int N,
                                                       float* __restrict__ coef /*[N][2][C]*/) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * C) return;
-  const int n = i / C, c = i - n * C;
-  const int cpg = C / G, g = c / cpg;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= N * G) return;
+  const int n = w / G, g = w - n * G;
+  const int cpg = C / G;
   double sa = 0, sb = 0;
-  for (int k = 0; k < nchunks; ++k) {
+  for (int k = lane; k < nchunks; k += 32) {
     const double* o = partial + ((static_cast<long long>(n) * nchunks + k) * G + g) * 2;
     sa += o[0]; sb += o[1];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, off);
+    sb += __shfl_xor_sync(0xffffffffu, sb, off);
   }
   const double cnt = static_cast<double>(HW) * cpg;
   const double m = sa / cnt;
   const double var = sb / cnt - m * m;
   const float rstd = rsqrtf(static_cast<float>(var > 0 ? var : 0) + 1e-6f);
-  const float a = rstd * gamma[c];
-  coef[(static_cast<long long>(n) * 2) * C + c] = a;
-  coef[(static_cast<long long>(n) * 2 + 1) * C + c] = beta[c] - static_cast<float>(m) * a;
+  for (int j = lane; j < cpg; j += 32) {
+    const int c = g * cpg + j;
+    const float a = rstd * gamma[c];
+    coef[(static_cast<long long>(n) * 2) * C + c] = a;
+    coef[(static_cast<long long>(n) * 2 + 1) * C + c] = beta[c] - static_cast<float>(m) * a;
+  }
 }
 
 // y = [silu](x * a + b): one 16-byte vector per thread per step, grid-stride; HBM-bound (read + write once)
@@ -293,7 +313,7 @@ int groupnorm_nhwc(const bf16* x, bf16* y, int N, int HW, int C, int G, const fl
   const int threads = (256 / nv) * nv;
   dim3 grid(nchunks, N);
   gn_stats_kernel<<<grid, threads, (threads * 16 + 2 * C) * sizeof(float), stream>>>(x, HW, C, G, stats_ws);
-  gn_coef_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>(stats_ws, nchunks, gamma, beta, HW, C, G, N, coef);
+  gn_coef_kernel<<<(N * G * 32 + 255) / 256, 256, 0, stream>>>(stats_ws, nchunks, gamma, beta, HW, C, G, N, coef);
   const long long total8 = static_cast<long long>(N) * HW * C / 8;
   long long blocks = (total8 + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 16;

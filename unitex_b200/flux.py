@@ -250,6 +250,8 @@ class FluxTransformer:
         pooled = pooled_projections.reshape(-1).to(self.device, torch.float32).contiguous()
         ids = ids.to(self.device, torch.float32).contiguous()
         nbytes = self.lib.utx_flux_workspace_bytes(self._handle, self.s_txt, self.s_img)
+        if nbytes == 0:
+            raise _lib.UtxError("utx_flux_workspace_bytes: the sequence length must be a multiple of the sequence-parallel world size")
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
         _lib.check(self.lib.utx_flux_prepare(self._handle, self._ws.data_ptr(), nbytes, ids.data_ptr(), enc.data_ptr(),
@@ -274,6 +276,16 @@ class FluxTransformer:
                                              sig.ctypes.data_as(_lib.fp), len(sig) - 1, float(guidance), ops._stream()),
                    "utx_flux_denoise")
         return latents
+
+    def set_sequence_parallel(self, comm=None):
+        """Sequence-parallel ("Ulysses") mode over the ranks of `comm` (a `parallel.TileComm`; None = off): ONE grid's tokens are
+        split over the ranks, see include/unitex_b200.h: utx_flux_set_sequence_parallel.  Every rank then calls prepare /
+        forward / denoise_ with the SAME arguments and ends with the same result.  Call prepare() again afterwards."""
+        self._sp_comm = comm                       # keep the communicator alive as long as the engine uses it
+        _lib.check(self.lib.utx_flux_set_sequence_parallel(self._handle, comm._handle if comm is not None else None),
+                   "utx_flux_set_sequence_parallel")
+        self._ws = None
+        return self
 
     def graph_replays(self) -> int:
         """Denoise steps that ran as one CUDA-graph launch (include/unitex_b200.h: utx_flux_graph_replays)."""
