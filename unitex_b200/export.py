@@ -71,7 +71,10 @@ class VideoExporter:
             V, F = mesh_path
         v = scale_to_bbox(torch.as_tensor(V, dtype=torch.float32, device=self.device), geometry_scale)
         f = torch.as_tensor(F, device=self.device).to(torch.int32).contiguous()
-        vn = vertex_normals(v, f)
+        # once per mesh, on the host: the device's index_add_ accumulates with atomics in an order that changes run to run, and
+        # a last-bit change of a normal can move a uint8 of the normal map -- the control image of the FLUX call -- so the same
+        # asset would not reproduce across processes / ranks (tests/test_gpu_batch.py holds 2 GPUs to the 1-GPU bytes)
+        vn = vertex_normals(v.cpu(), f.cpu()).to(self.device)
         if orbit:                                                              # :922-923
             c2ws = ub.generate_orbit_views_c2ws(n_views + 1, radius=2.8, height=0.0, theta_0=0.0, degree=True)[:n_views]
         else:
