@@ -404,32 +404,39 @@ def bench_single_grid_sp(eng, dev, ids, sig, world, rank, steps):
     from unitex_b200 import parallel as par
     if 24 % world or S_TOT % world:
         return {"unavailable": f"world size {world} does not divide 24 heads / {S_TOT} tokens"}
-    eng.set_sequence_parallel(par.tile_comm(dev))
-    eng.prepare(ids, None, None, s_txt=S_TXT)
-    lat = torch.randn(S_IMG, 64, generator=torch.Generator().manual_seed(63)).to(torch.bfloat16).to(dev)
-    dist.broadcast(lat, 0)
-    for i in range(2):
-        eng.denoise_(lat, S_NOISE, sig[i:i + 2], 3.5)
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        eng.denoise_(lat, S_NOISE, sig[i:i + 2], 3.5)
-    e1.record()
-    dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    chk = lat[:S_NOISE].float().sum().reshape(1)
-    allc = [torch.zeros_like(chk) for _ in range(world)]
-    dist.all_gather(allc, chk)
+    res = {}
+    for mode, direct in (("nccl_all_to_all", False), ("fused_peer_memory", True)):
+        eng.set_sequence_parallel(par.tile_comm(dev), direct=direct)
+        eng.prepare(ids, None, None, s_txt=S_TXT)
+        lat = torch.randn(S_IMG, 64, generator=torch.Generator().manual_seed(63)).to(torch.bfloat16).to(dev)
+        dist.broadcast(lat, 0)
+        for i in range(2):
+            eng.denoise_(lat, S_NOISE, sig[i:i + 2], 3.5)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            eng.denoise_(lat, S_NOISE, sig[i:i + 2], 3.5)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        chk = lat[:S_NOISE].float().sum().reshape(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        ms = t.item() / steps
+        res[mode] = {"value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "checksum": float(chk.item()),
+                     "ranks_agree": bool(all(torch.equal(c, allc[0]) for c in allc)), "finite": bool(torch.isfinite(chk).all())}
     eng.set_sequence_parallel(None)
-    ms = t.item() / steps
-    return {"metric": "single-grid denoise steps/s (one asset over all GPUs)", "value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms,
-            "n_gpus": world, "workload": WORKLOAD, "rows_per_rank": S_TOT // world, "heads_per_rank": 24 // world,
-            "collectives_per_step": "2 all-to-all per block (57 blocks) + 1 all-gather of v, NCCL over NVLink",
-            "ranks_agree": bool(all(torch.equal(c, allc[0]) for c in allc)), "finite": bool(torch.isfinite(chk).all())}
+    best = max(res.values(), key=lambda r: r["value"])
+    return {"metric": "single-grid denoise steps/s (one asset over all GPUs)", "value": best["value"], "unit": UNIT,
+            "ms_per_step": best["ms_per_step"], "n_gpus": world, "workload": WORKLOAD, "rows_per_rank": S_TOT // world,
+            "heads_per_rank": 24 // world, "modes": res, "modes_agree": res["nccl_all_to_all"]["checksum"] == res["fused_peer_memory"]["checksum"],
+            "modes_note": "nccl_all_to_all: 2 NCCL all-to-alls per block around the attention; fused_peer_memory: the QKV GEMM's and the "
+                          "attention kernel's epilogues store into the owning rank's buffers over NVLink, 2 flag barriers per block; "
+                          "both: 1 all-gather of v per step"}
 
 
 def bench_delight(eng, dev, sig):

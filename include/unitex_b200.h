@@ -337,6 +337,24 @@ int utx_comm_alltoall(utx_comm* c, const void* send, void* recv, size_t bytes_pe
 /* out [nranks * bytes_per_rank] (rank-major) <- every rank's tile [bytes_per_rank]; uneven shards are padded by the caller */
 int utx_allgather_tiles(utx_comm* c, const void* tile, void* out, size_t bytes_per_rank, void* stream);
 
+/* Peer memory for the fused compute + exchange kernels of the sequence-parallel mode: a device buffer allocated by one rank
+ * and mapped by the others (CUDA IPC, NVLink P2P inside one box).  alloc (zero-filled) / export a 64-byte handle on the owner;
+ * import / close on the peers; the host shares the handles out of band (torch.distributed.all_gather_object, MPI, ...). */
+int utx_peer_alloc(void** ptr, size_t bytes);
+void utx_peer_free(void* ptr);
+int utx_peer_export(void* ptr, void* handle64 /* host, 64 bytes out */);
+int utx_peer_import(const void* handle64 /* host */, void** ptr);
+void utx_peer_close(void* ptr);
+/* Bytes of the exchange region utx_flux_set_sp_peers expects for this sequence (0 = not in sequence-parallel mode). */
+size_t utx_flux_sp_region_bytes(const utx_flux* h, int s_txt, int s_img);
+/* Direct mode of utx_flux_set_sequence_parallel: regions[r] = rank r's exchange region as mapped into THIS process (host array
+ * [nranks]; regions[rank] is this rank's own utx_peer_alloc'ed buffer).  With it the two all-to-alls around each attention
+ * disappear: the QKV GEMM's epilogue stores every head's q | k | v rows straight into the owning rank's attention input over
+ * NVLink, the attention kernel's epilogue stores its output rows straight into the token owner's activation buffer, and a
+ * flag barrier over peer memory (one tiny kernel) replaces each collective -- the transfers overlap the tiles that are still
+ * being computed.  regions = NULL returns to the NCCL all-to-all data path.  Call utx_flux_prepare again afterwards. */
+int utx_flux_set_sp_peers(utx_flux* h, void* const* regions, size_t region_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,7 @@ def _engine(ocfg, P):
     return FluxTransformer(cfg).load_state_dict(P)
 
 
-def _worker(rank, world, port, s_txt, ref_path):
+def _worker(rank, world, port, s_txt, ref_path, direct):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import torch.distributed as dist
     torch.cuda.set_device(rank)
@@ -40,7 +40,7 @@ def _worker(rank, world, port, s_txt, ref_path):
     try:
         from unitex_b200 import parallel as par
         ocfg, P, ids, enc, lat, s_noise, sig = _problem(s_txt)
-        eng = _engine(ocfg, P).set_sequence_parallel(par.tile_comm(torch.device("cuda", rank)))
+        eng = _engine(ocfg, P).set_sequence_parallel(par.tile_comm(torch.device("cuda", rank)), direct=direct)
         eng.prepare(ids, enc, None, s_txt=s_txt)
         x = lat.cuda().contiguous()
         v = eng.forward(x, 0.62, 3.5)
@@ -49,14 +49,16 @@ def _worker(rank, world, port, s_txt, ref_path):
         ref = torch.load(ref_path)
         assert torch.equal(v.cpu(), ref["v"]), f"rank {rank}: forward differs from the single-GPU engine"
         assert torch.equal(x.cpu(), ref["x"]), f"rank {rank}: denoised latents differ from the single-GPU engine"
+        eng.set_sequence_parallel(None)                      # releases the peer region (collective)
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run under gpurun --gpus 2)")
+@pytest.mark.parametrize("direct", [False, True])  # NCCL all-to-alls / exchanges fused into the epilogues over NVLink peer memory
 @pytest.mark.parametrize("s_txt", [128, 64])      # 704 / 640 tokens: rank 0 holds the text rows + part of the image rows
-def test_two_rank_sequence_parallel_is_bit_identical(lib, tmp_path, s_txt):
+def test_two_rank_sequence_parallel_is_bit_identical(lib, tmp_path, s_txt, direct):
     import torch.multiprocessing as mp
     ocfg, P, ids, enc, lat, s_noise, sig = _problem(s_txt)
     eng = _engine(ocfg, P)
@@ -68,7 +70,7 @@ def test_two_rank_sequence_parallel_is_bit_identical(lib, tmp_path, s_txt):
     ref_path = str(tmp_path / "ref.pt")
     torch.save({"v": v.cpu(), "x": x.cpu()}, ref_path)
     del eng
-    mp.spawn(_worker, args=(2, 29500 + os.getpid() % 2000, s_txt, ref_path), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29500 + os.getpid() % 2000, s_txt, ref_path, direct), nprocs=2, join=True)
 
 
 def test_sequence_parallel_off_is_the_default(lib):

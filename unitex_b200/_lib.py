@@ -81,6 +81,13 @@ _SIGS = {
     "utx_flux_denoise": (i32, [vp, vp, i32, fp, i32, f32, vp]),
     "utx_flux_graph_replays": (C.c_long, [vp]),
     "utx_flux_set_sequence_parallel": (i32, [vp, vp]),
+    "utx_flux_sp_region_bytes": (C.c_size_t, [vp, i32, i32]),
+    "utx_flux_set_sp_peers": (i32, [vp, C.POINTER(vp), C.c_size_t]),
+    "utx_peer_alloc": (i32, [C.POINTER(vp), C.c_size_t]),
+    "utx_peer_free": (None, [vp]),
+    "utx_peer_export": (i32, [vp, vp]),
+    "utx_peer_import": (i32, [vp, C.POINTER(vp)]),
+    "utx_peer_close": (None, [vp]),
     "utx_flux_profile": (i32, [vp, i32]),
     "utx_flux_profile_read": (i32, [vp, C.POINTER(C.c_long), fp, i32]),
     "utx_lora_merge": (i32, [vp, lng, vp, vp, i32, i32, i32, f32, vp]),

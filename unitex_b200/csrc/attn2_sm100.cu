@@ -56,7 +56,7 @@ enum Bar { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL 
 template <int kPolyOf8>
 __global__ void __launch_bounds__(kThreads, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__ out, long ld_out, int S, int H,
-                  float scale_log2) {
+                  float scale_log2, const AttnScatter sc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -291,6 +291,13 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
     const float inv = 1.0f / l;
     const int row = q0 + x * BQ + r;
     bf16* orow = out + static_cast<long>(row) * ld_out + head * HD;
+    if (sc.rows_per_rank > 0) {          // sequence-parallel direct mode: the row's owner receives it over NVLink
+      const int owner = row / sc.rows_per_rank;
+      bf16* base = sc.base[0];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) base = owner == q ? sc.base[q] : base;
+      orow = base + static_cast<long>(row - owner * sc.rows_per_rank) * sc.ld + sc.col0 + head * HD;
+    }
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t ov[32];
@@ -320,7 +327,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
 
 }  // namespace
 
-int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream) {
+int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream,
+                    const AttnScatter* scatter) {
   UTX_CHECK(S > 0 && H > 0, "attention: empty problem");
   UTX_CHECK(ld_qkv >= 3L * H * HD && ld_out % 8 == 0, "attention: bad leading dimensions");
   CUtensorMap tm;
@@ -339,12 +347,14 @@ int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S,
     UTX_CUDA(cudaFuncSetAttribute(attention2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  AttnScatter sc{};
+  if (scatter) sc = *scatter;
   dim3 grid((S + 2 * BQ - 1) / (2 * BQ), H);
   switch (poly) {
-    case 0: attention2_kernel<0><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2); break;
-    case 1: attention2_kernel<1><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2); break;
-    case 3: attention2_kernel<3><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2); break;
-    default: attention2_kernel<2><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2); break;
+    case 0: attention2_kernel<0><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2, sc); break;
+    case 1: attention2_kernel<1><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2, sc); break;
+    case 3: attention2_kernel<3><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2, sc); break;
+    default: attention2_kernel<2><<<grid, kThreads, SMEM_TOTAL, stream>>>(tm, out, ld_out, S, H, scale_log2, sc); break;
   }
   UTX_CUDA(cudaGetLastError());
   return 0;
@@ -353,8 +363,9 @@ int attention2_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S,
 // The engine's attention entry point (kernels.h).  Round 1 kept two more kernels behind UTX_ATTN_IMPL (v1: one query tile per
 // CTA with P through shared memory; v3: S and P double-buffered in TMEM); both lost to this one in situ and were removed
 // from the product library (git history: attn_sm100.cu, attn3_sm100.cu; measurements in profiles/r01_summary.md).
-int attention_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream) {
-  return attention2_bf16(qkv, ld_qkv, out, ld_out, S, H, stream);
+int attention_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream,
+                   const AttnScatter* scatter) {
+  return attention2_bf16(qkv, ld_qkv, out, ld_out, S, H, stream, scatter);
 }
 
 }  // namespace utx

@@ -14,6 +14,7 @@
 
 #include "../../include/unitex_b200.h"
 #include "common.h"
+#include "ptx.cuh"
 
 using namespace utx;
 
@@ -75,7 +76,39 @@ struct utx_comm {
   int nranks = 0, rank = 0;
 };
 
+namespace {
+// Cross-GPU barrier over peer memory (NVLink P2P): thread p of one CTA publishes this rank's epoch in peer p's flag array
+// (after a system-scope fence, so every store this GPU issued before -- the previous kernels' writes into the peers' buffers
+// included: they are complete at the kernel boundary -- is visible first) and then waits until peer p has published the same
+// epoch here.  Bounded by the watchdog: a rank that never arrives becomes a trapped launch error on the others, not a hung box.
+__global__ void __launch_bounds__(32) peer_barrier_kernel(unsigned* const* __restrict__ peer_flags, unsigned* local_flags, int rank,
+                                                          int nranks, unsigned epoch) {
+  const int p = threadIdx.x;
+  if (p >= nranks) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[p] + rank), "r"(epoch) : "memory");
+  const uint64_t t0 = globaltimer_ns();
+  unsigned v = 0, spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local_flags + p) : "memory");
+    if (static_cast<int>(v - epoch) >= 0) break;
+    if ((++spins & 0xffu) == 0 && globaltimer_ns() - t0 > UTX_WATCHDOG_NS) {
+      printf("utx: peer barrier watchdog: rank %d waits for rank %d, epoch %u (has %u)\n", rank, p, epoch, v);
+      __trap();
+    }
+  }
+}
+}  // namespace
+
 namespace utx {
+// flags_dev: device array [nranks] of pointers to every rank's flag array (this process's mappings); local = flags_dev[rank]
+int peer_barrier(unsigned* const* flags_dev, unsigned* local_flags, int rank, int nranks, unsigned epoch, cudaStream_t stream) {
+  UTX_CHECK(nranks >= 1 && nranks <= 32, "peer_barrier: 1..32 ranks");
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(flags_dev, local_flags, rank, nranks, epoch);
+  UTX_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // used by the FLUX engine's sequence-parallel mode (flux_engine.cu)
 int comm_nranks(const utx_comm* c) { return c ? c->nranks : 1; }
 int comm_rank(const utx_comm* c) { return c ? c->rank : 0; }
@@ -132,6 +165,35 @@ void utx_comm_destroy(utx_comm* c) {
   if (!c) return;
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   delete c;
+}
+
+/* ---- peer memory: a device buffer every rank of the box can address (CUDA IPC over NVLink P2P) ---- */
+int utx_peer_alloc(void** ptr, size_t bytes) {
+  UTX_CHECK(ptr && bytes > 0, "utx_peer_alloc: bad argument");
+  UTX_CUDA(cudaMalloc(ptr, bytes));
+  UTX_CUDA(cudaMemset(*ptr, 0, bytes));
+  return 0;
+}
+void utx_peer_free(void* ptr) {
+  if (ptr) cudaFree(ptr);
+}
+int utx_peer_export(void* ptr, void* handle64) {
+  UTX_CHECK(ptr && handle64, "utx_peer_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hnd;
+  UTX_CUDA(cudaIpcGetMemHandle(&hnd, ptr));
+  std::memcpy(handle64, &hnd, 64);
+  return 0;
+}
+int utx_peer_import(const void* handle64, void** ptr) {
+  UTX_CHECK(ptr && handle64, "utx_peer_import: null pointer");
+  cudaIpcMemHandle_t hnd;
+  std::memcpy(&hnd, handle64, 64);
+  UTX_CUDA(cudaIpcOpenMemHandle(ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+void utx_peer_close(void* ptr) {
+  if (ptr) cudaIpcCloseMemHandle(ptr);
 }
 
 int utx_comm_alltoall(utx_comm* c, const void* send, void* recv, size_t bytes_per_peer, void* stream) {

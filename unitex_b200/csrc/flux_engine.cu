@@ -20,6 +20,7 @@ int comm_nranks(const utx_comm* c);
 int comm_rank(const utx_comm* c);
 int comm_alltoall(utx_comm* c, const void* send, void* recv, size_t bytes_per_peer, cudaStream_t stream);
 int comm_allgather(utx_comm* c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream);
+int peer_barrier(unsigned* const* flags_dev, unsigned* local_flags, int rank, int nranks, unsigned epoch, cudaStream_t stream);
 // elementwise.cu: cat[row, p * w + j] = recv[p][row][j]  (the received attention heads of peer p into their columns)
 int sp_unpack_heads(const bf16* recv, bf16* cat, long ld_cat, int rows, int w, int npeers, cudaStream_t stream);
 }  // namespace utx
@@ -38,6 +39,13 @@ struct utx_flux {
   // r0 = 0, S_loc = s_txt + s_img, st_loc = s_txt, si_loc = s_img.
   int r0 = 0, S_loc = 0, st_loc = 0, si_loc = 0, img0 = 0;
   bf16 *qkv_all = nullptr, *attn_all = nullptr, *attn_recv = nullptr, *v_loc = nullptr, *v_all = nullptr;
+  // direct mode: every rank's exchange region (cat | qkv_all | flags) mapped into this process; the epilogues of the QKV GEMM
+  // and of the attention kernel store into the peers' regions, a flag barrier replaces each all-to-all
+  std::vector<uint8_t*> sp_regions;
+  size_t sp_region_bytes = 0;
+  unsigned** sp_flags_dev = nullptr;   // device array [sp_n]: every rank's flag array
+  unsigned sp_epoch = 0;
+  size_t sp_off_cat = 0, sp_off_qkv = 0, sp_off_flags = 0;
   int s_txt = 0, s_img = 0;
   bf16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *cat = nullptr, *ctx0 = nullptr, *v_tmp = nullptr;
   float *cos_t = nullptr, *sin_t = nullptr, *mod = nullptr, *temb = nullptr, *sincos = nullptr, *hvec = nullptr,
@@ -152,16 +160,39 @@ WsLayout ws_layout(const utx_flux_config& c, int s_txt, int s_img, int P) {
   return L;
 }
 
+// direct mode: the q | k | v scatter of `p` targets the peers' attention inputs; rows are then global (r0 + local row)
+void set_peers(const utx_flux* h, GemmProblem& p, int local_row_base) {
+  if (h->sp_regions.empty()) return;
+  for (int r = 0; r < h->sp_n; ++r) p.sc_peer[r] = reinterpret_cast<bf16*>(h->sp_regions[r] + h->sp_off_qkv);
+  p.sc_row_base = h->r0 + local_row_base;
+}
+
+// exchange region of the direct mode: [cat (S_loc x 5D) | qkv_all (S x 3 * (H/P) * 128) | flags]
+struct RegionLayout {
+  size_t cat, qkv_all, flags, total;
+};
+RegionLayout region_layout(const utx_flux_config& c, int s_txt, int s_img, int P) {
+  const size_t S = static_cast<size_t>(s_txt) + s_img, D = D_of(c), Sl = S / P;
+  RegionLayout R{};
+  size_t off = 0;
+  R.cat = off; off += align_up(Sl * (1 + c.mlp_ratio) * D * 2);
+  R.qkv_all = off; off += align_up(Sl * 3 * D * 2);
+  R.flags = off; off += align_up(64 * sizeof(unsigned));
+  R.total = off;
+  return R;
+}
+
 int gemm1(const bf16* A, long lda, const bf16* W, long ldw, const bf16* bias, bf16* C, long ldc, int M, int N, int K,
           int epi, const float* gate, const bf16* res, long ldres, cudaStream_t st, int gelu_start = 0,
           int split_col = 0, bf16* C2 = nullptr, long ldc2 = 0, int qk_cols = 0, const bf16* wq = nullptr,
           const bf16* wk = nullptr, const float* cos_t = nullptr, const float* sin_t = nullptr, int row_offset = 0,
-          int sc_hl = 0, int sc_rows = 0, int sc_D = 0) {
+          int sc_hl = 0, int sc_rows = 0, int sc_D = 0, const utx_flux* peers_of = nullptr) {
   GemmArgs a{};
   a.N = N; a.K = K; a.epi = epi; a.gelu_col_start = gelu_start; a.nprob = 1;
   a.qk_cols = qk_cols; a.cos_t = cos_t; a.sin_t = sin_t;
   a.prob[0] = GemmProblem{A, lda, W, ldw, M, C, ldc, bias, gate, res, ldres, split_col, C2, ldc2, wq, wk, row_offset,
                           sc_hl, sc_rows, 0, sc_D};
+  if (peers_of) set_peers(peers_of, a.prob[0], 0);
   return gemm_bf16_tn(a, st);
 }
 
@@ -185,6 +216,10 @@ int gemm_streams(const utx_flux* h, const bf16* A, long lda, const void* W_txt, 
                           static_cast<const bf16*>(b_img), gate_img, res ? res + st_rows * ldres : nullptr, ldres, 0,
                           nullptr, 0, static_cast<const bf16*>(wq_img), static_cast<const bf16*>(wk_img), h->r0 + h->st_loc,
                           hl, h->S_loc, h->st_loc, D};
+  if (scatter) {
+    set_peers(h, a.prob[0], 0);
+    set_peers(h, a.prob[1], h->st_loc);
+  }
   return gemm_bf16_tn(a, st);
 }
 
@@ -200,6 +235,21 @@ int attention_block(utx_flux* h, cudaStream_t st) {
   }
   const int P = h->sp_n, Hl = H / P, S = h->S_loc * P;
   const size_t w = static_cast<size_t>(Hl) * 128;
+  if (!h->sp_regions.empty()) {
+    // direct mode: the QKV GEMM has stored this rank's rows of every head into the head owner's qkv_all; wait until every peer
+    // has done the same here, run the attention of MY heads over the whole sequence with an epilogue that stores each output row
+    // into the row owner's cat[:, my head columns], and wait again before the out-projection reads the local cat
+    unsigned* local_flags = reinterpret_cast<unsigned*>(h->sp_regions[h->sp_rank] + h->sp_off_flags);
+    CAT_OTHER(peer_barrier(h->sp_flags_dev, local_flags, h->sp_rank, P, ++h->sp_epoch, st));
+    AttnScatter sc{};
+    for (int r = 0; r < P; ++r) sc.base[r] = reinterpret_cast<bf16*>(h->sp_regions[r] + h->sp_off_cat);
+    sc.rows_per_rank = h->S_loc;
+    sc.ld = ldc5;
+    sc.col0 = h->sp_rank * static_cast<int>(w);
+    CAT_ATTN(attention_bf16(h->qkv_all, 3L * w, nullptr, ldc5, S, Hl, st, &sc));
+    CAT_OTHER(peer_barrier(h->sp_flags_dev, local_flags, h->sp_rank, P, ++h->sp_epoch, st));
+    return 0;
+  }
   CAT_OTHER(comm_alltoall(h->sp_comm, h->qkv, h->qkv_all, static_cast<size_t>(h->S_loc) * 3 * w * 2, st));
   CAT_ATTN(attention_bf16(h->qkv_all, 3L * w, h->attn_all, static_cast<long>(w), S, Hl, st));
   CAT_OTHER(comm_alltoall(h->sp_comm, h->attn_all, h->attn_recv, static_cast<size_t>(h->S_loc) * w * 2, st));
@@ -235,6 +285,7 @@ int utx_flux_create(const utx_flux_config* cfg, utx_flux** out) {
 void utx_flux_destroy(utx_flux* h) {
   if (!h) return;
   drop_graphs(h);
+  if (h->sp_flags_dev) cudaFree(h->sp_flags_dev);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
@@ -288,6 +339,19 @@ int utx_flux_prepare(utx_flux* h, void* workspace, size_t workspace_bytes, const
     h->qkv_all = reinterpret_cast<bf16*>(b + L.qkv_all); h->attn_all = reinterpret_cast<bf16*>(b + L.attn_all);
     h->attn_recv = reinterpret_cast<bf16*>(b + L.attn_recv); h->v_loc = reinterpret_cast<bf16*>(b + L.v_loc);
     h->v_all = reinterpret_cast<bf16*>(b + L.v_all);
+  }
+  if (!h->sp_regions.empty()) {
+    const RegionLayout R = region_layout(h->cfg, s_txt, s_img, P);
+    UTX_CHECK(h->sp_region_bytes >= R.total, "utx_flux_prepare: the peer exchange region is too small for this sequence");
+    h->sp_off_cat = R.cat; h->sp_off_qkv = R.qkv_all; h->sp_off_flags = R.flags;
+    uint8_t* mine = h->sp_regions[h->sp_rank];
+    h->cat = reinterpret_cast<bf16*>(mine + R.cat);
+    h->qkv_all = reinterpret_cast<bf16*>(mine + R.qkv_all);
+    std::vector<unsigned*> fl(P);
+    for (int r = 0; r < P; ++r) fl[r] = reinterpret_cast<unsigned*>(h->sp_regions[r] + R.flags);
+    if (!h->sp_flags_dev) UTX_CUDA(cudaMalloc(&h->sp_flags_dev, 32 * sizeof(unsigned*)));
+    UTX_CUDA(cudaMemcpyAsync(h->sp_flags_dev, fl.data(), P * sizeof(unsigned*), cudaMemcpyHostToDevice, st));
+    UTX_CUDA(cudaStreamSynchronize(st));          // fl is a stack object
   }
   drop_graphs(h);                 // buffers, sequence lengths or RoPE table may have changed
   const int D = D_of(h->cfg);
@@ -376,7 +440,7 @@ int forward_impl(utx_flux* h, const void* latents, float t_eff, float g_eff, con
     // (RMSNorm + RoPE of q and k fused into the same epilogue)
     CAT_GEMM(gemm1(h->xn, D, B(b.w_qkvmlp), D, B(b.b_qkvmlp), h->qkv, 3L * D, S, 7 * D, D, EPI_BIAS_GELU, nullptr,
                   nullptr, 0, st, 3 * D, 3 * D, h->cat + D, ldc5, 2 * D, B(b.rms_q), B(b.rms_k), h->cos_t, h->sin_t, h->r0,
-                  sc_hl, S, D));
+                  sc_hl, S, D, sp ? h : nullptr));
     UTX_TRY(attention_block(h, st));
     CAT_GEMM(gemm1(h->cat, ldc5, B(b.w_out), ldc5, B(b.b_out), h->x, D, S, D, 5 * D, EPI_GATE_RES, ms + 2L * D, h->x, D,
                   st));
@@ -490,8 +554,30 @@ int utx_flux_set_sequence_parallel(utx_flux* h, utx_comm* comm) {
   h->sp_comm = n > 1 ? comm : nullptr;
   h->sp_n = n;
   h->sp_rank = n > 1 ? comm_rank(comm) : 0;
+  h->sp_regions.clear();
   h->prepared = false;            // the workspace layout depends on the mode: prepare again
   drop_graphs(h);
+  return 0;
+}
+
+size_t utx_flux_sp_region_bytes(const utx_flux* h, int s_txt, int s_img) {
+  if (!h || h->sp_n <= 1 || (s_txt + s_img) % h->sp_n != 0) return 0;
+  return region_layout(h->cfg, s_txt, s_img, h->sp_n).total;
+}
+
+int utx_flux_set_sp_peers(utx_flux* h, void* const* regions, size_t region_bytes) {
+  UTX_CHECK(h, "utx_flux_set_sp_peers: null handle");
+  h->sp_regions.clear();
+  h->sp_region_bytes = 0;
+  h->prepared = false;
+  drop_graphs(h);
+  if (!regions) return 0;
+  UTX_CHECK(h->sp_n > 1 && h->sp_n <= 8, "utx_flux_set_sp_peers: needs sequence-parallel mode with 2..8 ranks");
+  for (int r = 0; r < h->sp_n; ++r) {
+    UTX_CHECK(regions[r] && (reinterpret_cast<uintptr_t>(regions[r]) & 255) == 0, "utx_flux_set_sp_peers: null / unaligned region");
+    h->sp_regions.push_back(static_cast<uint8_t*>(regions[r]));
+  }
+  h->sp_region_bytes = region_bytes;
   return 0;
 }
 

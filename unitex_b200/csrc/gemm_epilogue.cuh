@@ -30,6 +30,9 @@ struct EpiProblem {
   //   C[((p * sc_rows + sc_row_base + row) * 3 + third) * (sc_hl * 128) + (h % sc_hl) * 128 + c]
   // so that every peer's share is one contiguous chunk and, once received, reads as a [S, 3 * sc_hl * 128] qkv matrix.
   int sc_hl, sc_rows, sc_row_base, sc_D;
+  // direct mode (sc_peer[0] != nullptr): sc_peer[p] = rank p's attention input [S, 3 * sc_hl * 128] mapped over NVLink; the
+  // element goes straight there, at global row sc_row_base + row:  sc_peer[p][((sc_row_base + row) * 3 + third) * w + ...]
+  bf16* sc_peer[8];
 };
 struct EpiParams {
   int N, epi, gelu_col_start;
@@ -45,6 +48,12 @@ __device__ __forceinline__ bf16* epi_dst(const EpiProblem& pr, bf16* crow, int c
   const int h = within >> 7, c = within & 127;
   const int peer = h / pr.sc_hl, hl = h - peer * pr.sc_hl;
   const long w = static_cast<long>(pr.sc_hl) * 128;
+  if (pr.sc_peer[0] != nullptr) {
+    bf16* base = pr.sc_peer[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) base = peer == q ? pr.sc_peer[q] : base;      // (no dynamic indexing of a kernel parameter)
+    return base + ((static_cast<long>(pr.sc_row_base) + row) * 3 + third) * w + hl * 128 + c;
+  }
   return pr.C + ((static_cast<long>(peer) * pr.sc_rows + pr.sc_row_base + row) * 3 + third) * w + hl * 128 + c;
 }
 

@@ -232,7 +232,8 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
     const GemmProblem& g = a.prob[i];
     EpiProblem& d = p.prob[i];
     d = EpiProblem{g.M, (g.M + BM - 1) / BM, g.C, g.ldc, g.bias, g.gate, g.res, g.ldres, g.split_col, g.C2, g.ldc2, g.wq, g.wk,
-                   g.row_offset, g.sc_hl, g.sc_rows, g.sc_row_base, g.sc_D};
+                   g.row_offset, g.sc_hl, g.sc_rows, g.sc_row_base, g.sc_D,
+                   {g.sc_peer[0], g.sc_peer[1], g.sc_peer[2], g.sc_peer[3], g.sc_peer[4], g.sc_peer[5], g.sc_peer[6], g.sc_peer[7]}};
     total += d.tiles_m * p.tiles_n;
     if (a.conv_c > 0) {
       const int bw = a.conv_w < BM ? a.conv_w : BM;

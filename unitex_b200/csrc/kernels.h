@@ -41,6 +41,7 @@ struct GemmProblem {
   int row_offset;
   // sequence-parallel head scatter of the q | k | v columns into the all-to-all send layout (gemm_epilogue.cuh); sc_hl = 0: off
   int sc_hl, sc_rows, sc_row_base, sc_D;
+  bf16* sc_peer[8];   // direct mode: every rank's attention input mapped over NVLink (nullptr: send layout in C)
 };
 struct GemmArgs {
   int N, K;
@@ -61,7 +62,16 @@ int gemm_bf16_tn(const GemmArgs& args, cudaStream_t stream);
 // ------------------------------------------------------------------ fused joint attention (tcgen05 flash attention)
 // qkv: [S, 3*H*128] bf16 (q | k | v, head-major inside each third), already RMS-normed + RoPE'd.
 // out: [S, ld_out] bf16, head h written at columns [h*128, h*128+128).  softmax(q k^T / sqrt(128)) v, no mask.
-int attention_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream);
+// scatter != nullptr (sequence-parallel direct mode): output row r goes to rank r / rows_per_rank's buffer over NVLink,
+// base[owner][(r % rows_per_rank) * ld + col0 + head * 128 ...] instead of `out`
+struct AttnScatter {
+  bf16* base[8];
+  int rows_per_rank;
+  long ld;
+  int col0;
+};
+int attention_bf16(const bf16* qkv, long ld_qkv, bf16* out, long ld_out, int S, int H, cudaStream_t stream,
+                   const AttnScatter* scatter = nullptr);
 
 // ------------------------------------------------------------------ HBM-bound elementwise / reduction kernels
 // y[r,:] = LayerNorm(x[r,:], eps=1e-6, no affine) * (1 + scale) + shift; rows < rows0 use (shift0,scale0), others (shift1,scale1)

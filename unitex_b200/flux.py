@@ -249,6 +249,8 @@ class FluxTransformer:
         enc = encoder_hidden_states.reshape(s_txt, cfg.joint_attention_dim).to(self.device, torch.bfloat16).contiguous()
         pooled = pooled_projections.reshape(-1).to(self.device, torch.float32).contiguous()
         ids = ids.to(self.device, torch.float32).contiguous()
+        if getattr(self, "_sp_direct", False):
+            self._bind_peer_region()
         nbytes = self.lib.utx_flux_workspace_bytes(self._handle, self.s_txt, self.s_img)
         if nbytes == 0:
             raise _lib.UtxError("utx_flux_workspace_bytes: the sequence length must be a multiple of the sequence-parallel world size")
@@ -277,15 +279,36 @@ class FluxTransformer:
                    "utx_flux_denoise")
         return latents
 
-    def set_sequence_parallel(self, comm=None):
+    def set_sequence_parallel(self, comm=None, direct: bool = False):
         """Sequence-parallel ("Ulysses") mode over the ranks of `comm` (a `parallel.TileComm`; None = off): ONE grid's tokens are
         split over the ranks, see include/unitex_b200.h: utx_flux_set_sequence_parallel.  Every rank then calls prepare /
-        forward / denoise_ with the SAME arguments and ends with the same result.  Call prepare() again afterwards."""
+        forward / denoise_ with the SAME arguments and ends with the same result.  Call prepare() again afterwards.
+        direct=True: the exchanges around each attention are fused into the producing kernels' epilogues over NVLink peer memory
+        (utx_flux_set_sp_peers) instead of NCCL all-to-alls; the peer region is allocated at the next prepare()."""
         self._sp_comm = comm                       # keep the communicator alive as long as the engine uses it
+        self._sp_direct = bool(direct) and comm is not None
+        if getattr(self, "_sp_region", None) is not None:
+            _lib.check(self.lib.utx_flux_set_sp_peers(self._handle, None, 0), "utx_flux_set_sp_peers")
+            self._sp_region.close()
+            self._sp_region = None
         _lib.check(self.lib.utx_flux_set_sequence_parallel(self._handle, comm._handle if comm is not None else None),
                    "utx_flux_set_sequence_parallel")
         self._ws = None
         return self
+
+    def _bind_peer_region(self):
+        """direct mode: (re)allocate the peer exchange region for the current sequence and hand the mappings to the engine."""
+        from .parallel import PeerRegion
+        need = self.lib.utx_flux_sp_region_bytes(self._handle, self.s_txt, self.s_img)
+        reg = getattr(self, "_sp_region", None)
+        if reg is not None and reg.nbytes >= need:
+            return
+        if reg is not None:
+            _lib.check(self.lib.utx_flux_set_sp_peers(self._handle, None, 0), "utx_flux_set_sp_peers")
+            reg.close()
+        self._sp_region = PeerRegion(need, self.device)
+        arr = (_lib.vp * len(self._sp_region.ptrs))(*self._sp_region.ptrs)
+        _lib.check(self.lib.utx_flux_set_sp_peers(self._handle, arr, need), "utx_flux_set_sp_peers")
 
     def graph_replays(self) -> int:
         """Denoise steps that ran as one CUDA-graph launch (include/unitex_b200.h: utx_flux_graph_replays)."""

@@ -56,6 +56,60 @@ class TileComm:
             pass
 
 
+class PeerRegion:
+    """A device buffer of `nbytes` on every rank, each mapped into every other rank's address space (`utx_peer_*`: cudaMalloc +
+    CUDA IPC over NVLink P2P).  torch.distributed only carries the 64-byte handles.  `ptrs[r]` = rank r's buffer as seen from
+    this process (`ptrs[rank]` is the local allocation).  Zero-filled; one region per engine handle."""
+
+    def __init__(self, nbytes: int, device):
+        from . import _lib
+        self._lib_mod, self.lib = _lib, _lib.load()
+        self.device = torch.device(device)
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.nbytes = int(nbytes)
+        self.ptrs: List[int] = [0] * self.world
+        with torch.cuda.device(self.device):
+            mine = _lib.vp()
+            _lib.check(self.lib.utx_peer_alloc(C.byref(mine), self.nbytes), "utx_peer_alloc")
+            raw = (C.c_ubyte * 64)()
+            _lib.check(self.lib.utx_peer_export(mine, raw), "utx_peer_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(raw))
+            for r, hb in enumerate(handles):
+                if r == self.rank:
+                    self.ptrs[r] = mine.value
+                else:
+                    p = _lib.vp()
+                    _lib.check(self.lib.utx_peer_import((C.c_ubyte * 64)(*hb), C.byref(p)), "utx_peer_import")
+                    self.ptrs[r] = p.value
+            torch.cuda.synchronize()
+        dist.barrier()                               # every rank has mapped every region before anyone writes
+
+    def close(self):
+        if not self.ptrs:
+            return
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()                           # nobody still writes into a region that is about to go away
+        for r, p in enumerate(self.ptrs):
+            if p and r != self.rank:
+                self.lib.utx_peer_close(p)
+        if self.ptrs[self.rank]:
+            self.lib.utx_peer_free(self.ptrs[self.rank])
+        self.ptrs = []
+
+    def __del__(self):
+        try:
+            if self.ptrs and self.ptrs[self.rank]:
+                for r, p in enumerate(self.ptrs):
+                    if p and r != self.rank:
+                        self.lib.utx_peer_close(p)
+                self.lib.utx_peer_free(self.ptrs[self.rank])
+                self.ptrs = []
+        except Exception:
+            pass
+
+
 _TILE_COMM: Optional[TileComm] = None
 
 
