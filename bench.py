@@ -554,8 +554,8 @@ def bench_vae_decode(dev):
 
 # dram__bytes_read.sum + dram__bytes_write.sum summed over every kernel of ONE bake of the teaser_robot workload, from the ncu pass
 # committed as profiles/r02_bake_teaser_dram.csv (scripts/profile_bake_teaser.py under `ncu --metrics dram__bytes_read.sum,
-# dram__bytes_write.sum,gpu__time_duration.sum`); None until that capture exists
-BAKE_TRAFFIC_BYTES = None
+# dram__bytes_write.sum,gpu__time_duration.sum --profile-from-start off`)
+BAKE_TRAFFIC_BYTES = 1.296e9   # 1163.2 MB read + 133.2 MB written (cold caches between kernels: ncu flushes them)
 
 
 def _two_sphere_mesh():

@@ -8,7 +8,8 @@ for k in gemm2_bf16_tn attention2; do
     python scripts/profile_kernels.py 2 > gpurun_out/${R}_ncu_$k.log 2>&1
   echo "ncu $k exit $?"
 done
-# the implicit-GEMM convolution of the VAE: the third gemm2 launch of a decode is a 512-channel 3x3 convolution at 128^2
-timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:gemm2_bf16_tn -s 40 -c 1 -f -o gpurun_out/${R}_vae_conv_final \
-  python scripts/profile_vae.py > gpurun_out/${R}_ncu_vae.log 2>&1
+# the implicit-GEMM convolution of the VAE (256 -> 256 channels at 1024^2): profile_kernels.py launches it last; with 1 iteration
+# the script issues 2 plain gemm2 launches before it
+timeout -k 10 300 ncu --set full --clock-control none --import-source on -k regex:gemm2_bf16_tn -s 2 -c 1 -f -o gpurun_out/${R}_vae_conv_final \
+  python scripts/profile_kernels.py 1 > gpurun_out/${R}_ncu_vae.log 2>&1
 echo "ncu vae conv exit $?"
