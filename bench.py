@@ -432,8 +432,19 @@ def bench_single_grid_sp(eng, dev, ids, sig, world, rank, steps):
         allc = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(allc, chk)
         ms = t.item() / steps
+        # where the step goes (rank 0's view): the engine's per-launch CUDA events by category; "other" = the exchanges
+        # (all-to-alls + all-gather, or flag barriers + all-gather)
+        eng.profile(True)
+        eng.profile_read(reset=True)
+        for i in range(2):
+            eng.denoise_(lat, S_NOISE, sig[i:i + 2], 3.5)
+        torch.cuda.synchronize()
+        _, cat = eng.profile_read(reset=True)
+        eng.profile(False)
+        dist.barrier()
         res[mode] = {"value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "checksum": float(chk.item()),
-                     "ranks_agree": bool(all(torch.equal(c, allc[0]) for c in allc)), "finite": bool(torch.isfinite(chk).all())}
+                     "ranks_agree": bool(all(torch.equal(c, allc[0]) for c in allc)), "finite": bool(torch.isfinite(chk).all()),
+                     "rank0_ms_per_step": {k: v / 2 for k, v in cat.items()}}
     eng.set_sequence_parallel(None)
     best = max(res.values(), key=lambda r: r["value"])
     return {"metric": "single-grid denoise steps/s (one asset over all GPUs)", "value": best["value"], "unit": UNIT,
