@@ -298,12 +298,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
       for (int q = 1; q < 8; ++q) base = owner == q ? sc.base[q] : base;
       orow = base + static_cast<long>(row - owner * sc.rows_per_rank) * sc.ld + sc.col0 + head * HD;
     }
+    // direct (peer) mode: a row's 256 bytes go out as ONE contiguous burst per 16 lanes instead of 16-byte pieces of 32 rows per
+    // store instruction -- staged through this tile's Q buffer, which no MMA reads any more (O_FULL covers every earlier MMA)
+    const bool staged = sc.rows_per_rank > 0;
+    uint8_t* stage = smem + OFF_Q + x * TILE_BYTES + ew * 8192;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t ov[32];
       tmem_ld32(tO + c * 32, ov);
       tmem_ld_wait();
-      if (row < S) {
+      if (row < S || staged) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 o;
@@ -311,7 +315,25 @@ attention2_kernel(const __grid_constant__ CUtensorMap tm_qkv, bf16* __restrict__
           o.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
           o.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
           o.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+          if (staged) *reinterpret_cast<uint4*>(stage + lane * 256 + (((c * 4 + g) ^ (lane & 15)) << 4)) = o;
+          else *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = o;
+        }
+      }
+    }
+    if (staged) {
+      __syncwarp();
+      const int row0 = q0 + x * BQ + ew * 32;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int idx = i * 32 + lane, rr = idx >> 4, kc = idx & 15;
+        const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * 256 + ((kc ^ (rr & 15)) << 4));
+        const int grow = row0 + rr;
+        if (grow < S) {
+          const int owner = grow / sc.rows_per_rank;
+          bf16* base = sc.base[0];
+#pragma unroll
+          for (int q = 1; q < 8; ++q) base = owner == q ? sc.base[q] : base;
+          *reinterpret_cast<uint4*>(base + static_cast<long>(grow - owner * sc.rows_per_rank) * sc.ld + sc.col0 + head * HD + kc * 8) = v;
         }
       }
     }

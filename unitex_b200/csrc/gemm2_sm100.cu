@@ -33,7 +33,10 @@ struct Cfg {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr int EPI_STAGE_OFF = BAR_OFF + 256;            // 4 epilogue warps x 8 KB: staging of scattered stores (gemm_epilogue.cuh)
+  static constexpr int SMEM_TOTAL = EPI_STAGE_OFF + 4 * 8192 + 1024;
+  static_assert((2 * STAGES + 4) * 8 + 16 <= 256, "barrier block");
+  static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 };
 
 struct DevParams {
@@ -174,7 +177,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
       tc_fence_after();
       const int row = tc.m_blk * (2 * BM) + static_cast<int>(rank) * BM + ew * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-      epilogue_tile<BN>(p.e, pr, taddr, row, tc.n_blk * BN);
+      epilogue_tile<BN>(p.e, pr, taddr, row, tc.n_blk * BN, smem + Cfg<BN>::EPI_STAGE_OFF + ew * 8192);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty[as], 0);   // the leader's MMA thread waits for both CTAs' epilogues

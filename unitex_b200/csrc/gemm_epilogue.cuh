@@ -57,8 +57,30 @@ __device__ __forceinline__ bf16* epi_dst(const EpiProblem& pr, bf16* crow, int c
   return pr.C + ((static_cast<long>(peer) * pr.sc_rows + pr.sc_row_base + row) * 3 + third) * w + hl * 128 + c;
 }
 
+// Staging of scattered stores (sequence-parallel q | k | v): with one accumulator row per thread a store instruction writes 32
+// rows x 16 B -- 32 half-filled sectors at a 2-6 KB stride, which over NVLink (direct mode: the rows go to a PEER's memory) held
+// the QKV GEMM back by 57 % (profiles/r02_summary.md).  Instead a warp parks 128 columns of its 32 rows in 8 KB of shared
+// memory (16-byte chunks XOR-swizzled by the row, conflict-free both ways) and writes them out 2 rows x 256 contiguous bytes per
+// instruction.
+__device__ __forceinline__ void epi_stage16(uint8_t* stage, int lane, int chunk /* 0..15 */, const uint4& v) {
+  *reinterpret_cast<uint4*>(stage + lane * 256 + ((chunk ^ (lane & 15)) << 4)) = v;
+}
+__device__ __forceinline__ void epi_flush128(const EpiProblem& pr, const uint8_t* stage, int row0, int col0, int lane) {
+  __syncwarp();
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int idx = i * 32 + lane, r = idx >> 4, kc = idx & 15;
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 256 + ((kc ^ (r & 15)) << 4));
+    const int row = row0 + r;
+    if (row < pr.M) *reinterpret_cast<uint4*>(epi_dst(pr, nullptr, 0, row, col0 + kc * 8)) = v;
+  }
+  __syncwarp();
+}
+
+// stage != nullptr: the packed result is parked in the warp's staging buffer at 16-byte chunk `stage_chunk` instead of stored
 __device__ __forceinline__ void epi_store8(const EpiParams& p, const EpiProblem& pr, float (&f)[8], int row, int col,
-                                           bf16* crow, int col_shift, const bf16* rrow) {
+                                           bf16* crow, int col_shift, const bf16* rrow, uint8_t* stage = nullptr,
+                                           int stage_chunk = 0) {
   if (p.epi == EPI_BIAS_GELU) {
     if (col >= p.gelu_col_start) {
 #pragma unroll
@@ -78,8 +100,9 @@ __device__ __forceinline__ void epi_store8(const EpiParams& p, const EpiProblem&
     *reinterpret_cast<float4*>(c32 + 4) = make_float4(f[4] * p.out_scale, f[5] * p.out_scale, f[6] * p.out_scale, f[7] * p.out_scale);
     return;
   }
-  *reinterpret_cast<uint4*>(epi_dst(pr, crow, col_shift, row, col)) =
-      make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  const uint4 packed = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  if (stage) epi_stage16(stage, threadIdx.x & 31, stage_chunk, packed);
+  else *reinterpret_cast<uint4*>(epi_dst(pr, crow, col_shift, row, col)) = packed;
 }
 
 __device__ __forceinline__ void epi_add_bias8(const bf16* bias, int col, float (&f)[8]) {
@@ -91,9 +114,14 @@ __device__ __forceinline__ void epi_add_bias8(const bf16* bias, int col, float (
 }
 
 // taddr: TMEM address of this warp's lane quarter at the tile's first accumulator column.  All 32 lanes must call this.
+// stage: 8 KB of shared memory owned by the calling warp (or nullptr): used when this tile's columns are scattered
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& p, const EpiProblem& pr, uint32_t taddr, int row, int n0) {
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, const EpiProblem& pr, uint32_t taddr, int row, int n0,
+                                              uint8_t* stage = nullptr) {
   const bool row_ok = row < pr.M;
+  const int lane = threadIdx.x & 31;
+  const bool staged = stage != nullptr && pr.sc_hl != 0 && n0 < 3 * pr.sc_D;   // tile-uniform: tiles do not straddle 3 * sc_D
+  const int row0 = row - lane;
   bf16* crow;
   int col_shift = 0;
   if (pr.split_col > 0 && n0 >= pr.split_col) {
@@ -113,7 +141,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const EpiProbl
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32(taddr + hc * 128 + c * 32, v[c]);
       tmem_ld_wait();
-      if (!row_ok) continue;
+      if (!row_ok && !staged) continue;          // (staged: every lane takes part in the warp-wide flush; rows >= M are not written)
       float ss = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -153,9 +181,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const EpiProbl
             o[j] = x[j] * cv[j] - x[j + 1] * sv[j];
             o[j + 1] = x[j + 1] * cv[j + 1] + x[j] * sv[j + 1];
           }
-          *reinterpret_cast<uint4*>(epi_dst(pr, crow, col_shift, row, col0 + e)) =
-              make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          const uint4 packed = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          if (staged) epi_stage16(stage, lane, e >> 3, packed);
+          else *reinterpret_cast<uint4*>(epi_dst(pr, crow, col_shift, row, col0 + e)) = packed;
         }
+      if (staged) epi_flush128(pr, stage, row0, col0, lane);
     }
     return;
   }
@@ -165,7 +195,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const EpiProbl
     tmem_ld32(taddr + c * 32, v);
     tmem_ld_wait();
     const int col0 = n0 + c * 32;
-    if (row_ok) {
+    if (row_ok || staged) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int col = col0 + g * 8;
@@ -174,10 +204,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const EpiProbl
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
           epi_add_bias8(pr.bias, col, f);
-          epi_store8(p, pr, f, row, col, crow, col_shift, rrow);
+          epi_store8(p, pr, f, row, col, crow, col_shift, rrow, staged ? stage : nullptr, (c & 3) * 4 + g);
         }
       }
     }
+    if (staged && (c & 3) == 3) epi_flush128(pr, stage, row0, n0 + (c - 3) * 32, lane);   // 128 columns = one head's v (or q / k) block
   }
 }
 
