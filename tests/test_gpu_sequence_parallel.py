@@ -73,6 +73,62 @@ def test_two_rank_sequence_parallel_is_bit_identical(lib, tmp_path, s_txt, direc
     mp.spawn(_worker, args=(2, 29500 + os.getpid() % 2000, s_txt, ref_path, direct), nprocs=2, join=True)
 
 
+def _pipe_call(sp_comm=None):
+    """The public sampler call (PIL in -> VAE encode -> denoise -> VAE decode -> PIL out) on a tiny FLUX + tiny VAE."""
+    import numpy as np
+    from PIL import Image
+    from oracle import vae as ov
+    from flux_piplines.texturing.pipeline import PBRFluxPipeline
+    from unitex_b200.vae import AutoencoderKLB200
+    ocfg, P, *_ = _problem(128)
+    vcfg = ov.VaeConfig.tiny()
+    VP = {k: v.to(torch.bfloat16).float() for k, v in ov.init_params(vcfg, 5).items()}
+    vae = AutoencoderKLB200(VP, vcfg.block_out_channels, vcfg.layers_per_block, vcfg.latent_channels, vcfg.in_channels,
+                            vcfg.norm_num_groups, vcfg.scaling_factor, vcfg.shift_factor)
+    pipe = PBRFluxPipeline(_engine(ocfg, P), vae)
+    g = torch.Generator().manual_seed(1)
+    pipe.load_lora_weights({"transformer.transformer_blocks.0.attn.to_q.lora_A.weight": torch.randn(8, 512, generator=g) * 0.05,
+                            "transformer.transformer_blocks.0.attn.to_q.lora_B.weight": torch.randn(512, 8, generator=g) * 0.05}, adapter_name="texture")
+    pipe.set_adapters(["texture"], [1.0])
+    if sp_comm is not None:
+        pipe.set_sequence_parallel(sp_comm, direct=True)
+    rng = np.random.default_rng(0)
+    ctrl = Image.fromarray(rng.integers(0, 255, (256, 256, 3), dtype=np.uint8))
+    dual = Image.fromarray(rng.integers(0, 255, (128, 128, 3), dtype=np.uint8))
+    img = pipe(prompt="[MVFLUX]", control_image=ctrl, dual_image=dual, height=256, width=256, n_rows=1, n_cols=1,
+               num_inference_steps=3, guidance_scale=3.5, max_sequence_length=128, generator=torch.Generator().manual_seed(63)).images[0]
+    torch.cuda.synchronize()
+    if sp_comm is not None:
+        pipe.set_sequence_parallel(None)
+    return np.asarray(img)
+
+
+def _pipe_worker(rank, world, port, ref_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import numpy as np
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from unitex_b200 import parallel as par
+        img = _pipe_call(par.tile_comm(torch.device("cuda", rank)))
+        assert np.array_equal(img, np.load(ref_path)), f"rank {rank}: the image differs from the single-GPU call"
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run under gpurun --gpus 2)")
+def test_two_rank_pipeline_call_equals_one_gpu(lib, tmp_path):
+    """`PBRFluxPipeline.set_sequence_parallel`: the whole public call with a merged adapter, one asset over two GPUs (fused
+    peer-memory exchanges), returns the single-GPU image byte for byte on every rank."""
+    import numpy as np
+    import torch.multiprocessing as mp
+    ref_path = str(tmp_path / "img.npy")
+    np.save(ref_path, _pipe_call(None))
+    mp.spawn(_pipe_worker, args=(2, 29500 + (os.getpid() + 7) % 2000, ref_path), nprocs=2, join=True)
+
+
 def test_sequence_parallel_off_is_the_default(lib):
     """set_sequence_parallel(None) is the plain engine (and the mode needs a fresh prepare)."""
     ocfg, P, ids, enc, lat, s_noise, sig = _problem(128)

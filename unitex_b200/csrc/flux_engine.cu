@@ -402,8 +402,16 @@ int forward_impl(utx_flux* h, const void* latents, float t_eff, float g_eff, con
   }
   CAT_ELEM(gemv_bf16(B(w.w_p1), B(w.b_p1), h->pooled, h->hvec, D, c.pooled_projection_dim, 0, 0, st));
   CAT_ELEM(gemv_bf16(B(w.w_p2), B(w.b_p2), h->hvec, h->temb, D, D, 1, 1, st));
-  // every adaLN modulation vector of the step in one HBM-bound pass
-  CAT_ELEM(gemv_bf16(B(w.w_mod), B(w.b_mod), h->temb, h->mod, static_cast<int>(n_mod_rows(c)), D, 1, 0, st));
+  // every adaLN modulation vector of the step in one HBM-bound pass (6.5 GB of weights at the real size).  Sequence-parallel:
+  // the rows are independent, so each rank computes its 1/P of them and the vector (4 MB) is all-gathered in place
+  const long n_mod = n_mod_rows(c);
+  if (sp && n_mod % h->sp_n == 0) {
+    const long per = n_mod / h->sp_n, r_off = per * h->sp_rank;
+    CAT_ELEM(gemv_bf16(B(w.w_mod) + r_off * D, B(w.b_mod) + r_off, h->temb, h->mod + r_off, static_cast<int>(per), D, 1, 0, st));
+    CAT_OTHER(comm_allgather(h->sp_comm, h->mod + r_off, h->mod, static_cast<size_t>(per) * 4, st));
+  } else {
+    CAT_ELEM(gemv_bf16(B(w.w_mod), B(w.b_mod), h->temb, h->mod, static_cast<int>(n_mod), D, 1, 0, st));
+  }
 
   // embedders: x = [ctx0 | x_embedder(latents)] (this rank's rows of it)
   if (st_n > 0)

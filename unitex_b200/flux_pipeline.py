@@ -159,6 +159,16 @@ class PBRFluxPipeline:
             adapter_weights = [1.0] * len(adapter_names)
         self._active = tuple((n, float(w)) for n, w in zip(adapter_names, adapter_weights) if float(w) != 0.0)
 
+    def set_sequence_parallel(self, comm=None, direct: bool = True):
+        """ONE asset over all ranks of `comm` (`unitex_b200.parallel.tile_comm(device)`; None = off): every engine of this
+        pipeline -- the base weights and each merged adapter set -- splits the token sequence over the ranks
+        (`FluxTransformer.set_sequence_parallel`).  Every rank then makes the SAME `__call__` with the same arguments and generator
+        seed and gets the same images; the VAE passes are replicated (16 ms against 28 steps)."""
+        self._sp = (comm, bool(direct))
+        for eng in [self.transformer, *self._merged.values()]:
+            eng.set_sequence_parallel(comm, direct=direct)
+        return self
+
     def _engine(self) -> FluxTransformer:
         if not self._active:
             return self.transformer
@@ -168,6 +178,8 @@ class PBRFluxPipeline:
                 # LoRA deltas blend by weight; `modules_to_save` replacements (x_embedder) do not -- the last active adapter's
                 # copy is the one in effect (see FluxTransformer.merge_lora_)
                 eng.merge_lora_(self._adapters[name], w * self._adapter_scale[name], replace_modules=(i == len(self._active) - 1))
+            if getattr(self, "_sp", (None, False))[0] is not None:
+                eng.set_sequence_parallel(self._sp[0], direct=self._sp[1])
             self._merged[self._active] = eng
         return self._merged[self._active]
 
