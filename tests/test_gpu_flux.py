@@ -99,6 +99,33 @@ def test_graph_replay_is_bit_identical_to_eager(lib, monkeypatch):
     assert torch.equal(a, c) and torch.equal(b, c)
 
 
+def test_merge_lora_key_handling(lib):
+    """Adapter files: `.alpha` entries scale their module (kohya style), unknown suffixes / modules raise instead of being
+    broadcast into a bias, `modules_to_save` replacements are applied only when asked (the last active adapter's copy wins)."""
+    fd, fs, ocfg, P, eng, *_ = _setup(layers=(1, 1))
+    n = "transformer_blocks.0.attn.to_q"
+    g = torch.Generator().manual_seed(2)
+    A, B = torch.randn(4, 256, generator=g) * 0.1, torch.randn(256, 4, generator=g) * 0.1
+    k, r0, r1 = eng.where[n]
+    W0 = eng.T["w_" + k][r0:r1].clone()
+    eng.merge_lora_({n + ".lora_A.weight": A, n + ".lora_B.weight": B, n + ".alpha": torch.tensor(2.0)}, 1.0)
+    want = (W0.float().cpu() + (2.0 / 4) * (B @ A)).to(torch.bfloat16)
+    assert (eng.T["w_" + k][r0:r1].cpu().float() - want.float()).abs().max().item() <= 2 ** -7 * want.float().abs().max().item()
+    with pytest.raises(KeyError):
+        eng.merge_lora_({n + ".lora_A.weight": A, n + ".lora_B.weight": B, n + ".dora_scale": torch.ones(256)}, 1.0)
+    with pytest.raises(KeyError):
+        eng.merge_lora_({"no_such_block.lora_A.weight": A, "no_such_block.lora_B.weight": B}, 1.0)
+    xk = eng.where["x_embedder"][0]
+    X0 = eng.T["w_" + xk].clone()
+    rep = {"x_embedder.weight": torch.full((256, 64), 0.5), "x_embedder.bias": torch.zeros(256)}
+    eng.merge_lora_(rep, 1.0, replace_modules=False)
+    assert torch.equal(eng.T["w_" + xk], X0)
+    eng.merge_lora_(rep, 1.0)
+    assert torch.equal(eng.T["w_" + xk].float().cpu(), torch.full((256, 64), 0.5))
+    with pytest.raises(ValueError):
+        eng.merge_lora_({"x_embedder.weight": torch.zeros(3, 3)}, 1.0)
+
+
 def test_product_path_does_not_import_oracle():
     import subprocess, sys
     code = ("import sys; import unitex_b200.flux, unitex_b200.ops; "

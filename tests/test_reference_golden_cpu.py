@@ -245,3 +245,26 @@ def test_preprocess_reference_image_matches_reference(tmp_path):
     assert a_full.shape == tuple(z["pre.rembg_shape"]) and a_small.shape == tuple(z["pre.processed_shape"])
     assert np.array_equal(a_full[::64, ::64], z["pre.rembg_probe"]) and np.array_equal(a_small[::32, ::32], z["pre.processed_probe"])
     assert sha(a_full) == str(z["pre.rembg_sha"]) and sha(a_small) == str(z["pre.processed_sha"])
+
+
+def test_preprocess_reference_image_matte_hook_matches_reference(tmp_path):
+    """An RGB input without alpha + the constructor's `rembg_session` hook (what the reference builds from RMBG-2.0 / rembg,
+    pipeline.py:146-149): the same call the fixture was made with -- `rembg_session(image)` hands back the matte -- so the
+    outputs equal the reference's own `preprocess_reference_image` run byte for byte.  Without a session: a warning, not silence."""
+    import types
+    import warnings
+    from PIL import Image
+    import pipeline as drop_in
+    from tests.glue_fakes import reference_rgba, sha
+    z = np.load(os.path.join(G, "ref_glue.npz"))
+    rgba = Image.fromarray(reference_rgba(), mode="RGBA")
+    src = str(tmp_path / "ref_rgb.png")
+    rgba.convert("RGB").save(src)
+    me = types.SimpleNamespace(rembg_session=lambda image: rgba)
+    drop_in.CustomRGBTextureFullPipeline.preprocess_reference_image(me, str(tmp_path), src)
+    a_full, a_small = np.array(Image.open(tmp_path / "rembg_image.png")), np.array(Image.open(tmp_path / "processed_image.png"))
+    assert sha(a_full) == str(z["pre.rembg_sha"]) and sha(a_small) == str(z["pre.processed_sha"])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        drop_in.CustomRGBTextureFullPipeline.preprocess_reference_image(types.SimpleNamespace(rembg_session=None), str(tmp_path), src)
+    assert any("un-matted" in str(x.message) for x in w)
