@@ -50,6 +50,34 @@ __device__ __forceinline__ bool slab_pass(float te, float tx, float closest) {
   return !(m < te);
 }
 
+// Moller-Trumbore exactly as the reference evaluates it (intersect_test2.slang:26-61): 1e-9 determinant epsilon, u, v and u + v
+// range tests, NO t-range test (quirk a); every product / sum separately rounded (-fmad=false).
+__device__ __forceinline__ bool triangle_hit_dev(const float* __restrict__ vert, const int* __restrict__ tri, int p, const float* o,
+                                                 const float* d, float& t_out, float& u_out, float& v_out) {
+  const float *pa = vert + static_cast<size_t>(tri[p * 3]) * 3, *pb = vert + static_cast<size_t>(tri[p * 3 + 1]) * 3,
+              *pc = vert + static_cast<size_t>(tri[p * 3 + 2]) * 3;
+  float a[3], b[3], c[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { a[k] = pa[k]; b[k] = pb[k]; c[k] = pc[k]; }
+  const float e1x = b[0] - a[0], e1y = b[1] - a[1], e1z = b[2] - a[2];
+  const float e2x = c[0] - a[0], e2y = c[1] - a[1], e2z = c[2] - a[2];
+  const float px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;
+  const float det = dot3f(e1x, e1y, e1z, px, py, pz);
+  const float eps = 1e-9f;
+  if (det > -eps && det < eps) return false;
+  const float idet = 1.0f / det;
+  const float tx = o[0] - a[0], ty = o[1] - a[1], tz = o[2] - a[2];
+  const float u = dot3f(tx, ty, tz, px, py, pz) * idet;
+  if (u < 0 || u > 1) return false;
+  const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+  const float v = dot3f(d[0], d[1], d[2], qx, qy, qz) * idet;
+  if (v < 0 || u + v > 1) return false;
+  t_out = dot3f(e2x, e2y, e2z, qx, qy, qz) * idet;   // no t-range test (reference quirk)
+  u_out = u;
+  v_out = v;
+  return true;
+}
+
 // Traversal layout ("wide" records) written behind the reference-layout nodes by bvh_build / point_bvh_build: one 128 B
 // record per INTERNAL binary node n holding the boxes and references of its (up to) four grandchildren -- a child that is a leaf
 // stays as one entry -- in the order [left part, right part]:
@@ -148,25 +176,8 @@ __device__ __forceinline__ RayHit bvh_trace(const float4* __restrict__ W, const 
       cur_te = pend_te;
     } else {
       const int p = ~ref;
-      const float *pa = vert + static_cast<size_t>(tri[p * 3]) * 3, *pb = vert + static_cast<size_t>(tri[p * 3 + 1]) * 3,
-                  *pc = vert + static_cast<size_t>(tri[p * 3 + 2]) * 3;
-      float a[3], b[3], c[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { a[k] = pa[k]; b[k] = pb[k]; c[k] = pc[k]; }
-      const float e1x = b[0] - a[0], e1y = b[1] - a[1], e1z = b[2] - a[2];
-      const float e2x = c[0] - a[0], e2y = c[1] - a[1], e2z = c[2] - a[2];
-      const float px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;
-      const float det = dot3f(e1x, e1y, e1z, px, py, pz);
-      const float eps = 1e-9f;
-      if (det > -eps && det < eps) continue;
-      const float idet = 1.0f / det;
-      const float tx = o[0] - a[0], ty = o[1] - a[1], tz = o[2] - a[2];
-      const float u = dot3f(tx, ty, tz, px, py, pz) * idet;
-      if (u < 0 || u > 1) continue;
-      const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
-      const float v = dot3f(d[0], d[1], d[2], qx, qy, qz) * idet;
-      if (v < 0 || u + v > 1) continue;
-      const float t = dot3f(e2x, e2y, e2z, qx, qy, qz) * idet;   // no t-range test (reference quirk)
+      float t, u, v;
+      if (!triangle_hit_dev(vert, tri, p, o, d, t, u, v)) continue;
       closest = t < closest ? t : closest;
       h.any = 1; h.tid = p; h.t = closest; h.u = u; h.v = v;   // last accepted leaf wins (reference quirk)
     }

@@ -22,6 +22,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -195,6 +196,152 @@ __global__ void __launch_bounds__(128, UTX_WALK_MIN_BLOCKS) ray_kernel(const int
   d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
   const RayHit h = bvh_trace(wide, vert, tri, o, d);
   if (h.any && h.tid == f) atomicOr(raw_vis_words + (t >> 2), (1u << view) << ((t & 3) * 8));
+}
+
+// ------------------------------------------------------------------------------------------------ leaf grids for parallel rays
+// What the reference's tracer computes, restated (proof below, checked bit for bit at teaser_robot scale by
+// tests/test_gpu_teaser.py against the oracle's literal tree walk):
+//     scan the LEAVES in DESCENDING order of their position g in the Morton-sorted list; a leaf is "visited" iff its OWN box
+//     passes the slab test against the running closest t; a visited leaf whose triangle is hit sets closest = min(closest, t)
+//     and becomes the reported triangle (last accepted leaf wins).
+//  * order: an internal node of the Karras tree covers a contiguous range [first, last] of the sorted leaves, its left child
+//    [first, split], its right child [split + 1, last]; the reference pushes left, right and pops right first
+//    (intersect_test2.slang:104-121), so leaves are reached in strictly descending g;
+//  * ancestors do not matter: boxes nest (the refit takes exact min / max), the slab arithmetic is monotone in the box
+//    coordinates, so te_ancestor <= te_leaf and tx_ancestor >= tx_leaf; an ancestor is popped BEFORE the leaf, when closest is
+//    at least as large; hence "the leaf's own test passes" implies "every ancestor's test passed", and the converse is the
+//    leaf's own test.  (The 64-entry stack of the reference never overflows: its depth is at most the tree depth + 1.)
+// So the hierarchy is only an index for finding the leaves whose boxes a ray can pass -- and for the bake's rays, PARALLEL to a
+// coordinate axis (the six box views the reference bake is hard-wired to, renderer_inverse.py:171,256), a much better index
+// exists: a 2-D grid over the two other axes.  Per view, every leaf is entered into the cells its box rectangle (grown by
+// eps: the 1e-6 the reference substitutes for a zero direction component tilts the slab test by <= 1e-6 * t) overlaps, each
+// cell's list is sorted by descending g, and a ray walks ONE cell's list: ~15 box tests instead of ~300 tree nodes, the same
+// exact slab and Moller-Trumbore arithmetic.  teaser_robot: ray stage 4.28 ms (tree walk) -> 2.2 ms (grid build 0.8 + walk 1.4),
+// bake 9.49 -> 7.60 ms; two-sphere mesh 8.55 -> 6.28 ms; identical output checksums (profiles/r02_summary.md).
+struct GridCfg {
+  int n, G, F;
+  int axis[MAXV];
+};
+struct GridDev {   // written by grid_setup_kernel from the root box
+  float lo[3], scale[3], eps;
+};
+__device__ __forceinline__ int grid_cell(float x, float lo, float scale, int G) {   // monotone non-decreasing in x
+  const float f = floorf((x - lo) * scale);
+  return f < 0.f ? 0 : (f >= static_cast<float>(G) ? G - 1 : static_cast<int>(f));
+}
+__global__ void grid_setup_kernel(const float4* __restrict__ nodes4, int G, GridDev* gd) {
+  const float4 q0 = nodes4[0], q1 = nodes4[1];                       // root = node 0
+  const float lo[3] = {q0.x, q0.y, q0.z}, hi[3] = {q0.w, q1.x, q1.y};
+  float ext = 0.f;
+  for (int a = 0; a < 3; ++a) ext = fmaxf(ext, hi[a] - lo[a]);
+  // rays start 2 sqrt(3) before the texel (renderer_inverse.py:284): every t of interest is below ext + 8
+  gd->eps = 4e-6f * (ext + 8.0f);
+  for (int a = 0; a < 3; ++a) {
+    const float pad = fmaxf((hi[a] - lo[a]) * 1e-3f, 8.0f * gd->eps);
+    gd->lo[a] = lo[a] - pad;
+    gd->scale[a] = static_cast<float>(G) / fmaxf((hi[a] - lo[a]) + 2.0f * pad, 1e-20f);
+  }
+}
+// mode 0: count the leaves per cell; mode 1: write them (slot = start + cursor++)
+template <int kMode>
+__global__ void __launch_bounds__(256) grid_scatter_kernel(const float4* __restrict__ nodes4, const GridCfg gc, const GridDev* __restrict__ gdp,
+                                                           int* __restrict__ count, const int* __restrict__ start, int* __restrict__ list,
+                                                           long long cap) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(gc.n) * gc.F) return;
+  // threads walk the leaves from the LAST one down: the atomics then fill every cell in roughly descending g, which is the
+  // order grid_sort_kernel wants -- its insertion sort is linear on nearly sorted lists and quadratic on reversed ones
+  // (filled in ascending order it took 2.7 ms on teaser_robot, more than the tree walk it replaces saved)
+  const int view = static_cast<int>(idx / gc.F), g = gc.F - 1 - static_cast<int>(idx - static_cast<long long>(view) * gc.F);
+  const GridDev gd = *gdp;
+  const float4* nd = nodes4 + 3 * static_cast<size_t>(gc.F - 1 + g);
+  const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1);
+  const float lo[3] = {q0.x, q0.y, q0.z}, hi[3] = {q0.w, q1.x, q1.y};
+  const int a = gc.axis[view], b = (a + 1) % 3, c = (a + 2) % 3, G = gc.G;
+  const int b0 = grid_cell(lo[b] - gd.eps, gd.lo[b], gd.scale[b], G), b1 = grid_cell(hi[b] + gd.eps, gd.lo[b], gd.scale[b], G);
+  const int c0 = grid_cell(lo[c] - gd.eps, gd.lo[c], gd.scale[c], G), c1 = grid_cell(hi[c] + gd.eps, gd.lo[c], gd.scale[c], G);
+  for (int cc = c0; cc <= c1; ++cc)
+    for (int cb = b0; cb <= b1; ++cb) {
+      const int cell = (view * G + cc) * G + cb;
+      const int k = atomicAdd(count + cell, 1);
+      if (kMode == 1) {
+        const long long slot = static_cast<long long>(start[cell]) + k;
+        if (slot < cap) list[slot] = g;
+      }
+    }
+}
+// A cell whose list is longer than this is left to the tree walk: where the surface is tangent to the view direction (the limb
+// of a sphere) thousands of leaves pile up in one cell; one thread sorting such a list set the time of the whole sort kernel
+// (1.8 ms on teaser_robot, 10 ms on the two-sphere mesh), and a ray scanning it gains nothing over the hierarchy.
+constexpr int GRID_LMAX = 256;
+// One WARP per cell: the list as the atomics filled it (arbitrary order) -> descending g, by rank counting: an element's place
+// is the number of larger elements of its cell (the g of one cell are distinct).  Every lane reads the same list entries
+// (broadcast loads), there is no serial chain -- a one-thread-per-cell insertion sort in global memory took 1.9 ms on
+// teaser_robot because a single unsorted list of 256 entries is ~16 k dependent round trips.
+__global__ void __launch_bounds__(256) grid_sort_kernel(const int* __restrict__ start, int ncells, const int* __restrict__ in,
+                                                        int* __restrict__ out) {
+  const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (cell >= ncells) return;
+  const int k0 = start[cell], n = start[cell + 1] - k0;
+  if (n == 0 || n > GRID_LMAX) return;
+  for (int e = lane; e < n; e += 32) {
+    const int g = in[k0 + e];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += in[k0 + j] > g;
+    out[k0 + rank] = g;
+  }
+}
+__global__ void __launch_bounds__(128) ray_grid_kernel(const int* __restrict__ lists, const int* __restrict__ counts, int T,
+                                                       const float4* __restrict__ rast, const float* __restrict__ pos_in,
+                                                       const float* __restrict__ vert, const int* __restrict__ tri,
+                                                       const float4* __restrict__ nodes4, const GridCfg gc, const GridDev* __restrict__ gdp,
+                                                       const int* __restrict__ start, const int* __restrict__ glist, const Views vw,
+                                                       unsigned* raw_vis_words, int* __restrict__ lists2, int* __restrict__ counts2) {
+  const int view = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= counts[view]) return;
+  const int t = lists[static_cast<size_t>(view) * T + i];
+  const int f = static_cast<int>(rast[t].w) - 1;
+  const float pos[3] = {pos_in[static_cast<size_t>(t) * 3], pos_in[static_cast<size_t>(t) * 3 + 1], pos_in[static_cast<size_t>(t) * 3 + 2]};
+  const float k2s3 = 3.4641016151377544f;   // float32(2 * sqrt(3)), renderer_inverse.py:284
+  const float* dr = vw.dir[view];
+  const float o[3] = {pos[0] - k2s3 * dr[0], pos[1] - k2s3 * dr[1], pos[2] - k2s3 * dr[2]};      // :279-284 (orthographic)
+  const float dl = fmaxf(norm3(dr[0], dr[1], dr[2]), 1e-12f);
+  float d[3] = {dr[0] / dl, dr[1] / dl, dr[2] / dl};                    // F.normalize (:285)
+  const float len = norm3(d[0], d[1], d[2]);                            // the tracer normalises again (intersect_test2.slang:283)
+  d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
+  float inv[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float di = d[k];
+    if (di == 0.0f) di = 0.000001f;      // intersect_test2.slang:18-21
+    inv[k] = 1.0f / di;
+  }
+  const GridDev gd = *gdp;
+  const int a = gc.axis[view], b = (a + 1) % 3, c = (a + 2) % 3, G = gc.G;
+  const int cell = (view * G + grid_cell(o[c], gd.lo[c], gd.scale[c], G)) * G + grid_cell(o[b], gd.lo[b], gd.scale[b], G);
+  const int k0 = start[cell], k1 = start[cell + 1];
+  if (k1 - k0 > GRID_LMAX) {           // crowded cell (unsorted): this ray goes to the tree walk's list
+    lists2[static_cast<size_t>(view) * T + atomicAdd(counts2 + view, 1)] = t;
+    return;
+  }
+  float closest = 1e9f;
+  int htid = -1;
+  for (int k = k0; k < k1; ++k) {
+    const int g = __ldg(glist + k);
+    const float4* nd = nodes4 + 3 * static_cast<size_t>(gc.F - 1 + g);
+    const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1);
+    const float bb[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
+    float te, tx;
+    slab_params(o, inv, bb, te, tx);
+    if (!slab_pass(te, tx, closest)) continue;
+    const int p = __float_as_int(__ldg(nd + 2).x);
+    float th, u, v;
+    if (!triangle_hit_dev(vert, tri, p, o, d, th, u, v)) continue;
+    closest = th < closest ? th : closest;
+    htid = p;                                                            // last accepted leaf wins (reference quirk)
+  }
+  if (htid >= 0 && htid == f) atomicOr(raw_vis_words + (t >> 2), (1u << view) << ((t & 3) * 8));
 }
 
 // k = 3: conv >= 3  <=>  at least one of the 8 ring texels set (9 r - c >= 3, c <= 1)
@@ -710,6 +857,83 @@ int count_flags(const int* flags, int* offs, long long N, void* scan_tmp, size_t
   return 0;
 }
 
+
+// Builds the per-view leaf grids in the free part of the workspace (behind the ray lists) and traces the listed rays through
+// them.  *done stays false when the views are not axis-parallel orthographic ones, the mesh is tiny, or the lists do not fit.
+int trace_with_leaf_grids(const void* nodes, int F, int n_views, const float* view_dirs_host, int perspective, const int* lists, int T,
+                          const float4* rast, const float* vert, const int* tri, const Views& vw, const BakeWs& w, void* workspace,
+                          size_t ws_bytes, unsigned g128, cudaStream_t stream, bool* done) {
+  *done = false;
+  static const int mode = std::getenv("UTX_RAY_IMPL") ? std::atoi(std::getenv("UTX_RAY_IMPL")) : 0;   // 1: always the tree walk (A/B)
+  if (mode == 1 || perspective || F < 256) return 0;
+  GridCfg gc{};
+  gc.n = n_views;
+  gc.F = F;
+  for (int i = 0; i < n_views; ++i) {
+    const double x = view_dirs_host[i * 3], y = view_dirs_host[i * 3 + 1], z = view_dirs_host[i * 3 + 2];
+    const double l = std::sqrt(x * x + y * y + z * z);
+    if (!(l > 0)) return 0;
+    const double dn[3] = {std::fabs(x / l), std::fabs(y / l), std::fabs(z / l)};
+    int a = dn[0] > dn[1] ? (dn[0] > dn[2] ? 0 : 2) : (dn[1] > dn[2] ? 1 : 2);
+    if (dn[(a + 1) % 3] > 5e-7 || dn[(a + 2) % 3] > 5e-7) return 0;      // not parallel to an axis: eps would not cover the tilt
+    gc.axis[i] = a;
+  }
+  int G = 32;
+  while (G < 1024 && static_cast<long long>(G) * G * 2 < F) G *= 2;       // ~2 leaves per cell and view on average
+  static const int g_override = std::getenv("UTX_RAY_GRID") ? std::atoi(std::getenv("UTX_RAY_GRID")) : 0;   // tuning knob
+  if (g_override >= 8 && g_override <= 4096) G = g_override;
+  gc.G = G;
+  const long long ncells = static_cast<long long>(n_views) * G * G;
+  // workspace behind the ray lists [n_views][T]: second ray lists | GridDev | count [ncells] | start [ncells + 1] | scan temp | list [cap]
+  uint8_t* p = w.rest + al(static_cast<size_t>(n_views) * T * 4);
+  int* lists2 = reinterpret_cast<int*>(p);
+  p += al(static_cast<size_t>(n_views) * T * 4);
+  int* counts2 = w.counters + 16;      // (zeroed with the other counters before texel_prep)
+  uint8_t* end = static_cast<uint8_t*>(workspace) + ws_bytes;
+  auto take = [&](size_t b) { uint8_t* q = p; p += al(b); return q; };
+  GridDev* gd = reinterpret_cast<GridDev*>(take(sizeof(GridDev)));
+  int* count = reinterpret_cast<int*>(take(static_cast<size_t>(ncells + 1) * 4));
+  int* start = reinterpret_cast<int*>(take(static_cast<size_t>(ncells + 1) * 4));
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, count, start, static_cast<int>(ncells + 1));
+  void* scan_tmp = take(scan_bytes);
+  if (p >= end) return 0;
+  const long long cap = (end - p) / 8;                       // two lists: as filled, and sorted
+  int* gfill = reinterpret_cast<int*>(p);
+  int* glist = gfill + cap;
+  const float4* nodes4 = reinterpret_cast<const float4*>(nodes);
+  const long long work = static_cast<long long>(n_views) * F;
+  const unsigned gw = static_cast<unsigned>((work + 255) / 256);
+  grid_setup_kernel<<<1, 1, 0, stream>>>(nodes4, G, gd);
+  UTX_CUDA(cudaMemsetAsync(count, 0, static_cast<size_t>(ncells + 1) * 4, stream));
+  grid_scatter_kernel<0><<<gw, 256, 0, stream>>>(nodes4, gc, gd, count, nullptr, nullptr, 0);
+  UTX_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, count, start, static_cast<int>(ncells + 1), stream));
+  int total = 0;
+  UTX_CUDA(cudaMemcpyAsync(&total, start + ncells, 4, cudaMemcpyDeviceToHost, stream));
+  UTX_CUDA(cudaStreamSynchronize(stream));
+  if (total > cap) return 0;
+  UTX_CUDA(cudaMemsetAsync(count, 0, static_cast<size_t>(ncells) * 4, stream));
+  grid_scatter_kernel<1><<<gw, 256, 0, stream>>>(nodes4, gc, gd, count, start, gfill, cap);
+  grid_sort_kernel<<<static_cast<unsigned>((ncells * 32 + 255) / 256), 256, 0, stream>>>(start, static_cast<int>(ncells), gfill, glist);
+  ray_grid_kernel<<<dim3(g128, n_views), 128, 0, stream>>>(lists, w.counters, T, rast, w.pos, vert, tri, nodes4, gc, gd, start, glist, vw,
+                                                           reinterpret_cast<unsigned*>(w.raw), lists2, counts2);
+  // the rays of crowded cells through the hierarchy (blocks beyond the list's length exit at once)
+  const float4* wide = reinterpret_cast<const float4*>(static_cast<const uint8_t*>(nodes) + wide_offset_bytes(F));
+  ray_kernel<<<dim3(g128, n_views), 128, 0, stream>>>(lists2, counts2, T, rast, w.pos, vert, tri, wide, vw,
+                                                      reinterpret_cast<unsigned*>(w.raw));
+  UTX_CUDA(cudaGetLastError());
+  if (std::getenv("UTX_RAY_DEBUG")) {      // diagnosis: rays per view, and how many of them went to the tree walk
+    int c[24];
+    UTX_CUDA(cudaMemcpyAsync(c, w.counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
+    UTX_CUDA(cudaStreamSynchronize(stream));
+    long r = 0, r2 = 0;
+    for (int i = 0; i < n_views; ++i) { r += c[i]; r2 += c[16 + i]; }
+    std::fprintf(stderr, "utx: leaf grids G=%d pairs=%d rays=%ld to_tree_walk=%ld\n", G, total, r, r2);
+  }
+  *done = true;
+  return 0;
+}
+
 }  // namespace
 
 int transform_points(const float* vert, int V, const float* mats, int n, float* out, cudaStream_t stream) {
@@ -771,8 +995,12 @@ int uv_bake_visibility(const float* vert, int V, const int* tri, int F, const vo
   UTX_CUDA(cudaMemsetAsync(w.counters, 0, 256, stream));
   texel_prep_kernel<<<g128, 128, 0, stream>>>(rast, H2, W2, vert, tri, vw, images_rgba, H, W, cos_thresh, w.raw, w.aok, w.pos,
                                               lists, w.counters);
-  ray_kernel<<<dim3(g128, n_views), 128, 0, stream>>>(lists, w.counters, T, rast, w.pos, vert, tri, wide, vw,
-                                                      reinterpret_cast<unsigned*>(w.raw));
+  bool traced = false;
+  UTX_TRY(trace_with_leaf_grids(nodes, F, n_views, view_dirs_host, perspective, lists, T, rast, vert, tri, vw, w, workspace, ws_bytes,
+                                g128, stream, &traced));
+  if (!traced)       // perspective or oblique views, tiny meshes, or a grid that would not fit: the tree walk
+    ray_kernel<<<dim3(g128, n_views), 128, 0, stream>>>(lists, w.counters, T, rast, w.pos, vert, tri, wide, vw,
+                                                        reinterpret_cast<unsigned*>(w.raw));
   repair3_kernel<<<g256, 256, 0, stream>>>(w.raw, w.rep3, H2, W2);
   repair5_kernel<<<g256, 256, 0, stream>>>(w.rep3, w.rep5, H2, W2, n_views);
   compose_kernel<<<g128, 128, 0, stream>>>(rast, T, vert, tri, vw, images_rgba, H, W, w.rep5, w.aok, mask2d, mask_vis, w.owner, w.col_a);

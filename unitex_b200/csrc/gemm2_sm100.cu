@@ -64,7 +64,7 @@ __device__ __forceinline__ TileCoord decode_tile(const DevParams& p, int t) {
   return tc;
 }
 
-template <int BN>
+template <int BN, bool kScatter>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                      const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const DevParams p) {
@@ -177,7 +177,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
       tc_fence_after();
       const int row = tc.m_blk * (2 * BM) + static_cast<int>(rank) * BM + ew * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
-      epilogue_tile<BN>(p.e, pr, taddr, row, tc.n_blk * BN, smem + Cfg<BN>::EPI_STAGE_OFF + ew * 8192);
+      epilogue_tile<BN, kScatter>(p.e, pr, taddr, row, tc.n_blk * BN, smem + Cfg<BN>::EPI_STAGE_OFF + ew * 8192);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty[as], 0);   // the leader's MMA thread waits for both CTAs' epilogues
@@ -233,11 +233,15 @@ int launch2(const GemmArgs& a, cudaStream_t stream) {
   if (total == 0) return 0;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
-    UTX_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_TOTAL));
+    UTX_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_TOTAL));
+    UTX_CUDA(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_TOTAL));
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = total < max_pairs ? total : max_pairs;
-  gemm2_bf16_tn_kernel<BN><<<2 * pairs, kThreads, Cfg<BN>::SMEM_TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+  if (a.prob[0].sc_hl != 0)      // sequence-parallel scatter of q | k | v: its own instantiation (staged stores)
+    gemm2_bf16_tn_kernel<BN, true><<<2 * pairs, kThreads, Cfg<BN>::SMEM_TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+  else
+    gemm2_bf16_tn_kernel<BN, false><<<2 * pairs, kThreads, Cfg<BN>::SMEM_TOTAL, stream>>>(tm[0], tm[1], tm[2], tm[3], p);
   UTX_CUDA(cudaGetLastError());
   return 0;
 }

@@ -42,8 +42,9 @@ struct EpiParams {
   const float* sin_t;
 };
 
+template <bool kScatter = true>
 __device__ __forceinline__ bf16* epi_dst(const EpiProblem& pr, bf16* crow, int col_shift, int row, int col) {
-  if (pr.sc_hl == 0 || col >= 3 * pr.sc_D) return crow + (col - col_shift);
+  if (!kScatter || pr.sc_hl == 0 || col >= 3 * pr.sc_D) return crow + (col - col_shift);
   const int third = col / pr.sc_D, within = col - third * pr.sc_D;
   const int h = within >> 7, c = within & 127;
   const int peer = h / pr.sc_hl, hl = h - peer * pr.sc_hl;
@@ -78,6 +79,7 @@ __device__ __forceinline__ void epi_flush128(const EpiProblem& pr, const uint8_t
 }
 
 // stage != nullptr: the packed result is parked in the warp's staging buffer at 16-byte chunk `stage_chunk` instead of stored
+template <bool kScatter = false>
 __device__ __forceinline__ void epi_store8(const EpiParams& p, const EpiProblem& pr, float (&f)[8], int row, int col,
                                            bf16* crow, int col_shift, const bf16* rrow, uint8_t* stage = nullptr,
                                            int stage_chunk = 0) {
@@ -101,8 +103,8 @@ __device__ __forceinline__ void epi_store8(const EpiParams& p, const EpiProblem&
     return;
   }
   const uint4 packed = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-  if (stage) epi_stage16(stage, threadIdx.x & 31, stage_chunk, packed);
-  else *reinterpret_cast<uint4*>(epi_dst(pr, crow, col_shift, row, col)) = packed;
+  if (kScatter && stage) epi_stage16(stage, threadIdx.x & 31, stage_chunk, packed);
+  else *reinterpret_cast<uint4*>(epi_dst<kScatter>(pr, crow, col_shift, row, col)) = packed;
 }
 
 __device__ __forceinline__ void epi_add_bias8(const bf16* bias, int col, float (&f)[8]) {
@@ -114,13 +116,15 @@ __device__ __forceinline__ void epi_add_bias8(const bf16* bias, int col, float (
 }
 
 // taddr: TMEM address of this warp's lane quarter at the tile's first accumulator column.  All 32 lanes must call this.
-// stage: 8 KB of shared memory owned by the calling warp (or nullptr): used when this tile's columns are scattered
-template <int BN>
+// kScatter: the instantiation the sequence-parallel launches use (pr.sc_hl != 0).  stage: 8 KB of shared memory owned by the
+// calling warp, used when this tile's columns are scattered.  The plain instantiation carries none of that code: with the
+// staging decided at run time the single-block q|k|v|mlp GEMM lost 4-5 % (register pressure in the fused norm-RoPE path).
+template <int BN, bool kScatter = false>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const EpiProblem& pr, uint32_t taddr, int row, int n0,
                                               uint8_t* stage = nullptr) {
   const bool row_ok = row < pr.M;
   const int lane = threadIdx.x & 31;
-  const bool staged = stage != nullptr && pr.sc_hl != 0 && n0 < 3 * pr.sc_D;   // tile-uniform: tiles do not straddle 3 * sc_D
+  const bool staged = kScatter && stage != nullptr && pr.sc_hl != 0 && n0 < 3 * pr.sc_D;   // tile-uniform: tiles do not straddle 3 * sc_D
   const int row0 = row - lane;
   bf16* crow;
   int col_shift = 0;
@@ -183,7 +187,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const EpiProbl
           }
           const uint4 packed = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
           if (staged) epi_stage16(stage, lane, e >> 3, packed);
-          else *reinterpret_cast<uint4*>(epi_dst(pr, crow, col_shift, row, col0 + e)) = packed;
+          else *reinterpret_cast<uint4*>(epi_dst<kScatter>(pr, crow, col_shift, row, col0 + e)) = packed;
         }
       if (staged) epi_flush128(pr, stage, row0, col0, lane);
     }
@@ -204,7 +208,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, const EpiProbl
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
           epi_add_bias8(pr.bias, col, f);
-          epi_store8(p, pr, f, row, col, crow, col_shift, rrow, staged ? stage : nullptr, (c & 3) * 4 + g);
+          epi_store8<kScatter>(p, pr, f, row, col, crow, col_shift, rrow, staged ? stage : nullptr, (c & 3) * 4 + g);
         }
       }
     }

@@ -292,6 +292,7 @@ int gemm_bf16_tn(const GemmArgs& a_in, cudaStream_t stream) {
   UTX_CHECK(a.qk_cols == 0 || (a.qk_cols % 256 == 0 && a.N % 128 == 0 && a.cos_t && a.sin_t && a.epi != EPI_BIAS_F32 &&
                                a.epi != EPI_GATE_RES),
             "gemm: bad fused q/k norm-rope configuration");
+  UTX_CHECK(a.prob[0].sc_hl == 0, "gemm: the sequence-parallel q|k|v scatter is only built into the 2-CTA kernel (N % 128 == 0, UTX_GEMM_IMPL unset)");
   if (a.N % 256 == 0) return launch<256, 4>(a, stream);
   if (a.N % 128 == 0) return launch<128, 6>(a, stream);
   return launch<64, 8>(a, stream);
