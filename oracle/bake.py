@@ -85,6 +85,23 @@ def intersect(vert, tri, info, aabb, rays_o, rays_d):
     return hit.astype(bool), tid, pos, uv
 
 
+def intersect_leafscan(vert, tri, info, aabb, rays_o, rays_d):
+    """`intersect` without the hierarchy: leaves scanned in descending Morton position, each leaf's own box tested against the
+    running closest t (oracle/bake_ref.c: ora_intersect_leafscan).  Must equal `intersect` exactly."""
+    vert = np.ascontiguousarray(vert, np.float32)
+    tri = np.ascontiguousarray(tri, np.int32)
+    o = np.ascontiguousarray(rays_o, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(np.broadcast_to(rays_d, rays_o.shape), np.float32).reshape(-1, 3)
+    N = o.shape[0]
+    hit = np.zeros(N, np.uint8)
+    tid = np.zeros(N, np.int32)
+    pos = np.zeros((N, 3), np.float32)
+    uv = np.zeros((N, 2), np.float32)
+    lib().ora_intersect_leafscan(_ptr(vert), _ptr(tri), _ptr(info), _ptr(aabb), tri.shape[0], _ptr(o), _ptr(d), C.c_int64(N), _ptr(hit),
+                                 _ptr(tid), _ptr(pos), _ptr(uv))
+    return hit.astype(bool), tid, pos, uv
+
+
 # ------------------------------------------------------------------------------------------------ cameras
 def intr_to_proj_ortho(intr: torch.Tensor, near=0.01, far=1000.0) -> torch.Tensor:
     """camera/conversion.py:19-27, perspective=False branch + the y-row negation."""

@@ -348,3 +348,41 @@ void ora_intersect(const float* vert, const int32_t* tri, const int32_t* info, c
     }
   }
 }
+
+/* The same query WITHOUT the hierarchy: scan the leaves in descending order of their position g in the Morton-sorted list and
+ * test each leaf's own box against the running closest t.  Identical results to ora_intersect (tests/test_oracle_bake.py):
+ * the right-first depth-first walk reaches leaves in descending g, and because boxes nest and closest only shrinks, a leaf's own
+ * test passing implies every ancestor's test passed.  This is the statement the product's leaf-grid ray kernel rests on. */
+void ora_intersect_leafscan(const float* vert, const int32_t* tri, const int32_t* info, const float* aabb, int F, const float* rays_o,
+                            const float* rays_d, int64_t N, uint8_t* hit, int32_t* tid, float* pos, float* uv) {
+  const int LEAF = F - 1;
+  for (int64_t r = 0; r < N; ++r) {
+    v3 o = {rays_o[r * 3], rays_o[r * 3 + 1], rays_o[r * 3 + 2]};
+    v3 d = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
+    float len = sqrtf(dot3(d, d));
+    d.x = d.x / len; d.y = d.y / len; d.z = d.z / len;
+    float closest = 1e9f, hit_t = 0.f, hu = 0.f, hv = 0.f;
+    int any = 0, htid = -1;
+    for (int g = F - 1; g >= 0; --g) {
+      const int n = LEAF + g;
+      if (!aabb_hit(o, d, 0.0f, closest, aabb + (size_t)n * 6)) continue;
+      int p = info[n * 3 + 2];
+      const float *a = vert + (size_t)tri[p * 3] * 3, *b = vert + (size_t)tri[p * 3 + 1] * 3, *c = vert + (size_t)tri[p * 3 + 2] * 3;
+      v3 v0 = {a[0], a[1], a[2]}, v1 = {b[0], b[1], b[2]}, v2 = {c[0], c[1], c[2]};
+      float t, u, v;
+      if (triangle_hit(o, d, v0, v1, v2, &t, &u, &v)) {
+        closest = t < closest ? t : closest;
+        any = 1; htid = p; hit_t = closest; hu = u; hv = v;
+      }
+    }
+    hit[r] = (uint8_t)any;
+    tid[r] = any ? htid : -1;
+    if (any) {
+      pos[r * 3] = o.x + hit_t * d.x; pos[r * 3 + 1] = o.y + hit_t * d.y; pos[r * 3 + 2] = o.z + hit_t * d.z;
+      uv[r * 2] = hu; uv[r * 2 + 1] = hv;
+    } else {
+      pos[r * 3] = pos[r * 3 + 1] = pos[r * 3 + 2] = 0.f; uv[r * 2] = uv[r * 2 + 1] = 0.f;
+    }
+  }
+}
+
