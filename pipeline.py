@@ -2,9 +2,9 @@
 run.py:1-10) over the B200-native hot path.  Same constructor / `__call__(save_dir, input_image_path, input_mesh_path,
 clear_cache)` signature, same step sequence ['step_1_1', 'step_2_ablition'], same cache file names.
 
-What is NOT re-implemented (out of scope, CPU third-party): background matting (rembg / RMBG-2.0), mesh
-decimation + UV unwrapping (open3d / xatlas), the orbit mp4, super-resolution (TSD_SR).  The corresponding steps do the
-minimum the hot path needs: the reference image is resized/padded on a grey canvas, the mesh must already carry UVs.
+What is NOT re-implemented (out of scope, CPU third-party): background matting (rembg / RMBG-2.0: a `rembg_session`
+hook takes the reference's own object), mesh decimation + chart-based UV unwrapping (open3d / xatlas: a UV-less mesh gets a
+per-triangle atlas instead, unitex_b200/uv_atlas.py), the orbit mp4, super-resolution (TSD_SR).
 """
 from __future__ import annotations
 
@@ -104,10 +104,17 @@ class RGBTextureFullPipelineBase:
     def preprocess_blank_mesh(self, save_dir, input_mesh_path, min_faces=20_000, max_faces=200_000, scale=0.95):
         """reference :170-179 -> geometry/uv/uv_atlas.py:131-194: the bounding box is centred and its longest side scaled to
         2*scale (float64, like the open3d transform there) -- the bake's cameras assume that frame -- and the mesh is written as
-        processed_mesh.obj.  The UV unwrap of meshes without UVs (open3d compute_uvatlas [ext]) is out of scope: UVs are required."""
+        processed_mesh.obj.  A mesh without UVs gets a per-triangle atlas (the reference's open3d clean-up / decimation /
+        compute_uvatlas chain [ext] is out of scope), with a warning."""
         V, F, UV, Ft = ub.load_mesh(input_mesh_path)           # .obj or .glb, like the reference's test cases
         if len(UV) == 0:
-            raise NotImplementedError("mesh without UVs: UV-atlas generation (open3d/xatlas) is out of scope")
+            # the reference unwraps with open3d / UVAtlas after cleaning and decimating (uv_atlas.py:149-175: CPU third party, out
+            # of scope); here the mesh gets the simplest valid atlas, one slot per triangle (unitex_b200/uv_atlas.py)
+            from unitex_b200.uv_atlas import per_triangle_atlas
+            warnings.warn("preprocess_blank_mesh: the mesh has no UVs -- the reference would decimate it to <= 200 000 faces and unwrap it "
+                          "with open3d's compute_uvatlas; here every triangle gets its own atlas slot (a valid but less economical "
+                          "layout, every edge a seam)", stacklevel=2)
+            UV, Ft = per_triangle_atlas(len(F), 2048)
         V = np.asarray(V, dtype=np.float64)
         aaa, bbb = V.min(0), V.max(0)
         sss = (bbb - aaa).max() / (2.0 * scale)

@@ -112,3 +112,32 @@ def test_obj_reader_bulk_and_fallback_paths(tmp_path):
     open(n, "w").write("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//1 3//1\n")
     V, F, UV, Ft = ub.load_obj(n)
     assert F.tolist() == [[0, 1, 2]] and len(UV) == 0
+
+
+def test_per_triangle_atlas_is_a_valid_layout():
+    """UV-less meshes (the reference unwraps them with open3d / UVAtlas, uv_atlas.py:149-175 [ext]): every triangle gets its own
+    slot; slots do not overlap (checked with the oracle's rasteriser: every covered texel's barycentrics lie inside its own
+    triangle and the covered area equals the sum of the triangles' areas), stay inside the unit square and keep their gutters."""
+    import numpy as np
+    from oracle import bake as ob
+    from unitex_b200.uv_atlas import per_triangle_atlas
+    n = 1999
+    uv, ft = per_triangle_atlas(n, 512)
+    assert uv.shape == (3 * n, 2) and ft.shape == (n, 3) and uv.min() > 0 and uv.max() < 1
+    t = uv[ft] * 512.0                                                     # [F, 3, 2] texel coordinates
+    e1, e2 = t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]
+    area = 0.5 * (e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0])
+    assert (area > 1.0).all()                                              # counter-clockwise, more than a texel each
+    clip = np.concatenate([uv * 2 - 1, np.zeros((len(uv), 1), np.float32), np.ones((len(uv), 1), np.float32)], -1)[None].astype(np.float32)
+    rast = ob.rasterize(clip, ft, 512, 512)
+    tid = rast[0, ..., 3].astype(np.int64) - 1
+    assert set(np.unique(tid[tid >= 0])) == set(range(n))                  # every face owns at least one texel
+    # a texel centre inside two triangles would show up as covered area in excess of the sum of the areas (up to edge texels)
+    assert (tid >= 0).sum() <= area.sum() + 2.0 * n
+    # gutters: no two different faces on 4-adjacent texels
+    a, b = tid[:, :-1], tid[:, 1:]
+    assert not ((a >= 0) & (b >= 0) & (a != b)).any()
+    a, b = tid[:-1], tid[1:]
+    assert not ((a >= 0) & (b >= 0) & (a != b)).any()
+    with np.testing.assert_raises(ValueError):
+        per_triangle_atlas(400_000, 2048)                                  # 4-texel cells: refuse, the mesh has to be decimated first

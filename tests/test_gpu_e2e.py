@@ -41,3 +41,27 @@ def test_custom_rgb_texture_full_pipeline(lib, tmp_path):
     vis = np.asarray(Image.open(os.path.join(cache, "wo_LTM", "visable_uv_mask.png")))
     assert valid.shape == (2048, 2048) and (vis > 0).sum() > 0.5 * (valid > 0).sum()
     assert struct.unpack("<I", open(glb, "rb").read(4))[0] == 0x46546C67
+
+
+def test_full_pipeline_on_a_mesh_without_uvs(lib, tmp_path):
+    """A UV-less mesh goes through the drop-in call too: per-triangle atlas (unitex_b200/uv_atlas.py) instead of the reference's
+    open3d / UVAtlas chain [ext], with a warning; every cache file and the GLB are written, most covered texels are seen by a view."""
+    from PIL import Image
+    from pipeline import CustomRGBTextureFullPipeline
+    from unitex_b200.export import save_obj
+    from unitex_b200.flux import FluxConfig
+    v, f, _, _ = two_spheres(16, 32)
+    mesh_path, img_path = str(tmp_path / "mesh.obj"), str(tmp_path / "image.png")
+    save_obj(mesh_path, v, f)                                              # no vt lines
+    Image.fromarray(np.random.default_rng(1).integers(0, 255, (128, 128, 3), dtype=np.uint8)).save(img_path)
+    cfg = FluxConfig(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=256, pooled_projection_dim=64)
+    pipe = CustomRGBTextureFullPipeline(pretrain_models=cfg, seed=63)
+    pipe.pipeline._num_inference_steps = 2
+    with pytest.warns(UserWarning, match="no UVs"):
+        png, glb = pipe(str(tmp_path / "out"), img_path, mesh_path)
+    torch.cuda.synchronize()
+    assert os.path.exists(glb) and struct.unpack("<I", open(glb, "rb").read(4))[0] == 0x46546C67
+    cache = os.path.join(str(tmp_path / "out"), "cache", "wo_LTM")
+    valid = np.asarray(Image.open(os.path.join(cache, "valid_uv_mask.png")))
+    vis = np.asarray(Image.open(os.path.join(cache, "visable_uv_mask.png")))
+    assert (valid > 0).sum() > 20_000 and (vis > 0).sum() > 0.5 * (valid > 0).sum()
