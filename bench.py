@@ -569,9 +569,10 @@ def bench_vae_decode(dev):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum summed over every kernel of ONE bake of the teaser_robot workload, from the ncu pass
-# committed as profiles/r02_bake_teaser_dram.csv (scripts/profile_bake_teaser.py under `ncu --metrics dram__bytes_read.sum,
+# committed as profiles/r02_bake_launches_final.csv (scripts/profile_bake_teaser.py under `ncu --metrics dram__bytes_read.sum,
 # dram__bytes_write.sum,gpu__time_duration.sum --profile-from-start off`)
-BAKE_TRAFFIC_BYTES = 1.296e9   # 1163.2 MB read + 133.2 MB written (cold caches between kernels: ncu flushes them)
+BAKE_TRAFFIC_BYTES = 1.902e9   # 1553.0 MB read + 349.2 MB written (cold caches between kernels: ncu flushes them); the leaf grids of the
+                               # ray stage trade 0.6 GB of extra list traffic for 2 ms (the tree walk of round 1: 1.30 GB)
 
 
 def _two_sphere_mesh():
@@ -656,7 +657,7 @@ def bench_uv_bake(dev, return_tensors=False, mesh_name="teaser_robot", reps=20):
                        "nn_queries": int((nn >= 0).sum())},
             "roofline": {"bound": "hbm", "achieved": algo / (gpu_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                          "frac": algo / (gpu_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": algo, "traffic": traffic,
-                         "traffic_source": "profiles/r02_bake_teaser_dram.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum over every kernel of one bake)" if traffic else None,
+                         "traffic_source": "profiles/r02_bake_launches_final.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum over every kernel of one bake)" if traffic else None,
                          "note": "compulsory bytes of SURVEY 8d; the bake is BVH-traversal (latency) bound, not streaming"},
             "mrays_per_s": 6 * covered / 1e6 / (gpu_ms * 1e-3)}
 
