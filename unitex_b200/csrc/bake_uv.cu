@@ -554,40 +554,50 @@ __device__ __forceinline__ void nn_query_run_coop(const float q[3], const PointT
     if (ref < 0) {
       const int c = ~ref;
       const int j0 = c * PT_CLUSTER, j1 = min(j0 + PT_CLUSTER, pt.n);
-      for (int j = j0; j < j1; ++j) {
-        const float4 p = __ldg(pt.spts + j);                             // broadcast load
+      auto score = [&](const float4 p) {
         const float dx = p.x - q[0], dy = p.y - q[1], dz = p.z - q[2];
         const float d2 = (dx * dx + dy * dy) + dz * dz;
         const int id = __float_as_int(p.w);
         if (d2 < best || (d2 == best && id < best_id) || best_id < 0) { best = d2; best_id = id; }
+      };
+      if (j1 - j0 == PT_CLUSTER) {                                         // full leaf: all its loads in flight at once
+        float4 pbuf[PT_CLUSTER];
+#pragma unroll
+        for (int j = 0; j < PT_CLUSTER; ++j) pbuf[j] = __ldg(pt.spts + j0 + j);   // broadcast loads
+#pragma unroll
+        for (int j = 0; j < PT_CLUSTER; ++j) score(pbuf[j]);
+      } else {
+        for (int j = j0; j < j1; ++j) score(__ldg(pt.spts + j));
       }
       wbest = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(best)));   // non-negative floats order like their bits
       continue;
     }
     const WideRec r = wide_load(pt.wide, ref);                           // broadcast load
-    int e_ref[4];
-    float e_b[4];
-    int n_e = 0;
+    // per entry: the smallest bound over the lanes, or INFINITY when the slot is unused or no lane needs it (all warp-uniform)
+    float mb[4];
+    int rf[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (r.ref[k] == WIDE_EMPTY) continue;                              // warp-uniform
-      const float bd = box_dist2(r.bb + 6 * k, q) * 0.999999f;
-      const bool need = bd <= best;
-      if (__ballot_sync(FULL, need) == 0u) continue;
-      const float mb = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(bd)));
-      // insertion into e_* kept DESCENDING by bound, so the nearest entry ends up last (visited next) and the others are
-      // pushed farthest first (popped nearest first)
-      int j = n_e++;
-      while (j > 0 && e_b[j - 1] < mb) { e_b[j] = e_b[j - 1]; e_ref[j] = e_ref[j - 1]; --j; }
-      e_b[j] = mb;
-      e_ref[j] = r.ref[k];
+      const bool used = r.ref[k] != WIDE_EMPTY;                          // warp-uniform
+      const float bd = used ? box_dist2(r.bb + 6 * k, q) * 0.999999f : INFINITY;
+      const bool any = __ballot_sync(FULL, bd <= best) != 0u;
+      const float m = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(bd)));
+      mb[k] = (used && any) ? m : INFINITY;
+      rf[k] = r.ref[k];
     }
-    if (n_e == 0) continue;
-    for (int j = 0; j + 1 < n_e; ++j)
-      if (count < 64) { s_ref[count] = e_ref[j]; s_bound[count] = e_b[j]; ++count; }
+    // 4-element sorting network, DESCENDING by bound (registers only): the nearest entry ends up in slot 3 and is visited next,
+    // the others are pushed farthest first (popped nearest first); INFINITY entries sort to the front and are skipped
+#define UTX_CSWAP(a, b)                                                            \
+    if (mb[a] < mb[b]) { const float tf = mb[a]; mb[a] = mb[b]; mb[b] = tf; const int ti = rf[a]; rf[a] = rf[b]; rf[b] = ti; }
+    UTX_CSWAP(0, 1) UTX_CSWAP(2, 3) UTX_CSWAP(0, 2) UTX_CSWAP(1, 3) UTX_CSWAP(1, 2)
+#undef UTX_CSWAP
+    if (mb[3] == INFINITY) continue;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (mb[j] < INFINITY && count < 64) { s_ref[count] = rf[j]; s_bound[count] = mb[j]; ++count; }
     have = true;
-    ref = e_ref[n_e - 1];
-    bound = e_b[n_e - 1];
+    ref = rf[3];
+    bound = mb[3];
   }
   best_out = best;
   best_id_out = best_id;
