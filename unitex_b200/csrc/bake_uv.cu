@@ -327,19 +327,32 @@ __global__ void __launch_bounds__(128) ray_grid_kernel(const int* __restrict__ l
   }
   float closest = 1e9f;
   int htid = -1;
-  for (int k = k0; k < k1; ++k) {
-    const int g = __ldg(glist + k);
-    const float4* nd = nodes4 + 3 * static_cast<size_t>(gc.F - 1 + g);
-    const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1);
+  // one candidate: its own box against the running closest t, then (rarely) the triangle; strictly in list order
+  auto visit = [&](const float4* nd, const float4 q0, const float4 q1) {
     const float bb[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
     float te, tx;
     slab_params(o, inv, bb, te, tx);
-    if (!slab_pass(te, tx, closest)) continue;
+    if (!slab_pass(te, tx, closest)) return;
     const int p = __float_as_int(__ldg(nd + 2).x);
     float th, u, v;
-    if (!triangle_hit_dev(vert, tri, p, o, d, th, u, v)) continue;
+    if (!triangle_hit_dev(vert, tri, p, o, d, th, u, v)) return;
     closest = th < closest ? th : closest;
     htid = p;                                                            // last accepted leaf wins (reference quirk)
+  };
+  int k = k0;
+  for (; k + 4 <= k1; k += 4) {                                           // four candidates' boxes in flight at once
+    const float4* nd[4];
+    float4 q0[4], q1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) nd[j] = nodes4 + 3 * static_cast<size_t>(gc.F - 1 + __ldg(glist + k + j));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { q0[j] = __ldg(nd[j]); q1[j] = __ldg(nd[j] + 1); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) visit(nd[j], q0[j], q1[j]);
+  }
+  for (; k < k1; ++k) {
+    const float4* nd = nodes4 + 3 * static_cast<size_t>(gc.F - 1 + __ldg(glist + k));
+    visit(nd, __ldg(nd), __ldg(nd + 1));
   }
   if (htid >= 0 && htid == f) atomicOr(raw_vis_words + (t >> 2), (1u << view) << ((t & 3) * 8));
 }
