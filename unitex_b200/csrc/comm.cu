@@ -1,7 +1,12 @@
-// The path's one exchange as a C-ABI call: every rank contributes its finished uint8 view tile and receives all of them
-// (north_star: "a single NCCL all-gather of decoded tiles before UV projection").  Thin on purpose: the data plane
-// is one ncclAllGather over NVLink / NVSwitch of a few MB per asset batch -- latency-bound, nothing to fuse it with (the VAE
-// decode before it and the bake after it are per-asset local).
+// The multi-GPU plane of the library.
+//  * utx_allgather_tiles: the batch-sharded path's one exchange -- every rank contributes its finished uint8 view tile and
+//    receives all of them (north_star: "a single NCCL all-gather of decoded tiles before UV projection").  Thin on purpose: one
+//    ncclAllGather over NVLink / NVSwitch of a few MB per asset batch, latency-bound, nothing to fuse it with (the VAE decode
+//    before it and the bake after it are per-asset local).
+//  * utx_comm_alltoall / comm_allgather: the collectives of the engine's sequence-parallel mode (flux_engine.cu).
+//  * utx_peer_* + peer_barrier: CUDA-IPC peer regions and a flag barrier over them for the FUSED form of that mode, where the
+//    QKV GEMM's and the attention kernel's epilogues store straight into the peers' buffers and no collective is left around the
+//    attention.
 //
 // NCCL is resolved at run time (dlopen of libnccl.so.2: the copy torch already mapped when the caller is a torch process, the
 // system one otherwise), so the library links and loads on a box without NCCL and only these entry points fail there.
