@@ -180,8 +180,9 @@ __global__ void __launch_bounds__(128, UTX_WALK_MIN_BLOCKS) ray_kernel(const int
                                                   const float* __restrict__ vert, const int* __restrict__ tri,
                                                   const float4* __restrict__ wide, const Views vw, unsigned* raw_vis_words) {
   const int view = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= counts[view]) return;
+  // grid-stride over the view's list: the leaf-grid path hands this kernel a short list of unknown length (the rays of crowded
+  // cells) and launches a small grid instead of one thread per possible ray
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x, n_list = counts[view]; i < n_list; i += gridDim.x * blockDim.x) {
   const int t = lists[static_cast<size_t>(view) * T + i];
   const int f = static_cast<int>(rast[t].w) - 1;
   const float pos[3] = {pos_in[static_cast<size_t>(t) * 3], pos_in[static_cast<size_t>(t) * 3 + 1], pos_in[static_cast<size_t>(t) * 3 + 2]};
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(128, UTX_WALK_MIN_BLOCKS) ray_kernel(const int
   d[0] = d[0] / len; d[1] = d[1] / len; d[2] = d[2] / len;
   const RayHit h = bvh_trace(wide, vert, tri, o, d);
   if (h.any && h.tid == f) atomicOr(raw_vis_words + (t >> 2), (1u << view) << ((t & 3) * 8));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ leaf grids for parallel rays
@@ -934,7 +936,7 @@ int trace_with_leaf_grids(const void* nodes, int F, int n_views, const float* vi
   int total = 0;
   UTX_CUDA(cudaMemcpyAsync(&total, start + ncells, 4, cudaMemcpyDeviceToHost, stream));
   UTX_CUDA(cudaStreamSynchronize(stream));
-  if (total > cap) return 0;
+  if (total < 0 || total > cap) return 0;      // does not fit (or the 32-bit scan overflowed): the tree walk
   UTX_CUDA(cudaMemsetAsync(count, 0, static_cast<size_t>(ncells) * 4, stream));
   grid_scatter_kernel<1><<<gw, 256, 0, stream>>>(nodes4, gc, gd, count, start, gfill, cap);
   grid_sort_kernel<<<static_cast<unsigned>((ncells * 32 + 255) / 256), 256, 0, stream>>>(start, static_cast<int>(ncells), gfill, glist);
@@ -942,8 +944,8 @@ int trace_with_leaf_grids(const void* nodes, int F, int n_views, const float* vi
                                                            reinterpret_cast<unsigned*>(w.raw), lists2, counts2);
   // the rays of crowded cells through the hierarchy (blocks beyond the list's length exit at once)
   const float4* wide = reinterpret_cast<const float4*>(static_cast<const uint8_t*>(nodes) + wide_offset_bytes(F));
-  ray_kernel<<<dim3(g128, n_views), 128, 0, stream>>>(lists2, counts2, T, rast, w.pos, vert, tri, wide, vw,
-                                                      reinterpret_cast<unsigned*>(w.raw));
+  ray_kernel<<<dim3(static_cast<unsigned>(2 * num_sms()), n_views), 128, 0, stream>>>(lists2, counts2, T, rast, w.pos, vert, tri, wide, vw,
+                                                                                   reinterpret_cast<unsigned*>(w.raw));
   UTX_CUDA(cudaGetLastError());
   if (std::getenv("UTX_RAY_DEBUG")) {      // diagnosis: rays per view, and how many of them went to the tree walk
     int c[24];
