@@ -1,16 +1,22 @@
-"""BASELINE config 4 on the GPU box: the reference's own test case (teaser_robot mesh + image, copied into the git-ignored
-gpurun_in/ for this run only) through CustomRGBTextureFullPipeline with the FULL-SIZE random-init FLUX (19+38 blocks) and the
-reference's call shapes (6 views, 512 x 3072 strip, 28 steps per call, 2048^2 atlas).  Prints one JSON line of stage timings."""
+"""BASELINE config 4 on the GPU box: the reference's own test mesh (teaser_robot, from the committed lossless fixture
+tests/golden/teaser_robot.npz.xz, written out as an OBJ) and a synthetic reference image through CustomRGBTextureFullPipeline
+with the FULL-SIZE random-init FLUX (19+38 blocks) and the reference's call shapes (6 views, 512 x 3072 strip, 28 steps per
+call, 2048^2 atlas).  Prints one JSON line of stage timings."""
 import json, os, sys, time
 sys.path.insert(0, ".")
 import numpy as np
 import torch
 from PIL import Image
 
-mesh, image = "gpurun_in/teaser_inputmesh.obj", "gpurun_in/teaser_image.png"
-if not os.path.exists(mesh):
-    print(json.dumps({"skipped": "gpurun_in/teaser_inputmesh.obj absent (reference fixture is only staged by hand)"}))
-    sys.exit(0)
+import warnings
+warnings.simplefilter("ignore")
+from tests.bake_meshes import teaser_robot_raw
+from unitex_b200.export import save_obj
+os.makedirs("gpurun_out/teaser_run", exist_ok=True)
+mesh, image = "gpurun_out/teaser_run/inputmesh.obj", "gpurun_out/teaser_run/image.png"
+save_obj(mesh, *[teaser_robot_raw()[i] for i in (0, 1, 2, 3)])
+yy, xx = np.mgrid[0:1024, 0:1024]
+Image.fromarray(np.stack([(xx // 4) % 256, (yy // 4) % 256, ((xx + yy) // 8) % 256], -1).astype(np.uint8)).save(image)
 import pipeline as P
 
 def sync():
