@@ -12,8 +12,9 @@ import warnings
 warnings.simplefilter("ignore")
 from tests.bake_meshes import teaser_robot_raw
 from unitex_b200.export import save_obj
-os.makedirs("gpurun_out/teaser_run", exist_ok=True)
-mesh, image = "gpurun_out/teaser_run/inputmesh.obj", "gpurun_out/teaser_run/image.png"
+import tempfile
+_tmp = tempfile.mkdtemp()            # (the 55 MB OBJ must not land in gpurun_out/: that directory is copied back, 64 MiB at most)
+mesh, image = os.path.join(_tmp, "inputmesh.obj"), os.path.join(_tmp, "image.png")
 save_obj(mesh, *[teaser_robot_raw()[i] for i in (0, 1, 2, 3)])
 yy, xx = np.mgrid[0:1024, 0:1024]
 Image.fromarray(np.stack([(xx // 4) % 256, (yy // 4) % 256, ((xx + yy) // 8) % 256], -1).astype(np.uint8)).save(image)
@@ -27,7 +28,7 @@ t0 = sync()
 pipe = P.CustomRGBTextureFullPipeline(pretrain_models="random", super_resolutions=False, seed=63)
 t1 = sync()
 stages = {"build_pipeline_random_weights_s": t1 - t0}
-save_dir = "gpurun_out/teaser_run"
+save_dir = os.path.join(_tmp, "run")
 cache = os.path.join(save_dir, "cache")
 os.makedirs(cache, exist_ok=True)
 for name, fn in (("preprocess_blank_mesh", lambda: pipe.preprocess_blank_mesh(cache, mesh)),
