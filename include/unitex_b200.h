@@ -159,6 +159,19 @@ int utx_rasterize(const float* pos, int pos_batched, int V, const int32_t* tri, 
 /* dr.interpolate (renderer_inverse.py:188,277,288): out[b,y,x,:] = u a0 + v a1 + (1-u-v) a2 */
 int utx_interpolate(const float* attr, int attr_batched, int V, int C, const float* rast, const int32_t* tri, int B, int H,
                     int W, float* out, void* stream);
+/* The visible-pixel mask of mv_to_pcd(filt_gradient_points=True) (renderer_inverse.py:186-214): attrs [n,H,W,6] =
+ * dr.interpolate of (vertex position | vertex normal) (:188), rast [n,H,W,4], face_normals [F,3] (PBRMesh.normals), view_dirs
+ * DEVICE [n,3] = -c2w[:3,2] (perspective = 0) or the camera positions c2w[:3,3] (perspective = 1).  mask_vis u8 [n,H,W] = covered
+ * & cos(ray, face normal) < cos_thr & |torch.gradient(attrs)| < grad_thr on all 31 pixels x - 15 .. x + 15 of the row (the
+ * reference's MaxPool2d(31, 1, 15) on an [n,H,W,1] tensor erodes along x only; kept).  H, W >= 2 like torch.gradient. */
+int utx_mv_visibility_filter(const float* attrs, const float* rast, const float* face_normals, const float* view_dirs,
+                             int perspective, int n, int H, int W, float grad_thr, float cos_thr, unsigned char* mask_vis,
+                             void* stream);
+/* kdtree_method='mvpaint' (renderer_inverse.py:390-399): score / index [M,k] from utx_knn over the union pixel cloud, cloud_c /
+ * cloud_n [N,3] colour and face normal per cloud point, tex_n [M,3] face normal per texel -> out [M,3] = sum c w / sum w with
+ * w = normalize(1 / score, p = 1) x cosine_similarity(cloud_n[index], tex_n); non-finite results -> 0. */
+int utx_mvpaint_blend(const float* score, const long long* index, long long M, int k, const float* cloud_c,
+                      const float* cloud_n, const float* tex_n, float* out, void* stream);
 /* vertices_homo @ (P @ W2C)^T (renderer_inverse.py:178,263): out [n, V, 4] */
 int utx_transform_points(const float* vert, int V, const float* mats, int n, float* out, void* stream);
 /* RayTracing(vertices, faces) / update_raw (raytracing/__init__.py:12-80; rt_aprmis/bvhhelpers.py:20-83): builds the

@@ -247,3 +247,73 @@ def test_kdtree_bake_matches_committed_golden(lib):
                            kdtree_n_neighbors_invisiable=32, filt_gradient_points=False)
     torch.cuda.synchronize()
     assert np.abs(col.cpu().numpy() - zk["color_2d"].astype(np.float32)).max() < 2e-3
+
+
+@pytest.mark.parametrize("perspective", [False, True])
+@pytest.mark.parametrize("res", [(96, 96), (64, 300)])
+def test_mv_visibility_filter_matches_torch_chain(lib, perspective, res):
+    """mv_to_pcd(filt_gradient_points=True): the one-kernel filter against the reference's torch op chain (renderer_inverse.py:
+    186-214) run on the same rasters -- including rows wider than one 256-pixel block segment and pinhole views."""
+    import math
+    from unitex_b200 import bake as ub
+    F_ = torch.nn.functional
+    v, f, uv, fuv = two_spheres(14, 28)
+    if perspective:
+        c2ws, intr = ub.generate_box_views_c2ws(2.8)[[0, 1, 4, 2, 3, 5]], ub.generate_intrinsics(49.1, 49.1, fov=True, degree=True)
+    else:
+        c2ws, intr = _views()
+    r = ub.NVDiffRendererInverse(pbr_mesh=ub.BakeMesh(v, f, uv, fuv))
+    H, W = res
+    thr, ang = 0.2, 100.0
+    mv = r.mv_to_pcd(c2ws, intr, (H, W), perspective=perspective, grad_norm_threhold=thr, ray_normal_angle_threhold=ang,
+                     filt_gradient_points=True)
+    m, rast = r.pbr_mesh, mv["rast"]
+    n = c2ws.shape[0]
+    mask = rast[..., 3:4] > 0
+    attrs = ub.interpolate(torch.cat([m.vertices, m.vertex_normals], dim=-1).contiguous(), rast, m.faces)
+    a_dy, a_dx = torch.gradient(attrs, dim=(1, 2))
+    gnorm = (a_dx.square() + a_dy.square()).sum(dim=-1, keepdim=True).sqrt()
+    tid = rast[..., 3:4].to(torch.int64).sub(1)
+    fn = m.normals.gather(0, torch.where(mask, tid, 0).reshape(-1, 1).repeat(1, 3)).reshape(n, H, W, 3)
+    c2 = c2ws.cuda().float()
+    rays_d = attrs[..., 0:3] - c2[:, :3, 3][:, None, None] if perspective else c2[:, :3, 2].neg()[:, None, None]
+    rays_d = torch.broadcast_tensors(F_.normalize(rays_d, dim=-1), fn)[0]
+    cos = F_.cosine_similarity(rays_d, fn, dim=-1).unsqueeze(-1)
+    eroded = (1.0 - F_.max_pool2d(1.0 - (gnorm < thr).float(), kernel_size=31, stride=1, padding=15)).bool()
+    want = mask & (cos < math.cos(math.radians(ang))) & eroded
+    got = mv["mask_visiable"]
+    assert got.shape == want.shape and got.dtype == torch.bool
+    assert 100 < int(want.sum()) < int(mask.sum())        # the filter removes something and keeps something
+    assert int((got != want).sum()) == 0
+    assert torch.equal(mv["alpha_visiable"], want.float())
+
+
+@pytest.mark.parametrize("k", [1, 8, 32])
+def test_mvpaint_blend_matches_torch_chain(lib, k):
+    """utx_mvpaint_blend against the reference's weighting expression (renderer_inverse.py:390-399), with exact-zero distances
+    (1 / 0 -> the largest finite value under nan_to_num) and opposed normals (negative weights) in the table."""
+    import ctypes as C
+    from unitex_b200 import _lib
+    F_ = torch.nn.functional
+    g = torch.Generator(device="cuda").manual_seed(k)
+    N, M = 5000, 3000
+    cloud_c = torch.rand(N, 3, device="cuda", generator=g)
+    cloud_n = F_.normalize(torch.randn(N, 3, device="cuda", generator=g), dim=-1)
+    tex_n = F_.normalize(torch.randn(M, 3, device="cuda", generator=g), dim=-1)
+    index = torch.randint(0, N, (M, k), device="cuda", generator=g)
+    score = torch.rand(M, k, device="cuda", generator=g).sort(dim=-1).values
+    score[::7, 0] = 0.0
+    out = torch.empty(M, 3, device="cuda")
+    L = _lib.load()
+    _lib.check(L.utx_mvpaint_blend(C.c_void_p(score.data_ptr()), C.c_void_p(index.data_ptr()), M, k, C.c_void_p(cloud_c.data_ptr()),
+                                   C.c_void_p(cloud_n.data_ptr()), C.c_void_p(tex_n.data_ptr()), C.c_void_p(out.data_ptr()), None),
+               "utx_mvpaint_blend")
+    torch.cuda.synchronize()
+    weight = F_.normalize(score.reciprocal().nan_to_num(nan=0.0), p=1, dim=-1) * \
+        F_.cosine_similarity(cloud_n[index], tex_n.unsqueeze(-2), dim=-1)
+    weight = weight.unsqueeze(-1)
+    want = torch.nan_to_num((cloud_c[index] * weight).sum(dim=-2) / weight.sum(dim=-2), nan=0.0, posinf=0.0, neginf=0.0)
+    # sum w can cancel (opposed normals): compare where the denominator is well conditioned, and finiteness everywhere
+    cond = weight.sum(dim=-2).abs().squeeze(-1) > 1e-3 * weight.abs().sum(dim=-2).squeeze(-1)
+    assert torch.isfinite(out).all() and cond.float().mean() > 0.9
+    assert (out[cond] - want[cond]).abs().max().item() < 1e-3 * (1.0 + want[cond].abs().max().item())

@@ -129,6 +129,8 @@ _SIGS = {
     "utx_comm_destroy": (None, [vp]),
     "utx_allgather_tiles": (i32, [vp, vp, vp, C.c_size_t, vp]),
     "utx_comm_alltoall": (i32, [vp, vp, vp, C.c_size_t, vp]),
+    "utx_mv_visibility_filter": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, C.c_float, C.c_float, vp, vp]),
+    "utx_mvpaint_blend": (i32, [vp, vp, C.c_longlong, i32, vp, vp, vp, vp, vp]),
     "utx_knn1": (i32, [vp, i32, vp, C.c_longlong, vp, vp, vp, vp, C.c_size_t, vp]),
     "utx_knn": (i32, [vp, i32, vp, C.c_longlong, i32, vp, vp, vp, vp, C.c_size_t, vp]),
     "utx_uv_bake_workspace_bytes": (C.c_size_t, [i32, i32]),

@@ -500,24 +500,18 @@ class NVDiffRendererInverse:
         mask = rast[..., 3:4] > 0
         mask_vis = mask
         if filt_gradient_points:
-            F_ = torch.nn.functional
+            # one kernel (bake_filter.cu): torch.gradient of the interpolated attributes, ray / face-normal cosine and the
+            # reference's MaxPool2d(31, 1, 15) erosion, which on its [n,H,W,1] tensor runs along the image x axis only (:204-205)
             attrs = interpolate(torch.cat([m.vertices, m.vertex_normals], dim=-1).contiguous(), rast, m.faces)
-            a_dy, a_dx = torch.gradient(attrs, dim=(1, 2))
-            gnorm = (a_dx.square() + a_dy.square()).sum(dim=-1, keepdim=True).sqrt()
-            tid = rast[..., 3:4].to(torch.int64).sub(1)
-            fn = m.normals.gather(0, torch.where(mask, tid, 0).reshape(-1, 1).repeat(1, 3)).reshape(n, H, W, 3)
             c2 = c2ws.to(self.device, torch.float32)
-            if perspective:
-                rays_d = attrs[..., 0:3] - c2[:, :3, 3].unsqueeze(1).unsqueeze(1)
-            else:
-                rays_d = c2[:, :3, 2].neg().unsqueeze(1).unsqueeze(1)
-            rays_d = torch.broadcast_tensors(F_.normalize(rays_d, dim=-1), fn)[0]
-            cos = F_.cosine_similarity(rays_d, fn, dim=-1).unsqueeze(-1)
-            ok = gnorm < grad_norm_threhold
-            # the reference hands the [n,H,W,1] tensor to nn.MaxPool2d(31, 1, 15) as it stands (:204-205), which pools over
-            # (W, 1): the erosion runs along the image x axis only.  Same call, same effect.
-            eroded = (1.0 - F_.max_pool2d(1.0 - ok.float(), kernel_size=31, stride=1, padding=15)).bool()
-            mask_vis = mask & (cos < math.cos(math.radians(ray_normal_angle_threhold))) & eroded
+            view_dirs = (c2[:, :3, 3] if perspective else c2[:, :3, 2].neg()).contiguous()
+            vis = torch.empty(n, H, W, 1, device=self.device, dtype=torch.uint8)
+            face_n = m.normals.contiguous().float()
+            _lib.check(_lib.load().utx_mv_visibility_filter(
+                _p(attrs), _p(rast), _p(face_n), _p(view_dirs), int(bool(perspective)), n, H, W,
+                float(grad_norm_threhold), math.cos(math.radians(ray_normal_angle_threhold)), _p(vis), _stream()),
+                "utx_mv_visibility_filter")
+            mask_vis = vis.bool()
         return {"mask": mask, "alpha": mask.float(), "mask_visiable": mask_vis, "alpha_visiable": mask_vis.float(), "rast": rast}
 
     def query_field(self, vertices_visiable, colors_visiable, vertices_invisiable):
@@ -636,10 +630,9 @@ class NVDiffRendererInverse:
     def _mvpaint_fill(self, ws, mask2d, rgba, rast_mv, rast2d, H2D, W2D, k: int):
         """kdtree_method='mvpaint' (:390-399; MVPaint, arXiv 2411.02336 sec. 3.2): every covered texel takes its k nearest points of
         the union pixel cloud, weighted by normalised inverse distance x cosine between the face normals of point and texel.  The
-        neighbour search is `utx_knn`; the weighting of the [M, k] table is torch plumbing, written into the staged bake's colour
+        neighbour search is `utx_knn`, the weighting of the [M, k] table `utx_mvpaint_blend`, written into the staged bake's colour
         plane.  (`score` is the Euclidean distance here, the reference's scipy convention -- see INTEGRATION.md on torch_kdtree.)"""
         L = _lib.load()
-        F_ = torch.nn.functional
         off = [C.c_size_t() for _ in range(4)]
         _lib.check(L.utx_uv_bake_layout(H2D, W2D, *[C.byref(o) for o in off]), "utx_uv_bake_layout")
         T = H2D * W2D
@@ -653,11 +646,11 @@ class NVDiffRendererInverse:
         cloud_n = m.normals[(rast_mv[..., 3].to(torch.int64) - 1)[sel]]
         tex_n = m.normals[(rast2d[0, ..., 3].to(torch.int64) - 1).reshape(-1)[covered]]
         score, index = knn(cloud_p, pos[covered], k=k, device=self.device)
-        weight = F_.normalize(score.reciprocal().nan_to_num(nan=0.0), p=1, dim=-1) * \
-            F_.cosine_similarity(cloud_n[index], tex_n.unsqueeze(-2), dim=-1)
-        weight = weight.unsqueeze(-1)
-        out = (cloud_c[index] * weight).sum(dim=-2) / weight.sum(dim=-2)
-        col[covered] = torch.nan_to_num(out, nan=0.0, posinf=0.0, neginf=0.0)
+        cloud_c, cloud_n, tex_n = cloud_c.contiguous().float(), cloud_n.contiguous().float(), tex_n.contiguous().float()
+        out = torch.empty(index.shape[0], 3, device=self.device, dtype=torch.float32)
+        _lib.check(L.utx_mvpaint_blend(_p(score), _p(index), index.shape[0], k, _p(cloud_c), _p(cloud_n), _p(tex_n), _p(out),
+                                       _stream()), "utx_mvpaint_blend")
+        col[covered] = out
 
     def _field_fill(self, ws, mask2d, rgba, rast_mv, H2D, W2D, union_cloud: bool):
         """The `*_inpainting=True` branches: the registered query field colours the texels the views do not own

@@ -107,6 +107,18 @@ int utx_interpolate(const float* attr, int attr_batched, int V, int C, const flo
   UTX_CHECK(attr && rast && tri && out, "utx_interpolate: null pointer");
   return interpolate(attr, attr_batched, V, C, rast, tri, B, H, W, out, static_cast<cudaStream_t>(stream));
 }
+int utx_mv_visibility_filter(const float* attrs, const float* rast, const float* face_normals, const float* view_dirs,
+                             int perspective, int n, int H, int W, float grad_thr, float cos_thr, unsigned char* mask_vis,
+                             void* stream) {
+  UTX_CHECK(attrs && rast && face_normals && view_dirs && mask_vis, "utx_mv_visibility_filter: null pointer");
+  return mv_visibility_filter(attrs, rast, face_normals, view_dirs, perspective, n, H, W, grad_thr, cos_thr, mask_vis,
+                              static_cast<cudaStream_t>(stream));
+}
+int utx_mvpaint_blend(const float* score, const long long* index, long long M, int k, const float* cloud_c,
+                      const float* cloud_n, const float* tex_n, float* out, void* stream) {
+  UTX_CHECK(score && index && cloud_c && cloud_n && tex_n && out, "utx_mvpaint_blend: null pointer");
+  return mvpaint_blend(score, index, M, k, cloud_c, cloud_n, tex_n, out, static_cast<cudaStream_t>(stream));
+}
 int utx_transform_points(const float* vert, int V, const float* mats, int n, float* out, void* stream) {
   UTX_CHECK(vert && mats && out, "utx_transform_points: null pointer");
   return transform_points(vert, V, mats, n, out, static_cast<cudaStream_t>(stream));

@@ -107,6 +107,13 @@ int rasterize(const float* pos, int pos_batched, int V, const int* tri, int F, i
               void* workspace, cudaStream_t stream);
 int interpolate(const float* attr, int attr_batched, int V, int C, const float* rast, const int* tri, int B, int H, int W,
                 float* out, cudaStream_t stream);
+// mv_to_pcd(filt_gradient_points=True) (bake_filter.cu): attrs [n,H,W,6] = interpolated (position, vertex normal), view_dirs [n,3]
+// device (ray direction, or camera position when perspective) -> mask_vis u8 [n,H,W]
+int mv_visibility_filter(const float* attrs, const float* rast, const float* face_normals, const float* view_dirs, int perspective,
+                         int n, int H, int W, float grad_thr, float cos_thr, unsigned char* mask_vis, cudaStream_t stream);
+// kdtree_method='mvpaint' blend of a [M,k] neighbour table (bake_filter.cu) -> out [M,3]
+int mvpaint_blend(const float* score, const long long* index, long long M, int k, const float* cloud_c, const float* cloud_n,
+                  const float* tex_n, float* out, cudaStream_t stream);
 // out[b, v, :] = mats[b] (row-major 4x4) @ [vert[v], 1]
 int transform_points(const float* vert, int V, const float* mats, int n, float* out, cudaStream_t stream);
 size_t bvh_nodes_bytes(int F);
