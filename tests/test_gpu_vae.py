@@ -103,3 +103,21 @@ def test_implicit_conv3x3_matches_conv2d(lib, N, H, W, C, Co, with_res):
     torch.cuda.synchronize()
     err = (y.float() - ref).abs().max().item()
     assert err <= 2e-2 * ref.abs().max().item() + 1e-2, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("M,N,lds", [(64, 16384, 16384), (33, 1000, 1024), (17, 4096, 4096), (9, 1002, 1002), (5, 17000, 17000)])
+def test_softmax_rows(lib, M, N, lds):
+    """The mid block's row softmax (fp32 scores -> bf16 probabilities): the register-resident kernel (N % 4 == 0, N <= 16384,
+    ragged last float4 block, padded rows) and the three-pass kernel behind the same entry point."""
+    import ctypes as C
+    from unitex_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(N)
+    S = torch.randn(M, lds, device="cuda", generator=g) * 4.0
+    P = torch.full((M, lds), 7.0, device="cuda", dtype=torch.bfloat16)
+    _lib.check(_lib.load().utx_softmax_rows(C.c_void_p(S.data_ptr()), lds, C.c_void_p(P.data_ptr()), lds, M, N, None), "utx_softmax_rows")
+    torch.cuda.synchronize()
+    want = torch.softmax(S[:, :N].double(), dim=-1)
+    got = P[:, :N].double()
+    assert (got - want).abs().max().item() <= 2.0 ** -8 * want.max().item() + 1e-7      # one bf16 rounding of values <= max
+    assert (got.sum(-1) - 1.0).abs().max().item() < 2.0 ** -9 + 1e-4                  # every term within half a bf16 ulp
+    assert (P[:, N:] == 7.0).all()                                                    # nothing written past the row
