@@ -119,5 +119,5 @@ def test_softmax_rows(lib, M, N, lds):
     want = torch.softmax(S[:, :N].double(), dim=-1)
     got = P[:, :N].double()
     assert (got - want).abs().max().item() <= 2.0 ** -8 * want.max().item() + 1e-7      # one bf16 rounding of values <= max
-    assert (got.sum(-1) - 1.0).abs().max().item() < 2.0 ** -9 + 1e-4                  # every term within half a bf16 ulp
+    assert (got.sum(-1) - 1.0).abs().max().item() < 2.0 ** -8 + 1e-4                  # every term within half a bf16 ulp (<= 2^-8 relative)
     assert (P[:, N:] == 7.0).all()                                                    # nothing written past the row

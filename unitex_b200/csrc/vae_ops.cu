@@ -56,7 +56,13 @@ __global__ void __launch_bounds__(256) im2col_kernel(const bf16* __restrict__ x,
 // always owns the same 8 channels and a warp reads whole pixels contiguously (16-byte vectors).  Deterministic: per-thread
 // fp32 partials are folded per channel in a fixed order, per group in double, and every block writes its own slot of
 // `partial` [N][chunks][G][2]; gn_coef_kernel adds the chunks in order.  HBM-bound: the tensor is read once.
-constexpr int kGnRowsPerBlock = 2048;
+// Rows per block: a function of the shape only (the partials are added in chunk order, so the result does not depend on the
+// device), sized for ~1024 blocks per image.  With a fixed 2048 rows the 128^2 and 256^2 layers of the decoder ran on 8 and 32
+// blocks: 86 us per launch for 16 MB, 17 launches per decode (profiles/r02_vae_launches.csv).
+__host__ __device__ inline int gn_rows_per_block(int HW) {
+  const int r = (HW + 1023) / 1024;
+  return r < 64 ? 64 : (r + 63) / 64 * 64;
+}
 __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, int HW, int C, int G,
                                                        double* __restrict__ partial) {
   extern __shared__ float sm[];                       // [blockDim][16] partials, then [2][C] channel sums
@@ -64,7 +70,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
   const int nv = C >> 3;                              // vectors per pixel
   const int lanes = blockDim.x / nv;                  // pixels in flight per block step
   const int cv = threadIdx.x % nv;
-  const int r0 = blockIdx.x * kGnRowsPerBlock, r1 = min(r0 + kGnRowsPerBlock, HW);
+  const int rpb = gn_rows_per_block(HW);
+  const int r0 = blockIdx.x * rpb, r1 = min(r0 + rpb, HW);
   const uint4* xv = reinterpret_cast<const uint4*>(x + static_cast<long long>(n) * HW * C);
   float s[8], ss[8];
 #pragma unroll
@@ -139,29 +146,38 @@ __global__ void __launch_bounds__(256) gn_coef_kernel(const double* __restrict__
   }
 }
 
-// y = [silu](x * a + b): one 16-byte vector per thread per step, grid-stride; HBM-bound (read + write once)
-__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int HW, int C,
-                                                       const float* __restrict__ coef, int silu, long long total8) {
+// y = [silu](x * a + b), HBM-bound (read + write once).  grid (blocks, N); blockDim is a multiple of the C/8 vectors of a pixel,
+// so a thread keeps the same 8 channels through its grid-stride loop: its 16 coefficients are loaded once, there is no division
+// in the loop, and four 16-byte loads are in flight per thread.  (One vector per step with a 64-bit div / mod and four
+// coefficient loads each ran at 3.1 TB/s: 171 us for the 268 MB layers, profiles/r02_vae_launches.csv.)
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int C,
+                                                       const float* __restrict__ coef, int silu, long long per_img) {
   const int nv = C >> 3;
-  const long long per_img = static_cast<long long>(HW) * nv;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int n = static_cast<int>(i / per_img);
-    const int c0 = static_cast<int>(i % nv) * 8;
-    const float* ca = coef + static_cast<long long>(n) * 2 * C + c0;
-    const float4 a0 = *reinterpret_cast<const float4*>(ca), a1 = *reinterpret_cast<const float4*>(ca + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(ca + C), b1 = *reinterpret_cast<const float4*>(ca + C + 4);
-    const uint4 raw = reinterpret_cast<const uint4*>(x)[i];
-    float f[8] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y), bf16lo(raw.z), bf16hi(raw.z), bf16lo(raw.w), bf16hi(raw.w)};
-    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const int n = blockIdx.y;
+  const int c0 = (threadIdx.x % nv) * 8;
+  const float* ca = coef + static_cast<long long>(n) * 2 * C + c0;
+  const float4 a0 = *reinterpret_cast<const float4*>(ca), a1 = *reinterpret_cast<const float4*>(ca + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(ca + C), b1 = *reinterpret_cast<const float4*>(ca + C + 4);
+  const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + n * per_img;
+  uint4* yv = reinterpret_cast<uint4*>(y) + n * per_img;
+  auto f = [&](const uint4 raw) {
+    float v[8] = {bf16lo(raw.x), bf16hi(raw.x), bf16lo(raw.y), bf16hi(raw.y), bf16lo(raw.z), bf16hi(raw.z), bf16lo(raw.w), bf16hi(raw.w)};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v = fmaf(f[j], av[j], bv[j]);
-      if (silu) v = v / (1.0f + __expf(-v));
-      f[j] = v;
+      float t = fmaf(v[j], av[j], bv[j]);
+      if (silu) t = t / (1.0f + __expf(-t));
+      v[j] = t;
     }
-    reinterpret_cast<uint4*>(y)[i] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  };
+  const long long bd = static_cast<long long>(gridDim.x) * blockDim.x;      // a multiple of nv
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * bd < per_img; i += 4 * bd) {
+    const uint4 q0 = xv[i], q1 = xv[i + bd], q2 = xv[i + 2 * bd], q3 = xv[i + 3 * bd];
+    yv[i] = f(q0); yv[i + bd] = f(q1); yv[i + 2 * bd] = f(q2); yv[i + 3 * bd] = f(q3);
   }
+  for (; i < per_img; i += bd) yv[i] = f(xv[i]);
 }
 
 // nearest-neighbour 2x upsampling, NHWC (Upsample2D [ext] before its 3x3 convolution): one 16-byte vector per thread
@@ -348,7 +364,7 @@ int im2col3x3(const bf16* x, int N, int Hin, int Win, int C, int up, int stride,
 }
 
 size_t groupnorm_workspace_bytes(int N, int HW, int C, int G) {
-  const size_t nchunks = (static_cast<size_t>(HW) + kGnRowsPerBlock - 1) / kGnRowsPerBlock;
+  const size_t nchunks = (static_cast<size_t>(HW) + gn_rows_per_block(HW) - 1) / gn_rows_per_block(HW);
   return static_cast<size_t>(N) * nchunks * G * 2 * sizeof(double) + static_cast<size_t>(N) * 2 * C * sizeof(float);
 }
 
@@ -356,7 +372,7 @@ int groupnorm_nhwc(const bf16* x, bf16* y, int N, int HW, int C, int G, const fl
                    double* stats_ws, cudaStream_t stream) {
   UTX_CHECK(C % G == 0 && C % 8 == 0 && C <= 2048, "groupnorm: C must be a multiple of G and of 8, <= 2048");
   if (N == 0 || HW == 0) return 0;
-  const int nchunks = (HW + kGnRowsPerBlock - 1) / kGnRowsPerBlock;
+  const int nchunks = (HW + gn_rows_per_block(HW) - 1) / gn_rows_per_block(HW);
   // workspace (groupnorm_workspace_bytes): per-block moments [N][chunks][G][2] doubles, then [N][2][C] fp32 coefficients
   float* coef = reinterpret_cast<float*>(stats_ws + static_cast<size_t>(N) * nchunks * G * 2);
   const int nv = C / 8;
@@ -364,11 +380,11 @@ int groupnorm_nhwc(const bf16* x, bf16* y, int N, int HW, int C, int G, const fl
   dim3 grid(nchunks, N);
   gn_stats_kernel<<<grid, threads, (threads * 16 + 2 * C) * sizeof(float), stream>>>(x, HW, C, G, stats_ws);
   gn_coef_kernel<<<(N * G * 32 + 255) / 256, 256, 0, stream>>>(stats_ws, nchunks, gamma, beta, HW, C, G, N, coef);
-  const long long total8 = static_cast<long long>(N) * HW * C / 8;
-  long long blocks = (total8 + 255) / 256;
+  const long long per_img = static_cast<long long>(HW) * nv;
+  long long blocks = (per_img + 4 * threads - 1) / (4 * threads);
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  gn_apply_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, y, HW, C, coef, silu, total8);
+  gn_apply_kernel<<<dim3(static_cast<unsigned>(blocks), N), threads, 0, stream>>>(x, y, C, coef, silu, per_img);
   UTX_CUDA(cudaGetLastError());
   return 0;
 }
