@@ -1,4 +1,4 @@
-"""Times both attention kernels at the bench shape (S=9728, 24 heads) with CUDA events (not under a profiler)."""
+"""Times the attention kernel at the bench shape (S=9728, 24 heads) with CUDA events (not under a profiler)."""
 import os, sys, json
 import torch
 sys.path.insert(0, ".")
@@ -10,8 +10,7 @@ qkv = torch.randn(S, 3 * H * 128, device="cuda").to(torch.bfloat16)
 out = torch.empty(S, H * 128, device="cuda", dtype=torch.bfloat16)
 flops = 4.0 * H * 128 * S * S
 res = {}
-for impl in ("2",):
-    os.environ["UTX_ATTN_IMPL"] = impl
+for impl in ("2",):      # attention2_kernel (the two round-1 alternatives left the library)
     try:
         for _ in range(3):
             ops.attention(qkv, H, out=out)

@@ -90,17 +90,9 @@ def test_gemm_grouped_two_streams(lib, gemm_impl):
     _check_bf16(C[M0:], X[M0:].float() @ W1.float().T + b1.float(), name="grouped img")
 
 
-@pytest.fixture(params=["1", "2", "3"])
-def attn_impl(request, monkeypatch):
-    """All attention kernels stay under test: 1 = one query tile per CTA, P via smem; 2 = two-tile ping-pong, P in TMEM;
-    3 = one query tile, S and P double-buffered in TMEM, two softmax threads per row."""
-    monkeypatch.setenv("UTX_ATTN_IMPL", request.param)
-    return request.param
-
-
 @pytest.mark.parametrize("S,H,qscale", [(128, 2, 1.0), (256, 2, 1.0), (1280, 2, 1.0), (1000, 3, 1.0), (640, 2, 6.0),
                                         (2432, 4, 1.0), (300, 1, 1.0)])
-def test_attention(lib, attn_impl, S, H, qscale):
+def test_attention(lib, S, H, qscale):
     from unitex_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(S + H)
     qkv = torch.randn(S, 3 * H * 128, device="cuda", generator=g)
@@ -117,7 +109,7 @@ def test_attention(lib, attn_impl, S, H, qscale):
 
 
 @pytest.mark.parametrize("S,slope", [(640, 0.02), (1000, 0.05), (384, -0.03)])
-def test_attention_growing_logits(lib, attn_impl, S, slope):
+def test_attention_growing_logits(lib, S, slope):
     """Logits that climb (or fall) steadily along the key axis: every key tile outgrows the running reference, in both of
     its halves -- the lazy-reference fast path must fall back to the exact maximum and rescale O / l each time."""
     from unitex_b200 import ops
@@ -137,7 +129,7 @@ def test_attention_growing_logits(lib, attn_impl, S, slope):
     assert rel < 1.5e-2, f"attention rel err {rel}"
 
 
-def test_attention_matches_explicit_bf16_p(lib, attn_impl):
+def test_attention_matches_explicit_bf16_p(lib):
     """Tighter: emulate the kernel's one deliberate rounding (P -> bf16 before PV) in fp32 torch."""
     from unitex_b200 import ops
     S, H = 384, 2
