@@ -138,13 +138,24 @@ int utx_gemm_bf16_grouped2(const void* A0, long lda0, const void* W0, const void
                            int N, int K, int epi, const float* gate0, const float* gate1, void* stream);
 /* softmax(q k^T / sqrt(128)) v over qkv [S, 3*H*128] (attention_processor.py:89-91) */
 int utx_attention_bf16(const void* qkv, long ld_qkv, void* out, long ld_out, int S, int H, void* stream);
+/* LayerNorm(eps 1e-6, no affine) * (1 + scale) + shift per stream: rows [0, rows0) use (shift0, scale0), the rest (shift1, scale1).
+ * AdaLayerNormZero / AdaLayerNormZeroSingle / AdaLayerNormContinuous of diffusers' FluxTransformer2DModel [ext], reached from
+ * `self.transformer(...)` at flux_piplines/texturing/pipeline.py:646-656. */
 int utx_ln_modulate(const void* x, long ldx, void* y, long ldy, int rows, int D, int rows0, const float* shift0,
                     const float* scale0, const float* shift1, const float* scale1, void* stream);
+/* in place on the q and k thirds of qkv: per-head RMSNorm(eps 1e-6) x weight, then the rotary embedding
+ * (attention_processor.py:53-56 norm_q / norm_k, :86-87 apply_rotary_emb); rows [0, rows0) take (wq0, wk0), the rest (wq1, wk1) */
 int utx_rmsnorm_rope(void* qkv, long ld_qkv, int S, int H, int rows0, const void* wq0, const void* wk0,
                      const void* wq1, const void* wk1, const float* cos_t, const float* sin_t, void* stream);
+/* y[N] (+)= W[N,K] @ (silu_in ? silu(x) : x) + b: the timestep / guidance / pooled-text embedders and every block's modulation
+ * Linear(SiLU(temb)) [ext: CombinedTimestepGuidanceTextProjEmbeddings, AdaLayerNormZero.linear], one evaluation per step (:646-656) */
 int utx_gemv_bf16(const void* W, const void* b, const float* x, float* y, int N, int K, int silu_in, int accumulate,
                   void* stream);
+/* cos / sin [S,128] of FluxPosEmbed(theta 10000, axes_dim (16, 56, 56)) [ext] over the ids the sampler builds at
+ * flux_piplines/texturing/pipeline.py:303-393 (text ids | latent ids | condition ids with their offsets) */
 int utx_rope_table(const float* ids, int S, float* cos_t, float* sin_t, void* stream);
+/* FlowMatchEulerDiscreteScheduler.step [ext] as called at flux_piplines/texturing/pipeline.py:660:
+ * latents = bf16(fp32(latents) + bf16(dsigma * v)) on the first `rows` rows (the noise rows; the condition rows stay) */
 int utx_euler_update(void* latents, const void* v, int rows, int cols, float dsigma, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -260,7 +271,9 @@ int utx_groupnorm_nhwc(const void* x, void* y, int N, int HW, int C, int G, cons
 /* C fp32 [M,N] = scale * (A @ W^T + bias) */
 int utx_gemm_bf16_f32out(const void* A, long lda, const void* W, long ldw, const void* bias, float* C, long ldc, int M, int N,
                          int K, float scale, void* stream);
+/* P bf16 [M,N] = softmax over each row of the fp32 scores S (the mid block's single-head attention, Attention [ext]) */
 int utx_softmax_rows(const float* S, long lds, void* P, long ldp, int M, int N, void* stream);
+/* y [C,R] = x [R,C]^T (V^T operand of P @ V on the K-major GEMM) */
 int utx_transpose_bf16(const void* x, long ldx, void* y, long ldy, int R, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
