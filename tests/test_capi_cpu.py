@@ -64,3 +64,54 @@ def test_flux_handle_and_packing_on_cpu(lib):
     assert eng.lib.utx_flux_workspace_bytes(eng._handle, 128, 192) > (128 + 192) * D * 2 * 10
     # calling the engine without prepare() is an error, not a silent no-op
     assert eng.lib.utx_flux_forward(eng._handle, 1, 0.5, 3.5, 1, None) != 0
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: a cgo / JNI / FFI consumer must be able to include the header as C99 (no C++ constructs, no
+    torch or CUDA types in the signatures)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    hdr = ROOT / "include" / "unitex_b200.h"
+    src = tmp_path / "use.c"
+    src.write_text('#include "unitex_b200.h"\nint main(void) { return utx_version() < 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", f"-I{hdr.parent}", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    txt = hdr.read_text()
+    assert "torch" not in re.sub(r"/\*.*?\*/", "", txt, flags=re.S).lower() and "cudaStream_t" not in re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+
+
+def test_python_bindings_match_header():
+    """Every prototype of the header and its ctypes signature in unitex_b200/_lib.py take the same number of arguments of the same class
+    (pointer / int / 64-bit int / size_t / float) -- a binding that drifts from the header corrupts the call silently."""
+    from unitex_b200 import _lib
+    txt = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "unitex_b200.h").read_text(), flags=re.S)
+    protos = dict(re.findall(r"\b(utx_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S))
+    assert set(protos) == set(_lib._SIGS)
+    for name, args in protos.items():
+        args = " ".join(args.split())
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert n == len(_lib._SIGS[name][1]), f"{name}: header takes {n} arguments, _lib.py binds {len(_lib._SIGS[name][1])}"
+        if n == 0:
+            continue
+        for i, (decl, ct) in enumerate(zip(args.split(","), _lib._SIGS[name][1])):
+            assert _c_class(decl) == _ctypes_class(ct), f"{name} argument {i}: header `{decl.strip()}` vs binding {ct}"
+
+
+def _c_class(decl):
+    decl = decl.strip()
+    if "*" in decl:
+        return "ptr"
+    words = decl.replace("const", " ").replace("unsigned", " ").split()
+    words = words[:-1] if len(words) > 1 else words          # drop the parameter name
+    t = " ".join(words)
+    return {"int": "i32", "int32_t": "i32", "float": "f32", "double": "f64", "long": "i64", "long long": "i64", "size_t": "size"}[t]   # LP64: long = long long
+
+
+def _ctypes_class(ct):
+    if ct in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(ct, "contents") or issubclass(ct, ctypes._Pointer):
+        return "ptr"
+    assert ctypes.sizeof(ctypes.c_long) == 8
+    return {ctypes.c_int: "i32", ctypes.c_float: "f32", ctypes.c_double: "f64", ctypes.c_long: "i64", ctypes.c_longlong: "i64",
+            ctypes.c_size_t: "size"}[ct]
