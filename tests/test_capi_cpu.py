@@ -115,3 +115,37 @@ def _ctypes_class(ct):
     assert ctypes.sizeof(ctypes.c_long) == 8
     return {ctypes.c_int: "i32", ctypes.c_float: "f32", ctypes.c_double: "f64", ctypes.c_long: "i64", ctypes.c_longlong: "i64",
             ctypes.c_size_t: "size"}[ct]
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors of the header's structs (weights / config tables handed across the ABI by pointer) have the same
+    field names, order, offsets and sizes as the C declarations -- measured by compiling the header with gcc."""
+    import shutil
+    import subprocess
+    from unitex_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pairs = {"utx_flux_config": _lib.FluxConfigC, "utx_double_block": _lib.DoubleBlockC, "utx_single_block": _lib.SingleBlockC,
+             "utx_flux_weights": _lib.FluxWeightsC, "utx_vae_config": _lib.VaeConfigC, "utx_vae_resnet": _lib.VaeResnetC,
+             "utx_vae_attn": _lib.VaeAttnC, "utx_vae_mid": _lib.VaeMidC, "utx_vae_weights": _lib.VaeWeightsC}
+    txt = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "unitex_b200.h").read_text(), flags=re.S)
+    declared = set(re.findall(r"typedef struct (utx_[a-z_]+) \{", txt))
+    assert declared == set(pairs), declared ^ set(pairs)           # a new struct in the header needs a mirror and an entry here
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "unitex_b200.h"', 'int main(void) {']
+    for cname, ct in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    r = subprocess.run(["gcc", "-std=c99", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr                             # a field the mirror names but the header lacks fails here
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(ct), cname
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), txt, flags=re.S).group(1)
+        c_fields = [f for d in body.split(";") for f in re.findall(r"\**\s*([A-Za-z_][A-Za-z0-9_]*)\s*(?:\[\d+\])?\s*(?:,|$)", d.strip().split(" ", 1)[-1] if d.strip() else "")]
+        assert [n for n, _ in ct._fields_] == [f for f in c_fields if f not in ("const", "void", "float", "int")], cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
