@@ -1,4 +1,4 @@
-"""Times the 1-CTA and 2-CTA GEMM kernels at the DiT shapes with CUDA events (not under a profiler)."""
+"""Times the 2-CTA GEMM kernel at the DiT shapes with CUDA events (not under a profiler)."""
 import os, sys, json
 import torch
 sys.path.insert(0, ".")
